@@ -1,0 +1,45 @@
+// Host-side interface of the tcgen05 GEMM (see gemm_sm100.cu).
+#pragma once
+#include "common.cuh"
+
+namespace vlb {
+
+enum GemmOutKind : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_ATOMIC = 2 };
+enum GemmResidKind : int { RESID_NONE = 0, RESID_BF16 = 1, RESID_F32 = 2 };
+enum GemmAct : int {
+  ACT_NONE = 0,
+  ACT_GELU = 1,       // x = gelu_erf(x); if aux != null the pre-activation is stored there (bf16)
+  ACT_RELU = 2,
+  ACT_DGELU_MUL = 3,  // x = x * gelu_erf'(aux[row, col])      (aux: bf16 pre-activation)
+  ACT_DRELU_MUL = 4,  // x = aux[row, col] > 0 ? x : 0         (aux: bf16 post-activation)
+};
+// Operand layout modes.  "K-major" = reduction dimension contiguous in memory.
+//   GEMM_NT : C[M,N] = A[M,K] * B[N,K]^T      (forward  y = x W^T ; A, B K-major)
+//   GEMM_NN : C[M,N] = A[M,K] * B[K,N]        (dgrad    dx = dy W ; B is N-contiguous = MN-major)
+//   GEMM_TN : C[M,N] = A[K,M]^T * B[K,N]      (wgrad    dW = dy^T x ; both MN-major)
+enum GemmMode : int { GEMM_NT = 0, GEMM_NN = 1, GEMM_TN = 2 };
+
+struct GemmEpilogue {
+  void* out = nullptr;
+  int ldo = 0;
+  int out_kind = OUT_BF16;
+  const float* bias = nullptr;   // [N] fp32, optional
+  const void* resid = nullptr;   // [M, ldr], optional
+  int ldr = 0;
+  int resid_kind = RESID_NONE;
+  int act = ACT_NONE;
+  void* aux = nullptr;           // bf16 [M, ld_aux]
+  int ld_aux = 0;
+  float alpha = 1.0f;            // scale applied to the accumulator before everything else
+};
+
+// All matrices are bf16 row-major with leading dimensions in elements (multiples of 8).
+int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
+              const GemmEpilogue& epi, int split_k, int force_bn, cudaStream_t stream);
+
+// TMA descriptor helper shared with the attention kernels: 2D bf16 row-major [rows, cols] with
+// 128B swizzle; box = {box_cols (<=64), box_rows (<=256)}.
+int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_cols, uint32_t box_rows);
+
+}  // namespace vlb
