@@ -1,0 +1,312 @@
+"""TEST INFRASTRUCTURE ONLY -- portable fp32 CPU restatement of the reference hot path.
+
+This file is the ORACLE the CUDA path is checked against on the GPU box (where /root/reference does
+not exist).  It restates, in plain torch fp32 ops, the algorithms of
+
+  * common/visual_linguistic_bert.py:95-241        VisualLinguisticBert.forward / .embedding
+  * external/pytorch_pretrained_bert/modeling.py   gelu :114-120, BertLayerNorm :218-235,
+        BertSelfAttention :290-319, BertSelfOutput :329-333, BertIntermediate :361-364,
+        BertOutput :374-378, BertLayer :388-397, BertEncoder :406-421, BertPooler :430-436
+  * common/fast_rcnn.py:128-203 (precomputed-feature path), common/utils/bbox.py:33-65,
+        common/utils/pad_sequence.py:4-17
+
+It is PINNED against the real reference modules: tests/test_oracle_vs_reference.py imports the
+unmodified reference (oracle/ref_shim.py) in the build container and checks equality, and
+oracle/make_golden.py writes reference-generated fixtures to tests/golden/ which the oracle is
+re-checked against on every CPU test run (those fixtures travel; the reference does not).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import
+this module.  The product (vl-bert_b200/) never does.
+"""
+import math
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def default_config(**over):
+    """NETWORK.VLBERT defaults for BERT-base (reference: pretrain/function/config.py:87-115)."""
+    cfg = dict(
+        vocab_size=30522, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+        intermediate_size=3072, hidden_act="gelu", hidden_dropout_prob=0.0,
+        attention_probs_dropout_prob=0.0, max_position_embeddings=512, type_vocab_size=3,
+        initializer_range=0.02, visual_size=768, visual_scale_text_init=1.0, visual_scale_object_init=1.0,
+        visual_ln=True, word_embedding_frozen=False, with_pooler=True, position_padding_idx=-1,
+        obj_pos_id_relative=True,
+    )
+    cfg.update(over)
+    return SimpleNamespace(**cfg)
+
+
+# ------------------------------------------------------------------------------------------------
+# primitives
+# ------------------------------------------------------------------------------------------------
+def gelu_erf(x):
+    """modeling.py:120 -- exact erf form."""
+    return x * 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+def layer_norm_tf(x, weight, bias, eps=1e-12):
+    """modeling.py:231-235 -- biased variance, eps inside the sqrt."""
+    mu = x.mean(-1, keepdim=True)
+    var = (x - mu).pow(2).mean(-1, keepdim=True)
+    return weight * ((x - mu) / torch.sqrt(var + eps)) + bias
+
+
+def self_attention(x, add_mask, wq, bq, wk, bk, wv, bv, num_heads):
+    """modeling.py:290-315 (dropout p=0).  x [B,S,H]; add_mask [B,1,1,S] additive (0 / -10000)."""
+    B, S, H = x.shape
+    d = H // num_heads
+
+    def split(t):
+        return t.view(B, S, num_heads, d).permute(0, 2, 1, 3)
+
+    q, k, v = split(F.linear(x, wq, bq)), split(F.linear(x, wk, bk)), split(F.linear(x, wv, bv))
+    scores = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(d) + add_mask
+    probs = torch.softmax(scores, dim=-1)
+    ctx = torch.matmul(probs, v).permute(0, 2, 1, 3).contiguous().view(B, S, H)
+    return ctx
+
+
+def bert_layer(x, add_mask, p, num_heads, eps=1e-12):
+    """modeling.py:388-397.  `p` maps the reference's per-layer state_dict suffixes to tensors."""
+    ctx = self_attention(x, add_mask,
+                         p["attention.self.query.weight"], p["attention.self.query.bias"],
+                         p["attention.self.key.weight"], p["attention.self.key.bias"],
+                         p["attention.self.value.weight"], p["attention.self.value.bias"], num_heads)
+    a = F.linear(ctx, p["attention.output.dense.weight"], p["attention.output.dense.bias"]) + x
+    h = layer_norm_tf(a, p["attention.output.LayerNorm.weight"], p["attention.output.LayerNorm.bias"], eps)
+    u = gelu_erf(F.linear(h, p["intermediate.dense.weight"], p["intermediate.dense.bias"]))
+    y = F.linear(u, p["output.dense.weight"], p["output.dense.bias"]) + h
+    return layer_norm_tf(y, p["output.LayerNorm.weight"], p["output.LayerNorm.bias"], eps)
+
+
+def pack_indices(text_mask, object_mask):
+    """Integer index math of the left-packed [text ; regions ; END ; pad] sequence
+    (visual_linguistic_bert.py:200-227,235).  Returns int64 tensors, all [B, S]:
+      kind   0 text, 1 region, 2 END, 3 pad
+      src    source column inside text (kind 0) / object (kind 1) arrays, else 0
+      pos    position id minus (position_padding_idx + 1)
+      and text_end [B], object_end [B], S (python int).
+    The k-th True of text_mask[b] lands at packed position k, exactly what the reference's
+    boolean-mask assignment `vl[grid_pos < text_end] = text_vl[text_mask]` does."""
+    B = text_mask.shape[0]
+    text_end = text_mask.sum(1)
+    object_end = text_end + object_mask.sum(1)
+    S = int(object_end.max().item()) + 1
+    pos = torch.arange(S, dtype=torch.long).unsqueeze(0).expand(B, S)
+    te, oe = text_end.unsqueeze(1), object_end.unsqueeze(1)
+    kind = torch.full((B, S), 3, dtype=torch.long)
+    kind[pos < te] = 0
+    kind[(pos >= te) & (pos < oe)] = 1
+    kind[pos == oe] = 2
+    src = torch.zeros((B, S), dtype=torch.long)
+    for b in range(B):
+        t_idx = torch.nonzero(text_mask[b], as_tuple=False).flatten()
+        o_idx = torch.nonzero(object_mask[b], as_tuple=False).flatten()
+        src[b, : t_idx.numel()] = t_idx
+        src[b, t_idx.numel(): t_idx.numel() + o_idx.numel()] = o_idx
+    pos_id = pos.clone()
+    pos_id = torch.where(kind == 1, te.expand(B, S), pos_id)
+    pos_id = torch.where(kind == 2, (te + 1).expand(B, S), pos_id)
+    return kind, src, pos_id, text_end, object_end, S
+
+
+class _LN(nn.Module):
+    def __init__(self, n, eps=1e-12):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(n))
+        self.bias = nn.Parameter(torch.zeros(n))
+        self.eps = eps
+
+    def forward(self, x):
+        return layer_norm_tf(x, self.weight, self.bias, self.eps)
+
+
+class _SelfAtt(nn.Module):
+    def __init__(self, H):
+        super().__init__()
+        self.query, self.key, self.value = nn.Linear(H, H), nn.Linear(H, H), nn.Linear(H, H)
+
+
+class _SelfOut(nn.Module):
+    def __init__(self, I, H):
+        super().__init__()
+        self.dense = nn.Linear(I, H)
+        self.LayerNorm = _LN(H)
+
+
+class _Att(nn.Module):
+    def __init__(self, H):
+        super().__init__()
+        self.self = _SelfAtt(H)
+        self.output = _SelfOut(H, H)
+
+
+class _Inter(nn.Module):
+    def __init__(self, H, I):
+        super().__init__()
+        self.dense = nn.Linear(H, I)
+
+
+class _Layer(nn.Module):
+    def __init__(self, H, I):
+        super().__init__()
+        self.attention = _Att(H)
+        self.intermediate = _Inter(H, I)
+        self.output = _SelfOut(I, H)
+
+
+class _Encoder(nn.Module):
+    def __init__(self, L, H, I):
+        super().__init__()
+        self.layer = nn.ModuleList([_Layer(H, I) for _ in range(L)])
+
+
+class _Pooler(nn.Module):
+    def __init__(self, H):
+        super().__init__()
+        self.dense = nn.Linear(H, H)
+
+
+class VisualLinguisticBertOracle(nn.Module):
+    """Same constructor config, forward signature, return structure and state_dict keys as the
+    reference VisualLinguisticBert (common/visual_linguistic_bert.py:31-171) for the configuration
+    space the shipped cfgs use (visual_ln on, no word_embedding_frozen, obj_pos_id_relative)."""
+
+    def __init__(self, config, language_pretrained_model_path=None):
+        super().__init__()
+        assert language_pretrained_model_path is None
+        assert config.visual_ln and not config.word_embedding_frozen and config.obj_pos_id_relative
+        self.config = config
+        H = config.hidden_size
+        self.word_embeddings = nn.Embedding(config.vocab_size, H)
+        self.end_embedding = nn.Embedding(1, H)
+        self.position_embeddings = nn.Embedding(config.max_position_embeddings, H)
+        self.token_type_embeddings = nn.Embedding(config.type_vocab_size, H)
+        self.embedding_LayerNorm = _LN(H)
+        self.visual_1x1_text = None
+        self.visual_1x1_object = None
+        if config.visual_size != H:
+            self.visual_1x1_text = nn.Linear(config.visual_size, H)
+            self.visual_1x1_object = nn.Linear(config.visual_size, H)
+        self.visual_ln_text = _LN(H)
+        self.visual_ln_object = _LN(H)
+        self.encoder = _Encoder(config.num_hidden_layers, H, config.intermediate_size)
+        if config.with_pooler:
+            self.pooler = _Pooler(H)
+        self.position_padding_idx = config.position_padding_idx
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        std = self.config.initializer_range
+        for m in self.modules():
+            if isinstance(m, (nn.Linear, nn.Embedding)):
+                m.weight.data.normal_(mean=0.0, std=std)
+            if isinstance(m, nn.Linear):
+                m.bias.data.zero_()
+            if isinstance(m, _LN):
+                m.weight.data.fill_(1.0)
+                m.bias.data.zero_()
+        self.visual_ln_text.weight.data.fill_(self.config.visual_scale_text_init)
+        self.visual_ln_object.weight.data.fill_(self.config.visual_scale_object_init)
+
+    # -- embedding (visual_linguistic_bert.py:173-241) ---------------------------------------------
+    def embedding(self, text_input_ids, text_token_type_ids, text_visual_embeddings, text_mask,
+                  object_vl_embeddings, object_mask):
+        cfg = self.config
+        VS = cfg.visual_size
+        tv = text_visual_embeddings
+        ov = object_vl_embeddings[:, :, :VS]
+        if self.visual_1x1_text is not None:
+            tv = self.visual_1x1_text(tv)
+            ov = self.visual_1x1_object(ov)
+        text_vl = self.word_embeddings(text_input_ids) + self.visual_ln_text(tv)
+        obj_vl = object_vl_embeddings[:, :, VS:] + self.visual_ln_object(ov)
+
+        kind, src, pos_id, text_end, object_end, S = pack_indices(text_mask, object_mask)
+        B, H = text_vl.shape[0], text_vl.shape[-1]
+        bidx = torch.arange(B).unsqueeze(1).expand(B, S)
+        vl = text_vl.new_zeros((B, S, H))
+        is_t, is_o, is_e = kind == 0, kind == 1, kind == 2
+        vl[is_t] = text_vl[bidx[is_t], src[is_t]]
+        vl[is_o] = obj_vl[bidx[is_o], src[is_o]]
+        vl[is_e] = self.end_embedding.weight[0]
+        type_ids = torch.zeros((B, S), dtype=torch.long)
+        type_ids[is_t] = text_token_type_ids[bidx[is_t], src[is_t]]
+        type_ids[is_o | is_e] = 2
+        position_ids = pos_id + self.position_padding_idx + 1
+        emb = vl + self.position_embeddings(position_ids) + self.token_type_embeddings(type_ids)
+        emb = self.embedding_LayerNorm(emb)
+        mask = (kind != 3).to(text_mask.dtype)
+        return emb, mask, is_t, is_o
+
+    def _layer_params(self, i):
+        prefix = "encoder.layer.%d." % i
+        sd = dict(self.named_parameters())
+        return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+    def forward(self, text_input_ids, text_token_type_ids, text_visual_embeddings, text_mask,
+                object_vl_embeddings, object_mask, output_all_encoded_layers=True,
+                output_text_and_object_separately=False, output_attention_probs=False):
+        assert not output_attention_probs
+        emb, mask, is_t, is_o = self.embedding(text_input_ids, text_token_type_ids, text_visual_embeddings,
+                                               text_mask, object_vl_embeddings, object_mask)
+        add_mask = (1.0 - mask.to(emb.dtype)).unsqueeze(1).unsqueeze(2) * -10000.0
+        layers = []
+        h = emb
+        for i in range(self.config.num_hidden_layers):
+            h = bert_layer(h, add_mask, self._layer_params(i), self.config.num_attention_heads)
+            layers.append(h)
+        pooled = torch.tanh(self.pooler.dense(h[:, 0])) if self.config.with_pooler else None
+        encoded = layers if output_all_encoded_layers else layers[-1]
+        if not output_text_and_object_separately:
+            return encoded, pooled
+        T, R = text_input_ids.shape[1], object_vl_embeddings.shape[1]
+        lst = encoded if output_all_encoded_layers else [encoded]
+        texts, objs = [], []
+        for e in lst:
+            texts.append(e[:, :T])
+            o = e.new_zeros((e.shape[0], R, e.shape[2]))
+            o[object_mask] = e[is_o]
+            objs.append(o)
+        if not output_all_encoded_layers:
+            texts, objs = texts[0], objs[0]
+        return texts, objs, pooled
+
+
+# ------------------------------------------------------------------------------------------------
+# region-feature front end, precomputed-feature path
+# ------------------------------------------------------------------------------------------------
+def coordinate_embeddings(boxes6, dim=256):
+    """common/utils/bbox.py:33-65.  boxes6 [K,6] = (x1,y1,x2,y2,W,H) -> [K,4,2*dim]."""
+    x1, y1, x2, y2, W, Hh = boxes6.unbind(1)
+    pos = torch.stack(((x1 + x2) / 2 / W * 100, (y1 + y2) / 2 / Hh * 100, (x2 - x1) / W * 100, (y2 - y1) / Hh * 100), 1)
+    dim_mat = 1000 ** (torch.arange(dim, dtype=boxes6.dtype) / dim)
+    arg = pos.unsqueeze(-1) / dim_mat.view(1, 1, -1)
+    return torch.cat((arg.sin(), arg.cos()), dim=-1)
+
+
+def fast_rcnn_precomputed(boxes, box_mask, im_info, weight, bias, mvrc_ops=None, mask_visual_embed=None):
+    """common/fast_rcnn.py:136-193 with IMAGE_FEAT_PRECOMPUTED, no classes/segms, dropout p=0.
+    boxes [B,R,4+2048]; weight [final_dim,4096]; returns (obj_reps [B,R,final_dim], obj_reps_raw [B,R,2048])."""
+    B, R = box_mask.shape
+    idx = box_mask.nonzero()
+    assert idx.shape[0] > 0
+    feats = boxes[idx[:, 0], idx[:, 1]][:, 4:]
+    coords = boxes[idx[:, 0], idx[:, 1]][:, :4]
+    if mvrc_ops is not None and mask_visual_embed is not None:
+        feats = feats.clone()
+        feats[(mvrc_ops == 1)[idx[:, 0], idx[:, 1]]] = mask_visual_embed
+    ce = coordinate_embeddings(torch.cat((coords, im_info[idx[:, 0], :2]), 1), 256)
+    x = torch.cat((ce.reshape(ce.shape[0], -1), feats), -1)
+    final = torch.relu(F.linear(x, weight, bias))
+    # pad_sequence (common/utils/pad_sequence.py): the k-th valid box of sample b lands in slot k
+    slot = torch.cumsum(box_mask.long(), 1) - 1
+    obj_reps = final.new_zeros((B, R, final.shape[1]))
+    raw = feats.new_zeros((B, R, feats.shape[1]))
+    obj_reps[idx[:, 0], slot[idx[:, 0], idx[:, 1]]] = final
+    raw[idx[:, 0], slot[idx[:, 0], idx[:, 1]]] = feats
+    return obj_reps, raw
