@@ -1,0 +1,205 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by executing the UNMODIFIED reference
+(/root/reference, via oracle/ref_shim.py) on seeded synthetic inputs.  Run in the build container:
+
+    python oracle/make_golden.py
+
+Fixtures (kept small enough to commit):
+  vlbert_tiny.npz        VisualLinguisticBert, H=128 (2 heads x 64), I=256, L=2, vocab 200: full
+                         state_dict + inputs + every output + gradients of every parameter/input.
+  vlbert_c1_base.npz     BASELINE config 1 shape (base width 768/12 heads, L=2, B=2, T=8, R=4, S<=13):
+                         weights are re-generated from a seed by the test (too big to commit);
+                         outputs + small gradients + norms of the big gradients are stored.
+  fastrcnn_prec.npz      FastRCNN precomputed-feature path (final_dim=32) incl. coordinate embeddings.
+  roi_align_debug.npz    common/lib/roi_pooling/debug.py inputs + a 38x63 realistic case through the
+                         reference's own CPU kernel (oracle/_ref, built by oracle/build_ref.py).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402
+
+GOLD = os.path.join(HERE, "..", "tests", "golden")
+
+
+def synth_vlbert_inputs(B, T, R, H, vocab, seed, ragged=True):
+    """Shared with the tests (tests/synth.py re-implements the same calls in the same order)."""
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(min(1000, vocab // 2), vocab, (B, T), generator=g)
+    types = torch.randint(0, 2, (B, T), generator=g)
+    tvis = torch.randn(B, T, H, generator=g)
+    ovl = torch.randn(B, R, 2 * H, generator=g)
+    tmask = torch.ones(B, T, dtype=torch.bool)
+    omask = torch.ones(B, R, dtype=torch.bool)
+    if ragged:
+        for b in range(B):
+            tl = int(torch.randint(max(1, T // 2), T + 1, (1,), generator=g))
+            ol = int(torch.randint(1, R + 1, (1,), generator=g))
+            if b == 0:
+                tl, ol = T, R  # one full sample so S = T + R + 1
+            tmask[b, tl:] = False
+            omask[b, ol:] = False
+        ids = ids * tmask
+    return ids, types, tvis, tmask, ovl, omask
+
+
+def seeded_state_dict(model, seed, std=0.02):
+    """Deterministic weights: N(0, std) for matrices/embeddings, LayerNorm weight ~ 1 + N(0, .1),
+    biases N(0, .02) -- non-trivial values everywhere so that no term hides behind a zero."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, v in model.state_dict().items():
+        if "LayerNorm.weight" in k or k.startswith("visual_ln") and k.endswith("weight"):
+            sd[k] = 1.0 + 0.1 * torch.randn(v.shape, generator=g)
+        elif k.endswith("bias"):
+            sd[k] = 0.02 * torch.randn(v.shape, generator=g)
+        else:
+            sd[k] = std * torch.randn(v.shape, generator=g)
+    return sd
+
+
+def run_vlbert(model, inputs, seed):
+    ids, types, tvis, tmask, ovl, omask = inputs
+    tvis = tvis.clone().requires_grad_(True)
+    ovl = ovl.clone().requires_grad_(True)
+    layers, pooled = model(ids, types, tvis, tmask, ovl, omask, output_all_encoded_layers=True,
+                           output_text_and_object_separately=False)
+    g = torch.Generator().manual_seed(seed + 1)
+    gw = [torch.randn(l.shape, generator=g) for l in layers]
+    gp = torch.randn(pooled.shape, generator=g)
+    loss = sum((l * w).sum() for l, w in zip(layers, gw)) * 0.5 + (pooled * gp).sum()
+    # heavier weight on the last layer, all layers get gradient (output_all_encoded_layers=True)
+    loss = loss + (layers[-1] * gw[-1]).sum() * 0.5
+    model.zero_grad()
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    return layers, pooled, loss.detach(), grads, tvis.grad, ovl.grad
+
+
+def golden_vlbert_tiny():
+    from common.visual_linguistic_bert import VisualLinguisticBert
+    cfg = ref_shim.vlbert_config(vocab_size=200, hidden_size=128, num_hidden_layers=2, num_attention_heads=2,
+                                 intermediate_size=256, max_position_embeddings=64, visual_size=128)
+    torch.manual_seed(0)
+    model = VisualLinguisticBert(cfg).eval()
+    sd = seeded_state_dict(model, 11, std=0.05)
+    model.load_state_dict(sd)
+    inputs = synth_vlbert_inputs(B=3, T=9, R=5, H=128, vocab=200, seed=21)
+    layers, pooled, loss, grads, gtv, gov = run_vlbert(model, inputs, 31)
+    # also the text/object split outputs
+    with torch.no_grad():
+        tx, ob, _ = model(*inputs, output_all_encoded_layers=False, output_text_and_object_separately=True)
+        emb, mask, is_t, is_o = model.embedding(*inputs)
+    out = {"sd." + k: v.numpy() for k, v in sd.items()}
+    out.update({"grad." + k: v.numpy() for k, v in grads.items()})
+    for i, l in enumerate(layers):
+        out["layer%d" % i] = l.detach().numpy()
+    out.update(pooled=pooled.detach().numpy(), loss=loss.numpy(), grad_text_visual=gtv.numpy(), grad_object_vl=gov.numpy(),
+               split_text=tx.numpy(), split_object=ob.numpy(), embedding=emb.numpy(), mask=mask.numpy(),
+               is_text=is_t.numpy(), is_object=is_o.numpy())
+    np.savez_compressed(os.path.join(GOLD, "vlbert_tiny.npz"), **out)
+    print("vlbert_tiny: loss", float(loss), "S", layers[0].shape[1])
+
+
+def golden_vlbert_c1():
+    from common.visual_linguistic_bert import VisualLinguisticBert
+    cfg = ref_shim.vlbert_config(num_hidden_layers=2)
+    torch.manual_seed(0)
+    model = VisualLinguisticBert(cfg).eval()
+    sd = seeded_state_dict(model, 12)
+    model.load_state_dict(sd)
+    inputs = synth_vlbert_inputs(B=2, T=8, R=4, H=768, vocab=30522, seed=22)
+    layers, pooled, loss, grads, gtv, gov = run_vlbert(model, inputs, 32)
+    out = {}
+    for i, l in enumerate(layers):
+        out["layer%d" % i] = l.detach().numpy()
+    out.update(pooled=pooled.detach().numpy(), loss=loss.numpy(), grad_text_visual=gtv.numpy(), grad_object_vl=gov.numpy())
+    for k, v in grads.items():
+        if v.numel() <= 4096:
+            out["grad." + k] = v.numpy()
+        else:
+            out["gradnorm." + k] = np.float64(v.double().norm().item())
+            out["gradhead." + k] = v.flatten()[:256].numpy()
+    np.savez_compressed(os.path.join(GOLD, "vlbert_c1_base.npz"), **out)
+    print("vlbert_c1_base: loss", float(loss), "S", layers[0].shape[1])
+
+
+def golden_fastrcnn():
+    from easydict import EasyDict
+    from common.fast_rcnn import FastRCNN
+    cfg = EasyDict({"NETWORK": {"IMAGE_FEAT_PRECOMPUTED": True, "IMAGE_SEMANTIC": False}})
+    torch.manual_seed(0)
+    m = FastRCNN(cfg, average_pool=True, final_dim=32, enable_cnn_reg_loss=False).eval()
+    g = torch.Generator().manual_seed(41)
+    B, R = 3, 6
+    w = 0.02 * torch.randn(32, 4096, generator=g)
+    b = 0.02 * torch.randn(32, generator=g)
+    m.obj_downsample[1].weight.data.copy_(w)
+    m.obj_downsample[1].bias.data.copy_(b)
+    im_info = torch.tensor([[600., 400., 1, 1], [512., 384., 1, 1], [1000., 600., 1, 1]])
+    x1 = torch.rand(B, R, generator=g) * im_info[:, None, 0] * 0.6
+    y1 = torch.rand(B, R, generator=g) * im_info[:, None, 1] * 0.6
+    x2 = x1 + 8 + torch.rand(B, R, generator=g) * im_info[:, None, 0] * 0.39
+    y2 = y1 + 8 + torch.rand(B, R, generator=g) * im_info[:, None, 1] * 0.39
+    feats = torch.randn(B, R, 2048, generator=g)
+    boxes = torch.cat((torch.stack((x1, y1, x2, y2), -1), feats), -1)
+    box_mask = torch.ones(B, R, dtype=torch.bool)
+    box_mask[1, 4:] = False
+    box_mask[2, 1:] = False
+    boxes[~box_mask] = -2.0  # pretrain/data/collate_batch.py:39 pads with -2
+    boxes_in = boxes.clone().requires_grad_(True)
+    out = m(images=None, boxes=boxes_in, box_mask=box_mask, im_info=im_info)
+    gw = torch.randn(out["obj_reps"].shape, generator=g)
+    (out["obj_reps"] * gw).sum().backward()
+    from common.utils.bbox import coordinate_embeddings
+    idx = box_mask.nonzero()
+    ce = coordinate_embeddings(torch.cat((boxes[idx[:, 0], idx[:, 1]][:, :4], im_info[idx[:, 0], :2]), 1), 256)
+    np.savez_compressed(os.path.join(GOLD, "fastrcnn_prec.npz"), weight=w.numpy(), bias=b.numpy(), boxes=boxes.numpy(),
+                        box_mask=box_mask.numpy(), im_info=im_info.numpy(), obj_reps=out["obj_reps"].detach().numpy(),
+                        obj_reps_raw=out["obj_reps_raw"].detach().numpy(), grad_out=gw.numpy(),
+                        grad_weight=m.obj_downsample[1].weight.grad.numpy(), grad_bias=m.obj_downsample[1].bias.grad.numpy(),
+                        grad_boxes=boxes_in.grad.numpy(), coord_embed=ce.numpy())
+    print("fastrcnn_prec: obj_reps", tuple(out["obj_reps"].shape))
+
+
+def golden_roi_align():
+    import build_ref
+    ref = build_ref.load()
+    out = {}
+    f = torch.arange(81 * 2 * 3).view(2, 3, 9, 9).float()
+    rois = torch.tensor([[0, 0, 0, 9, 9], [1, 0, 0, 9, 9], [1, 0, 0, 7, 7]]).float()
+    out["debug_feature"], out["debug_rois"] = f.numpy(), rois.numpy()
+    for sr in (1, 2, 0):
+        out["debug_out_sr%d" % sr] = ref.roi_align_forward(f, rois, 1.0, 3, 3, sr).numpy()
+    g = torch.Generator().manual_seed(51)
+    f = torch.randn(2, 16, 38, 63, generator=g)
+    K = 24
+    x1 = torch.rand(K, generator=g) * 800
+    y1 = torch.rand(K, generator=g) * 500
+    w = torch.rand(K, generator=g) * 400 + 2
+    h = torch.rand(K, generator=g) * 300 + 2
+    rois = torch.stack([torch.randint(0, 2, (K,), generator=g).float(), x1, y1, x1 + w, y1 + h], 1)
+    rois[0] = torch.tensor([0, -40., -30., 20., 10.])      # partially outside
+    rois[1] = torch.tensor([1, 100., 100., 100.2, 100.1])  # degenerate -> clamped to 1x1 (ROIAlign_cuda.cu:92-93)
+    rois[2] = torch.tensor([1, 990., 590., 1100., 700.])   # beyond the 1008x608 extent
+    out["real_feature"], out["real_rois"] = f.numpy(), rois.numpy()
+    out["real_out_sr1"] = ref.roi_align_forward(f, rois, 1.0 / 16, 14, 14, 1).numpy()
+    out["real_out_sr2"] = ref.roi_align_forward(f, rois, 1.0 / 16, 14, 14, 2).numpy()
+    np.savez_compressed(os.path.join(GOLD, "roi_align_debug.npz"), **out)
+    print("roi_align_debug: from the reference's own CPU kernel (oracle/_ref)")
+
+
+if __name__ == "__main__":
+    ref_shim.install()
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(8)
+    golden_vlbert_tiny()
+    golden_vlbert_c1()
+    golden_fastrcnn()
+    golden_roi_align()
+    for f in sorted(os.listdir(GOLD)):
+        print(f, os.path.getsize(os.path.join(GOLD, f)) // 1024, "KiB")

@@ -1,0 +1,51 @@
+"""CPU, build container only: the oracle against the LIVE unmodified reference (skipped where
+/root/reference is absent, e.g. on the GPU box -- there the committed fixtures pin it)."""
+import numpy as np
+import pytest
+import torch
+
+import ref_shim
+import vlbert_oracle as vo
+from synth import seeded_state_dict, synth_vlbert_inputs
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_oracle_equals_reference_module(ragged):
+    ref_shim.install()
+    from common.visual_linguistic_bert import VisualLinguisticBert
+    kw = dict(vocab_size=300, hidden_size=128, num_hidden_layers=3, num_attention_heads=2, intermediate_size=512,
+              max_position_embeddings=80, visual_size=128, with_pooler=True)
+    torch.manual_seed(0)
+    ref = VisualLinguisticBert(ref_shim.vlbert_config(**kw)).eval()
+    ora = vo.VisualLinguisticBertOracle(vo.default_config(**kw)).eval()
+    sd = seeded_state_dict(ref, 5, std=0.05)
+    ref.load_state_dict(sd)
+    ora.load_state_dict(sd, strict=True)
+    inputs = synth_vlbert_inputs(B=4, T=12, R=7, H=128, vocab=300, seed=9, ragged=ragged)
+    with torch.no_grad():
+        a = ref(*inputs, output_all_encoded_layers=True, output_text_and_object_separately=True)
+        b = ora(*inputs, output_all_encoded_layers=True, output_text_and_object_separately=True)
+    for la, lb in zip(a[0], b[0]):
+        assert torch.allclose(la, lb, atol=2e-5, rtol=1e-5)
+    for la, lb in zip(a[1], b[1]):
+        assert torch.allclose(la, lb, atol=2e-5, rtol=1e-5)
+    assert torch.allclose(a[2], b[2], atol=2e-5, rtol=1e-5)
+
+
+def test_reference_cpu_roialign_equals_c_oracle():
+    import build_ref
+    import roi_align as ro
+    ref = build_ref.load()
+    g = torch.Generator().manual_seed(3)
+    f = torch.randn(2, 8, 38, 63, generator=g)
+    K = 40
+    x1 = torch.rand(K, generator=g) * 900
+    y1 = torch.rand(K, generator=g) * 550
+    rois = torch.stack([torch.randint(0, 2, (K,), generator=g).float(), x1, y1, x1 + torch.rand(K, generator=g) * 300,
+                        y1 + torch.rand(K, generator=g) * 300], 1)
+    for sr in (1, 2, 0):
+        a = ref.roi_align_forward(f, rois, 1 / 16.0, 14, 14, sr).numpy()
+        b = ro.roi_align_forward(f.numpy(), rois.numpy(), 1 / 16.0, 14, 14, sr)
+        assert np.array_equal(a, b)
