@@ -38,6 +38,13 @@ const char* vlb_last_error_string(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t vlb_launch_count(void);
 
+/* Per-launch device timing for bench.py's roofline.  While enabled, GEMM / attention / LayerNorm launchers bracket
+ * their kernel with CUDA events on the launch stream.  vlb_profile_collect() waits for the recorded events and
+ * returns, per category (0 gemm NT, 1 gemm NN, 2 gemm TN, 3 mhsa fwd, 4 mhsa bwd, 5 LN fwd, 6 LN bwd, 7 other; arrays
+ * of 8), the summed milliseconds, algorithmic work (FLOPs for 0-4, bytes for 5-6) and launch count, then resets. */
+void vlb_profile_enable(int on);
+int vlb_profile_collect(double* ms, double* work, int64_t* launches);
+
 /* ---- GEMM (tcgen05) --------------------------------------------------------------------------
  * Replaces the torch.nn.Linear / F.linear calls of the encoder layer and their autograd backward
  * (modeling.py:291-293, :330, :362, :375; common/fast_rcnn.py:105-109 obj_downsample).
@@ -57,6 +64,158 @@ int vlb_gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const v
 
 /* bring-up aid: override the MN-major shared-memory descriptor geometry (0 = default). */
 void vlb_debug_gemm_desc(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t mn_kadv);
+
+/* ---- fused multi-head self-attention ---------------------------------------------------------
+ * Replaces BertSelfAttention.forward after the three Linear layers (modeling.py:295-315):
+ *   ctx[b*S+s, h*64:(h+1)*64] = softmax(q k^T / 8 + add_mask[b, :]) v        head size 64, S <= 128
+ * qkv: bf16 [B*S, 3H] (q | k | v column blocks, the output of one fused QKV GEMM); add_mask: f32 [B,S]
+ * additive (0 / -10000, common/visual_linguistic_bert.py:119-127) or NULL; ctx: bf16 [B*S, H];
+ * lse: f32 [B, heads, S] log-sum-exp of the masked scaled scores (saved for backward; may be NULL
+ * in forward-only use).  Backward writes dqkv bf16 [B*S, 3H] from dctx bf16 [B*S, H].
+ */
+int vlb_mhsa_forward(const void* qkv, const float* add_mask, void* ctx, float* lse, int B, int S, int H,
+                     int heads, void* stream);
+int vlb_mhsa_backward(const void* qkv, const float* add_mask, const void* ctx, const float* lse,
+                      const void* dctx, void* dqkv, int B, int S, int H, int heads, void* stream);
+
+/* ---- LayerNorm (TF style, eps inside the sqrt) -----------------------------------------------
+ * Replaces BertLayerNorm.forward (modeling.py:231-235) and its autograd backward.
+ * forward : x f32 [M, H] (row stride ldx) -> y bf16 and/or f32 [M, H]; mean / rstd f32 [M] (optional)
+ * backward: dy = dy_bf16 (+ dy_f32), either may be NULL; dx to bf16 [M,H] and/or f32 (row stride ld_dx);
+ *           dgamma / dbeta / dcolsum f32 [H] are ACCUMULATED (+=), each optional.
+ *           dcolsum = sum over rows of dx = bias gradient of the Linear that produced x.
+ */
+int vlb_layernorm_forward(const float* x, int ldx, const float* gamma, const float* beta, void* y_bf16,
+                          float* y_f32, float* mean, float* rstd, int M, int H, float eps, void* stream);
+int vlb_layernorm_backward(const void* dy_bf16, const float* dy_f32, const float* x, int ldx,
+                           const float* mean, const float* rstd, const float* gamma, void* dx_bf16,
+                           float* dx_f32, int ld_dx, float* dgamma, float* dbeta, float* dcolsum, int M,
+                           int H, void* stream);
+/* out[n] += sum_m x[m, n]   (x bf16 [M, N], ld in elements) -- bias gradients */
+int vlb_colsum_bf16(const void* x, int ld, float* out, int M, int N, void* stream);
+int vlb_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
+int vlb_cast_bf16_to_f32(const void* in, float* out, int64_t n, void* stream);
+/* Many casts/copies in one launch (the fp32 master weights -> bf16 operand copies of a whole encoder).
+ * `descs_device` is a DEVICE array of `count` descriptors; src is f32, 16-byte aligned when bf16 dst. */
+typedef struct VlbCastDesc {
+  const void* src;     /* f32 */
+  void* dst;           /* bf16 if dst_is_bf16 else f32 */
+  int64_t n;           /* elements */
+  int64_t dst_is_bf16;
+} VlbCastDesc;
+int vlb_multi_cast(const VlbCastDesc* descs_device, int count, int blocks_per_tensor, void* stream);
+
+/* ---- embedding gather / sequence packing -----------------------------------------------------
+ * Replaces VisualLinguisticBert.embedding (common/visual_linguistic_bert.py:173-241) index math and
+ * gathers, and the output un-packing (:146-159).
+ * vlb_pack_index: masks are uint8 [B,T] / [B,R]; S = caller's max_length (>= max_b(text_end+object_end)+1).
+ *   kind/src/pos_id/type_id int32 [B,S]; add_mask f32 [B,S]; obj_row int32 [B,R]; lens int32 [B,2];
+ *   err int32[1] is OR-ed with 1 (S too small), 2 (position id out of range), 4 (token id out of range).
+ *   pos_offset = position_padding_idx + 1.
+ * vlb_pack_forward: e f32 [B*S, H] = vl + position_emb + token_type_emb (pre-LayerNorm sum).
+ *   text_vis_ln f32 [B*T,H] / obj_vis_ln f32 [B*R,H] are the already LayerNorm-ed visual streams;
+ *   object_vl f32 [B*R, ld_obj], its linguistic half starts at column lin_off.
+ * vlb_pack_backward: scatters de f32 [B*S,H] into the embedding-table gradients (atomic +=, optional)
+ *   and into dense d_text_vl [B*T,H] / d_obj_vl [B*R,H] (plain stores; caller zero-fills).
+ */
+int vlb_pack_index(const uint8_t* text_mask, const uint8_t* object_mask, const int64_t* text_type_ids,
+                   int B, int T, int R, int S, int pos_offset, int32_t* kind, int32_t* src, int32_t* pos_id,
+                   int32_t* type_id, float* add_mask, int32_t* obj_row, int32_t* lens, int32_t* err,
+                   void* stream);
+int vlb_pack_forward(const int32_t* kind, const int32_t* src, const int32_t* pos_id, const int32_t* type_id,
+                     const int64_t* ids, const float* word_emb, const float* end_emb, const float* pos_emb,
+                     const float* type_emb, const float* text_vis_ln, const float* obj_vis_ln,
+                     const float* object_vl, int ld_obj, int lin_off, float* e, int B, int T, int R, int S,
+                     int H, int vocab, int max_pos, int32_t* err, void* stream);
+int vlb_pack_backward(const int32_t* kind, const int32_t* src, const int32_t* pos_id, const int32_t* type_id,
+                      const int64_t* ids, const float* de, float* d_word, float* d_end, float* d_pos,
+                      float* d_type, float* d_text_vl, float* d_obj_vl, int B, int T, int R, int S, int H,
+                      int vocab, int max_pos, void* stream);
+/* out[i,:] = idx[i] >= 0 ? in[idx[i],:] : 0     /    out[idx[i],:] += in[i,:] (idx[i] >= 0, out f32) */
+int vlb_gather_rows(const void* in, int in_is_bf16, int ld_in, const int32_t* idx, void* out, int out_is_bf16,
+                    int ld_out, int n_out, int H, void* stream);
+int vlb_scatter_rows_add(const void* in, int in_is_bf16, int ld_in, const int32_t* idx, float* out, int ld_out,
+                         int n_in, int H, void* stream);
+
+/* ---- RoIAlign ---------------------------------------------------------------------------------
+ * Replaces the reference's only native extension, pybind11 module C_ROIPooling
+ * (common/lib/roi_pooling/vision.cpp:6-11):
+ *   roi_align_forward (Tensor input[N,C,H,W], Tensor rois[K,5], float spatial_scale, int pooled_h,
+ *                      int pooled_w, int sampling_ratio) -> Tensor[K,C,ph,pw]        (ROIAlign.h:11-25)
+ *   roi_align_backward(Tensor grad[K,C,ph,pw], rois, spatial_scale, ph, pw, batch_size, channels, height,
+ *                      width, sampling_ratio) -> Tensor[N,C,H,W]                     (ROIAlign.h:27-45)
+ * fp32, NCHW, contiguous (the reference forces .float() and .contiguous(), roi_align.py:69,
+ * ROIAlign_cuda.cu:286,294).  K == 0 is a no-op (ROIAlign_cuda.cu:278-281).  Backward zero-fills grad_in.
+ * roi_pool_* of the same module is dead code on the hot path (ROIPool is never instantiated,
+ * common/fast_rcnn.py:10,66) and is not provided.
+ */
+int vlb_roi_align_forward(const float* input, const float* rois, float* out, int K, int C, int H, int W,
+                          int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio, void* stream);
+int vlb_roi_align_backward(const float* grad_out, const float* rois, float* grad_in, int K, int N, int C, int H,
+                           int W, int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio,
+                           void* stream);
+/* Precomputed-feature path of FastRCNN.forward (common/fast_rcnn.py:140-142,170-174 + bbox.py:33-65):
+ * builds the bf16 operand A [B*R, 2048 + feat_dim] = [coordinate embedding | feature] for the
+ * obj_downsample GEMM (all-zero rows where box_mask == 0) and the pad_sequence gather index
+ * (gather_idx int32 [B*R]: slot k of sample b <- k-th valid box, else -1).  boxes f32 [B*R, ld_box]
+ * with (x1,y1,x2,y2,feat...); im_info f32 [B, ld_info] = (W, H, ...); mvrc_ops int64 [B*R] and
+ * mask_visual_embed f32 [feat_dim] optional (NULL). */
+int vlb_region_operand(const float* boxes, int ld_box, const uint8_t* box_mask, const float* im_info,
+                       int ld_info, const int64_t* mvrc_ops, const float* mask_visual_embed, void* A,
+                       int32_t* gather_idx, int B, int R, int feat_dim, void* stream);
+
+/* ---- one BertLayer, forward and backward -------------------------------------------------------
+ * Replaces BertLayer.forward (modeling.py:388-397) = BertAttention + BertIntermediate + BertOutput and
+ * its autograd backward, as a fixed sequence of the kernels above on `stream`
+ * (dropout probabilities are 0 on this path).  M = B*S rows.
+ */
+typedef struct VlbLayerWeights {
+  const void* w_qkv;   /* bf16 [3H, H]  rows: query | key | value weights (modeling.py:277-279) */
+  const float* b_qkv;  /* f32 [3H] */
+  const void* w_o;     /* bf16 [H, H]   attention.output.dense */
+  const float* b_o;
+  const float* ln1_g;  /* attention.output.LayerNorm */
+  const float* ln1_b;
+  const void* w_1;     /* bf16 [I, H]   intermediate.dense */
+  const float* b_1;
+  const void* w_2;     /* bf16 [H, I]   output.dense */
+  const float* b_2;
+  const float* ln2_g;  /* output.LayerNorm */
+  const float* ln2_b;
+} VlbLayerWeights;
+
+typedef struct VlbLayerActs { /* saved activations of one layer, caller-allocated */
+  void* qkv;       /* bf16 [M, 3H] */
+  void* ctx;       /* bf16 [M, H]  */
+  float* lse;      /* f32 [B, heads, S] */
+  float* a;        /* f32 [M, H]   dense(ctx) + x, input of LayerNorm 1 */
+  float* ln1_mean; /* f32 [M] */
+  float* ln1_rstd;
+  void* h;         /* bf16 [M, H]  attention output */
+  void* z;         /* bf16 [M, I]  pre-GELU */
+  void* u;         /* bf16 [M, I]  GELU output */
+  float* y0;       /* f32 [M, H]   dense(u) + h, input of LayerNorm 2 */
+  float* ln2_mean;
+  float* ln2_rstd;
+  void* y;         /* bf16 [M, H]  layer output */
+  float* y_f32;    /* optional f32 copy of the layer output (NULL to skip) */
+} VlbLayerActs;
+
+typedef struct VlbLayerGrads { /* f32, ACCUMULATED (+=); caller zero-fills or passes existing .grad */
+  float* dw_qkv; float* db_qkv; float* dw_o; float* db_o; float* dln1_g; float* dln1_b;
+  float* dw_1; float* db_1; float* dw_2; float* db_2; float* dln2_g; float* dln2_b;
+} VlbLayerGrads;
+
+int vlb_bert_layer_forward(const VlbLayerWeights* w, const void* x_bf16, const float* add_mask,
+                           const VlbLayerActs* acts, int B, int S, int H, int heads, int I, float eps,
+                           void* stream);
+/* bytes of scratch vlb_bert_layer_backward needs */
+int64_t vlb_bert_layer_backward_workspace(int M, int H, int I);
+/* dy = dy_bf16 (+ dy_f32), either may be NULL; dx_bf16 [M, H] receives the gradient wrt x. */
+int vlb_bert_layer_backward(const VlbLayerWeights* w, const VlbLayerActs* acts, const void* x_bf16,
+                            const float* add_mask, const void* dy_bf16, const float* dy_f32, void* dx_bf16,
+                            const VlbLayerGrads* grads, void* workspace, int64_t workspace_bytes, int B, int S,
+                            int H, int heads, int I, void* stream);
 
 #ifdef __cplusplus
 }

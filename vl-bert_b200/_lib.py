@@ -33,6 +33,58 @@ def _declare(lib):
     lib.vlb_debug_gemm_desc.restype = None
     lib.vlb_debug_gemm_desc.argtypes = [c_uint32, c_uint32, c_uint32]
 
+    P, I, F, L = c_void_p, c_int, c_float, c_int64
+
+    def decl(name, args, res=c_int):
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+
+    decl("vlb_profile_enable", [I], None)
+    decl("vlb_profile_collect", [P, P, P])
+    decl("vlb_mhsa_forward", [P, P, P, P, I, I, I, I, P])
+    decl("vlb_mhsa_backward", [P, P, P, P, P, P, I, I, I, I, P])
+    decl("vlb_layernorm_forward", [P, I, P, P, P, P, P, P, I, I, F, P])
+    decl("vlb_layernorm_backward", [P, P, P, I, P, P, P, P, P, I, P, P, P, I, I, P])
+    decl("vlb_colsum_bf16", [P, I, P, I, I, P])
+    decl("vlb_cast_f32_to_bf16", [P, P, L, P])
+    decl("vlb_cast_bf16_to_f32", [P, P, L, P])
+    decl("vlb_multi_cast", [P, I, I, P])
+    decl("vlb_pack_index", [P, P, P, I, I, I, I, I, P, P, P, P, P, P, P, P, P])
+    decl("vlb_pack_forward", [P, P, P, P, P, P, P, P, P, P, P, P, I, I, P, I, I, I, I, I, I, I, P, P])
+    decl("vlb_pack_backward", [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P])
+    decl("vlb_gather_rows", [P, I, I, P, P, I, I, I, I, P])
+    decl("vlb_scatter_rows_add", [P, I, I, P, P, I, I, I, P])
+    decl("vlb_roi_align_forward", [P, P, P, I, I, I, I, I, I, F, I, P])
+    decl("vlb_roi_align_backward", [P, P, P, I, I, I, I, I, I, I, F, I, P])
+    decl("vlb_region_operand", [P, I, P, P, I, P, P, P, P, I, I, I, P])
+    decl("vlb_bert_layer_forward", [P, P, P, P, I, I, I, I, I, F, P])
+    decl("vlb_bert_layer_backward_workspace", [I, I, I], L)
+    decl("vlb_bert_layer_backward", [P, P, P, P, P, P, P, P, P, L, I, I, I, I, I, P])
+
+
+class LayerWeights(ctypes.Structure):
+    """VlbLayerWeights (include/vlbert_b200.h)"""
+    _fields_ = [(n, c_void_p) for n in ("w_qkv", "b_qkv", "w_o", "b_o", "ln1_g", "ln1_b", "w_1", "b_1", "w_2", "b_2",
+                                        "ln2_g", "ln2_b")]
+
+
+class LayerActs(ctypes.Structure):
+    """VlbLayerActs"""
+    _fields_ = [(n, c_void_p) for n in ("qkv", "ctx", "lse", "a", "ln1_mean", "ln1_rstd", "h", "z", "u", "y0", "ln2_mean",
+                                        "ln2_rstd", "y", "y_f32")]
+
+
+class LayerGrads(ctypes.Structure):
+    """VlbLayerGrads"""
+    _fields_ = [(n, c_void_p) for n in ("dw_qkv", "db_qkv", "dw_o", "db_o", "dln1_g", "dln1_b", "dw_1", "db_1", "dw_2",
+                                        "db_2", "dln2_g", "dln2_b")]
+
+
+class CastDesc(ctypes.Structure):
+    """VlbCastDesc"""
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("n", c_int64), ("dst_is_bf16", c_int64)]
+
 
 def lib():
     """Load (once) and return the ctypes handle; raises if the library has not been built."""

@@ -2,10 +2,12 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <vector>
 
 #include "../../include/vlbert_b200.h"
 #include "common.cuh"
 #include "gemm_sm100.cuh"
+#include "ops.cuh"
 
 namespace vlb {
 
@@ -37,8 +39,36 @@ int num_sms() {
   return n;
 }
 
+namespace {
+struct ProfRec { cudaEvent_t a, b; int cat; double work; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_event_pool;
+cudaEvent_t prof_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+}  // namespace
+
+ProfScope::ProfScope(int cat, double work, cudaStream_t stream) : idx_(-1), stream_(stream) {
+  if (!g_prof_on) return;
+  ProfRec r; r.a = prof_event(); r.b = prof_event(); r.cat = cat; r.work = work;
+  cudaEventRecord(r.a, stream);
+  idx_ = (int)g_prof.size();
+  g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (idx_ >= 0) cudaEventRecord(g_prof[idx_].b, stream_);
+}
+
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 void gemm_debug_override(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t mn_kadv);
+int bert_layer_forward(const VlbLayerWeights& w, const void* x, const float* add_mask, const VlbLayerActs& a, int B, int S, int H,
+                       int heads, int I, float eps, cudaStream_t st);
+int64_t bert_layer_backward_workspace(int M, int H, int I);
+int bert_layer_backward(const VlbLayerWeights& w, const VlbLayerActs& a, const void* x, const float* add_mask, const void* dy16,
+                        const float* dy32, void* dx, const VlbLayerGrads& g, void* workspace, int64_t ws_bytes, int B, int S,
+                        int H, int heads, int I, cudaStream_t st);
 
 }  // namespace vlb
 
@@ -65,6 +95,112 @@ int vlb_gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const v
 
 void vlb_debug_gemm_desc(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t mn_kadv) {
   gemm_debug_override(mn_lbo, mn_sbo, mn_kadv);
+}
+
+void vlb_profile_enable(int on) { g_prof_on = on != 0; }
+int vlb_profile_collect(double* ms, double* work, int64_t* launches) {
+  for (int i = 0; i < PROF_NUM; ++i) { ms[i] = 0; work[i] = 0; launches[i] = 0; }
+  for (auto& r : g_prof) {
+    cudaError_t e = cudaEventSynchronize(r.b);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize");
+    float t = 0;
+    e = cudaEventElapsedTime(&t, r.a, r.b);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaEventElapsedTime");
+    ms[r.cat] += t; work[r.cat] += r.work; launches[r.cat] += 1;
+    g_event_pool.push_back(r.a); g_event_pool.push_back(r.b);
+  }
+  g_prof.clear();
+  return VLB_OK;
+}
+
+#define ST static_cast<cudaStream_t>(stream)
+#define COUNTED(n, call) do { int _rc = (call); if (_rc == VLB_OK) count_launch(n); return _rc; } while (0)
+
+int vlb_mhsa_forward(const void* qkv, const float* add_mask, void* ctx, float* lse, int B, int S, int H, int heads,
+                     void* stream) {
+  COUNTED(1, mhsa_forward(qkv, add_mask, ctx, lse, B, S, H, heads, ST));
+}
+int vlb_mhsa_backward(const void* qkv, const float* add_mask, const void* ctx, const float* lse, const void* dctx, void* dqkv,
+                      int B, int S, int H, int heads, void* stream) {
+  COUNTED(1, mhsa_backward(qkv, add_mask, ctx, lse, dctx, dqkv, B, S, H, heads, ST));
+}
+int vlb_layernorm_forward(const float* x, int ldx, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
+                          float* mean, float* rstd, int M, int H, float eps, void* stream) {
+  COUNTED(1, layernorm_forward(x, ldx, gamma, beta, y_bf16, y_f32, mean, rstd, M, H, eps, ST));
+}
+int vlb_layernorm_backward(const void* dy_bf16, const float* dy_f32, const float* x, int ldx, const float* mean,
+                           const float* rstd, const float* gamma, void* dx_bf16, float* dx_f32, int ld_dx, float* dgamma,
+                           float* dbeta, float* dcolsum, int M, int H, void* stream) {
+  COUNTED(1, layernorm_backward(dy_bf16, dy_f32, x, ldx, mean, rstd, gamma, dx_bf16, dx_f32, ld_dx, dgamma, dbeta, dcolsum, M, H, ST));
+}
+int vlb_colsum_bf16(const void* x, int ld, float* out, int M, int N, void* stream) {
+  COUNTED(1, colsum_bf16(x, ld, out, M, N, ST));
+}
+int vlb_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream) {
+  COUNTED(1, cast_f32_to_bf16(in, out, (size_t)n, ST));
+}
+int vlb_cast_bf16_to_f32(const void* in, float* out, int64_t n, void* stream) {
+  COUNTED(1, cast_bf16_to_f32(in, out, (size_t)n, ST));
+}
+int vlb_multi_cast(const VlbCastDesc* descs_device, int count, int blocks_per_tensor, void* stream) {
+  COUNTED(1, multi_cast(descs_device, count, blocks_per_tensor, ST));
+}
+int vlb_pack_index(const uint8_t* text_mask, const uint8_t* object_mask, const int64_t* text_type_ids, int B, int T, int R,
+                   int S, int pos_offset, int32_t* kind, int32_t* src, int32_t* pos_id, int32_t* type_id, float* add_mask,
+                   int32_t* obj_row, int32_t* lens, int32_t* err, void* stream) {
+  COUNTED(1, pack_index(text_mask, object_mask, text_type_ids, B, T, R, S, pos_offset, kind, src, pos_id, type_id, add_mask,
+                        obj_row, lens, err, ST));
+}
+int vlb_pack_forward(const int32_t* kind, const int32_t* src, const int32_t* pos_id, const int32_t* type_id, const int64_t* ids,
+                     const float* word_emb, const float* end_emb, const float* pos_emb, const float* type_emb,
+                     const float* text_vis_ln, const float* obj_vis_ln, const float* object_vl, int ld_obj, int lin_off, float* e,
+                     int B, int T, int R, int S, int H, int vocab, int max_pos, int32_t* err, void* stream) {
+  COUNTED(1, pack_forward(kind, src, pos_id, type_id, ids, word_emb, end_emb, pos_emb, type_emb, text_vis_ln, obj_vis_ln,
+                          object_vl, ld_obj, lin_off, e, B, T, R, S, H, vocab, max_pos, err, ST));
+}
+int vlb_pack_backward(const int32_t* kind, const int32_t* src, const int32_t* pos_id, const int32_t* type_id, const int64_t* ids,
+                      const float* de, float* d_word, float* d_end, float* d_pos, float* d_type, float* d_text_vl,
+                      float* d_obj_vl, int B, int T, int R, int S, int H, int vocab, int max_pos, void* stream) {
+  COUNTED(1, pack_backward(kind, src, pos_id, type_id, ids, de, d_word, d_end, d_pos, d_type, d_text_vl, d_obj_vl, B, T, R, S,
+                           H, vocab, max_pos, ST));
+}
+int vlb_gather_rows(const void* in, int in_is_bf16, int ld_in, const int32_t* idx, void* out, int out_is_bf16, int ld_out,
+                    int n_out, int H, void* stream) {
+  COUNTED(1, gather_rows(in, in_is_bf16, ld_in, idx, out, out_is_bf16, ld_out, n_out, H, ST));
+}
+int vlb_scatter_rows_add(const void* in, int in_is_bf16, int ld_in, const int32_t* idx, float* out, int ld_out, int n_in, int H,
+                         void* stream) {
+  COUNTED(1, scatter_rows_add(in, in_is_bf16, ld_in, idx, out, ld_out, n_in, H, ST));
+}
+int vlb_roi_align_forward(const float* input, const float* rois, float* out, int K, int C, int H, int W, int pooled_h,
+                          int pooled_w, float spatial_scale, int sampling_ratio, void* stream) {
+  COUNTED(1, roi_align_forward(input, rois, out, K, C, H, W, pooled_h, pooled_w, spatial_scale, sampling_ratio, ST));
+}
+int vlb_roi_align_backward(const float* grad_out, const float* rois, float* grad_in, int K, int N, int C, int H, int W,
+                           int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio, void* stream) {
+  COUNTED(1, roi_align_backward(grad_out, rois, grad_in, K, N, C, H, W, pooled_h, pooled_w, spatial_scale, sampling_ratio, ST));
+}
+int vlb_region_operand(const float* boxes, int ld_box, const uint8_t* box_mask, const float* im_info, int ld_info,
+                       const int64_t* mvrc_ops, const float* mask_visual_embed, void* A, int32_t* gather_idx, int B, int R,
+                       int feat_dim, void* stream) {
+  COUNTED(2, region_operand(boxes, ld_box, box_mask, im_info, ld_info, mvrc_ops, mask_visual_embed, A, gather_idx, B, R,
+                            feat_dim, ST));
+}
+int vlb_bert_layer_forward(const VlbLayerWeights* w, const void* x_bf16, const float* add_mask, const VlbLayerActs* acts, int B,
+                           int S, int H, int heads, int I, float eps, void* stream) {
+  if (!w || !acts || !x_bf16) { set_last_error("vlb_bert_layer_forward: null pointer"); return VLB_ERR_INVALID; }
+  return bert_layer_forward(*w, x_bf16, add_mask, *acts, B, S, H, heads, I, eps, ST);
+}
+int64_t vlb_bert_layer_backward_workspace(int M, int H, int I) { return bert_layer_backward_workspace(M, H, I); }
+int vlb_bert_layer_backward(const VlbLayerWeights* w, const VlbLayerActs* acts, const void* x_bf16, const float* add_mask,
+                            const void* dy_bf16, const float* dy_f32, void* dx_bf16, const VlbLayerGrads* grads, void* workspace,
+                            int64_t workspace_bytes, int B, int S, int H, int heads, int I, void* stream) {
+  if (!w || !acts || !x_bf16 || !grads || !workspace || !dx_bf16 || (!dy_bf16 && !dy_f32)) {
+    set_last_error("vlb_bert_layer_backward: null pointer");
+    return VLB_ERR_INVALID;
+  }
+  return bert_layer_backward(*w, *acts, x_bf16, add_mask, dy_bf16, dy_f32, dx_bf16, *grads, workspace, workspace_bytes, B, S, H,
+                             heads, I, ST);
 }
 
 }  // extern "C"

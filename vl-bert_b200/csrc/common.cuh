@@ -37,6 +37,17 @@ int cuda_fail(cudaError_t e, const char* what);
 
 int num_sms();
 
+// Optional per-launch timing (bench.py's roofline): when enabled through vlb_profile_enable(), launchers bracket their
+// kernel with CUDA events on the launch stream; vlb_profile_collect() sums elapsed time / work per category.
+enum ProfCat : int { PROF_GEMM_NT = 0, PROF_GEMM_NN, PROF_GEMM_TN, PROF_MHSA_FWD, PROF_MHSA_BWD, PROF_LN_FWD, PROF_LN_BWD,
+                     PROF_OTHER, PROF_NUM };
+struct ProfScope {
+  ProfScope(int cat, double work, cudaStream_t stream);
+  ~ProfScope();
+  int idx_;
+  cudaStream_t stream_;
+};
+
 // ----------------------------------------------------------------------------------------------
 // device helpers
 // ----------------------------------------------------------------------------------------------

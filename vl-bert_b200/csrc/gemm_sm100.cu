@@ -441,6 +441,7 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
   else       rc = make_tmap_bf16_2d(&tb, B, K, N, ldb, 64, 64);       // B stored [K, N]
   if (rc != VLB_OK) return rc;
 
+  ProfScope prof(mode == GEMM_NT ? PROF_GEMM_NT : (mode == GEMM_NN ? PROF_GEMM_NN : PROF_GEMM_TN), 2.0 * M * N * K, stream);
 #define VLB_GEMM_DISPATCH(BN_)                                                         \
   if (!a_mn && !b_mn) return launch<BN_, false, false>(ta, tb, p, stream);             \
   if (!a_mn && b_mn) return launch<BN_, false, true>(ta, tb, p, stream);               \

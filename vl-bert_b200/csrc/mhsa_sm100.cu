@@ -1,0 +1,420 @@
+// Fused multi-head self-attention for the VL-BERT encoder on sm_100a (tcgen05 + TMEM + TMA).
+//
+// Reference semantics: BertSelfAttention.forward, external/pytorch_pretrained_bert/modeling.py:290-315
+//   scores = Q K^T / sqrt(d_h) + additive_mask[b, key]   (mask = 0 / -10000, common/visual_linguistic_bert.py:119-127)
+//   probs  = softmax(scores) ; ctx = probs V ; ctx written back in [B*S, H] layout (the permute+contiguous
+//   of :313-315 is folded into the store).  Dropout (modeling.py:310) is p = 0 here.
+//
+// The whole [text ; region ; END] sequence of a sample fits one tile (S <= 128), so there is one CTA per
+// (batch, head): Q/K/V head slices arrive by TMA straight from the fused QKV activation [B*S, 3H],
+// S = QK^T and O = PV run on the tensor cores with accumulators in TMEM, the S x S score / probability
+// matrices never touch HBM.  Thread t of the CTA owns query row t (TMEM lane t).
+//
+// Backward recomputes P from Q, K and the saved log-sum-exp, then dV = P^T dO, dP = dO V^T,
+// dS = P o (dP - rowsum(dO o O)) / sqrt(d_h), dQ = dS K, dK = dS^T Q -- five tensor-core products per
+// (batch, head) with P and dS staged once in shared memory and consumed in both orientations
+// (K-major for dQ, MN-major for dK / dV).
+#include "common.cuh"
+#include "gemm_sm100.cuh"
+
+namespace vlb {
+
+namespace {
+
+constexpr int D_HEAD = 64;
+constexpr int TQ = 128;  // query rows per CTA (= TMEM lanes)
+constexpr int NK = 128;  // keys per CTA
+
+struct MhsaParams {
+  int B, S, H, heads;
+  float scale;            // 1 / sqrt(d_h)
+  const float* add_mask;  // [B, S] additive (0 / -10000), may be null
+  __nv_bfloat16* ctx;     // [B*S, H]
+  float* lse;             // [B, heads, S]
+  // backward
+  const __nv_bfloat16* dctx;  // [B*S, H]
+  __nv_bfloat16* dqkv;        // [B*S, 3H]
+};
+
+// shared memory map (bytes, from a 1024-aligned base)
+constexpr int SM_Q = 0;
+constexpr int SM_K = SM_Q + TQ * 128;
+constexpr int SM_V = SM_K + NK * 128;
+constexpr int SM_P = SM_V + NK * 128;             // [TQ x NK] bf16, two 64-key atoms of 16 KB
+constexpr int FWD_SM_MASK = SM_P + TQ * NK * 2;   // NK floats
+constexpr int FWD_SM_BAR = FWD_SM_MASK + NK * 4;
+constexpr int FWD_SMEM = FWD_SM_BAR + 64 + 1024;
+
+constexpr int SM_DO = SM_P + TQ * NK * 2;
+constexpr int SM_DS = SM_DO + TQ * 128;
+constexpr int BWD_SM_MASK = SM_DS + TQ * NK * 2;
+constexpr int BWD_SM_BAR = BWD_SM_MASK + NK * 4;
+constexpr int BWD_SMEM = BWD_SM_BAR + 64 + 1024;
+
+// Write 32 consecutive keys (c0 .. c0+31) of row r into a K-major 128B-swizzled [128 x NK] bf16 tile.
+__device__ __forceinline__ void store_tile_row32(uint8_t* tile, int r, int c0, const float (&x)[32]) {
+  uint8_t* atom = tile + (c0 >> 6) * (TQ * 128) + r * 128;
+  const int j0 = (c0 & 63) >> 3;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint4 o;
+    o.x = pack_bf16x2(x[g * 8 + 0], x[g * 8 + 1]);
+    o.y = pack_bf16x2(x[g * 8 + 2], x[g * 8 + 3]);
+    o.z = pack_bf16x2(x[g * 8 + 4], x[g * 8 + 5]);
+    o.w = pack_bf16x2(x[g * 8 + 6], x[g * 8 + 7]);
+    *reinterpret_cast<uint4*>(atom + (((j0 + g) ^ (r & 7)) << 4)) = o;
+  }
+}
+
+__device__ __forceinline__ void load_mask_to_smem(float* smask, const MhsaParams& p, int b) {
+  for (int c = threadIdx.x; c < NK; c += blockDim.x) {
+    float m = -INFINITY;
+    if (c < p.S) m = p.add_mask ? p.add_mask[(size_t)b * p.S + c] : 0.0f;
+    smask[c] = m;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const MhsaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FWD_SM_BAR);  // [0] load, [1] S ready, [2] O ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  float* smask = reinterpret_cast<float*>(smem + FWD_SM_MASK);
+
+  const int t = threadIdx.x, warp = t >> 5;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int row0 = b * p.S;
+  constexpr uint32_t TMEM_COLS = 256;  // S: [0,128)  O: [128,192)
+
+  if (t == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    mbar_init(smem_u32(&bars[2]), 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tmem_relinquish();
+  }
+  load_mask_to_smem(smask, p, b);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (t == 0) {
+    const uint32_t bl = smem_u32(&bars[0]);
+    mbar_arrive_expect_tx(bl, (TQ + 2 * NK) * 128);
+    tma_load_2d(smem_u32(smem + SM_Q), &tm_qkv, bl, h * D_HEAD, row0);
+    tma_load_2d(smem_u32(smem + SM_K), &tm_qkv, bl, p.H + h * D_HEAD, row0);
+    tma_load_2d(smem_u32(smem + SM_V), &tm_qkv, bl, 2 * p.H + h * D_HEAD, row0);
+    mbar_wait(bl, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc_s = make_idesc_bf16(TQ, NK, 0, 0);
+    const uint32_t sq = smem_u32(smem + SM_Q), sk = smem_u32(smem + SM_K);
+#pragma unroll
+    for (int k = 0; k < D_HEAD / 16; ++k)
+      umma_bf16_ss(tmem, make_smem_desc_sw128(sq + k * 32, 16, 1024), make_smem_desc_sw128(sk + k * 32, 16, 1024),
+                   idesc_s, k > 0);
+    umma_commit(smem_u32(&bars[1]));
+  }
+
+  mbar_wait(smem_u32(&bars[1]), 0);
+  tc_fence_after();
+  const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  // pass 1: row maximum of scale * s + mask
+  float m = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < NK / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld32(t_row + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) m = fmaxf(m, fmaf(__uint_as_float(v[j]), p.scale, smask[c * 32 + j]));
+  }
+  // pass 2: p = exp(x - m), row sum, stage P (bf16) for the second product
+  float l = 0.0f;
+#pragma unroll 1
+  for (int c = 0; c < NK / 32; ++c) {
+    uint32_t v[32];
+    float x[32];
+    tmem_ld32(t_row + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      x[j] = __expf(fmaf(__uint_as_float(v[j]), p.scale, smask[c * 32 + j]) - m);
+      l += x[j];
+    }
+    store_tile_row32(smem + SM_P, t, c * 32, x);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (t == 0) {
+    tc_fence_after();
+    constexpr uint32_t idesc_o = make_idesc_bf16(TQ, D_HEAD, 0, 1);
+    const uint32_t sp = smem_u32(smem + SM_P), sv = smem_u32(smem + SM_V);
+#pragma unroll
+    for (int j = 0; j < NK / 16; ++j)
+      umma_bf16_ss(tmem + 128, make_smem_desc_sw128(sp + (j >> 2) * (TQ * 128) + (j & 3) * 32, 16, 1024),
+                   make_smem_desc_sw128(sv + j * 2048, 8192, 1024), idesc_o, j > 0);
+    umma_commit(smem_u32(&bars[2]));
+  }
+  mbar_wait(smem_u32(&bars[2]), 0);
+  tc_fence_after();
+  {
+    const float inv = 1.0f / l;
+    uint32_t v0[32], v1[32];
+    tmem_ld32(t_row + 128, v0);
+    tmem_ld32(t_row + 160, v1);
+    tmem_ld_wait();
+    if (t < p.S) {
+      __nv_bfloat16* dst = p.ctx + (size_t)(row0 + t) * p.H + h * D_HEAD;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(v0[g * 8 + 0]) * inv, __uint_as_float(v0[g * 8 + 1]) * inv);
+        o.y = pack_bf16x2(__uint_as_float(v0[g * 8 + 2]) * inv, __uint_as_float(v0[g * 8 + 3]) * inv);
+        o.z = pack_bf16x2(__uint_as_float(v0[g * 8 + 4]) * inv, __uint_as_float(v0[g * 8 + 5]) * inv);
+        o.w = pack_bf16x2(__uint_as_float(v0[g * 8 + 6]) * inv, __uint_as_float(v0[g * 8 + 7]) * inv);
+        *reinterpret_cast<uint4*>(dst + g * 8) = o;
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(v1[g * 8 + 0]) * inv, __uint_as_float(v1[g * 8 + 1]) * inv);
+        o.y = pack_bf16x2(__uint_as_float(v1[g * 8 + 2]) * inv, __uint_as_float(v1[g * 8 + 3]) * inv);
+        o.z = pack_bf16x2(__uint_as_float(v1[g * 8 + 4]) * inv, __uint_as_float(v1[g * 8 + 5]) * inv);
+        o.w = pack_bf16x2(__uint_as_float(v1[g * 8 + 6]) * inv, __uint_as_float(v1[g * 8 + 7]) * inv);
+        *reinterpret_cast<uint4*>(dst + 32 + g * 8) = o;
+      }
+      if (p.lse) p.lse[((size_t)b * p.heads + h) * p.S + t] = m + __logf(l);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_row64(__nv_bfloat16* dst, uint32_t tcol_addr) {
+  uint32_t v0[32], v1[32];
+  tmem_ld32(tcol_addr, v0);
+  tmem_ld32(tcol_addr + 32, v1);
+  tmem_ld_wait();
+  if (dst != nullptr) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 o;
+      o.x = pack_bf16x2(__uint_as_float(v0[g * 8 + 0]), __uint_as_float(v0[g * 8 + 1]));
+      o.y = pack_bf16x2(__uint_as_float(v0[g * 8 + 2]), __uint_as_float(v0[g * 8 + 3]));
+      o.z = pack_bf16x2(__uint_as_float(v0[g * 8 + 4]), __uint_as_float(v0[g * 8 + 5]));
+      o.w = pack_bf16x2(__uint_as_float(v0[g * 8 + 6]), __uint_as_float(v0[g * 8 + 7]));
+      *reinterpret_cast<uint4*>(dst + g * 8) = o;
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 o;
+      o.x = pack_bf16x2(__uint_as_float(v1[g * 8 + 0]), __uint_as_float(v1[g * 8 + 1]));
+      o.y = pack_bf16x2(__uint_as_float(v1[g * 8 + 2]), __uint_as_float(v1[g * 8 + 3]));
+      o.z = pack_bf16x2(__uint_as_float(v1[g * 8 + 4]), __uint_as_float(v1[g * 8 + 5]));
+      o.w = pack_bf16x2(__uint_as_float(v1[g * 8 + 6]), __uint_as_float(v1[g * 8 + 7]));
+      *reinterpret_cast<uint4*>(dst + 32 + g * 8) = o;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) mhsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv,
+                                                       const __grid_constant__ CUtensorMap tm_dctx, const MhsaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BWD_SM_BAR);  // [0] load, [1] S & dP ready, [2] grads ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  float* smask = reinterpret_cast<float*>(smem + BWD_SM_MASK);
+
+  const int t = threadIdx.x, warp = t >> 5;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int row0 = b * p.S;
+  constexpr uint32_t TMEM_COLS = 512;  // S [0,128) dP [128,256) dQ [256,320) dK [320,384) dV [384,448)
+
+  if (t == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_dctx);
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    mbar_init(smem_u32(&bars[2]), 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tmem_relinquish();
+  }
+  load_mask_to_smem(smask, p, b);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const uint32_t sq = smem_u32(smem + SM_Q), sk = smem_u32(smem + SM_K), sv = smem_u32(smem + SM_V);
+  const uint32_t sp = smem_u32(smem + SM_P), sdo = smem_u32(smem + SM_DO), sds = smem_u32(smem + SM_DS);
+
+  if (t == 0) {
+    const uint32_t bl = smem_u32(&bars[0]);
+    mbar_arrive_expect_tx(bl, (2 * TQ + 2 * NK) * 128);
+    tma_load_2d(sq, &tm_qkv, bl, h * D_HEAD, row0);
+    tma_load_2d(sk, &tm_qkv, bl, p.H + h * D_HEAD, row0);
+    tma_load_2d(sv, &tm_qkv, bl, 2 * p.H + h * D_HEAD, row0);
+    tma_load_2d(sdo, &tm_dctx, bl, h * D_HEAD, row0);
+    mbar_wait(bl, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_bf16(TQ, NK, 0, 0);
+#pragma unroll
+    for (int k = 0; k < D_HEAD / 16; ++k)  // S = Q K^T
+      umma_bf16_ss(tmem, make_smem_desc_sw128(sq + k * 32, 16, 1024), make_smem_desc_sw128(sk + k * 32, 16, 1024),
+                   idesc, k > 0);
+#pragma unroll
+    for (int k = 0; k < D_HEAD / 16; ++k)  // dP = dO V^T
+      umma_bf16_ss(tmem + 128, make_smem_desc_sw128(sdo + k * 32, 16, 1024),
+                   make_smem_desc_sw128(sv + k * 32, 16, 1024), idesc, k > 0);
+    umma_commit(smem_u32(&bars[1]));
+  }
+
+  // D = rowsum(dO o O) and the saved log-sum-exp for this query row (overlaps the MMAs above)
+  float Dsum = 0.0f, lse = 0.0f;
+  const bool valid = t < p.S;
+  if (valid) {
+    const uint4* po = reinterpret_cast<const uint4*>(p.ctx + (size_t)(row0 + t) * p.H + h * D_HEAD);
+    const uint4* pd = reinterpret_cast<const uint4*>(p.dctx + (size_t)(row0 + t) * p.H + h * D_HEAD);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const uint4 a = po[g], d = pd[g];
+      const uint32_t aa[4] = {a.x, a.y, a.z, a.w}, dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Dsum += bf16lo(aa[j]) * bf16lo(dd[j]) + bf16hi(aa[j]) * bf16hi(dd[j]);
+    }
+    lse = p.lse[((size_t)b * p.heads + h) * p.S + t];
+  }
+
+  mbar_wait(smem_u32(&bars[1]), 0);
+  tc_fence_after();
+  const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+#pragma unroll 1
+  for (int c = 0; c < NK / 32; ++c) {
+    uint32_t vs[32], vd[32];
+    float pr[32], ds[32];
+    tmem_ld32(t_row + c * 32, vs);
+    tmem_ld32(t_row + 128 + c * 32, vd);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      // query rows beyond this sample's sequence must contribute nothing to dK / dV
+      const float pj = valid ? __expf(fmaf(__uint_as_float(vs[j]), p.scale, smask[c * 32 + j]) - lse) : 0.0f;
+      pr[j] = pj;
+      ds[j] = pj * (__uint_as_float(vd[j]) - Dsum) * p.scale;
+    }
+    store_tile_row32(smem + SM_P, t, c * 32, pr);
+    store_tile_row32(smem + SM_DS, t, c * 32, ds);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (t == 0) {
+    tc_fence_after();
+    constexpr uint32_t idesc_q = make_idesc_bf16(TQ, D_HEAD, 0, 1);   // dQ = dS K      (A K-major, B MN-major)
+    constexpr uint32_t idesc_kv = make_idesc_bf16(NK, D_HEAD, 1, 1);  // dK = dS^T Q, dV = P^T dO (both MN-major)
+#pragma unroll
+    for (int j = 0; j < NK / 16; ++j)
+      umma_bf16_ss(tmem + 256, make_smem_desc_sw128(sds + (j >> 2) * (TQ * 128) + (j & 3) * 32, 16, 1024),
+                   make_smem_desc_sw128(sk + j * 2048, 8192, 1024), idesc_q, j > 0);
+#pragma unroll
+    for (int j = 0; j < TQ / 16; ++j)
+      umma_bf16_ss(tmem + 320, make_smem_desc_sw128(sds + j * 2048, TQ * 128, 1024),
+                   make_smem_desc_sw128(sq + j * 2048, 8192, 1024), idesc_kv, j > 0);
+#pragma unroll
+    for (int j = 0; j < TQ / 16; ++j)
+      umma_bf16_ss(tmem + 384, make_smem_desc_sw128(sp + j * 2048, TQ * 128, 1024),
+                   make_smem_desc_sw128(sdo + j * 2048, 8192, 1024), idesc_kv, j > 0);
+    umma_commit(smem_u32(&bars[2]));
+  }
+  mbar_wait(smem_u32(&bars[2]), 0);
+  tc_fence_after();
+  {
+    __nv_bfloat16* base = valid ? p.dqkv + (size_t)(row0 + t) * (3 * p.H) + h * D_HEAD : nullptr;
+    store_row64(base, t_row + 256);
+    store_row64(valid ? base + p.H : nullptr, t_row + 320);
+    store_row64(valid ? base + 2 * p.H : nullptr, t_row + 384);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
+}  // namespace
+
+int mhsa_forward(const void* qkv, const float* add_mask, void* ctx, float* lse, int B, int S, int H, int heads,
+                 cudaStream_t stream) {
+  VLB_REQUIRE(qkv && ctx, "mhsa_forward: null pointer");
+  VLB_REQUIRE(H == heads * D_HEAD, "mhsa: head size must be 64 (H=%d heads=%d)", H, heads);
+  VLB_REQUIRE(S >= 1 && S <= NK, "mhsa: sequence length %d not supported (1..%d)", S, NK);
+  MhsaParams p{};
+  p.B = B; p.S = S; p.H = H; p.heads = heads;
+  p.scale = 0.125f;
+  p.add_mask = add_mask;
+  p.ctx = static_cast<__nv_bfloat16*>(ctx);
+  p.lse = lse;
+  CUtensorMap tm;
+  int rc = make_tmap_bf16_2d(&tm, qkv, (uint64_t)B * S, 3 * H, 3 * H, 64, 128);
+  if (rc != VLB_OK) return rc;
+  static bool attr = false;
+  if (!attr) {
+    VLB_CHECK_CUDA(cudaFuncSetAttribute(mhsa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    attr = true;
+  }
+  ProfScope prof(PROF_MHSA_FWD, 4.0 * B * heads * (double)S * S * D_HEAD, stream);
+  mhsa_fwd_kernel<<<dim3(heads, B), 128, FWD_SMEM, stream>>>(tm, p);
+  VLB_CHECK_LAUNCH();
+  return VLB_OK;
+}
+
+int mhsa_backward(const void* qkv, const float* add_mask, const void* ctx, const float* lse, const void* dctx, void* dqkv,
+                  int B, int S, int H, int heads, cudaStream_t stream) {
+  VLB_REQUIRE(qkv && ctx && lse && dctx && dqkv, "mhsa_backward: null pointer");
+  VLB_REQUIRE(H == heads * D_HEAD, "mhsa: head size must be 64 (H=%d heads=%d)", H, heads);
+  VLB_REQUIRE(S >= 1 && S <= NK, "mhsa: sequence length %d not supported (1..%d)", S, NK);
+  MhsaParams p{};
+  p.B = B; p.S = S; p.H = H; p.heads = heads;
+  p.scale = 0.125f;
+  p.add_mask = add_mask;
+  p.ctx = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(ctx));
+  p.lse = const_cast<float*>(lse);
+  p.dctx = static_cast<const __nv_bfloat16*>(dctx);
+  p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  CUtensorMap tm, tmd;
+  int rc = make_tmap_bf16_2d(&tm, qkv, (uint64_t)B * S, 3 * H, 3 * H, 64, 128);
+  if (rc != VLB_OK) return rc;
+  rc = make_tmap_bf16_2d(&tmd, dctx, (uint64_t)B * S, H, H, 64, 128);
+  if (rc != VLB_OK) return rc;
+  static bool attr = false;
+  if (!attr) {
+    VLB_CHECK_CUDA(cudaFuncSetAttribute(mhsa_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    attr = true;
+  }
+  ProfScope prof(PROF_MHSA_BWD, 8.0 * B * heads * (double)S * S * D_HEAD, stream);
+  mhsa_bwd_kernel<<<dim3(heads, B), 128, BWD_SMEM, stream>>>(tm, tmd, p);
+  VLB_CHECK_LAUNCH();
+  return VLB_OK;
+}
+
+}  // namespace vlb

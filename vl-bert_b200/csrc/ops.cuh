@@ -1,0 +1,52 @@
+// Internal host-side declarations of the kernels' launchers (definitions in the .cu files).
+#pragma once
+#include "common.cuh"
+#include "gemm_sm100.cuh"
+
+namespace vlb {
+
+void count_launch(int n);
+
+// mhsa_sm100.cu
+int mhsa_forward(const void* qkv, const float* add_mask, void* ctx, float* lse, int B, int S, int H, int heads,
+                 cudaStream_t stream);
+int mhsa_backward(const void* qkv, const float* add_mask, const void* ctx, const float* lse, const void* dctx, void* dqkv,
+                  int B, int S, int H, int heads, cudaStream_t stream);
+
+// rowops.cu
+int layernorm_forward(const float* x, int ldx, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean,
+                      float* rstd, int M, int H, float eps, cudaStream_t stream);
+int layernorm_backward(const void* dy_bf16, const float* dy_f32, const float* x, int ldx, const float* mean, const float* rstd,
+                       const float* gamma, void* dx_bf16, float* dx_f32, int ld_dx, float* dgamma, float* dbeta, float* dcolsum,
+                       int M, int H, cudaStream_t stream);
+int colsum_bf16(const void* x, int ld, float* out, int M, int N, cudaStream_t stream);
+int cast_f32_to_bf16(const float* in, void* out, size_t n, cudaStream_t stream);
+int cast_bf16_to_f32(const void* in, float* out, size_t n, cudaStream_t stream);
+int multi_cast(const VlbCastDesc* descs_device, int count, int blocks_per_tensor, cudaStream_t stream);
+
+// embed.cu
+int pack_index(const uint8_t* text_mask, const uint8_t* object_mask, const int64_t* text_type_ids, int B, int T, int R, int S,
+               int pos_offset, int32_t* kind, int32_t* src, int32_t* pos_id, int32_t* type_id, float* add_mask,
+               int32_t* obj_row, int32_t* lens, int32_t* err, cudaStream_t stream);
+int pack_forward(const int32_t* kind, const int32_t* src, const int32_t* pos_id, const int32_t* type_id, const int64_t* ids,
+                 const float* word_emb, const float* end_emb, const float* pos_emb, const float* type_emb,
+                 const float* text_vis_ln, const float* obj_vis_ln, const float* object_vl, int ld_obj, int lin_off, float* e,
+                 int B, int T, int R, int S, int H, int vocab, int max_pos, int32_t* err, cudaStream_t stream);
+int pack_backward(const int32_t* kind, const int32_t* src, const int32_t* pos_id, const int32_t* type_id, const int64_t* ids,
+                  const float* de, float* d_word, float* d_end, float* d_pos, float* d_type, float* d_text_vl, float* d_obj_vl,
+                  int B, int T, int R, int S, int H, int vocab, int max_pos, cudaStream_t stream);
+int gather_rows(const void* in, int in_is_bf16, int ld_in, const int32_t* idx, void* out, int out_is_bf16, int ld_out, int n_out,
+                int H, cudaStream_t stream);
+int scatter_rows_add(const void* in, int in_is_bf16, int ld_in, const int32_t* idx, float* out, int ld_out, int n_in, int H,
+                     cudaStream_t stream);
+
+// roi_align.cu
+int roi_align_forward(const float* input, const float* rois, float* out, int K, int C, int H, int W, int ph, int pw,
+                      float spatial_scale, int sampling_ratio, cudaStream_t stream);
+int roi_align_backward(const float* grad_out, const float* rois, float* grad_in, int K, int N, int C, int H, int W, int ph,
+                       int pw, float spatial_scale, int sampling_ratio, cudaStream_t stream);
+int region_operand(const float* boxes, int ld_box, const uint8_t* box_mask, const float* im_info, int ld_info,
+                   const int64_t* mvrc_ops, const float* mask_visual_embed, void* A, int32_t* gather_idx, int B, int R,
+                   int feat_dim, cudaStream_t stream);
+
+}  // namespace vlb

@@ -1,0 +1,382 @@
+// HBM-bound row kernels around the GEMMs: TF-style LayerNorm forward/backward (reference:
+// external/pytorch_pretrained_bert/modeling.py:231-235 -- biased variance, eps INSIDE the sqrt, eps = 1e-12),
+// column sums for bias gradients, fp32 -> bf16 casts.  One warp per row, 128-bit loads, warp-shuffle
+// reductions, statistics in fp32.
+#include "common.cuh"
+
+namespace vlb {
+
+namespace {
+
+constexpr int LN_WARPS = 4;  // rows per block per iteration
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward: x fp32 [M, H] -> y bf16 [M, H] (+ optional fp32 copy), mean/rstd fp32 [M]
+// ITERS = ceil(H / 256): each lane holds ITERS vectors of 8 values.
+// ------------------------------------------------------------------------------------------------
+template <int ITERS>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     __nv_bfloat16* __restrict__ y, float* __restrict__ y32, float* __restrict__ mean,
+                     float* __restrict__ rstd, int M, int H, int ldx, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int nvec = H >> 3;
+  float v[ITERS][8];
+  const float* xr = x + (size_t)row * ldx;
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const float4 a = *reinterpret_cast<const float4*>(xr + vi * 8);
+      const float4 b = *reinterpret_cast<const float4*>(xr + vi * 8 + 4);
+      v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w;
+      v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = 0.0f;
+    }
+  }
+  const float mu = warp_sum(s) / (float)H;
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    if (lane + i * 32 < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mu;
+        q += d * d;
+      }
+    }
+  }
+  const float var = warp_sum(q) / (float)H;
+  const float rs = 1.0f / sqrtf(var + eps);
+  if (lane == 0) {
+    if (mean) mean[row] = mu;
+    if (rstd) rstd[row] = rs;
+  }
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = gg[j] * ((v[i][j] - mu) * rs) + bb[j];
+      uint4 pk;
+      pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
+      pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
+      if (y) *reinterpret_cast<uint4*>(y + (size_t)row * H + vi * 8) = pk;
+      if (y32) {
+        *reinterpret_cast<float4*>(y32 + (size_t)row * H + vi * 8) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(y32 + (size_t)row * H + vi * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward.  dy = dy_bf16 (optional) + dy_f32 (optional).
+//   xhat = (x - mean) * rstd ; g = dy * gamma
+//   dx = rstd * (g - mean_H(g) - xhat * mean_H(g * xhat))          -> bf16 (and/or fp32)
+//   dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy ; dbias_prev += sum_rows dx   (fp32 atomics)
+// Persistent blocks stride over rows and keep per-lane column partials in registers.
+// ------------------------------------------------------------------------------------------------
+template <int ITERS>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ dy32,
+                     const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx16, float* __restrict__ dx32,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcolsum, int M, int H,
+                     int ldx, int ld_dx) {
+  __shared__ float red[3][LN_WARPS][32 * 8 + 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = H >> 3;
+  float gam[ITERS][8];
+  float acc_g[ITERS][8], acc_b[ITERS][8], acc_c[ITERS][8];
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    const int vi = lane + i * 32;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      gam[i][j] = (vi < nvec) ? __ldg(gamma + vi * 8 + j) : 0.0f;
+      acc_g[i][j] = acc_b[i][j] = acc_c[i][j] = 0.0f;
+    }
+  }
+  for (int row = blockIdx.x * LN_WARPS + warp; row < M; row += gridDim.x * LN_WARPS) {
+    const float mu = mean[row], rs = rstd[row];
+    float dy[ITERS][8], xh[ITERS][8];
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        const size_t off = (size_t)row * H + vi * 8;
+        const size_t xoff = (size_t)row * ldx + vi * 8;
+        const float4 a = *reinterpret_cast<const float4*>(x + xoff);
+        const float4 b = *reinterpret_cast<const float4*>(x + xoff + 4);
+        const float xv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        float d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (dy16) {
+          const uint4 u = *reinterpret_cast<const uint4*>(dy16 + off);
+          d[0] = bf16lo(u.x); d[1] = bf16hi(u.x); d[2] = bf16lo(u.y); d[3] = bf16hi(u.y);
+          d[4] = bf16lo(u.z); d[5] = bf16hi(u.z); d[6] = bf16lo(u.w); d[7] = bf16hi(u.w);
+        }
+        if (dy32) {
+          const float4 c = *reinterpret_cast<const float4*>(dy32 + off);
+          const float4 e = *reinterpret_cast<const float4*>(dy32 + off + 4);
+          d[0] += c.x; d[1] += c.y; d[2] += c.z; d[3] += c.w;
+          d[4] += e.x; d[5] += e.y; d[6] += e.z; d[7] += e.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dy[i][j] = d[j];
+          xh[i][j] = (xv[j] - mu) * rs;
+          const float g = d[j] * gam[i][j];
+          s1 += g;
+          s2 += g * xh[i][j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dy[i][j] = xh[i][j] = 0.0f;
+      }
+    }
+    const float m1 = warp_sum(s1) / (float)H;
+    const float m2 = warp_sum(s2) / (float)H;
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          o[j] = rs * (dy[i][j] * gam[i][j] - m1 - xh[i][j] * m2);
+          acc_g[i][j] += dy[i][j] * xh[i][j];
+          acc_b[i][j] += dy[i][j];
+          acc_c[i][j] += o[j];
+        }
+        const size_t off = (size_t)row * H + vi * 8;
+        if (dx16) {
+          uint4 pk;
+          pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
+          pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
+          *reinterpret_cast<uint4*>(dx16 + off) = pk;
+        }
+        if (dx32) {
+          const size_t doff = (size_t)row * ld_dx + vi * 8;
+          *reinterpret_cast<float4*>(dx32 + doff) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(dx32 + doff + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+      }
+    }
+  }
+  // block reduction of the column partials (over the LN_WARPS warps), then one atomic per column per block
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      red[0][warp][lane * 8 + j] = acc_g[i][j];
+      red[1][warp][lane * 8 + j] = acc_b[i][j];
+      red[2][warp][lane * 8 + j] = acc_c[i][j];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 256; e += LN_WARPS * 32) {
+      const int col = i * 256 + e;
+      if (col < H) {
+        float a = 0.0f, b = 0.0f, c = 0.0f;
+#pragma unroll
+        for (int w = 0; w < LN_WARPS; ++w) {
+          a += red[0][w][e];
+          b += red[1][w][e];
+          c += red[2][w][e];
+        }
+        if (dgamma) atomicAdd(dgamma + col, a);
+        if (dbeta) atomicAdd(dbeta + col, b);
+        if (dcolsum) atomicAdd(dcolsum + col, c);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums of a bf16 matrix: out[n] += sum_m x[m, n]      (bias gradients)
+// block = 256 threads = 32 column-groups (8 cols each) x 8 row lanes ; grid.x over column chunks of 256,
+// grid.y over row slabs.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int ld, float* __restrict__ out, int M, int N, int rows_per_block) {
+  __shared__ float red[8][256 + 8];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + cg * 8;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (col < N) {
+    for (int r = r0 + rl; r < r1; r += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + (size_t)r * ld + col);
+      acc[0] += bf16lo(u.x); acc[1] += bf16hi(u.x); acc[2] += bf16lo(u.y); acc[3] += bf16hi(u.y);
+      acc[4] += bf16lo(u.z); acc[5] += bf16hi(u.z); acc[6] += bf16lo(u.w); acc[7] += bf16hi(u.w);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[rl][cg * 8 + j] = acc[j];
+  __syncthreads();
+  const int e = threadIdx.x;
+  const int c = blockIdx.x * 256 + e;
+  if (c < N) {
+    float s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][e];
+    atomicAdd(out + c, s);
+  }
+}
+
+// fp32 -> bf16 (weights, inputs); n multiple of 8 handled vectorised, tail scalar.
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+  const size_t nv = n >> 3;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = *reinterpret_cast<const float4*>(in + i * 8);
+    const float4 b = *reinterpret_cast<const float4*>(in + i * 8 + 4);
+    uint4 pk;
+    pk.x = pack_bf16x2(a.x, a.y); pk.y = pack_bf16x2(a.z, a.w);
+    pk.z = pack_bf16x2(b.x, b.y); pk.w = pack_bf16x2(b.z, b.w);
+    *reinterpret_cast<uint4*>(out + i * 8) = pk;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const size_t i = (nv << 3) + threadIdx.x;
+    out[i] = __float2bfloat16(in[i]);
+  }
+}
+
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __bfloat162float(in[i]);
+}
+
+// many tensors, one launch: descriptor table lives in device memory (grid.y = tensor)
+__global__ void multi_cast_kernel(const VlbCastDesc* __restrict__ descs) {
+  const VlbCastDesc d = descs[blockIdx.y];
+  const float* in = static_cast<const float*>(d.src);
+  const size_t n = (size_t)d.n;
+  const size_t nv = n >> 3;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if (d.dst_is_bf16) {
+    __nv_bfloat16* out = static_cast<__nv_bfloat16*>(d.dst);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nv; i += stride) {
+      const float4 a = *reinterpret_cast<const float4*>(in + i * 8);
+      const float4 b = *reinterpret_cast<const float4*>(in + i * 8 + 4);
+      uint4 pk;
+      pk.x = pack_bf16x2(a.x, a.y); pk.y = pack_bf16x2(a.z, a.w);
+      pk.z = pack_bf16x2(b.x, b.y); pk.w = pack_bf16x2(b.z, b.w);
+      *reinterpret_cast<uint4*>(out + i * 8) = pk;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 7)) out[(nv << 3) + threadIdx.x] = __float2bfloat16(in[(nv << 3) + threadIdx.x]);
+  } else {
+    float* out = static_cast<float*>(d.dst);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += stride) out[i] = in[i];
+  }
+}
+
+}  // namespace
+
+int multi_cast(const VlbCastDesc* descs_device, int count, int blocks_per_tensor, cudaStream_t stream) {
+  VLB_REQUIRE(descs_device && count > 0, "multi_cast: bad arguments");
+  if (blocks_per_tensor < 1) blocks_per_tensor = 16;
+  multi_cast_kernel<<<dim3(blocks_per_tensor, count), 256, 0, stream>>>(descs_device);
+  VLB_CHECK_LAUNCH();
+  return VLB_OK;
+}
+
+#define VLB_LN_DISPATCH(ITERS_EXPR, CALL)                     \
+  switch (ITERS_EXPR) {                                       \
+    case 1: { constexpr int IT = 1; CALL; } break;            \
+    case 2: { constexpr int IT = 2; CALL; } break;            \
+    case 3: { constexpr int IT = 3; CALL; } break;            \
+    case 4: { constexpr int IT = 4; CALL; } break;            \
+    case 5: case 6: { constexpr int IT = 6; CALL; } break;    \
+    default: { constexpr int IT = 8; CALL; } break;           \
+  }
+
+int layernorm_forward(const float* x, int ldx, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean,
+                      float* rstd, int M, int H, float eps, cudaStream_t stream) {
+  VLB_REQUIRE(x && gamma && beta && (y_bf16 || y_f32), "layernorm_forward: null pointer");
+  VLB_REQUIRE(ldx % 4 == 0 && ldx >= H, "layernorm_forward: bad ldx %d", ldx);
+  VLB_REQUIRE(H % 8 == 0 && H >= 8 && H <= 2048, "layernorm: H=%d must be a multiple of 8 in [8, 2048]", H);
+  if (M <= 0) return VLB_OK;
+  const int iters = (H + 255) / 256;
+  const int grid = (M + LN_WARPS - 1) / LN_WARPS;
+  ProfScope prof(PROF_LN_FWD, (double)M * H * (4.0 + (y_bf16 ? 2.0 : 0.0) + (y_f32 ? 4.0 : 0.0)), stream);
+  VLB_LN_DISPATCH(iters, (layernorm_fwd_kernel<IT><<<grid, LN_WARPS * 32, 0, stream>>>(
+                             x, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, M, H, ldx, eps)));
+  VLB_CHECK_LAUNCH();
+  return VLB_OK;
+}
+
+int layernorm_backward(const void* dy_bf16, const float* dy_f32, const float* x, int ldx, const float* mean, const float* rstd,
+                       const float* gamma, void* dx_bf16, float* dx_f32, int ld_dx, float* dgamma, float* dbeta, float* dcolsum,
+                       int M, int H, cudaStream_t stream) {
+  VLB_REQUIRE(ldx % 4 == 0 && ldx >= H && (dx_f32 == nullptr || (ld_dx % 4 == 0 && ld_dx >= H)), "layernorm_backward: bad ld");
+  VLB_REQUIRE((dy_bf16 || dy_f32) && x && mean && rstd && gamma, "layernorm_backward: null pointer");
+  VLB_REQUIRE(H % 8 == 0 && H >= 8 && H <= 2048, "layernorm: H=%d must be a multiple of 8 in [8, 2048]", H);
+  if (M <= 0) return VLB_OK;
+  const int iters = (H + 255) / 256;
+  int grid = (M + LN_WARPS - 1) / LN_WARPS;
+  const int cap = num_sms() * 4;
+  if (grid > cap) grid = cap;
+  ProfScope prof(PROF_LN_BWD, (double)M * H * (4.0 + (dy_bf16 ? 2.0 : 0.0) + (dy_f32 ? 4.0 : 0.0) + (dx_bf16 ? 2.0 : 0.0) + (dx_f32 ? 4.0 : 0.0)), stream);
+  VLB_LN_DISPATCH(iters, (layernorm_bwd_kernel<IT><<<grid, LN_WARPS * 32, 0, stream>>>(
+                             static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, mean, rstd, gamma,
+                             static_cast<__nv_bfloat16*>(dx_bf16), dx_f32, dgamma, dbeta, dcolsum, M, H, ldx, ld_dx)));
+  VLB_CHECK_LAUNCH();
+  return VLB_OK;
+}
+
+int colsum_bf16(const void* x, int ld, float* out, int M, int N, cudaStream_t stream) {
+  VLB_REQUIRE(x && out, "colsum: null pointer");
+  VLB_REQUIRE(N % 8 == 0 && ld % 8 == 0, "colsum: N and ld must be multiples of 8");
+  if (M <= 0) return VLB_OK;
+  const int col_blocks = (N + 255) / 256;
+  int slabs = (num_sms() * 4 + col_blocks - 1) / col_blocks;
+  int rows_per = (M + slabs - 1) / slabs;
+  if (rows_per < 32) rows_per = 32;
+  slabs = (M + rows_per - 1) / rows_per;
+  colsum_bf16_kernel<<<dim3(col_blocks, slabs), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ld, out, M, N,
+                                                                  rows_per);
+  VLB_CHECK_LAUNCH();
+  return VLB_OK;
+}
+
+int cast_f32_to_bf16(const float* in, void* out, size_t n, cudaStream_t stream) {
+  VLB_REQUIRE(in && out, "cast: null pointer");
+  if (n == 0) return VLB_OK;
+  VLB_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+              "cast: pointers must be 16-byte aligned");
+  size_t blocks = ((n >> 3) + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > (size_t)num_sms() * 8) blocks = (size_t)num_sms() * 8;
+  cast_f32_bf16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out), n);
+  VLB_CHECK_LAUNCH();
+  return VLB_OK;
+}
+
+int cast_bf16_to_f32(const void* in, float* out, size_t n, cudaStream_t stream) {
+  VLB_REQUIRE(in && out, "cast: null pointer");
+  if (n == 0) return VLB_OK;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > (size_t)num_sms() * 8) blocks = (size_t)num_sms() * 8;
+  cast_bf16_f32_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), out, n);
+  VLB_CHECK_LAUNCH();
+  return VLB_OK;
+}
+
+}  // namespace vlb

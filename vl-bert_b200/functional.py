@@ -1,0 +1,515 @@
+"""torch.autograd front ends of the C ABI (include/vlbert_b200.h).
+
+PyTorch is used here only for device memory, streams and autograd bookkeeping; every FLOP of the
+hot path runs in libvlbert_b200.so.  All calls enqueue on torch's current CUDA stream.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(rc):
+    if rc != 0:
+        _lib.check(rc)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("vlbert_b200 has no CPU path: expected CUDA tensors (got %s)" % t.device)
+
+
+def _align(n, a=256):
+    return (n + a - 1) // a * a
+
+
+class _Carver(object):
+    """Carves typed sub-tensors out of one flat uint8 allocation (256-byte aligned)."""
+
+    def __init__(self, specs, device):
+        self.offsets = {}
+        off = 0
+        for name, shape, dtype in specs:
+            n = 1
+            for s in shape:
+                n *= s
+            self.offsets[name] = (off, shape, dtype, n)
+            off += _align(n * torch.empty((), dtype=dtype).element_size())
+        self.nbytes = off
+        self.buf = torch.empty(max(off, 256), dtype=torch.uint8, device=device)
+
+    def get(self, name):
+        off, shape, dtype, n = self.offsets[name]
+        esz = torch.empty((), dtype=dtype).element_size()
+        return self.buf[off: off + n * esz].view(dtype).view(*shape)
+
+
+# ------------------------------------------------------------------------------------------------
+# primitive wrappers (used by tests and by the composites below)
+# ------------------------------------------------------------------------------------------------
+def gemm(mode, A, B, out, bias=None, resid=None, act=0, aux=None, alpha=1.0, split_k=1, force_bn=0, M=None, N=None, K=None):
+    """See vlb_gemm_bf16.  A/B bf16 2-D (row-major, last dim contiguous); out bf16 or f32 2-D."""
+    _require_cuda(A, B, out)
+    if mode == 0:
+        m, k = A.shape; n = B.shape[0]
+    elif mode == 1:
+        m, k = A.shape; n = B.shape[1]
+    else:
+        k, m = A.shape; n = B.shape[1]
+    M, N, K = M or m, N or n, K or k
+    out_kind = 0 if out.dtype == BF16 else (2 if split_k > 1 or getattr(out, "_vlb_accumulate", False) else 1)
+    resid_kind = 0 if resid is None else (1 if resid.dtype == BF16 else 2)
+    _chk(_lib.lib().vlb_gemm_bf16(mode, M, N, K, _p(A), A.stride(0), _p(B), B.stride(0), _p(out), out.stride(0), out_kind,
+                                  _p(bias), _p(resid), resid.stride(0) if resid is not None else 0, resid_kind, act,
+                                  _p(aux), aux.stride(0) if aux is not None else 0, float(alpha), split_k, force_bn, _stream()))
+    return out
+
+
+def layernorm_forward(x, gamma, beta, eps=1e-12, want_bf16=True, want_f32=False, ldx=None, H=None):
+    M = x.numel() // x.shape[-1] if ldx is None else x.shape[0]
+    H = H or x.shape[-1]
+    ldx = ldx or H
+    dev = x.device
+    y16 = torch.empty((M, H), dtype=BF16, device=dev) if want_bf16 else None
+    y32 = torch.empty((M, H), dtype=F32, device=dev) if want_f32 else None
+    mean = torch.empty((M,), dtype=F32, device=dev)
+    rstd = torch.empty((M,), dtype=F32, device=dev)
+    _chk(_lib.lib().vlb_layernorm_forward(_p(x), ldx, _p(gamma), _p(beta), _p(y16), _p(y32), _p(mean), _p(rstd), M, H,
+                                          float(eps), _stream()))
+    return y16, y32, mean, rstd
+
+
+def layernorm_backward(dy16, dy32, x, mean, rstd, gamma, dgamma, dbeta, dcolsum=None, want_bf16=True, want_f32=False,
+                       ldx=None, H=None, dx32=None, ld_dx=None):
+    H = H or x.shape[-1]
+    M = mean.numel()
+    ldx = ldx or H
+    dev = x.device
+    dx16 = torch.empty((M, H), dtype=BF16, device=dev) if want_bf16 else None
+    if want_f32 and dx32 is None:
+        dx32 = torch.empty((M, H), dtype=F32, device=dev)
+        ld_dx = H
+    _chk(_lib.lib().vlb_layernorm_backward(_p(dy16), _p(dy32), _p(x), ldx, _p(mean), _p(rstd), _p(gamma), _p(dx16), _p(dx32),
+                                           ld_dx or 0, _p(dgamma), _p(dbeta), _p(dcolsum), M, H, _stream()))
+    return dx16, dx32
+
+
+def mhsa_forward(qkv, add_mask, B, S, H, heads):
+    ctx = torch.empty((B * S, H), dtype=BF16, device=qkv.device)
+    lse = torch.empty((B, heads, S), dtype=F32, device=qkv.device)
+    _chk(_lib.lib().vlb_mhsa_forward(_p(qkv), _p(add_mask), _p(ctx), _p(lse), B, S, H, heads, _stream()))
+    return ctx, lse
+
+
+def mhsa_backward(qkv, add_mask, ctx, lse, dctx, B, S, H, heads):
+    dqkv = torch.empty((B * S, 3 * H), dtype=BF16, device=qkv.device)
+    _chk(_lib.lib().vlb_mhsa_backward(_p(qkv), _p(add_mask), _p(ctx), _p(lse), _p(dctx), _p(dqkv), B, S, H, heads, _stream()))
+    return dqkv
+
+
+def gather_rows(src2d, idx, n_out, out_dtype=F32):
+    H = src2d.shape[1]
+    out = torch.empty((n_out, H), dtype=out_dtype, device=src2d.device)
+    _chk(_lib.lib().vlb_gather_rows(_p(src2d), int(src2d.dtype == BF16), src2d.stride(0), _p(idx), _p(out),
+                                    int(out_dtype == BF16), H, n_out, H, _stream()))
+    return out
+
+
+def scatter_rows_add(src2d, idx, out2d):
+    H = src2d.shape[1]
+    _chk(_lib.lib().vlb_scatter_rows_add(_p(src2d), int(src2d.dtype == BF16), src2d.stride(0), _p(idx), _p(out2d),
+                                         out2d.stride(0), src2d.shape[0], H, _stream()))
+    return out2d
+
+
+# ------------------------------------------------------------------------------------------------
+# weights: fp32 master parameters -> bf16 GEMM operands (one launch for the whole encoder)
+# ------------------------------------------------------------------------------------------------
+class EncoderWeights(object):
+    """Persistent bf16 operand copies of L BertLayers + the device descriptor table of the cast."""
+
+    PER_LAYER = ("query.w", "query.b", "key.w", "key.b", "value.w", "value.b", "o.w", "o.b", "ln1.w", "ln1.b",
+                 "i.w", "i.b", "out.w", "out.b", "ln2.w", "ln2.b")
+
+    def __init__(self, L, H, I, device):
+        self.L, self.H, self.I = L, H, I
+        self.w_qkv = torch.empty((L, 3 * H, H), dtype=BF16, device=device)
+        self.w_o = torch.empty((L, H, H), dtype=BF16, device=device)
+        self.w_1 = torch.empty((L, I, H), dtype=BF16, device=device)
+        self.w_2 = torch.empty((L, H, I), dtype=BF16, device=device)
+        self.b_qkv = torch.empty((L, 3 * H), dtype=F32, device=device)
+        self._key = None
+        self._table = None
+        self._count = 0
+
+    def refresh(self, params):
+        """params: flat list, 16 tensors per layer in PER_LAYER order (fp32, contiguous)."""
+        L, H = self.L, self.H
+        key = tuple(p.data_ptr() for p in params)
+        if key != self._key:
+            descs = []
+            for l in range(L):
+                q = params[16 * l: 16 * l + 16]
+                for j, (w, b) in enumerate(((q[0], q[1]), (q[2], q[3]), (q[4], q[5]))):
+                    descs.append((w.data_ptr(), self.w_qkv[l, j * H].data_ptr(), H * H, 1))
+                    descs.append((b.data_ptr(), self.b_qkv[l, j * H:].data_ptr(), H, 0))
+                descs.append((q[6].data_ptr(), self.w_o[l].data_ptr(), H * H, 1))
+                descs.append((q[10].data_ptr(), self.w_1[l].data_ptr(), self.I * H, 1))
+                descs.append((q[12].data_ptr(), self.w_2[l].data_ptr(), H * self.I, 1))
+            arr = (_lib.CastDesc * len(descs))()
+            for i, (s, d, n, k) in enumerate(descs):
+                arr[i].src, arr[i].dst, arr[i].n, arr[i].dst_is_bf16 = s, d, n, k
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            self._table = host.to(self.w_qkv.device)
+            self._count = len(descs)
+            self._key = key
+        _chk(_lib.lib().vlb_multi_cast(_p(self._table), self._count, 24, _stream()))
+
+    def layer_struct(self, l, params):
+        q = params[16 * l: 16 * l + 16]
+        w = _lib.LayerWeights()
+        w.w_qkv, w.b_qkv = self.w_qkv[l].data_ptr(), self.b_qkv[l].data_ptr()
+        w.w_o, w.b_o = self.w_o[l].data_ptr(), q[7].data_ptr()
+        w.ln1_g, w.ln1_b = q[8].data_ptr(), q[9].data_ptr()
+        w.w_1, w.b_1 = self.w_1[l].data_ptr(), q[11].data_ptr()
+        w.w_2, w.b_2 = self.w_2[l].data_ptr(), q[13].data_ptr()
+        w.ln2_g, w.ln2_b = q[14].data_ptr(), q[15].data_ptr()
+        return w
+
+
+def _act_specs(l, B, S, H, heads, I, want_f32):
+    M = B * S
+    sp = [("qkv%d" % l, (M, 3 * H), BF16), ("ctx%d" % l, (M, H), BF16), ("lse%d" % l, (B, heads, S), F32),
+          ("a%d" % l, (M, H), F32), ("m1_%d" % l, (M,), F32), ("r1_%d" % l, (M,), F32), ("h%d" % l, (M, H), BF16),
+          ("z%d" % l, (M, I), BF16), ("u%d" % l, (M, I), BF16), ("y0_%d" % l, (M, H), F32), ("m2_%d" % l, (M,), F32),
+          ("r2_%d" % l, (M,), F32), ("y%d" % l, (M, H), BF16)]
+    return sp
+
+
+def _acts_struct(car, l, y_f32):
+    a = _lib.LayerActs()
+    g = lambda n: car.get(n % l).data_ptr()  # noqa: E731
+    a.qkv, a.ctx, a.lse, a.a = g("qkv%d"), g("ctx%d"), g("lse%d"), g("a%d")
+    a.ln1_mean, a.ln1_rstd, a.h, a.z, a.u = g("m1_%d"), g("r1_%d"), g("h%d"), g("z%d"), g("u%d")
+    a.y0, a.ln2_mean, a.ln2_rstd, a.y = g("y0_%d"), g("m2_%d"), g("r2_%d"), g("y%d")
+    a.y_f32 = None if y_f32 is None else y_f32.data_ptr()
+    return a
+
+
+class EncoderFn(torch.autograd.Function):
+    """L BertLayers (BertEncoder.forward, modeling.py:406-421) on vlb_bert_layer_forward/backward.
+
+    forward(emb_bf16 [B,S,H], add_mask f32 [B,S], meta, *params) -> tuple of fp32 [B,S,H] outputs, one per
+    requested layer (all layers when meta.all_layers else the last one only)."""
+
+    @staticmethod
+    def forward(ctx, emb, add_mask, meta, *params):
+        _require_cuda(emb, add_mask)
+        B, S, H = emb.shape
+        L, heads, I = meta.L, meta.heads, meta.I
+        lib = _lib.lib()
+        st = _stream()
+        meta.weights.refresh(params)
+        specs = []
+        for l in range(L):
+            specs += _act_specs(l, B, S, H, heads, I, False)
+        car = _Carver(specs, emb.device)
+        outs = []
+        x = emb.contiguous().view(B * S, H)
+        for l in range(L):
+            want = meta.all_layers or l == L - 1
+            y32 = torch.empty((B, S, H), dtype=F32, device=emb.device) if want else None
+            w = meta.weights.layer_struct(l, params)
+            a = _acts_struct(car, l, y32)
+            _chk(lib.vlb_bert_layer_forward(ctypes.byref(w), x.data_ptr(), _p(add_mask), ctypes.byref(a), B, S, H, heads, I,
+                                            float(meta.eps), st))
+            x = car.get("y%d" % l)
+            if want:
+                outs.append(y32)
+        ctx.meta = meta
+        ctx.car = car
+        ctx.dims = (B, S, H)
+        ctx.emb = emb
+        ctx.add_mask = add_mask
+        ctx.params = params
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grad_outs):
+        meta, car = ctx.meta, ctx.car
+        B, S, H = ctx.dims
+        L, heads, I = meta.L, meta.heads, meta.I
+        M = B * S
+        lib = _lib.lib()
+        st = _stream()
+        dev = ctx.emb.device
+        params = ctx.params
+        per = 3 * H * H + 3 * H + H * H + H + 2 * H + I * H + I + H * I + H + 2 * H
+        flat = torch.zeros((L, per), dtype=F32, device=dev)
+        ws_bytes = int(lib.vlb_bert_layer_backward_workspace(M, H, I))
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        dx = [torch.empty((M, H), dtype=BF16, device=dev), torch.empty((M, H), dtype=BF16, device=dev)]
+        gouts = list(grad_outs)
+        if not meta.all_layers:
+            gouts = [None] * (L - 1) + gouts
+        dy16 = None
+        grads = [None] * (16 * L)
+        for l in range(L - 1, -1, -1):
+            dy32 = gouts[l]
+            if dy32 is not None:
+                dy32 = dy32.contiguous().float()
+            if dy16 is None and dy32 is None:
+                dy32 = torch.zeros((M, H), dtype=F32, device=dev)
+            f = flat[l]
+            o = 0
+
+            def take(n, shape):
+                nonlocal o
+                t = f[o: o + n].view(*shape)
+                o += n
+                return t
+            dw_qkv, db_qkv = take(3 * H * H, (3 * H, H)), take(3 * H, (3 * H,))
+            dw_o, db_o = take(H * H, (H, H)), take(H, (H,))
+            dg1, dbt1 = take(H, (H,)), take(H, (H,))
+            dw_1, db_1 = take(I * H, (I, H)), take(I, (I,))
+            dw_2, db_2 = take(H * I, (H, I)), take(H, (H,))
+            dg2, dbt2 = take(H, (H,)), take(H, (H,))
+            g = _lib.LayerGrads()
+            g.dw_qkv, g.db_qkv, g.dw_o, g.db_o = dw_qkv.data_ptr(), db_qkv.data_ptr(), dw_o.data_ptr(), db_o.data_ptr()
+            g.dln1_g, g.dln1_b, g.dw_1, g.db_1 = dg1.data_ptr(), dbt1.data_ptr(), dw_1.data_ptr(), db_1.data_ptr()
+            g.dw_2, g.db_2, g.dln2_g, g.dln2_b = dw_2.data_ptr(), db_2.data_ptr(), dg2.data_ptr(), dbt2.data_ptr()
+            w = meta.weights.layer_struct(l, params)
+            a = _acts_struct(car, l, None)
+            x = ctx.emb.view(M, H) if l == 0 else car.get("y%d" % (l - 1))
+            out_dx = dx[l & 1]
+            _chk(lib.vlb_bert_layer_backward(ctypes.byref(w), ctypes.byref(a), x.data_ptr(), _p(ctx.add_mask), _p(dy16),
+                                             _p(dy32), out_dx.data_ptr(), ctypes.byref(g), ws.data_ptr(), ws_bytes, B, S, H,
+                                             heads, I, st))
+            dy16 = out_dx
+            if meta.reducer is not None:
+                meta.reducer.launch(f)
+            grads[16 * l: 16 * l + 16] = [dw_qkv[0:H], db_qkv[0:H], dw_qkv[H:2 * H], db_qkv[H:2 * H], dw_qkv[2 * H:],
+                                          db_qkv[2 * H:], dw_o, db_o, dg1, dbt1, dw_1, db_1, dw_2, db_2, dg2, dbt2]
+        if meta.reducer is not None:
+            meta.reducer.drain()
+        d_emb = dy16.view(B, S, H)
+        ctx.car = None
+        return (d_emb, None, None) + tuple(grads)
+
+
+# ------------------------------------------------------------------------------------------------
+# embedding + packing (VisualLinguisticBert.embedding, common/visual_linguistic_bert.py:173-241)
+# ------------------------------------------------------------------------------------------------
+class PackIndex(object):
+    """Device-side index tensors of the packed sequence (vlb_pack_index)."""
+
+    def __init__(self, text_mask, object_mask, text_token_type_ids, S, pos_offset):
+        _require_cuda(text_mask, object_mask, text_token_type_ids)
+        B, T = text_mask.shape
+        R = object_mask.shape[1]
+        dev = text_mask.device
+        self.B, self.T, self.R, self.S = B, T, R, S
+        i32 = torch.int32
+        self.kind = torch.empty((B, S), dtype=i32, device=dev)
+        self.src = torch.empty((B, S), dtype=i32, device=dev)
+        self.pos_id = torch.empty((B, S), dtype=i32, device=dev)
+        self.type_id = torch.empty((B, S), dtype=i32, device=dev)
+        self.add_mask = torch.empty((B, S), dtype=F32, device=dev)
+        self.obj_row = torch.empty((B, R), dtype=i32, device=dev)
+        self.lens = torch.empty((B, 2), dtype=i32, device=dev)
+        self.err = torch.zeros((1,), dtype=i32, device=dev)
+        self.text_mask_u8 = text_mask.to(torch.uint8).contiguous()
+        self.object_mask_u8 = object_mask.to(torch.uint8).contiguous()
+        self.type_ids = text_token_type_ids.to(torch.int64).contiguous()
+        _chk(_lib.lib().vlb_pack_index(_p(self.text_mask_u8), _p(self.object_mask_u8), _p(self.type_ids), B, T, R, S,
+                                       pos_offset, _p(self.kind), _p(self.src), _p(self.pos_id), _p(self.type_id),
+                                       _p(self.add_mask), _p(self.obj_row), _p(self.lens), _p(self.err), _stream()))
+
+
+class EmbeddingFn(torch.autograd.Function):
+    """forward(text_visual f32 [B,T,H], object_vl f32 [B,R,2H], word, end, pos, type, ln_w, ln_b, vt_w, vt_b, vo_w, vo_b,
+    ids int64 [B,T], pidx: PackIndex, eps) -> emb bf16 [B,S,H]"""
+
+    @staticmethod
+    def forward(ctx, text_visual, object_vl, word, end, pos, typ, ln_w, ln_b, vt_w, vt_b, vo_w, vo_b, ids, pidx, eps):
+        _require_cuda(text_visual, object_vl, word)
+        B, T, R, S = pidx.B, pidx.T, pidx.R, pidx.S
+        H = word.shape[1]
+        lib = _lib.lib()
+        st = _stream()
+        tv = text_visual.contiguous().float()
+        ov = object_vl.contiguous().float()
+        assert tv.shape[-1] == H and ov.shape[-1] == 2 * H
+        _, tv_ln, tv_mean, tv_rstd = layernorm_forward(tv.view(B * T, H), vt_w, vt_b, eps, want_bf16=False, want_f32=True)
+        _, ov_ln, ov_mean, ov_rstd = layernorm_forward(ov.view(B * R, 2 * H), vo_w, vo_b, eps, want_bf16=False, want_f32=True,
+                                                       ldx=2 * H, H=H)
+        e = torch.empty((B * S, H), dtype=F32, device=tv.device)
+        ids = ids.contiguous()
+        _chk(lib.vlb_pack_forward(_p(pidx.kind), _p(pidx.src), _p(pidx.pos_id), _p(pidx.type_id), _p(ids), _p(word), _p(end),
+                                  _p(pos), _p(typ), _p(tv_ln), _p(ov_ln), _p(ov), 2 * H, H, _p(e), B, T, R, S, H,
+                                  word.shape[0], pos.shape[0], _p(pidx.err), st))
+        emb, _, e_mean, e_rstd = layernorm_forward(e, ln_w, ln_b, eps)
+        ctx.save_for_backward(tv, ov, word, end, pos, typ, ln_w, vt_w, vo_w, ids, e, e_mean, e_rstd, tv_mean, tv_rstd,
+                              ov_mean, ov_rstd)
+        ctx.pidx = pidx
+        ctx.dims = (B, T, R, S, H)
+        return emb.view(B, S, H)
+
+    @staticmethod
+    def backward(ctx, d_emb):
+        (tv, ov, word, end, pos, typ, ln_w, vt_w, vo_w, ids, e, e_mean, e_rstd, tv_mean, tv_rstd, ov_mean,
+         ov_rstd) = ctx.saved_tensors
+        pidx = ctx.pidx
+        B, T, R, S, H = ctx.dims
+        lib = _lib.lib()
+        st = _stream()
+        dev = e.device
+        z = lambda *s: torch.zeros(s, dtype=F32, device=dev)  # noqa: E731
+        d_ln_w, d_ln_b, d_vt_w, d_vt_b, d_vo_w, d_vo_b = z(H), z(H), z(H), z(H), z(H), z(H)
+        d16 = d_emb.contiguous().view(B * S, H)
+        dy16, dy32 = (d16, None) if d16.dtype == BF16 else (None, d16.float())
+        _, de = layernorm_backward(dy16, dy32, e, e_mean, e_rstd, ln_w, d_ln_w, d_ln_b, want_bf16=False, want_f32=True)
+        d_word, d_end, d_pos, d_typ = z(*word.shape), z(*end.shape), z(*pos.shape), z(*typ.shape)
+        d_text_vl, d_obj_vl = z(B * T, H), z(B * R, H)
+        _chk(lib.vlb_pack_backward(_p(pidx.kind), _p(pidx.src), _p(pidx.pos_id), _p(pidx.type_id), _p(ids), _p(de), _p(d_word),
+                                   _p(d_end), _p(d_pos), _p(d_typ), _p(d_text_vl), _p(d_obj_vl), B, T, R, S, H, word.shape[0],
+                                   pos.shape[0], st))
+        _, d_tv = layernorm_backward(None, d_text_vl, tv.view(B * T, H), tv_mean, tv_rstd, vt_w, d_vt_w, d_vt_b,
+                                     want_bf16=False, want_f32=True)
+        d_ov = torch.empty((B * R, 2 * H), dtype=F32, device=dev)
+        layernorm_backward(None, d_obj_vl, ov.view(B * R, 2 * H), ov_mean, ov_rstd, vo_w, d_vo_w, d_vo_b, want_bf16=False,
+                           want_f32=True, ldx=2 * H, H=H, dx32=d_ov, ld_dx=2 * H)
+        d_ov[:, H:] = d_obj_vl
+        return (d_tv.view(B, T, H), d_ov.view(B, R, 2 * H), d_word, d_end, d_pos, d_typ, d_ln_w, d_ln_b, d_vt_w, d_vt_b,
+                d_vo_w, d_vo_b, None, None, None)
+
+
+class GatherRowsFn(torch.autograd.Function):
+    """out[i] = idx[i] >= 0 ? src[idx[i]] : 0 ; src 2-D (bf16 or f32) -> f32.  Each source row is referenced at most once."""
+
+    @staticmethod
+    def forward(ctx, src2d, idx, n_out):
+        ctx.save_for_backward(idx)
+        ctx.n_src = src2d.shape[0]
+        return gather_rows(src2d.contiguous(), idx, n_out, F32)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        out = torch.zeros((ctx.n_src, g.shape[1]), dtype=F32, device=g.device)
+        scatter_rows_add(g.contiguous(), idx, out)
+        return out, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# region-feature front end
+# ------------------------------------------------------------------------------------------------
+class RegionFn(torch.autograd.Function):
+    """Precomputed-feature path of FastRCNN.forward (common/fast_rcnn.py:136-193):
+    forward(boxes f32 [B,R,4+F], weight f32 [D, 2048+F], bias f32 [D], box_mask bool [B,R], im_info f32 [B,>=2])
+      -> obj_reps f32 [B,R,D], obj_reps_raw f32 [B,R,F]   (both re-padded: k-th valid box in slot k)"""
+
+    @staticmethod
+    def forward(ctx, boxes, weight, bias, box_mask, im_info):
+        _require_cuda(boxes, weight, bias, box_mask, im_info)
+        B, R, C = boxes.shape
+        Fd = C - 4
+        D = weight.shape[0]
+        lib = _lib.lib()
+        st = _stream()
+        dev = boxes.device
+        bx = boxes.contiguous().float()
+        info = im_info.contiguous().float()
+        mask_u8 = box_mask.to(torch.uint8).contiguous()
+        A = torch.empty((B * R, 2048 + Fd), dtype=BF16, device=dev)
+        gidx = torch.empty((B * R,), dtype=torch.int32, device=dev)
+        _chk(lib.vlb_region_operand(_p(bx), C, _p(mask_u8), _p(info), info.shape[1], None, None, _p(A), _p(gidx), B, R, Fd, st))
+        w16 = torch.empty(weight.shape, dtype=BF16, device=dev)
+        _chk(lib.vlb_cast_f32_to_bf16(_p(weight.contiguous()), _p(w16), weight.numel(), st))
+        Y = torch.empty((B * R, D), dtype=BF16, device=dev)
+        gemm(0, A, w16, Y, bias=bias.contiguous().float(), act=2)
+        obj = gather_rows(Y, gidx, B * R, F32).view(B, R, D)
+        raw = torch.empty((B * R, Fd), dtype=F32, device=dev)
+        _chk(lib.vlb_gather_rows(bx.data_ptr() + 16, 0, C, _p(gidx), _p(raw), 0, Fd, B * R, Fd, st))
+        ctx.save_for_backward(A, w16, Y, gidx)
+        ctx.dims = (B, R, C, D)
+        ctx.mark_non_differentiable(raw)
+        return obj, raw.view(B, R, Fd)
+
+    @staticmethod
+    def backward(ctx, d_obj, _d_raw):
+        A, w16, Y, gidx = ctx.saved_tensors
+        B, R, C, D = ctx.dims
+        Fd = C - 4
+        lib = _lib.lib()
+        st = _stream()
+        dev = A.device
+        # un-gather: dY[gidx[i]] = d_obj[i]
+        dY32 = torch.zeros((B * R, D), dtype=F32, device=dev)
+        scatter_rows_add(d_obj.contiguous().view(B * R, D).float(), gidx, dY32)
+        # ReLU mask and bf16 operand
+        dY = (dY32 * (Y > 0)).to(BF16)
+        d_bias = torch.zeros((D,), dtype=F32, device=dev)
+        _chk(lib.vlb_colsum_bf16(_p(dY), D, _p(d_bias), B * R, D, st))
+        d_w = torch.zeros((D, 2048 + Fd), dtype=F32, device=dev)
+        d_w._vlb_accumulate = True
+        gemm(2, dY, A, d_w, split_k=max(1, min(16, (B * R) // 256)))
+        # gradient wrt the feature half of boxes (the coordinate half is not propagated: the reference's boxes are data)
+        d_boxes = torch.zeros((B * R, C), dtype=F32, device=dev)
+        d_feat = torch.empty((B * R, Fd), dtype=BF16, device=dev)
+        gemm(1, dY, w16[:, 2048:], d_feat, M=B * R, N=Fd, K=D)
+        d_boxes[:, 4:] = d_feat.float()
+        return d_boxes.view(B, R, C), d_w, d_bias, None, None
+
+
+class RoIAlignFn(torch.autograd.Function):
+    """_ROIAlign (common/lib/roi_pooling/roi_align.py:11-43) on vlb_roi_align_forward/backward."""
+
+    @staticmethod
+    def forward(ctx, input, rois, output_size, spatial_scale, sampling_ratio):
+        ctx.save_for_backward(rois)
+        ctx.cfg = (tuple(output_size), float(spatial_scale), int(sampling_ratio), tuple(input.shape))
+        return roi_align_forward(input, rois, spatial_scale, output_size[0], output_size[1], sampling_ratio)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (rois,) = ctx.saved_tensors
+        (ph, pw), scale, sr, (N, C, H, W) = ctx.cfg
+        return roi_align_backward(grad, rois, scale, ph, pw, N, C, H, W, sr), None, None, None, None
+
+
+def roi_align_forward(input, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio):
+    """C_ROIPooling.roi_align_forward (common/lib/roi_pooling/ROIAlign.h:11-25)."""
+    _require_cuda(input, rois)
+    inp = input.contiguous().float()
+    r = rois.contiguous().float()
+    N, C, H, W = inp.shape
+    K = r.shape[0]
+    out = torch.empty((K, C, pooled_h, pooled_w), dtype=F32, device=inp.device)
+    _chk(_lib.lib().vlb_roi_align_forward(_p(inp), _p(r), _p(out), K, C, H, W, pooled_h, pooled_w, float(spatial_scale),
+                                          int(sampling_ratio), _stream()))
+    return out
+
+
+def roi_align_backward(grad, rois, spatial_scale, pooled_h, pooled_w, batch_size, channels, height, width, sampling_ratio):
+    """C_ROIPooling.roi_align_backward (common/lib/roi_pooling/ROIAlign.h:27-45)."""
+    _require_cuda(grad, rois)
+    g = grad.contiguous().float()
+    r = rois.contiguous().float()
+    gin = torch.empty((batch_size, channels, height, width), dtype=F32, device=g.device)
+    _chk(_lib.lib().vlb_roi_align_backward(_p(g), _p(r), _p(gin), r.shape[0], batch_size, channels, height, width, pooled_h,
+                                           pooled_w, float(spatial_scale), int(sampling_ratio), _stream()))
+    return gin

@@ -1,0 +1,449 @@
+"""Drop-in nn.Modules: same constructor arguments, forward signatures, return structures and
+state_dict keys as the reference classes they replace, with the compute routed to libvlbert_b200.so.
+
+  VisualLinguisticBert                <- common/visual_linguistic_bert.py:31-241
+  VisualLinguisticBertForPretraining  <- common/visual_linguistic_bert.py:312-380 (heads: torch for now)
+  FastRCNN                            <- common/fast_rcnn.py:17-203
+  ROIAlign / C_ROIPooling             <- common/lib/roi_pooling/roi_align.py:46-78, vision.cpp:6-11
+
+There is no CPU / eager fallback: a forward on CPU tensors raises.
+"""
+import math
+import types
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as VF
+
+NUM_SPECIAL_WORDS = 1000
+
+
+def default_config(**over):
+    """NETWORK.VLBERT defaults for VL-BERT-base (reference: pretrain/function/config.py:87-115, cfgs/pretrain/base_*.yaml)
+    with the dropout probabilities at 0 (the fused path has no dropout yet)."""
+    cfg = dict(vocab_size=30522, hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072,
+               hidden_act="gelu", hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, max_position_embeddings=512,
+               type_vocab_size=3, initializer_range=0.02, visual_size=768, visual_scale_text_init=1.0,
+               visual_scale_object_init=1.0, visual_ln=True, word_embedding_frozen=False, with_pooler=True,
+               position_padding_idx=-1, obj_pos_id_relative=True)
+    cfg.update(over)
+    return types.SimpleNamespace(**cfg)
+
+
+class BertLayerNorm(nn.Module):
+    """Parameter holder with the reference's names (modeling.py:222-229); compute happens in the kernels.
+    Calling it directly (heads) uses the TF-style formula in torch."""
+
+    def __init__(self, hidden_size, eps=1e-12):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(hidden_size))
+        self.bias = nn.Parameter(torch.zeros(hidden_size))
+        self.variance_epsilon = eps
+
+    def forward(self, x):
+        u = x.mean(-1, keepdim=True)
+        s = (x - u).pow(2).mean(-1, keepdim=True)
+        return self.weight * ((x - u) / torch.sqrt(s + self.variance_epsilon)) + self.bias
+
+
+class _SelfAttention(nn.Module):
+    def __init__(self, H):
+        super().__init__()
+        self.query, self.key, self.value = nn.Linear(H, H), nn.Linear(H, H), nn.Linear(H, H)
+
+
+class _DenseLN(nn.Module):
+    def __init__(self, fan_in, H):
+        super().__init__()
+        self.dense = nn.Linear(fan_in, H)
+        self.LayerNorm = BertLayerNorm(H, eps=1e-12)
+
+
+class _Attention(nn.Module):
+    def __init__(self, H):
+        super().__init__()
+        self.self = _SelfAttention(H)
+        self.output = _DenseLN(H, H)
+
+
+class _Intermediate(nn.Module):
+    def __init__(self, H, I):
+        super().__init__()
+        self.dense = nn.Linear(H, I)
+
+
+class BertLayer(nn.Module):
+    def __init__(self, H, I):
+        super().__init__()
+        self.attention = _Attention(H)
+        self.intermediate = _Intermediate(H, I)
+        self.output = _DenseLN(I, H)
+
+    def flat_params(self):
+        a, o = self.attention, self.output
+        return [a.self.query.weight, a.self.query.bias, a.self.key.weight, a.self.key.bias, a.self.value.weight,
+                a.self.value.bias, a.output.dense.weight, a.output.dense.bias, a.output.LayerNorm.weight,
+                a.output.LayerNorm.bias, self.intermediate.dense.weight, self.intermediate.dense.bias, o.dense.weight,
+                o.dense.bias, o.LayerNorm.weight, o.LayerNorm.bias]
+
+
+class BertEncoder(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.layer = nn.ModuleList([BertLayer(config.hidden_size, config.intermediate_size)
+                                    for _ in range(config.num_hidden_layers)])
+
+
+class BertPooler(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(config.hidden_size, config.hidden_size)
+
+    def forward(self, hidden_states):
+        return torch.tanh(self.dense(hidden_states[:, 0]))
+
+
+class BaseModel(nn.Module):
+    def __init__(self, config, **kwargs):
+        self.config = config
+        super().__init__()
+
+    def init_weights(self, module):
+        """common/visual_linguistic_bert.py:14-25"""
+        if isinstance(module, (nn.Linear, nn.Embedding)):
+            module.weight.data.normal_(mean=0.0, std=self.config.initializer_range)
+        elif isinstance(module, BertLayerNorm):
+            module.bias.data.zero_()
+            module.weight.data.fill_(1.0)
+        if isinstance(module, nn.Linear) and module.bias is not None:
+            module.bias.data.zero_()
+
+
+class VisualLinguisticBert(BaseModel):
+    def __init__(self, config, language_pretrained_model_path=None):
+        super().__init__(config)
+        H = config.hidden_size
+        if config.hidden_act != "gelu":
+            raise ValueError("vlbert_b200: only hidden_act='gelu' (erf form) is implemented")
+        if H % config.num_attention_heads != 0 or H // config.num_attention_heads != 64:
+            raise ValueError("vlbert_b200: attention head size must be 64 (hidden %d, heads %d)" % (H, config.num_attention_heads))
+        if getattr(config, "word_embedding_frozen", False):
+            raise ValueError("vlbert_b200: word_embedding_frozen is not implemented")
+        if not config.visual_ln:
+            raise ValueError("vlbert_b200: visual_ln=False (scalar visual scale) is not implemented")
+        if not config.obj_pos_id_relative:
+            raise AssertionError("Don't use position id 510/511 for objects and [END]!!!")  # visual_linguistic_bert.py:229
+        if config.hidden_dropout_prob != 0 or config.attention_probs_dropout_prob != 0:
+            import warnings
+            warnings.warn("vlbert_b200: dropout is not implemented on the fused path; running with p = 0")
+        self.word_embeddings = nn.Embedding(config.vocab_size, H)
+        self.end_embedding = nn.Embedding(1, H)
+        self.position_embeddings = nn.Embedding(config.max_position_embeddings, H)
+        self.token_type_embeddings = nn.Embedding(config.type_vocab_size, H)
+        self.embedding_LayerNorm = BertLayerNorm(H, eps=1e-12)
+        self.position_padding_idx = config.position_padding_idx
+        self.visual_1x1_text = None
+        self.visual_1x1_object = None
+        if config.visual_size != H:
+            self.visual_1x1_text = nn.Linear(config.visual_size, H)
+            self.visual_1x1_object = nn.Linear(config.visual_size, H)
+        self.visual_ln_text = BertLayerNorm(H, eps=1e-12)
+        self.visual_ln_object = BertLayerNorm(H, eps=1e-12)
+        self.encoder = BertEncoder(config)
+        if config.with_pooler:
+            self.pooler = BertPooler(config)
+        self.apply(self.init_weights)
+        self.visual_ln_text.weight.data.fill_(config.visual_scale_text_init)
+        self.visual_ln_object.weight.data.fill_(config.visual_scale_object_init)
+        if language_pretrained_model_path is not None:
+            self.load_language_pretrained_model(language_pretrained_model_path)
+        # Upper bound for the packed length; when set, no device->host sync is needed to size the outputs
+        # (the reference's `max_length = (...).max() + 1`, visual_linguistic_bert.py:202, syncs every forward).
+        self.max_length_hint = None
+        self._weights = None
+
+    # -- helpers -----------------------------------------------------------------------------------
+    def _encoder_meta(self, all_layers, device):
+        cfg = self.config
+        if self._weights is None or self._weights.w_qkv.device != device:
+            self._weights = VF.EncoderWeights(cfg.num_hidden_layers, cfg.hidden_size, cfg.intermediate_size, device)
+        return types.SimpleNamespace(L=cfg.num_hidden_layers, H=cfg.hidden_size, heads=cfg.num_attention_heads,
+                                     I=cfg.intermediate_size, eps=1e-12, all_layers=all_layers, weights=self._weights,
+                                     reducer=getattr(self, "_grad_reducer", None))
+
+    def _packed_length(self, text_mask, object_mask):
+        T, R = text_mask.shape[1], object_mask.shape[1]
+        if self.max_length_hint is not None:
+            return min(int(self.max_length_hint), T + R + 1)
+        return int((text_mask.sum(1) + object_mask.sum(1)).max().item()) + 1
+
+    def embedding(self, text_input_ids, text_token_type_ids, text_visual_embeddings, text_mask, object_vl_embeddings,
+                  object_mask):
+        emb, pidx = self._embedding_impl(text_input_ids, text_token_type_ids, text_visual_embeddings, text_mask,
+                                         object_vl_embeddings, object_mask)
+        kind = pidx.kind
+        return emb.float(), (kind != 3).to(text_mask.dtype), kind == 0, kind == 1
+
+    def _embedding_impl(self, text_input_ids, text_token_type_ids, text_visual_embeddings, text_mask, object_vl_embeddings,
+                        object_mask):
+        cfg = self.config
+        VS = cfg.visual_size
+        if self.visual_1x1_text is not None:
+            text_visual_embeddings = self.visual_1x1_text(text_visual_embeddings)
+            object_vl_embeddings = torch.cat((self.visual_1x1_object(object_vl_embeddings[:, :, :VS]),
+                                              object_vl_embeddings[:, :, VS:]), -1)
+        S = self._packed_length(text_mask, object_mask)
+        pidx = VF.PackIndex(text_mask, object_mask, text_token_type_ids, S, self.position_padding_idx + 1)
+        emb = VF.EmbeddingFn.apply(text_visual_embeddings, object_vl_embeddings, self.word_embeddings.weight,
+                                   self.end_embedding.weight, self.position_embeddings.weight,
+                                   self.token_type_embeddings.weight, self.embedding_LayerNorm.weight,
+                                   self.embedding_LayerNorm.bias, self.visual_ln_text.weight, self.visual_ln_text.bias,
+                                   self.visual_ln_object.weight, self.visual_ln_object.bias, text_input_ids, pidx, 1e-12)
+        return emb, pidx
+
+    def forward(self, text_input_ids, text_token_type_ids, text_visual_embeddings, text_mask, object_vl_embeddings,
+                object_mask, output_all_encoded_layers=True, output_text_and_object_separately=False,
+                output_attention_probs=False):
+        if output_attention_probs:
+            raise NotImplementedError("vlbert_b200: the fused attention never materialises probabilities "
+                                      "(output_attention_probs is a visualisation-only path of the reference)")
+        emb, pidx = self._embedding_impl(text_input_ids, text_token_type_ids, text_visual_embeddings, text_mask,
+                                         object_vl_embeddings, object_mask)
+        meta = self._encoder_meta(bool(output_all_encoded_layers), emb.device)
+        params = []
+        for layer in self.encoder.layer:
+            params += layer.flat_params()
+        outs = VF.EncoderFn.apply(emb, pidx.add_mask, meta, *params)
+        encoded_layers = list(outs)
+        sequence_output = encoded_layers[-1]
+        pooled_output = self.pooler(sequence_output) if self.config.with_pooler else None
+        if not output_all_encoded_layers:
+            encoded_layers = encoded_layers[-1]
+        if not output_text_and_object_separately:
+            return encoded_layers, pooled_output
+        lst = encoded_layers if output_all_encoded_layers else [encoded_layers]
+        B, S, H = lst[0].shape
+        T, R = text_input_ids.shape[1], object_vl_embeddings.shape[1]
+        texts, objs = [], []
+        for enc in lst:
+            texts.append(enc[:, :T])
+            objs.append(VF.GatherRowsFn.apply(enc.reshape(B * S, H), pidx.obj_row.view(-1), B * R).view(B, R, H))
+        if not output_all_encoded_layers:
+            texts, objs = texts[0], objs[0]
+        return texts, objs, pooled_output
+
+    def load_language_pretrained_model(self, language_pretrained_model_path):
+        """HF BERT checkpoint key remapping (common/visual_linguistic_bert.py:243-309)."""
+        sd = torch.load(language_pretrained_model_path, map_location="cpu")
+        enc, pool, emb_ln, unexpected = {}, {}, {}, []
+        for k, v in sd.items():
+            if k.startswith("bert."):
+                k = k[len("bert."):]
+            elif k.startswith("roberta."):
+                k = k[len("roberta."):]
+            else:
+                unexpected.append(k)
+                continue
+            k = k.replace("gamma", "weight").replace("beta", "bias")
+            if k.startswith("encoder."):
+                enc[k[len("encoder."):]] = v
+            elif k.startswith("embeddings."):
+                k = k[len("embeddings."):]
+                if k.startswith("word_embeddings."):
+                    self.word_embeddings.weight.data = v.to(self.word_embeddings.weight.dtype)
+                elif k.startswith("position_embeddings."):
+                    self.position_embeddings.weight.data = v.to(self.position_embeddings.weight.dtype)
+                elif k.startswith("token_type_embeddings."):
+                    n = v.size(0)
+                    self.token_type_embeddings.weight.data[:n] = v.to(self.token_type_embeddings.weight.dtype)
+                    if n == 1:  # roberta: replicate for the second sentence type
+                        self.token_type_embeddings.weight.data[1] = v[0].clone().to(self.token_type_embeddings.weight.dtype)
+                elif k.startswith("LayerNorm."):
+                    emb_ln[k[len("LayerNorm."):]] = v
+                else:
+                    unexpected.append(k)
+            elif self.config.with_pooler and k.startswith("pooler."):
+                pool[k[len("pooler."):]] = v
+            else:
+                unexpected.append(k)
+        if unexpected:
+            print("Warnings: Unexpected keys: {}.".format(unexpected))
+        self.embedding_LayerNorm.load_state_dict(emb_ln)
+        self.encoder.load_state_dict(enc)
+        if self.config.with_pooler and pool:
+            self.pooler.load_state_dict(pool)
+
+
+# ------------------------------------------------------------------------------------------------
+# pre-training heads (reference: common/visual_linguistic_bert.py:312-380, :473-502; modeling.py:439-472).
+# Torch ops for now -- SURVEY.md 8(f) ranks the fused vocab GEMM + CE as the first "next" row.
+# ------------------------------------------------------------------------------------------------
+def _gelu(x):
+    return x * 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+class BertPredictionHeadTransform(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(config.hidden_size, config.hidden_size)
+        self.LayerNorm = BertLayerNorm(config.hidden_size, eps=1e-12)
+
+    def forward(self, x):
+        return self.LayerNorm(_gelu(self.dense(x)))
+
+
+class BertLMPredictionHead(nn.Module):
+    def __init__(self, config, bert_model_embedding_weights):
+        super().__init__()
+        self.transform = BertPredictionHeadTransform(config)
+        self.decoder = nn.Linear(bert_model_embedding_weights.size(1), bert_model_embedding_weights.size(0), bias=False)
+        self.decoder.weight = bert_model_embedding_weights
+        self.bias = nn.Parameter(torch.zeros(bert_model_embedding_weights.size(0)))
+
+    def forward(self, x):
+        return self.decoder(self.transform(x)) + self.bias
+
+
+class BertOnlyMLMHead(nn.Module):
+    def __init__(self, config, bert_model_embedding_weights):
+        super().__init__()
+        self.predictions = BertLMPredictionHead(config, bert_model_embedding_weights)
+
+    def forward(self, x):
+        return self.predictions(x)
+
+
+class VisualLinguisticBertMVRCHeadTransform(BaseModel):
+    def __init__(self, config):
+        super().__init__(config)
+        self.dense = nn.Linear(config.hidden_size, config.hidden_size)
+        self.apply(self.init_weights)
+
+    def forward(self, x):
+        return _gelu(self.dense(x))
+
+
+class VisualLinguisticBertMVRCHead(BaseModel):
+    def __init__(self, config):
+        super().__init__(config)
+        self.transform = VisualLinguisticBertMVRCHeadTransform(config)
+        self.region_cls_pred = nn.Linear(config.hidden_size, config.visual_region_classes)
+        self.apply(self.init_weights)
+
+    def forward(self, x):
+        return self.region_cls_pred(self.transform(x))
+
+
+class VisualLinguisticBertRelationshipPredictionHead(BaseModel):
+    def __init__(self, config):
+        super().__init__(config)
+        self.caption_image_relationship = nn.Linear(config.hidden_size, 2)
+        self.apply(self.init_weights)
+
+    def forward(self, pooled_rep):
+        return self.caption_image_relationship(pooled_rep)
+
+
+class VisualLinguisticBertForPretraining(VisualLinguisticBert):
+    def __init__(self, config, language_pretrained_model_path=None, with_rel_head=True, with_mlm_head=True,
+                 with_mvrc_head=True):
+        super().__init__(config, language_pretrained_model_path=None)
+        self.with_rel_head, self.with_mlm_head, self.with_mvrc_head = with_rel_head, with_mlm_head, with_mvrc_head
+        if with_rel_head:
+            self.relationsip_head = VisualLinguisticBertRelationshipPredictionHead(config)  # (sic) reference key name
+        if with_mlm_head:
+            self.mlm_head = BertOnlyMLMHead(config, self.word_embeddings.weight)
+        if with_mvrc_head:
+            self.mvrc_head = VisualLinguisticBertMVRCHead(config)
+        self.apply(self.init_weights)
+        self.visual_ln_text.weight.data.fill_(config.visual_scale_text_init)
+        self.visual_ln_object.weight.data.fill_(config.visual_scale_object_init)
+        if language_pretrained_model_path is not None:
+            self.load_language_pretrained_model(language_pretrained_model_path)
+
+    def forward(self, text_input_ids, text_token_type_ids, text_visual_embeddings, text_mask, object_vl_embeddings,
+                object_mask, output_all_encoded_layers=True, output_text_and_object_separately=False):
+        text_out, object_out, pooled_rep = super().forward(text_input_ids, text_token_type_ids, text_visual_embeddings,
+                                                           text_mask, object_vl_embeddings, object_mask,
+                                                           output_all_encoded_layers=False,
+                                                           output_text_and_object_separately=True)
+        relationship_logits = self.relationsip_head(pooled_rep) if self.with_rel_head else None
+        mlm_logits = self.mlm_head(text_out) if self.with_mlm_head else None
+        mvrc_logits = self.mvrc_head(object_out) if self.with_mvrc_head else None
+        return relationship_logits, mlm_logits, mvrc_logits
+
+
+# ------------------------------------------------------------------------------------------------
+# region-feature front end
+# ------------------------------------------------------------------------------------------------
+class ROIAlign(nn.Module):
+    """common/lib/roi_pooling/roi_align.py:46-78"""
+
+    def __init__(self, output_size, spatial_scale, sampling_ratio=1):
+        super().__init__()
+        self.output_size = output_size
+        self.spatial_scale = spatial_scale
+        self.sampling_ratio = sampling_ratio
+
+    def forward(self, input, rois):
+        return VF.RoIAlignFn.apply(input.float(), rois.float(), self.output_size, self.spatial_scale, self.sampling_ratio)
+
+    def __repr__(self):
+        return "%s(output_size=%s, spatial_scale=%s, sampling_ratio=%s)" % (self.__class__.__name__, self.output_size,
+                                                                            self.spatial_scale, self.sampling_ratio)
+
+
+def _roi_pool_unavailable(*a, **k):
+    raise RuntimeError("vlbert_b200: roi_pool_* is dead code on the reference's hot path and is not provided")
+
+
+#: module object with the reference extension's function names (common/lib/roi_pooling/vision.cpp:6-11)
+C_ROIPooling = types.SimpleNamespace(roi_align_forward=VF.roi_align_forward, roi_align_backward=VF.roi_align_backward,
+                                     roi_pool_forward=_roi_pool_unavailable, roi_pool_backward=_roi_pool_unavailable)
+
+
+class FastRCNN(nn.Module):
+    """common/fast_rcnn.py:17-203.  The precomputed-feature path (IMAGE_FEAT_PRECOMPUTED, BASELINE configs 1-4) runs
+    entirely on the library; the end-to-end path keeps the ResNet-101 C4 / res5 convolutions on torch (cuDNN) for now and
+    uses the library's RoIAlign and region projection (conv rows K13/K14 are the next widening)."""
+
+    def __init__(self, config, average_pool=True, final_dim=768, enable_cnn_reg_loss=False):
+        super().__init__()
+        self.average_pool = average_pool
+        self.enable_cnn_reg_loss = enable_cnn_reg_loss
+        self.final_dim = final_dim
+        self.image_feat_precomputed = config.NETWORK.IMAGE_FEAT_PRECOMPUTED
+        if config.NETWORK.IMAGE_SEMANTIC:
+            raise ValueError("vlbert_b200: IMAGE_SEMANTIC (object class embedding) is not implemented")
+        self.object_embed = None
+        if not self.image_feat_precomputed:
+            raise NotImplementedError("vlbert_b200: the end-to-end ResNet path is assembled by vlbert_b200.dropin "
+                                      "(reference backbone + library RoIAlign); construct the reference FastRCNN there")
+        self.obj_downsample = torch.nn.Sequential(
+            torch.nn.Dropout(p=0.1),
+            torch.nn.Linear(2 * 2048, final_dim),
+            torch.nn.ReLU(inplace=True),
+        )
+
+    def init_weight(self):
+        pass
+
+    def bn_eval(self):
+        pass
+
+    def forward(self, images, boxes, box_mask, im_info, classes=None, segms=None, mvrc_ops=None, mask_visual_embed=None):
+        if classes is not None or segms is not None:
+            raise NotImplementedError("vlbert_b200: classes/segms inputs are not implemented on the precomputed path")
+        if self.training and self.obj_downsample[0].p > 0 and not getattr(self, "_warned", False):
+            import warnings
+            warnings.warn("vlbert_b200: obj_downsample dropout is not implemented on the fused path; running with p = 0")
+            self._warned = True
+        lin = self.obj_downsample[1]
+        if mvrc_ops is not None and mask_visual_embed is not None:
+            feats = boxes[:, :, 4:].clone()
+            feats[mvrc_ops == 1] = mask_visual_embed
+            boxes = torch.cat((boxes[:, :, :4], feats), -1)
+        obj_reps, raw = VF.RegionFn.apply(boxes, lin.weight, lin.bias, box_mask, im_info)
+        return {"obj_reps_raw": raw, "obj_reps": obj_reps}
