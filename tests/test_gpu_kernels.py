@@ -44,9 +44,11 @@ def bf(x):
 # ------------------------------------------------------------------------------------------------ GEMM
 @pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("shape", [(128, 128, 64), (6464, 768, 768), (26, 768, 768), (1000, 1608, 200), (300, 2304, 768)])
-@pytest.mark.parametrize("bn", [0, 64, 128, 256])
+@pytest.mark.parametrize("bn", [0, 64, 128, 192, 256])
 def test_gemm_modes_against_fp32_matmul(VF, mode, shape, bn):
     M, N, K = shape
+    if mode == 2 and M % 8:
+        pytest.skip("TN stores A as [K, M]: M must be a multiple of 8 (16-byte rows for TMA)")
     g = torch.Generator().manual_seed(1000 * mode + M + N + K)
     a = bf(torch.randn(M, K, generator=g))
     b = bf(torch.randn(N, K, generator=g))
@@ -144,9 +146,11 @@ def test_mhsa_forward_backward(VF, B, S, heads):
     assert rel(ctx.float(), ref.detach()) <= 4e-3  # P and ctx are bf16 on the tensor-core path
     dqkv = VF.mhsa_backward(qkv.to(DEV, BF16), add_mask.to(DEV), ctx, lse, dctx.to(DEV, BF16), B, S, H, heads)
     assert rel(dqkv.float(), qt.grad) <= 8e-3
-    for blk in range(3):  # dq, dk, dv separately
+    scale = qt.grad.norm().item() / 3 ** 0.5
+    for blk in range(3):  # dq, dk, dv separately (dq = dk = 0 exactly when S == 1: absolute check against the overall scale)
         sl = slice(blk * H, (blk + 1) * H)
-        assert rel(dqkv[:, sl].float(), qt.grad[:, sl]) <= 1e-2
+        err = (dqkv[:, sl].float().cpu() - qt.grad[:, sl]).norm().item()
+        assert err <= 1e-2 * max(qt.grad[:, sl].norm().item(), 0.05 * scale)
 
 
 # ------------------------------------------------------------------------------------------------ RoIAlign

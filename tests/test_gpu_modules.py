@@ -24,6 +24,16 @@ def rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
+def grad_ok(k, ours, ref, all_ref, tol):
+    """Relative L2 on one parameter gradient.  attention.self.key.bias has an EXACTLY zero gradient in exact arithmetic
+    (a constant added to every key's score cancels in the softmax); the reference's fp32 value is rounding noise, so it is
+    checked in absolute terms against the scale of the sibling query.bias gradient instead."""
+    if k.endswith("attention.self.key.bias"):
+        scale = all_ref[k.replace("key.bias", "query.bias")].double().norm().item()
+        return ours.double().cpu().norm().item() <= tol * scale
+    return rel(ours, ref) <= tol
+
+
 def _run(model, inputs, seed, dev):
     ids, types, tvis, tmask, ovl, omask = [t.to(dev) for t in inputs]
     tvis = tvis.clone().requires_grad_(True)
@@ -44,7 +54,7 @@ def _compare(ours, ref, tol_out=TOL_OUT, tol_grad=TOL_GRAD):
     assert rel(tv1, tv2) <= tol_grad and rel(ov1, ov2) <= tol_grad
     assert set(g1.keys()) == set(g2.keys())
     for k in g2:
-        assert rel(g1[k], g2[k]) <= tol_grad, (k, rel(g1[k], g2[k]))
+        assert grad_ok(k, g1[k], g2[k], g2, tol_grad), (k, rel(g1[k], g2[k]))
 
 
 def test_tiny_model_against_reference_fixture(golden_dir):
@@ -63,8 +73,9 @@ def test_tiny_model_against_reference_fixture(golden_dir):
     assert rel(pooled, torch.from_numpy(G["pooled"])) <= TOL_OUT
     assert rel(gtv, torch.from_numpy(G["grad_text_visual"])) <= TOL_GRAD
     assert rel(gov, torch.from_numpy(G["grad_object_vl"])) <= TOL_GRAD
+    gref = {k[5:]: torch.from_numpy(G[k]) for k in G.files if k.startswith("grad.") and k[5:] in grads}
     for k, g in grads.items():
-        assert rel(g, torch.from_numpy(G["grad." + k])) <= TOL_GRAD, k
+        assert grad_ok(k, g, gref[k], gref, TOL_GRAD), (k, rel(g, gref[k]))
     # index outputs: bit-exact
     emb, mask, is_t, is_o = model.embedding(*[t.to(DEV) for t in inputs])
     assert np.array_equal(mask.cpu().numpy(), G["mask"])

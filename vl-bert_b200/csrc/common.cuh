@@ -224,6 +224,32 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
+// erf-GELU with erf from Abramowitz & Stegun 7.1.26 (|abs error| <= 1.5e-7, i.e. fp32-erff accuracy) built on the MUFU
+// exp2 / rcp units: ~15 instructions per element instead of erff's ~40 -- the GEMM epilogues are instruction-bound.
+//   Phi(x) = 0.5 (1 + erf(x / sqrt 2)),  erf(u) = 1 - (a1 t + ... + a5 t^5) exp(-u^2),  t = 1 / (1 + p u),  u >= 0
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
+  const float u = fabsf(x) * 0.70710678118654752440f;
+  float t, ex;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.0f)));                    // 1 MUFU
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-0.72134752044448170368f * x * x));            // exp(-x^2/2), 1 MUFU
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erfc_half = 0.5f * poly * t * ex;  // 0.5 * erfc(u)
+  cdf = x >= 0.0f ? 1.0f - erfc_half : erfc_half;
+  pdf = 0.39894228040143267794f * ex;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float cdf, pdf;
+  gelu_parts(x, cdf, pdf);
+  return x * cdf;
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  float cdf, pdf;
+  gelu_parts(x, cdf, pdf);
+  return fmaf(x, pdf, cdf);
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);

@@ -6,6 +6,7 @@
 // residual, :362-363 intermediate dense + erf-GELU, :375-378 output dense + residual) and their
 // backward passes (dgrad with fused GELU' / residual-gradient add, wgrad with split-K fp32
 // reduction).
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -17,7 +18,20 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 192;  // warp0 = TMA, warp1 = MMA + TMEM alloc, warps 2..5 = epilogue
+constexpr int EPI_WARPS = 8;        // two warps per TMEM lane quarter, each takes every other 32-column chunk
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;  // warp0 = TMA, warp1 = MMA + TMEM alloc, warps 2..9 = epilogue
+constexpr int STAGE_F32_PER_WARP = 32 * 32;        // 4 KB transposition buffer per epilogue warp
+
+// Compile-time epilogue variants for the hot launches of the encoder layer (0 = generic, flags read at run time).
+enum : int { EPI_GENERIC = 0, EPI_BIAS_BF16, EPI_BIAS_RESID16_F32, EPI_BIAS_GELU_AUX_BF16, EPI_DGELU_BF16, EPI_RESID16_BF16,
+             EPI_ATOMIC_F32, EPI_NUM };
+template <int EPI> struct EpiTraits { static constexpr bool kStatic = false; static constexpr bool bias = false; static constexpr int act = 0, resid = 0, out = 0; };
+template <> struct EpiTraits<EPI_BIAS_BF16>          { static constexpr bool kStatic = true; static constexpr bool bias = true;  static constexpr int act = ACT_NONE, resid = RESID_NONE, out = OUT_BF16; };
+template <> struct EpiTraits<EPI_BIAS_RESID16_F32>   { static constexpr bool kStatic = true; static constexpr bool bias = true;  static constexpr int act = ACT_NONE, resid = RESID_BF16, out = OUT_F32; };
+template <> struct EpiTraits<EPI_BIAS_GELU_AUX_BF16> { static constexpr bool kStatic = true; static constexpr bool bias = true;  static constexpr int act = ACT_GELU, resid = RESID_NONE, out = OUT_BF16; };
+template <> struct EpiTraits<EPI_DGELU_BF16>         { static constexpr bool kStatic = true; static constexpr bool bias = false; static constexpr int act = ACT_DGELU_MUL, resid = RESID_NONE, out = OUT_BF16; };
+template <> struct EpiTraits<EPI_RESID16_BF16>       { static constexpr bool kStatic = true; static constexpr bool bias = false; static constexpr int act = ACT_NONE, resid = RESID_BF16, out = OUT_BF16; };
+template <> struct EpiTraits<EPI_ATOMIC_F32>         { static constexpr bool kStatic = true; static constexpr bool bias = false; static constexpr int act = ACT_NONE, resid = RESID_NONE, out = OUT_F32_ATOMIC; };
 
 struct GemmParams {
   int M, N, K;
@@ -35,101 +49,118 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int EPI_STAGE_BYTES = EPI_WARPS * STAGE_F32_PER_WARP * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-// One 32-column slice of a row of the accumulator -> global memory, with the fused epilogue.
-__device__ __forceinline__ void epilogue_store32(const GemmEpilogue& e, const uint32_t (&v)[32], int row,
-                                                 int col0, int N) {
+// Epilogue of one 32-row x 32-column accumulator chunk owned by a warp.
+//   tcgen05.ld gives thread t row t (32 consecutive columns).  Writing those rows straight to global memory would make
+//   every warp store touch 32 different cache lines, so the chunk is first transposed through a 4 KB XOR-swizzled
+//   shared-memory buffer: afterwards lane (r = lane/8, g = lane%8) owns 4 consecutive columns of rows r, r+4, ...,
+//   and all global loads (bias, residual, saved pre-activation) and stores are row-contiguous.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint32_t (&v)[32], float* stage, int lane,
+                                               int row_base, int col0, int M, int N) {
+  using T = EpiTraits<EPI>;
+  const bool has_bias = T::kStatic ? T::bias : (e.bias != nullptr);
+  const int act = T::kStatic ? T::act : e.act;
+  const int resid_kind = T::kStatic ? T::resid : e.resid_kind;
+  const int out_kind = T::kStatic ? T::out : e.out_kind;
+  const bool need_aux_in = (act == ACT_DGELU_MUL || act == ACT_DRELU_MUL);
+  const int g = lane & 7;
+  const int col = col0 + g * 4;
+  const bool col_ok = col < N;
+  const int r0 = lane >> 3;
+  // ---- phase 0: issue every global load of this chunk up front (8 independent requests per lane in flight) ----
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (has_bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+  uint2 in16[8];   // bf16 residual or saved pre-activation
+  float4 in32[8];  // fp32 residual (generic path only)
+  if (resid_kind == RESID_BF16 || need_aux_in) {
+    const __nv_bfloat16* __restrict__ src = reinterpret_cast<const __nv_bfloat16*>(need_aux_in ? e.aux : e.resid);
+    const int ld = need_aux_in ? e.ld_aux : e.ldr;
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const int col = col0 + g * 8;
-    if (col >= N) break;
-    float x[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g * 8 + j]) * e.alpha;
-    if (e.bias != nullptr) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + col + 4));
-      x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-      x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+    for (int i = 0; i < 8; ++i) {
+      const int row = row_base + i * 4 + r0;
+      in16[i] = (row < M && col_ok) ? __ldg(reinterpret_cast<const uint2*>(src + (size_t)row * ld + col)) : make_uint2(0u, 0u);
     }
-    if (e.act == ACT_GELU) {
-      if (e.aux != nullptr) {
-        uint4 z;
-        z.x = pack_bf16x2(x[0], x[1]); z.y = pack_bf16x2(x[2], x[3]);
-        z.z = pack_bf16x2(x[4], x[5]); z.w = pack_bf16x2(x[6], x[7]);
-        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.aux) + (size_t)row * e.ld_aux + col) = z;
+  }
+  if (resid_kind == RESID_F32) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row_base + i * 4 + r0;
+      in32[i] = (row < M && col_ok) ? __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.resid) + (size_t)row * e.ldr + col))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  // ---- phase 1: transpose the accumulator chunk through shared memory ----
+  {
+    float4* dst = reinterpret_cast<float4*>(stage + lane * 32);
+#pragma unroll
+    for (int gg = 0; gg < 8; ++gg)
+      dst[gg ^ (lane & 7)] = make_float4(__uint_as_float(v[4 * gg]), __uint_as_float(v[4 * gg + 1]),
+                                         __uint_as_float(v[4 * gg + 2]), __uint_as_float(v[4 * gg + 3]));
+  }
+  __syncwarp();
+  // ---- phase 2: math + row-contiguous stores ----
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + r0;
+    const int row = row_base + r;
+    const float4 a = reinterpret_cast<const float4*>(stage + r * 32)[g ^ (r & 7)];
+    if (row < M && col_ok) {
+      float x[4] = {fmaf(a.x, e.alpha, bias4.x), fmaf(a.y, e.alpha, bias4.y), fmaf(a.z, e.alpha, bias4.z), fmaf(a.w, e.alpha, bias4.w)};
+      if (act == ACT_GELU) {
+        if (e.aux != nullptr) {
+          uint2 z;
+          z.x = pack_bf16x2(x[0], x[1]);
+          z.y = pack_bf16x2(x[2], x[3]);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.aux) + (size_t)row * e.ld_aux + col) = z;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = gelu_fast(x[j]);
+      } else if (act == ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.0f);
+      } else if (need_aux_in) {
+        const float zz[4] = {bf16lo(in16[i].x), bf16hi(in16[i].x), bf16lo(in16[i].y), bf16hi(in16[i].y)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = (act == ACT_DGELU_MUL) ? x[j] * gelu_grad_fast(zz[j]) : (zz[j] > 0.0f ? x[j] : 0.0f);
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
-    } else if (e.act == ACT_RELU) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = fmaxf(x[j], 0.0f);
-    } else if (e.act == ACT_DGELU_MUL || e.act == ACT_DRELU_MUL) {
-      const uint4 z = *reinterpret_cast<const uint4*>(
-          reinterpret_cast<const __nv_bfloat16*>(e.aux) + (size_t)row * e.ld_aux + col);
-      const uint32_t zz[4] = {z.x, z.y, z.z, z.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float z0 = bf16lo(zz[j]), z1 = bf16hi(zz[j]);
-        if (e.act == ACT_DGELU_MUL) {
-          x[2 * j] *= gelu_erf_grad(z0);
-          x[2 * j + 1] *= gelu_erf_grad(z1);
+      if (resid_kind == RESID_BF16) {
+        x[0] += bf16lo(in16[i].x); x[1] += bf16hi(in16[i].x); x[2] += bf16lo(in16[i].y); x[3] += bf16hi(in16[i].y);
+      } else if (resid_kind == RESID_F32) {
+        x[0] += in32[i].x; x[1] += in32[i].y; x[2] += in32[i].z; x[3] += in32[i].w;
+      }
+      if (out_kind == OUT_BF16) {
+        uint2 o;
+        o.x = pack_bf16x2(x[0], x[1]);
+        o.y = pack_bf16x2(x[2], x[3]);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + (size_t)row * e.ldo + col) = o;
+      } else {
+        float* op = reinterpret_cast<float*>(e.out) + (size_t)row * e.ldo + col;
+        if (out_kind == OUT_F32) {
+          *reinterpret_cast<float4*>(op) = make_float4(x[0], x[1], x[2], x[3]);
         } else {
-          x[2 * j] = z0 > 0.0f ? x[2 * j] : 0.0f;
-          x[2 * j + 1] = z1 > 0.0f ? x[2 * j + 1] : 0.0f;
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(op), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
         }
       }
     }
-    if (e.resid_kind == RESID_BF16) {
-      const uint4 r = *reinterpret_cast<const uint4*>(
-          reinterpret_cast<const __nv_bfloat16*>(e.resid) + (size_t)row * e.ldr + col);
-      const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        x[2 * j] += bf16lo(rr[j]);
-        x[2 * j + 1] += bf16hi(rr[j]);
-      }
-    } else if (e.resid_kind == RESID_F32) {
-      const float* rp = reinterpret_cast<const float*>(e.resid) + (size_t)row * e.ldr + col;
-      const float4 r0 = *reinterpret_cast<const float4*>(rp);
-      const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
-      x[0] += r0.x; x[1] += r0.y; x[2] += r0.z; x[3] += r0.w;
-      x[4] += r1.x; x[5] += r1.y; x[6] += r1.z; x[7] += r1.w;
-    }
-    if (e.out_kind == OUT_BF16) {
-      uint4 o;
-      o.x = pack_bf16x2(x[0], x[1]); o.y = pack_bf16x2(x[2], x[3]);
-      o.z = pack_bf16x2(x[4], x[5]); o.w = pack_bf16x2(x[6], x[7]);
-      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out) + (size_t)row * e.ldo + col) = o;
-    } else {
-      float* op = reinterpret_cast<float*>(e.out) + (size_t)row * e.ldo + col;
-      if (e.out_kind == OUT_F32) {
-        *reinterpret_cast<float4*>(op) = make_float4(x[0], x[1], x[2], x[3]);
-        *reinterpret_cast<float4*>(op + 4) = make_float4(x[4], x[5], x[6], x[7]);
-      } else {
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(op), "f"(x[0]), "f"(x[1]),
-                     "f"(x[2]), "f"(x[3])
-                     : "memory");
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(op + 4), "f"(x[4]), "f"(x[5]),
-                     "f"(x[6]), "f"(x[7])
-                     : "memory");
-      }
-    }
   }
+  __syncwarp();
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const GemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  float* epi_stage = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::EPI_STAGE_BYTES);
   uint64_t* full_bar = bars;                     // [STAGES]
   uint64_t* empty_bar = bars + C::STAGES;        // [STAGES]
   uint64_t* tfull_bar = bars + 2 * C::STAGES;    // [2]
@@ -149,8 +180,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
     mbar_init(smem_u32(&tfull_bar[0]), 1);
     mbar_init(smem_u32(&tfull_bar[1]), 1);
-    mbar_init(smem_u32(&tempty_bar[0]), 4);
-    mbar_init(smem_u32(&tempty_bar[1]), 4);
+    mbar_init(smem_u32(&tempty_bar[0]), EPI_WARPS);
+    mbar_init(smem_u32(&tempty_bar[1]), EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -235,7 +266,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
   } else {
     // ===================== epilogue warps =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // which of the two warps sharing that quarter
+    float* stage = epi_stage + (warp - 2) * STAGE_F32_PER_WARP;
     int it = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
       const int rem = item % items_per_split;
@@ -245,15 +278,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const uint32_t use = static_cast<uint32_t>(it >> 1);
       mbar_wait(smem_u32(&tfull_bar[buf]), use & 1u);
       tc_fence_after();
-      const int row = m_blk * BM + q * 32 + lane;
+      const int row_base = m_blk * BM + q * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         uint32_t v[32];
         tmem_ld32(t_row + c * 32, v);
         tmem_ld_wait();
         const int col0 = n_blk * BN + c * 32;
-        if (row < p.M && col0 < p.N) epilogue_store32(p.e, v, row, col0, p.N);
+        if (row_base < p.M && col0 < p.N) epilogue_chunk<EPI>(p.e, v, stage, lane, row_base, col0, p.M, p.N);
       }
       tc_fence_before();
       __syncwarp();
@@ -309,19 +342,35 @@ struct TmapKeyHash {
   }
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int EPI>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    VLB_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VLB_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         C::SMEM_BYTES));
     attr_set = true;
   }
   const int grid = p.num_items < num_sms() ? p.num_items : num_sms();
-  gemm_kernel<BN, A_MN, B_MN><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  gemm_kernel<BN, A_MN, B_MN, EPI><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
   VLB_CHECK_LAUNCH();
   return VLB_OK;
+}
+
+// which compile-time epilogue matches this runtime description (EPI_GENERIC if none)
+int classify_epilogue(int mode, const GemmEpilogue& e) {
+  const bool bias = e.bias != nullptr;
+  if (mode == GEMM_NT) {
+    if (bias && e.act == ACT_NONE && e.resid_kind == RESID_NONE && e.out_kind == OUT_BF16) return EPI_BIAS_BF16;
+    if (bias && e.act == ACT_NONE && e.resid_kind == RESID_BF16 && e.out_kind == OUT_F32) return EPI_BIAS_RESID16_F32;
+    if (bias && e.act == ACT_GELU && e.resid_kind == RESID_NONE && e.out_kind == OUT_BF16) return EPI_BIAS_GELU_AUX_BF16;
+  } else if (mode == GEMM_NN) {
+    if (!bias && e.act == ACT_DGELU_MUL && e.resid_kind == RESID_NONE && e.out_kind == OUT_BF16) return EPI_DGELU_BF16;
+    if (!bias && e.act == ACT_NONE && e.resid_kind == RESID_BF16 && e.out_kind == OUT_BF16) return EPI_RESID16_BF16;
+  } else {
+    if (!bias && e.act == ACT_NONE && e.resid_kind == RESID_NONE && e.out_kind == OUT_F32_ATOMIC) return EPI_ATOMIC_F32;
+  }
+  return EPI_GENERIC;
 }
 
 // debug override of the MN-major descriptor geometry (bring-up aid, see tools/gemm_probe.py)
@@ -380,7 +429,8 @@ void gemm_debug_override(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t mn_kadv) {
 }
 
 int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
-              const GemmEpilogue& epi, int split_k, int force_bn, cudaStream_t stream) {
+              const GemmEpilogue& epi_in, int split_k, int force_bn, cudaStream_t stream) {
+  const GemmEpilogue& epi = epi_in;
   VLB_REQUIRE(mode >= GEMM_NT && mode <= GEMM_TN, "gemm: bad mode %d", mode);
   VLB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   VLB_REQUIRE(A && B && epi.out, "gemm: null pointer");
@@ -393,20 +443,26 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
   const bool b_mn = (mode != GEMM_NT);
 
   // Tile-N choice: fewest "rounds" of the persistent grid weighted by tile cost.
+  static const int env_bn = [] { const char* v = getenv("VLB_FORCE_BN"); return v ? atoi(v) : 0; }();  // tuning aid
+  if (force_bn == 0 && env_bn != 0 && (N >= env_bn || env_bn == 64)) force_bn = env_bn;
   int bn = 128;
-  if (force_bn == 128 || force_bn == 256 || force_bn == 64) {
+  if (force_bn == 128 || force_bn == 256 || force_bn == 64 || force_bn == 192) {
     bn = force_bn;
   } else {
     const int sms = num_sms();
     const int mb = (M + BM - 1) / BM;
+    // cost = rounds of the persistent grid x measured relative time of one 128 x b tile
+    // (profiles/r01_gemm_bringup_probe.log: 4.8 / 5.4 / 8.0 us per round at K = 768 for b = 64 / 128 / 256).
     auto cost = [&](int b) {
       const long items = (long)mb * ((N + b - 1) / b) * (split_k > 1 ? split_k : 1);
       const long rounds = (items + sms - 1) / sms;
-      return rounds * b;  // time ~ rounds * tile width
+      const double w = b == 64 ? 0.60 : (b == 128 ? 0.68 : (b == 192 ? 0.84 : 1.0));
+      return rounds * w;
     };
     bn = 128;
-    long best = cost(128);
+    double best = cost(128);
     if (N >= 256 && cost(256) < best) { best = cost(256); bn = 256; }
+    if (N >= 192 && cost(192) < best) { best = cost(192); bn = 192; }
     if (cost(64) < best) { best = cost(64); bn = 64; }
   }
 
@@ -442,11 +498,23 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
   if (rc != VLB_OK) return rc;
 
   ProfScope prof(mode == GEMM_NT ? PROF_GEMM_NT : (mode == GEMM_NN ? PROF_GEMM_NN : PROF_GEMM_TN), 2.0 * M * N * K, stream);
-#define VLB_GEMM_DISPATCH(BN_)                                                         \
-  if (!a_mn && !b_mn) return launch<BN_, false, false>(ta, tb, p, stream);             \
-  if (!a_mn && b_mn) return launch<BN_, false, true>(ta, tb, p, stream);               \
-  return launch<BN_, true, true>(ta, tb, p, stream);
+#define VLB_GEMM_DISPATCH(BN_)                                                                        \
+  if (!a_mn && !b_mn) {                                                                               \
+    if (epi_id == EPI_BIAS_BF16) return launch<BN_, false, false, EPI_BIAS_BF16>(ta, tb, p, stream);     \
+    if (epi_id == EPI_BIAS_RESID16_F32) return launch<BN_, false, false, EPI_BIAS_RESID16_F32>(ta, tb, p, stream); \
+    if (epi_id == EPI_BIAS_GELU_AUX_BF16) return launch<BN_, false, false, EPI_BIAS_GELU_AUX_BF16>(ta, tb, p, stream); \
+    return launch<BN_, false, false, EPI_GENERIC>(ta, tb, p, stream);                                 \
+  }                                                                                                   \
+  if (!a_mn && b_mn) {                                                                                \
+    if (epi_id == EPI_DGELU_BF16) return launch<BN_, false, true, EPI_DGELU_BF16>(ta, tb, p, stream);    \
+    if (epi_id == EPI_RESID16_BF16) return launch<BN_, false, true, EPI_RESID16_BF16>(ta, tb, p, stream); \
+    return launch<BN_, false, true, EPI_GENERIC>(ta, tb, p, stream);                                  \
+  }                                                                                                   \
+  if (epi_id == EPI_ATOMIC_F32) return launch<BN_, true, true, EPI_ATOMIC_F32>(ta, tb, p, stream);       \
+  return launch<BN_, true, true, EPI_GENERIC>(ta, tb, p, stream);
+  const int epi_id = classify_epilogue(mode, epi_in);
   if (bn == 256) { VLB_GEMM_DISPATCH(256) }
+  if (bn == 192) { VLB_GEMM_DISPATCH(192) }
   if (bn == 64) { VLB_GEMM_DISPATCH(64) }
   VLB_GEMM_DISPATCH(128)
 #undef VLB_GEMM_DISPATCH

@@ -12,75 +12,94 @@ constexpr int LN_WARPS = 4;  // rows per block per iteration
 
 // ------------------------------------------------------------------------------------------------
 // LayerNorm forward: x fp32 [M, H] -> y bf16 [M, H] (+ optional fp32 copy), mean/rstd fp32 [M]
-// ITERS = ceil(H / 256): each lane holds ITERS vectors of 8 values.
+// ITERS = ceil(H / 256): each lane holds ITERS vectors of 8 values.  Warps stride over rows and prefetch the next
+// row's vectors before reducing the current one, so every warp keeps 2 x ITERS x 32 B x 32 lanes in flight.
 // ------------------------------------------------------------------------------------------------
+template <int ITERS>
+struct RowRaw {
+  float4 a[ITERS], b[ITERS];
+};
+
+template <int ITERS>
+__device__ __forceinline__ void load_row_f32(RowRaw<ITERS>& r, const float* __restrict__ xr, int lane, int nvec) {
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      r.a[i] = __ldg(reinterpret_cast<const float4*>(xr + vi * 8));
+      r.b[i] = __ldg(reinterpret_cast<const float4*>(xr + vi * 8 + 4));
+    } else {
+      r.a[i] = r.b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
 template <int ITERS>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      __nv_bfloat16* __restrict__ y, float* __restrict__ y32, float* __restrict__ mean,
                      float* __restrict__ rstd, int M, int H, int ldx, float eps) {
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
-  if (row >= M) return;
   const int nvec = H >> 3;
-  float v[ITERS][8];
-  const float* xr = x + (size_t)row * ldx;
-  float s = 0.0f;
+  const int wstride = gridDim.x * LN_WARPS;
+  int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= M) return;
+  RowRaw<ITERS> cur, nxt;
+  load_row_f32<ITERS>(cur, x + (size_t)row * ldx, lane, nvec);
+  for (; row < M; row += wstride) {
+    const int nrow = row + wstride;
+    if (nrow < M) load_row_f32<ITERS>(nxt, x + (size_t)nrow * ldx, lane, nvec);
+    float v[ITERS][8];
+    float s = 0.0f;
 #pragma unroll
-  for (int i = 0; i < ITERS; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
-      const float4 a = *reinterpret_cast<const float4*>(xr + vi * 8);
-      const float4 b = *reinterpret_cast<const float4*>(xr + vi * 8 + 4);
-      v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w;
-      v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
+    for (int i = 0; i < ITERS; ++i) {
+      v[i][0] = cur.a[i].x; v[i][1] = cur.a[i].y; v[i][2] = cur.a[i].z; v[i][3] = cur.a[i].w;
+      v[i][4] = cur.b[i].x; v[i][5] = cur.b[i].y; v[i][6] = cur.b[i].z; v[i][7] = cur.b[i].w;
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += v[i][j];
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[i][j] = 0.0f;
     }
-  }
-  const float mu = warp_sum(s) / (float)H;
-  float q = 0.0f;
+    const float mu = warp_sum(s) / (float)H;
+    float q = 0.0f;
 #pragma unroll
-  for (int i = 0; i < ITERS; ++i) {
-    if (lane + i * 32 < nvec) {
+    for (int i = 0; i < ITERS; ++i) {
+      if (lane + i * 32 < nvec) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = v[i][j] - mu;
-        q += d * d;
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[i][j] - mu;
+          q += d * d;
+        }
       }
     }
-  }
-  const float var = warp_sum(q) / (float)H;
-  const float rs = 1.0f / sqrtf(var + eps);
-  if (lane == 0) {
-    if (mean) mean[row] = mu;
-    if (rstd) rstd[row] = rs;
-  }
+    const float var = warp_sum(q) / (float)H;
+    const float rs = 1.0f / sqrtf(var + eps);
+    if (lane == 0) {
+      if (mean) mean[row] = mu;
+      if (rstd) rstd[row] = rs;
+    }
 #pragma unroll
-  for (int i = 0; i < ITERS; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      float o[8];
+    for (int i = 0; i < ITERS; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = gg[j] * ((v[i][j] - mu) * rs) + bb[j];
-      uint4 pk;
-      pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
-      pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
-      if (y) *reinterpret_cast<uint4*>(y + (size_t)row * H + vi * 8) = pk;
-      if (y32) {
-        *reinterpret_cast<float4*>(y32 + (size_t)row * H + vi * 8) = make_float4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<float4*>(y32 + (size_t)row * H + vi * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        for (int j = 0; j < 8; ++j) o[j] = gg[j] * ((v[i][j] - mu) * rs) + bb[j];
+        uint4 pk;
+        pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
+        pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
+        if (y) *reinterpret_cast<uint4*>(y + (size_t)row * H + vi * 8) = pk;
+        if (y32) {
+          *reinterpret_cast<float4*>(y32 + (size_t)row * H + vi * 8) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(y32 + (size_t)row * H + vi * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
       }
     }
+    cur = nxt;
   }
 }
 
@@ -89,9 +108,34 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
 //   xhat = (x - mean) * rstd ; g = dy * gamma
 //   dx = rstd * (g - mean_H(g) - xhat * mean_H(g * xhat))          -> bf16 (and/or fp32)
 //   dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy ; dbias_prev += sum_rows dx   (fp32 atomics)
-// Persistent blocks stride over rows and keep per-lane column partials in registers.
+// Persistent warps stride over rows, keep per-lane column partials in registers and prefetch the next row.
 // ------------------------------------------------------------------------------------------------
 template <int ITERS>
+struct RowRawB {
+  float4 xa[ITERS], xb[ITERS];
+  uint4 d16[ITERS];
+  float4 da[ITERS], db[ITERS];
+};
+
+template <int ITERS, bool HAS16, bool HAS32>
+__device__ __forceinline__ void load_row_bwd(RowRawB<ITERS>& r, const float* __restrict__ xr, const __nv_bfloat16* __restrict__ d16r,
+                                             const float* __restrict__ d32r, int lane, int nvec) {
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      r.xa[i] = __ldg(reinterpret_cast<const float4*>(xr + vi * 8));
+      r.xb[i] = __ldg(reinterpret_cast<const float4*>(xr + vi * 8 + 4));
+      if (HAS16) r.d16[i] = __ldg(reinterpret_cast<const uint4*>(d16r + vi * 8));
+      if (HAS32) {
+        r.da[i] = __ldg(reinterpret_cast<const float4*>(d32r + vi * 8));
+        r.db[i] = __ldg(reinterpret_cast<const float4*>(d32r + vi * 8 + 4));
+      }
+    }
+  }
+}
+
+template <int ITERS, bool HAS16, bool HAS32>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ dy32,
                      const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -101,6 +145,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
   __shared__ float red[3][LN_WARPS][32 * 8 + 8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = H >> 3;
+  const int wstride = gridDim.x * LN_WARPS;
   float gam[ITERS][8];
   float acc_g[ITERS][8], acc_b[ITERS][8], acc_c[ITERS][8];
 #pragma unroll
@@ -112,7 +157,13 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
       acc_g[i][j] = acc_b[i][j] = acc_c[i][j] = 0.0f;
     }
   }
-  for (int row = blockIdx.x * LN_WARPS + warp; row < M; row += gridDim.x * LN_WARPS) {
+  int row = blockIdx.x * LN_WARPS + warp;
+  RowRawB<ITERS> cur, nxt;
+  if (row < M) load_row_bwd<ITERS, HAS16, HAS32>(cur, x + (size_t)row * ldx, dy16 + (size_t)row * H, dy32 + (size_t)row * H, lane, nvec);
+  for (; row < M; row += wstride) {
+    const int nrow = row + wstride;
+    if (nrow < M)
+      load_row_bwd<ITERS, HAS16, HAS32>(nxt, x + (size_t)nrow * ldx, dy16 + (size_t)nrow * H, dy32 + (size_t)nrow * H, lane, nvec);
     const float mu = mean[row], rs = rstd[row];
     float dy[ITERS][8], xh[ITERS][8];
     float s1 = 0.0f, s2 = 0.0f;
@@ -120,22 +171,16 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
     for (int i = 0; i < ITERS; ++i) {
       const int vi = lane + i * 32;
       if (vi < nvec) {
-        const size_t off = (size_t)row * H + vi * 8;
-        const size_t xoff = (size_t)row * ldx + vi * 8;
-        const float4 a = *reinterpret_cast<const float4*>(x + xoff);
-        const float4 b = *reinterpret_cast<const float4*>(x + xoff + 4);
-        const float xv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        const float xv[8] = {cur.xa[i].x, cur.xa[i].y, cur.xa[i].z, cur.xa[i].w, cur.xb[i].x, cur.xb[i].y, cur.xb[i].z, cur.xb[i].w};
         float d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (dy16) {
-          const uint4 u = *reinterpret_cast<const uint4*>(dy16 + off);
+        if (HAS16) {
+          const uint4 u = cur.d16[i];
           d[0] = bf16lo(u.x); d[1] = bf16hi(u.x); d[2] = bf16lo(u.y); d[3] = bf16hi(u.y);
           d[4] = bf16lo(u.z); d[5] = bf16hi(u.z); d[6] = bf16lo(u.w); d[7] = bf16hi(u.w);
         }
-        if (dy32) {
-          const float4 c = *reinterpret_cast<const float4*>(dy32 + off);
-          const float4 e = *reinterpret_cast<const float4*>(dy32 + off + 4);
-          d[0] += c.x; d[1] += c.y; d[2] += c.z; d[3] += c.w;
-          d[4] += e.x; d[5] += e.y; d[6] += e.z; d[7] += e.w;
+        if (HAS32) {
+          d[0] += cur.da[i].x; d[1] += cur.da[i].y; d[2] += cur.da[i].z; d[3] += cur.da[i].w;
+          d[4] += cur.db[i].x; d[5] += cur.db[i].y; d[6] += cur.db[i].z; d[7] += cur.db[i].w;
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -178,6 +223,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
         }
       }
     }
+    cur = nxt;
   }
   // block reduction of the column partials (over the LN_WARPS warps), then one atomic per column per block
 #pragma unroll
@@ -314,7 +360,8 @@ int layernorm_forward(const float* x, int ldx, const float* gamma, const float* 
   VLB_REQUIRE(H % 8 == 0 && H >= 8 && H <= 2048, "layernorm: H=%d must be a multiple of 8 in [8, 2048]", H);
   if (M <= 0) return VLB_OK;
   const int iters = (H + 255) / 256;
-  const int grid = (M + LN_WARPS - 1) / LN_WARPS;
+  int grid = (M + LN_WARPS - 1) / LN_WARPS;
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
   ProfScope prof(PROF_LN_FWD, (double)M * H * (4.0 + (y_bf16 ? 2.0 : 0.0) + (y_f32 ? 4.0 : 0.0)), stream);
   VLB_LN_DISPATCH(iters, (layernorm_fwd_kernel<IT><<<grid, LN_WARPS * 32, 0, stream>>>(
                              x, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, M, H, ldx, eps)));
@@ -331,12 +378,17 @@ int layernorm_backward(const void* dy_bf16, const float* dy_f32, const float* x,
   if (M <= 0) return VLB_OK;
   const int iters = (H + 255) / 256;
   int grid = (M + LN_WARPS - 1) / LN_WARPS;
-  const int cap = num_sms() * 4;
+  const int cap = num_sms() * 3;
   if (grid > cap) grid = cap;
   ProfScope prof(PROF_LN_BWD, (double)M * H * (4.0 + (dy_bf16 ? 2.0 : 0.0) + (dy_f32 ? 4.0 : 0.0) + (dx_bf16 ? 2.0 : 0.0) + (dx_f32 ? 4.0 : 0.0)), stream);
-  VLB_LN_DISPATCH(iters, (layernorm_bwd_kernel<IT><<<grid, LN_WARPS * 32, 0, stream>>>(
-                             static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, mean, rstd, gamma,
-                             static_cast<__nv_bfloat16*>(dx_bf16), dx_f32, dgamma, dbeta, dcolsum, M, H, ldx, ld_dx)));
+#define VLB_LN_BWD(H16, H32)                                                                                    \
+  VLB_LN_DISPATCH(iters, (layernorm_bwd_kernel<IT, H16, H32><<<grid, LN_WARPS * 32, 0, stream>>>(                  \
+                             static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, mean, rstd, gamma,             \
+                             static_cast<__nv_bfloat16*>(dx_bf16), dx_f32, dgamma, dbeta, dcolsum, M, H, ldx, ld_dx)))
+  if (dy_bf16 && dy_f32) { VLB_LN_BWD(true, true) }
+  else if (dy_bf16) { VLB_LN_BWD(true, false) }
+  else { VLB_LN_BWD(false, true) }
+#undef VLB_LN_BWD
   VLB_CHECK_LAUNCH();
   return VLB_OK;
 }
