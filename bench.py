@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="samples per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-input arm")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -159,10 +160,13 @@ def main():
     other_params = [p for p in model.parameters() if id(p) not in enc_param_ids]
     reducer = vlbert_b200.ddp.attach(model) if world > 1 else None
 
-    def step(ins):
+    def loss_fn(m, *ins):
+        out, _ = m(*ins, output_all_encoded_layers=False)
+        return (out.float() ** 2).mean()
+
+    def eager_step(ins):
         model.zero_grad(set_to_none=True)
-        out, _ = model(*ins, output_all_encoded_layers=False)
-        loss = (out.float() ** 2).mean()
+        loss = loss_fn(model, *ins)
         loss.backward()
         if reducer is not None:
             reducer.reduce_params(other_params)
@@ -173,8 +177,40 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident arm ----------------
     dev_inputs = make_inputs(B, 12345 + rank, dev)
+    # The public step API: vlbert_b200.GraphedStep (CUDA-graph replay of forward+backward) when shapes are static.
+    # NCCL collectives are captured with the graph (N > 1) unless --no-graph.
+    use_graph = (not args.no_graph) and (world == 1 or os.environ.get("VLB_GRAPH_DDP") == "1")
+    graphed = None
+    if use_graph:
+        try:
+            graphed = vlbert_b200.GraphedStep(model, loss_fn, dev_inputs, warmup=3, reducer_params=other_params if reducer else None)
+        except Exception as e:  # noqa
+            print("[bench] CUDA graph capture failed (%s); running eagerly" % str(e)[:200], file=sys.stderr)
+            use_graph = False
+            graphed = None
+            torch.cuda.synchronize()
+
+    def step(ins):
+        if graphed is not None:
+            return graphed(*ins)
+        return eager_step(ins)
+
+    # ---------------- per-kernel device timing (roofline): a separate eager pass, events on the launch stream ----------
+    for _ in range(3):
+        eager_step(dev_inputs)
+    barrier()
+    lib.vlb_profile_enable(1)
+    prof_steps = max(2, min(args.steps, 5))
+    for _ in range(prof_steps):
+        eager_step(dev_inputs)
+    barrier()
+    lib.vlb_profile_enable(0)
+    import ctypes
+    pms, pwork, pcnt = (ctypes.c_double * 8)(), (ctypes.c_double * 8)(), (ctypes.c_int64 * 8)()
+    vlbert_b200._lib.check(lib.vlb_profile_collect(pms, pwork, pcnt))
+
+    # ---------------- device-resident arm ----------------
     for _ in range(max(3, args.warmup)):
         step(dev_inputs)
     barrier()
@@ -182,7 +218,6 @@ def main():
     if sampler:
         sampler.start()
     n0 = vlbert_b200._lib.launch_count()
-    lib.vlb_profile_enable(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -190,18 +225,21 @@ def main():
         step(dev_inputs)
     e1.record()
     barrier()
-    lib.vlb_profile_enable(0)
-    launches = (vlbert_b200._lib.launch_count() - n0) // max(1, args.steps)
+    launches_eager = 0
+    if graphed is None:
+        launches_eager = (vlbert_b200._lib.launch_count() - n0) // max(1, args.steps)
     if sampler:
         sampler.stop_flag = True
     ms = e0.elapsed_time(e1) / args.steps
-    import ctypes
-    pms, pwork, pcnt = (ctypes.c_double * 8)(), (ctypes.c_double * 8)(), (ctypes.c_int64 * 8)()
-    vlbert_b200._lib.check(lib.vlb_profile_collect(pms, pwork, pcnt))
     t = torch.tensor([ms], device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.item()
+    # kernels of the library per step (a graph replay launches the same kernels the capture recorded)
+    n1 = vlbert_b200._lib.launch_count()
+    eager_step(dev_inputs)
+    torch.cuda.synchronize()
+    launches = vlbert_b200._lib.launch_count() - n1
 
     # ---------------- end-to-end arm: pinned host inputs -> H2D -> step -> loss read back ----------------
     host_inputs = [make_inputs(B, 777 + rank + i, dev, pin=True) for i in range(2)]
@@ -217,6 +255,8 @@ def main():
         return ts, ev
 
     def e2e_loop(n):
+        # every step: H2D of that step's inputs from pinned memory (prefetched on a copy stream one step ahead), the step
+        # through the public API, and a D2H read of the loss.
         nxt = prefetch(0)
         for i in range(n):
             ts, ev = nxt
@@ -257,7 +297,7 @@ def main():
     gemm_flops = pwork[0] + pwork[1] + pwork[2]
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
     peak_tf = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
-    prof = {n: {"ms_per_step": pms[i] / args.steps, "launches_per_step": pcnt[i] / args.steps}
+    prof = {n: {"ms_per_step": pms[i] / prof_steps, "launches_per_step": pcnt[i] / prof_steps}
             for i, n in enumerate(["gemm_nt", "gemm_nn", "gemm_tn", "mhsa_fwd", "mhsa_bwd", "ln_fwd", "ln_bwd", "other"])}
     line = {
         "metric": "samples/sec VL-BERT-base fwd+bwd", "value": world * B / (ms * 1e-3), "unit": "samples/s",
@@ -271,11 +311,12 @@ def main():
         "model_flops_tflops": world * B * FLOP_PER_SAMPLE / (ms * 1e-3) / 1e12,
         "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms, "last_loss": last_loss},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "cuda_graph": graphed is not None,
         "roofline": {"bound": "tensor", "kernel": "gemm_kernel<BN,A_MN,B_MN> (all tcgen05 GEMM launches of the step)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
                      "peak_kind": pk_kind + " bf16_tflops_sustained", "traffic": None,
-                     "share_of_step": gemm_ms / args.steps / ms if ms > 0 else None},
+                     "share_of_step": gemm_ms / prof_steps / ms if ms > 0 else None,
+                     "measured": "CUDA events around every GEMM launch on the launch stream, %d eager steps of the same workload inside this run" % prof_steps},
         "kernel_profile": prof,
         "clocks": sampler.summary() if sampler else None,
     }

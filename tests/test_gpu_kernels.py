@@ -61,6 +61,29 @@ def test_gemm_modes_against_fp32_matmul(VF, mode, shape, bn):
     assert rel(out, ref) <= 2e-5  # measured ~1e-6: fp32 accumulation, only the summation order differs
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(256, 256, 64), (6464, 768, 768), (6464, 2304, 768), (264, 3072, 768), (3072, 768, 6464), (1000, 1608, 200)])
+@pytest.mark.parametrize("bn", [1128, 1256])
+def test_gemm_cta_pair_mode(VF, mode, shape, bn):
+    """cta_group::2: a cluster of two CTAs computes 256 x BN tiles (force_bn = 1000 + BN)."""
+    M, N, K = shape
+    if mode == 2 and M % 8:
+        pytest.skip("TN stores A as [K, M]: M must be a multiple of 8")
+    g = torch.Generator().manual_seed(7000 + 10 * mode + M + N + K)
+    a = bf(torch.randn(M, K, generator=g))
+    b = bf(torch.randn(N, K, generator=g))
+    ref = a @ b.t()
+    A = a.to(DEV, BF16) if mode != 2 else a.t().contiguous().to(DEV, BF16)
+    Bm = b.to(DEV, BF16) if mode == 0 else b.t().contiguous().to(DEV, BF16)
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32)
+    VF.gemm(mode, A, Bm, out, force_bn=bn)
+    assert rel(out, ref) <= 2e-5
+    if mode == 2:  # split-K accumulate through the pair path
+        acc = torch.zeros(M, N, device=DEV, dtype=torch.float32)
+        VF.gemm(mode, A, Bm, acc, force_bn=bn, split_k=3)
+        assert rel(acc, ref) <= 2e-5
+
+
 def test_gemm_epilogues(VF):
     M, N, K = 777, 1536, 512
     g = torch.Generator().manual_seed(5)

@@ -52,7 +52,7 @@ def _declare(lib):
     decl("vlb_multi_cast", [P, I, I, P])
     decl("vlb_pack_index", [P, P, P, I, I, I, I, I, P, P, P, P, P, P, P, P, P])
     decl("vlb_pack_forward", [P, P, P, P, P, P, P, P, P, P, P, P, I, I, P, I, I, I, I, I, I, I, P, P])
-    decl("vlb_pack_backward", [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, P])
+    decl("vlb_pack_backward", [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P])
     decl("vlb_gather_rows", [P, I, I, P, P, I, I, I, I, P])
     decl("vlb_scatter_rows_add", [P, I, I, P, P, I, I, I, P])
     decl("vlb_roi_align_forward", [P, P, P, I, I, I, I, I, I, F, I, P])

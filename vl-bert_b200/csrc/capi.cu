@@ -160,9 +160,9 @@ int vlb_pack_forward(const int32_t* kind, const int32_t* src, const int32_t* pos
 }
 int vlb_pack_backward(const int32_t* kind, const int32_t* src, const int32_t* pos_id, const int32_t* type_id, const int64_t* ids,
                       const float* de, float* d_word, float* d_end, float* d_pos, float* d_type, float* d_text_vl,
-                      float* d_obj_vl, int B, int T, int R, int S, int H, int vocab, int max_pos, void* stream) {
+                      float* d_obj_vl, int B, int T, int R, int S, int H, int vocab, int max_pos, int pos_offset, void* stream) {
   COUNTED(1, pack_backward(kind, src, pos_id, type_id, ids, de, d_word, d_end, d_pos, d_type, d_text_vl, d_obj_vl, B, T, R, S,
-                           H, vocab, max_pos, ST));
+                           H, vocab, max_pos, pos_offset, ST));
 }
 int vlb_gather_rows(const void* in, int in_is_bf16, int ld_in, const int32_t* idx, void* out, int out_is_bf16, int ld_out,
                     int n_out, int H, void* stream) {

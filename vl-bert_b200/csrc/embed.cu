@@ -125,47 +125,61 @@ __device__ __forceinline__ void atomic_add8(float* dst, const float (&v)[8]) {
 
 // ------------------------------------------------------------------------------------------------
 // pack backward: de [B*S, H] fp32 (gradient wrt the pre-LayerNorm sum) is scattered to
-//   d_word_emb[ids] / d_end_emb / d_pos_emb[pos_id] / d_type_emb[type_id]      (fp32 atomics; tables zero-initialised
-//   by the caller or accumulated into existing .grad buffers)
+//   d_word_emb[ids] / d_end_emb / d_pos_emb[pos_id] / d_type_emb[type_id]      (fp32 atomics, "+=")
 //   d_text_vl[b, src, :]  (dense [B*T, H], written once per referenced row; caller zero-fills)
 //   d_obj_vl [b, src, :]  (dense [B*R, H])
+// One block per (sample, 256-column slab); a thread owns one column and walks the sample's S rows.  The heavily shared
+// destinations (the 3 token-type rows; the position row shared by all regions of a sample) are first accumulated
+// per block -- types in registers, positions in shared memory [S+2][256] -- and flushed with one atomic per
+// (row, column) per block, instead of one contended atomic per token.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 pack_bwd_kernel(const int32_t* __restrict__ kind, const int32_t* __restrict__ src, const int32_t* __restrict__ pos_id,
                 const int32_t* __restrict__ type_id, const int64_t* __restrict__ ids, const float* __restrict__ de,
                 float* __restrict__ d_word, float* __restrict__ d_end, float* __restrict__ d_pos, float* __restrict__ d_type,
-                float* __restrict__ d_text_vl, float* __restrict__ d_obj_vl, int B, int T, int R, int S, int H, int vocab,
-                int max_pos) {
-  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= B * S) return;
-  const int b = row / S;
-  const int k = kind[row], sr = src[row];
-  int pid = pos_id[row];
-  if (pid < 0 || pid >= max_pos) pid = 0;
-  float* gp = d_pos ? d_pos + (size_t)pid * H : nullptr;
-  float* gt = d_type ? d_type + (size_t)type_id[row] * H : nullptr;
-  float* ga = nullptr;   // atomic target (embedding table row)
-  float* gw = nullptr;   // plain write target (dense activation gradient)
-  if (k == 0) {
-    int64_t id = ids[(size_t)b * T + sr];
-    if (id < 0 || id >= vocab) id = 0;
-    ga = d_word ? d_word + (size_t)id * H : nullptr;
-    gw = d_text_vl ? d_text_vl + ((size_t)b * T + sr) * H : nullptr;
-  } else if (k == 1) {
-    gw = d_obj_vl ? d_obj_vl + ((size_t)b * R + sr) * H : nullptr;
-  } else if (k == 2) {
-    ga = d_end;
+                float* __restrict__ d_text_vl, float* __restrict__ d_obj_vl, int T, int R, int S, int H, int vocab,
+                int max_pos, int pos_offset) {
+  extern __shared__ float pos_acc[];  // [S + 2][256]
+  const int b = blockIdx.x;
+  const int c = blockIdx.y * 256 + threadIdx.x;
+  const bool col_ok = c < H;
+  for (int i = threadIdx.x; i < (S + 2) * 256; i += 256) pos_acc[i] = 0.0f;
+  __syncthreads();
+  float ty0 = 0.0f, ty1 = 0.0f, ty2 = 0.0f;
+  for (int s = 0; s < S; ++s) {
+    const int row = b * S + s;
+    const int k = kind[row], sr = src[row];
+    const float v = col_ok ? __ldg(de + (size_t)row * H + c) : 0.0f;
+    int li = pos_id[row] - pos_offset;
+    li = li < 0 ? 0 : (li > S + 1 ? S + 1 : li);
+    pos_acc[li * 256 + threadIdx.x] += v;
+    const int ty = type_id[row];
+    ty0 += (ty == 0) ? v : 0.0f;
+    ty1 += (ty == 1) ? v : 0.0f;
+    ty2 += (ty == 2) ? v : 0.0f;
+    if (!col_ok) continue;
+    if (k == 0) {
+      int64_t id = ids[(size_t)b * T + sr];
+      if (id < 0 || id >= vocab) id = 0;
+      if (d_word) atomicAdd(d_word + (size_t)id * H + c, v);
+      if (d_text_vl) d_text_vl[((size_t)b * T + sr) * H + c] = v;
+    } else if (k == 1) {
+      if (d_obj_vl) d_obj_vl[((size_t)b * R + sr) * H + c] = v;
+    } else if (k == 2) {
+      if (d_end) atomicAdd(d_end + c, v);
+    }
   }
-  for (int c = lane * 8; c < H; c += 256) {
-    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    add8(v, de + (size_t)row * H + c);
-    if (gp) atomic_add8(gp + c, v);
-    if (gt) atomic_add8(gt + c, v);
-    if (ga) atomic_add8(ga + c, v);
-    if (gw) {
-      *reinterpret_cast<float4*>(gw + c) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(gw + c + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  if (!col_ok) return;
+  if (d_type) {
+    if (ty0 != 0.0f) atomicAdd(d_type + c, ty0);
+    if (ty1 != 0.0f) atomicAdd(d_type + H + c, ty1);
+    if (ty2 != 0.0f) atomicAdd(d_type + 2 * H + c, ty2);
+  }
+  if (d_pos) {
+    for (int li = 0; li < S + 2; ++li) {
+      const float v = pos_acc[li * 256 + threadIdx.x];
+      const int pid = li + pos_offset;
+      if (v != 0.0f && pid >= 0 && pid < max_pos) atomicAdd(d_pos + (size_t)pid * H + c, v);
     }
   }
 }
@@ -265,12 +279,17 @@ int pack_forward(const int32_t* kind, const int32_t* src, const int32_t* pos_id,
 
 int pack_backward(const int32_t* kind, const int32_t* src, const int32_t* pos_id, const int32_t* type_id, const int64_t* ids,
                   const float* de, float* d_word, float* d_end, float* d_pos, float* d_type, float* d_text_vl, float* d_obj_vl,
-                  int B, int T, int R, int S, int H, int vocab, int max_pos, cudaStream_t stream) {
+                  int B, int T, int R, int S, int H, int vocab, int max_pos, int pos_offset, cudaStream_t stream) {
   VLB_REQUIRE(kind && src && pos_id && type_id && ids && de, "pack_backward: null pointer");
-  VLB_REQUIRE(H % 8 == 0, "pack_backward: H must be a multiple of 8");
-  const int rows = B * S;
-  pack_bwd_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(kind, src, pos_id, type_id, ids, de, d_word, d_end, d_pos, d_type,
-                                                      d_text_vl, d_obj_vl, B, T, R, S, H, vocab, max_pos);
+  const int smem = (S + 2) * 256 * (int)sizeof(float);
+  VLB_REQUIRE(smem <= 200 * 1024, "pack_backward: packed length %d too large", S);
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    VLB_CHECK_CUDA(cudaFuncSetAttribute(pack_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  pack_bwd_kernel<<<dim3(B, (H + 255) / 256), 256, smem, stream>>>(kind, src, pos_id, type_id, ids, de, d_word, d_end, d_pos,
+                                                                d_type, d_text_vl, d_obj_vl, T, R, S, H, vocab, max_pos, pos_offset);
   VLB_CHECK_LAUNCH();
   return VLB_OK;
 }

@@ -56,7 +56,7 @@ int64_t bert_layer_backward_workspace(int M, int H, int I) {
   return al((int64_t)M * H * 2) * 4 + al((int64_t)M * I * 2) + al((int64_t)M * 3 * H * 2);
 }
 
-// Backward: 15 launches.
+// Backward: 12 launches.
 int bert_layer_backward(const VlbLayerWeights& w, const VlbLayerActs& a, const void* x, const float* add_mask, const void* dy16,
                         const float* dy32, void* dx, const VlbLayerGrads& g, void* workspace, int64_t ws_bytes, int B, int S,
                         int H, int heads, int I, cudaStream_t st) {
@@ -79,11 +79,11 @@ int bert_layer_backward(const VlbLayerWeights& w, const VlbLayerActs& a, const v
   // dW2 += d_y0^T u
   e = GemmEpilogue(); e.out = g.dw_2; e.ldo = I; e.out_kind = OUT_F32_ATOMIC;
   if ((rc = gemm_bf16(GEMM_TN, H, I, M, d_y0, H, a.u, I, e, wgrad_split(H, I, M), 0, st))) return rc;
-  // dz = (d_y0 W2) o gelu'(z)
+  // dz = (d_y0 W2) o gelu'(z) ; db_1 += colsum(dz) fused into the same epilogue
   e = GemmEpilogue(); e.out = dz; e.ldo = I; e.out_kind = OUT_BF16; e.act = ACT_DGELU_MUL; e.aux = a.z; e.ld_aux = I;
+  e.colsum = g.db_1;
   if ((rc = gemm_bf16(GEMM_NN, M, I, H, d_y0, H, w.w_2, I, e, 1, 0, st))) return rc;
-  // db_1 += colsum(dz) ; dW1 += dz^T h
-  if ((rc = colsum_bf16(dz, I, g.db_1, M, I, st))) return rc;
+  // dW1 += dz^T h
   e = GemmEpilogue(); e.out = g.dw_1; e.ldo = H; e.out_kind = OUT_F32_ATOMIC;
   if ((rc = gemm_bf16(GEMM_TN, I, H, M, dz, I, a.h, H, e, wgrad_split(I, H, M), 0, st))) return rc;
   // dh = dz W1 + d_y0 (residual)
@@ -105,7 +105,7 @@ int bert_layer_backward(const VlbLayerWeights& w, const VlbLayerActs& a, const v
   if ((rc = gemm_bf16(GEMM_TN, 3 * H, H, M, dqkv, 3 * H, x, H, e, wgrad_split(3 * H, H, M), 0, st))) return rc;
   e = GemmEpilogue(); e.out = dx; e.ldo = H; e.out_kind = OUT_BF16; e.resid = d_a; e.ldr = H; e.resid_kind = RESID_BF16;
   if ((rc = gemm_bf16(GEMM_NN, M, H, 3 * H, dqkv, 3 * H, w.w_qkv, H, e, 1, 0, st))) return rc;
-  count_launch(13);
+  count_launch(12);
   return VLB_OK;
 }
 

@@ -44,12 +44,15 @@ struct GemmParams {
   GemmEpilogue e;
 };
 
-template <int BN>
+// CG2 = CTA-pair mode (tcgen05 cta_group::2): a cluster of two CTAs computes a 256 x BN tile; each CTA stages its own 128
+// rows of A and one HALF of the B tile, so the B operand crosses the L2->SM fabric once per pair instead of once per CTA.
+template <int BN, bool CG2 = false>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_ROWS = CG2 ? BN / 2 : BN;   // rows (n) of the B tile this CTA stages
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8));
+  static constexpr int STAGES = CG2 ? (BN == 256 ? 6 : 8) : ((BN == 256) ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8)));
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int EPI_STAGE_BYTES = EPI_WARPS * STAGE_F32_PER_WARP * 4;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -105,6 +108,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
   }
   __syncwarp();
   // ---- phase 2: math + row-contiguous stores ----
+  float csum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = i * 4 + r0;
@@ -139,6 +143,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
         o.x = pack_bf16x2(x[0], x[1]);
         o.y = pack_bf16x2(x[2], x[3]);
         *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + (size_t)row * e.ldo + col) = o;
+        if (e.colsum != nullptr) {  // sum what was actually stored (bf16-rounded), like a separate column-sum pass would
+          csum[0] += bf16lo(o.x); csum[1] += bf16hi(o.x); csum[2] += bf16lo(o.y); csum[3] += bf16hi(o.y);
+        }
       } else {
         float* op = reinterpret_cast<float*>(e.out) + (size_t)row * e.ldo + col;
         if (out_kind == OUT_F32) {
@@ -146,17 +153,32 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
         } else {
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(op), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
         }
+        if (e.colsum != nullptr) { csum[0] += x[0]; csum[1] += x[1]; csum[2] += x[2]; csum[3] += x[3]; }
       }
     }
+  }
+  if (e.colsum != nullptr) {
+    // lanes with equal (lane & 7) own the same 4 columns: reduce over the 4 row groups, then one atomic per column
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      csum[j] += __shfl_xor_sync(0xffffffffu, csum[j], 8);
+      csum[j] += __shfl_xor_sync(0xffffffffu, csum[j], 16);
+    }
+    if (lane < 8 && col_ok)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(e.colsum + col), "f"(csum[0]), "f"(csum[1]), "f"(csum[2]), "f"(csum[3]) : "memory");
   }
   __syncwarp();
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool CG2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const GemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG2>;
+  const uint32_t rank = CG2 ? cluster_ctarank() : 0u;       // CTA rank inside the pair
+  const bool leader = rank == 0;                            // the leader issues the MMAs for both CTAs
+  const int worker = CG2 ? (blockIdx.x >> 1) : blockIdx.x;  // persistent work-loop index (a pair shares it)
+  const int nworkers = CG2 ? (gridDim.x >> 1) : gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* epi_stage = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -175,21 +197,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     tma_prefetch_desc(&tma_b);
 #pragma unroll
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&full_bar[s]), CG2 ? 2 : 1);   // pair mode: one arrive(+expect_tx) per CTA, on the leader's barrier
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     mbar_init(smem_u32(&tfull_bar[0]), 1);
     mbar_init(smem_u32(&tfull_bar[1]), 1);
-    mbar_init(smem_u32(&tempty_bar[0]), EPI_WARPS);
-    mbar_init(smem_u32(&tempty_bar[1]), EPI_WARPS);
+    mbar_init(smem_u32(&tempty_bar[0]), CG2 ? 2 * EPI_WARPS : EPI_WARPS);
+    mbar_init(smem_u32(&tempty_bar[1]), CG2 ? 2 * EPI_WARPS : EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
-    tmem_relinquish();
+    if (CG2) { tmem_alloc_cg2(smem_u32(tmem_slot), C::TMEM_COLS); tmem_relinquish_cg2(); }
+    else     { tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -200,32 +222,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      for (int item = worker; item < p.num_items; item += nworkers) {
         const int split = item / items_per_split;
         const int rem = item - split * items_per_split;
         const int m_blk = rem / p.num_n_blocks;
         const int n_blk = rem - m_blk * p.num_n_blocks;
-        const int m0 = m_blk * BM, n0 = n_blk * BN;
+        const int m0 = (m_blk * (CG2 ? 2 : 1) + (int)rank) * BM;          // this CTA's 128 rows of the (256-row) tile
+        const int n0 = n_blk * BN + (int)rank * (CG2 ? BN / 2 : 0);       // this CTA's half of the B tile
         const int kb_begin = split * p.kb_per_split;
         const int kb_end = min(p.num_k_blocks, kb_begin + p.kb_per_split);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-          const uint32_t fb = smem_u32(&full_bar[stage]);
-          mbar_arrive_expect_tx(fb, C::STAGE_BYTES);
+          // pair mode: both CTAs signal the LEADER's full barrier (the leader's MMA thread consumes both halves)
+          const uint32_t fb = CG2 ? mapa_cluster(smem_u32(&full_bar[stage]), 0) : smem_u32(&full_bar[stage]);
+          // (default .release.cta semantics as in CUTLASS: a cluster-scope release here costs ~1000 cycles per k-block)
+          if (CG2 && !leader) mbar_arrive_expect_tx_cluster(fb, C::STAGE_BYTES);
+          else mbar_arrive_expect_tx(smem_u32(&full_bar[stage]), C::STAGE_BYTES);
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t sb = sa + C::A_BYTES;
           const int k0 = kb * BK;
+          auto load = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1) {
+            if (CG2) tma_load_2d_cg2(dst, tm, fb, c0, c1); else tma_load_2d(dst, tm, fb, c0, c1);
+          };
           if (!A_MN) {
-            tma_load_2d(sa, &tma_a, fb, k0, m0);  // box {64 k, 128 rows}
+            load(sa, &tma_a, k0, m0);  // box {64 k, 128 rows}
           } else {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * 8192, &tma_a, fb, m0 + c * 64, k0);
+            for (int c = 0; c < BM / 64; ++c) load(sa + c * 8192, &tma_a, m0 + c * 64, k0);
           }
           if (!B_MN) {
-            tma_load_2d(sb, &tma_b, fb, k0, n0);  // box {64 k, BN rows}
+            load(sb, &tma_b, k0, n0);  // box {64 k, B_ROWS rows}
           } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &tma_b, fb, n0 + c * 64, k0);
+            for (int c = 0; c < C::B_ROWS / 64; ++c) load(sb + c * 8192, &tma_b, n0 + c * 64, k0);
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -233,12 +262,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(CG2 ? 2 * BM : BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+      for (int item = worker; item < p.num_items; item += nworkers, ++it) {
         const int split = item / items_per_split;
         const int kb_begin = split * p.kb_per_split;
         const int kb_end = min(p.num_k_blocks, kb_begin + p.kb_per_split);
@@ -256,12 +285,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t adesc = make_smem_desc_sw128(sa + k * p.a_kadv, p.a_lbo, p.a_sbo);
             const uint64_t bdesc = make_smem_desc_sw128(sb + k * p.b_kadv, p.b_lbo, p.b_sbo);
-            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            if (CG2) umma_bf16_ss_cg2(d_tmem, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            else umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
-          umma_commit(smem_u32(&empty_bar[stage]));  // frees the smem slot once these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+          if (CG2) umma_commit_cg2_mc(smem_u32(&empty_bar[stage]), 3); else umma_commit(smem_u32(&empty_bar[stage]));
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(smem_u32(&tfull_bar[buf]));  // accumulator ready for the epilogue
+        // accumulator ready for the epilogue warps (of both CTAs)
+        if (CG2) umma_commit_cg2_mc(smem_u32(&tfull_bar[buf]), 3); else umma_commit(smem_u32(&tfull_bar[buf]));
       }
     }
   } else {
@@ -270,7 +302,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const int half = (warp - 2) >> 2;  // which of the two warps sharing that quarter
     float* stage = epi_stage + (warp - 2) * STAGE_F32_PER_WARP;
     int it = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+    for (int item = worker; item < p.num_items; item += nworkers, ++it) {
       const int rem = item % items_per_split;
       const int m_blk = rem / p.num_n_blocks;
       const int n_blk = rem - m_blk * p.num_n_blocks;
@@ -278,7 +310,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const uint32_t use = static_cast<uint32_t>(it >> 1);
       mbar_wait(smem_u32(&tfull_bar[buf]), use & 1u);
       tc_fence_after();
-      const int row_base = m_blk * BM + q * 32;
+      const int row_base = (m_blk * (CG2 ? 2 : 1) + (int)rank) * BM + q * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
@@ -290,15 +322,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
+      if (lane == 0) {
+        if (CG2 && !leader) mbar_arrive_cluster(mapa_cluster(smem_u32(&tempty_bar[buf]), 0));  // the leader's MMA thread owns both TMEMs
+        else mbar_arrive(smem_u32(&tempty_bar[buf]));
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG2) cluster_sync_all(); else __syncthreads();   // the peer's shared memory / TMEM must outlive the leader's MMAs
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (CG2) tmem_dealloc_cg2(tmem_base, C::TMEM_COLS); else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -342,18 +377,36 @@ struct TmapKeyHash {
   }
 };
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool CG2>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG2>;
   static bool attr_set = false;
   if (!attr_set) {
-    VLB_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VLB_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, A_MN, B_MN, EPI, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         C::SMEM_BYTES));
     attr_set = true;
   }
-  const int grid = p.num_items < num_sms() ? p.num_items : num_sms();
-  gemm_kernel<BN, A_MN, B_MN, EPI><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
-  VLB_CHECK_LAUNCH();
+  if (!CG2) {
+    const int grid = p.num_items < num_sms() ? p.num_items : num_sms();
+    gemm_kernel<BN, A_MN, B_MN, EPI, CG2><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+    VLB_CHECK_LAUNCH();
+    return VLB_OK;
+  }
+  const int pairs = num_sms() / 2;
+  const int nclusters = p.num_items < pairs ? p.num_items : pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * nclusters);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VLB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, A_MN, B_MN, EPI, CG2>, ta, tb, p));
   return VLB_OK;
 }
 
@@ -443,32 +496,49 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
   const bool b_mn = (mode != GEMM_NT);
 
   // Tile-N choice: fewest "rounds" of the persistent grid weighted by tile cost.
-  static const int env_bn = [] { const char* v = getenv("VLB_FORCE_BN"); return v ? atoi(v) : 0; }();  // tuning aid
-  if (force_bn == 0 && env_bn != 0 && (N >= env_bn || env_bn == 64)) force_bn = env_bn;
+  // force_bn: 0 = heuristic; 64/128/192/256 = single-CTA tile width; 1128/1256 = CTA-pair (cta_group::2) 256 x {128,256} tiles.
+  static const int env_bn = [] { const char* v = getenv("VLB_FORCE_BN"); return v ? atoi(v) : 0; }();  // tuning aids
+  static const int env_cg2 = [] { const char* v = getenv("VLB_CG2"); return v ? atoi(v) : -1; }();
+  if (force_bn == 0 && env_bn != 0 && (N >= (env_bn % 1000) || env_bn == 64)) force_bn = env_bn;
   int bn = 128;
-  if (force_bn == 128 || force_bn == 256 || force_bn == 64 || force_bn == 192) {
+  bool cg2 = false;
+  const int sms = num_sms();
+  if (force_bn >= 1000) {
+    cg2 = true;
+    bn = force_bn - 1000;
+    VLB_REQUIRE(bn == 128 || bn == 256, "gemm: pair mode supports BN 128 / 256");
+  } else if (force_bn == 128 || force_bn == 256 || force_bn == 64 || force_bn == 192) {
     bn = force_bn;
   } else {
-    const int sms = num_sms();
-    const int mb = (M + BM - 1) / BM;
-    // cost = rounds of the persistent grid x measured relative time of one 128 x b tile
-    // (profiles/r01_gemm_bringup_probe.log: 4.8 / 5.4 / 8.0 us per round at K = 768 for b = 64 / 128 / 256).
-    auto cost = [&](int b) {
-      const long items = (long)mb * ((N + b - 1) / b) * (split_k > 1 ? split_k : 1);
+    // cost = rounds of the persistent grid x measured relative time of one tile
+    const int sk = split_k > 1 ? split_k : 1;
+    auto cost1 = [&](int b) {
+      const long items = (long)((M + BM - 1) / BM) * ((N + b - 1) / b) * sk;
       const long rounds = (items + sms - 1) / sms;
       const double w = b == 64 ? 0.60 : (b == 128 ? 0.68 : (b == 192 ? 0.84 : 1.0));
       return rounds * w;
     };
+    auto cost2 = [&](int b) {  // pair tiles: half the B traffic per CTA, same MMA time per round as the 128 x b tile
+      const long items = (long)((M + 2 * BM - 1) / (2 * BM)) * ((N + b - 1) / b) * sk;
+      const long rounds = (items + sms / 2 - 1) / (sms / 2);
+      const double w = b == 128 ? 0.55 : 0.80;
+      return rounds * w;
+    };
     bn = 128;
-    double best = cost(128);
-    if (N >= 256 && cost(256) < best) { best = cost(256); bn = 256; }
-    if (N >= 192 && cost(192) < best) { best = cost(192); bn = 192; }
-    if (cost(64) < best) { best = cost(64); bn = 64; }
+    double best = cost1(128);
+    if (N >= 256 && cost1(256) < best) { best = cost1(256); bn = 256; }
+    if (N >= 192 && cost1(192) < best) { best = cost1(192); bn = 192; }
+    if (cost1(64) < best) { best = cost1(64); bn = 64; }
+    if (env_cg2 != 0) {
+      const bool force = env_cg2 == 1;
+      if (N >= 256 && (cost2(256) < best || force)) { best = cost2(256); bn = 256; cg2 = true; }
+      if (N >= 128 && (cost2(128) < best || (force && !cg2))) { best = cost2(128); bn = 128; cg2 = true; }
+    }
   }
 
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
-  p.num_m_blocks = (M + BM - 1) / BM;
+  p.num_m_blocks = cg2 ? (M + 2 * BM - 1) / (2 * BM) : (M + BM - 1) / BM;
   p.num_n_blocks = (N + bn - 1) / bn;
   p.num_k_blocks = (K + BK - 1) / BK;
   int sk = split_k < 1 ? 1 : split_k;
@@ -493,30 +563,34 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
   if (!a_mn) rc = make_tmap_bf16_2d(&ta, A, M, K, lda, 64, BM);       // A [M, K]
   else       rc = make_tmap_bf16_2d(&ta, A, K, M, lda, 64, 64);       // A stored [K, M]
   if (rc != VLB_OK) return rc;
-  if (!b_mn) rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, 64, bn);       // B [N, K]
+  if (!b_mn) rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, 64, cg2 ? bn / 2 : bn);  // B [N, K]
   else       rc = make_tmap_bf16_2d(&tb, B, K, N, ldb, 64, 64);       // B stored [K, N]
   if (rc != VLB_OK) return rc;
 
   ProfScope prof(mode == GEMM_NT ? PROF_GEMM_NT : (mode == GEMM_NN ? PROF_GEMM_NN : PROF_GEMM_TN), 2.0 * M * N * K, stream);
-#define VLB_GEMM_DISPATCH(BN_)                                                                        \
-  if (!a_mn && !b_mn) {                                                                               \
-    if (epi_id == EPI_BIAS_BF16) return launch<BN_, false, false, EPI_BIAS_BF16>(ta, tb, p, stream);     \
-    if (epi_id == EPI_BIAS_RESID16_F32) return launch<BN_, false, false, EPI_BIAS_RESID16_F32>(ta, tb, p, stream); \
-    if (epi_id == EPI_BIAS_GELU_AUX_BF16) return launch<BN_, false, false, EPI_BIAS_GELU_AUX_BF16>(ta, tb, p, stream); \
-    return launch<BN_, false, false, EPI_GENERIC>(ta, tb, p, stream);                                 \
-  }                                                                                                   \
-  if (!a_mn && b_mn) {                                                                                \
-    if (epi_id == EPI_DGELU_BF16) return launch<BN_, false, true, EPI_DGELU_BF16>(ta, tb, p, stream);    \
-    if (epi_id == EPI_RESID16_BF16) return launch<BN_, false, true, EPI_RESID16_BF16>(ta, tb, p, stream); \
-    return launch<BN_, false, true, EPI_GENERIC>(ta, tb, p, stream);                                  \
-  }                                                                                                   \
-  if (epi_id == EPI_ATOMIC_F32) return launch<BN_, true, true, EPI_ATOMIC_F32>(ta, tb, p, stream);       \
-  return launch<BN_, true, true, EPI_GENERIC>(ta, tb, p, stream);
+#define VLB_GEMM_DISPATCH(BN_, CG_)                                                                          \
+  if (!a_mn && !b_mn) {                                                                                      \
+    if (epi_id == EPI_BIAS_BF16) return launch<BN_, false, false, EPI_BIAS_BF16, CG_>(ta, tb, p, stream);     \
+    if (epi_id == EPI_BIAS_RESID16_F32) return launch<BN_, false, false, EPI_BIAS_RESID16_F32, CG_>(ta, tb, p, stream); \
+    if (epi_id == EPI_BIAS_GELU_AUX_BF16) return launch<BN_, false, false, EPI_BIAS_GELU_AUX_BF16, CG_>(ta, tb, p, stream); \
+    return launch<BN_, false, false, EPI_GENERIC, CG_>(ta, tb, p, stream);                                    \
+  }                                                                                                          \
+  if (!a_mn && b_mn) {                                                                                       \
+    if (epi_id == EPI_DGELU_BF16) return launch<BN_, false, true, EPI_DGELU_BF16, CG_>(ta, tb, p, stream);    \
+    if (epi_id == EPI_RESID16_BF16) return launch<BN_, false, true, EPI_RESID16_BF16, CG_>(ta, tb, p, stream); \
+    return launch<BN_, false, true, EPI_GENERIC, CG_>(ta, tb, p, stream);                                     \
+  }                                                                                                          \
+  if (epi_id == EPI_ATOMIC_F32) return launch<BN_, true, true, EPI_ATOMIC_F32, CG_>(ta, tb, p, stream);       \
+  return launch<BN_, true, true, EPI_GENERIC, CG_>(ta, tb, p, stream);
   const int epi_id = classify_epilogue(mode, epi_in);
-  if (bn == 256) { VLB_GEMM_DISPATCH(256) }
-  if (bn == 192) { VLB_GEMM_DISPATCH(192) }
-  if (bn == 64) { VLB_GEMM_DISPATCH(64) }
-  VLB_GEMM_DISPATCH(128)
+  if (cg2) {
+    if (bn == 256) { VLB_GEMM_DISPATCH(256, true) }
+    VLB_GEMM_DISPATCH(128, true)
+  }
+  if (bn == 256) { VLB_GEMM_DISPATCH(256, false) }
+  if (bn == 192) { VLB_GEMM_DISPATCH(192, false) }
+  if (bn == 64) { VLB_GEMM_DISPATCH(64, false) }
+  VLB_GEMM_DISPATCH(128, false)
 #undef VLB_GEMM_DISPATCH
 }
 

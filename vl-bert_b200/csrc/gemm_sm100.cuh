@@ -31,6 +31,7 @@ struct GemmEpilogue {
   void* aux = nullptr;           // bf16 [M, ld_aux]
   int ld_aux = 0;
   float alpha = 1.0f;            // scale applied to the accumulator before everything else
+  float* colsum = nullptr;       // optional [N] fp32: += column sums of the stored values (bias gradient of the producer)
 };
 
 // All matrices are bf16 row-major with leading dimensions in elements (multiples of 8).

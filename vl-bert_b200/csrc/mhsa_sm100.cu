@@ -206,10 +206,10 @@ __global__ void __launch_bounds__(128) mhsa_fwd_kernel(const __grid_constant__ C
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_row64(__nv_bfloat16* dst, uint32_t tcol_addr) {
-  uint32_t v0[32], v1[32];
+// 32 accumulator columns of one row -> 32 bf16 values in global memory
+__device__ __forceinline__ void store_row32(__nv_bfloat16* dst, uint32_t tcol_addr) {
+  uint32_t v0[32];
   tmem_ld32(tcol_addr, v0);
-  tmem_ld32(tcol_addr + 32, v1);
   tmem_ld_wait();
   if (dst != nullptr) {
 #pragma unroll
@@ -221,32 +221,29 @@ __device__ __forceinline__ void store_row64(__nv_bfloat16* dst, uint32_t tcol_ad
       o.w = pack_bf16x2(__uint_as_float(v0[g * 8 + 6]), __uint_as_float(v0[g * 8 + 7]));
       *reinterpret_cast<uint4*>(dst + g * 8) = o;
     }
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      uint4 o;
-      o.x = pack_bf16x2(__uint_as_float(v1[g * 8 + 0]), __uint_as_float(v1[g * 8 + 1]));
-      o.y = pack_bf16x2(__uint_as_float(v1[g * 8 + 2]), __uint_as_float(v1[g * 8 + 3]));
-      o.z = pack_bf16x2(__uint_as_float(v1[g * 8 + 4]), __uint_as_float(v1[g * 8 + 5]));
-      o.w = pack_bf16x2(__uint_as_float(v1[g * 8 + 6]), __uint_as_float(v1[g * 8 + 7]));
-      *reinterpret_cast<uint4*>(dst + 32 + g * 8) = o;
-    }
   }
 }
 
-__global__ void __launch_bounds__(128) mhsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv,
-                                                       const __grid_constant__ CUtensorMap tm_dctx, const MhsaParams p) {
+// 256 threads: warps w and w+4 share TMEM lane quarter (w % 4); thread pair (t, t+128) owns query/key row t % 128 and
+// splits the 128 key columns (softmax / dS phase) resp. the 64 head-dim columns (store phase) in halves.
+constexpr int BWD_THREADS = 256;
+
+__global__ void __launch_bounds__(BWD_THREADS) mhsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv,
+                                                               const __grid_constant__ CUtensorMap tm_dctx, const MhsaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BWD_SM_BAR);  // [0] load, [1] S & dP ready, [2] grads ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
   float* smask = reinterpret_cast<float*>(smem + BWD_SM_MASK);
 
-  const int t = threadIdx.x, warp = t >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int t = tid & 127;        // row owned by this thread
+  const int half = tid >> 7;      // which half of the columns
   const int h = blockIdx.x, b = blockIdx.y;
   const int row0 = b * p.S;
   constexpr uint32_t TMEM_COLS = 512;  // S [0,128) dP [128,256) dQ [256,320) dK [320,384) dV [384,448)
 
-  if (t == 0) {
+  if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_dctx);
     mbar_init(smem_u32(&bars[0]), 1);
@@ -267,7 +264,7 @@ __global__ void __launch_bounds__(128) mhsa_bwd_kernel(const __grid_constant__ C
   const uint32_t sq = smem_u32(smem + SM_Q), sk = smem_u32(smem + SM_K), sv = smem_u32(smem + SM_V);
   const uint32_t sp = smem_u32(smem + SM_P), sdo = smem_u32(smem + SM_DO), sds = smem_u32(smem + SM_DS);
 
-  if (t == 0) {
+  if (tid == 0) {
     const uint32_t bl = smem_u32(&bars[0]);
     mbar_arrive_expect_tx(bl, (2 * TQ + 2 * NK) * 128);
     tma_load_2d(sq, &tm_qkv, bl, h * D_HEAD, row0);
@@ -288,16 +285,18 @@ __global__ void __launch_bounds__(128) mhsa_bwd_kernel(const __grid_constant__ C
     umma_commit(smem_u32(&bars[1]));
   }
 
-  // D = rowsum(dO o O) and the saved log-sum-exp for this query row (overlaps the MMAs above)
+  // D = rowsum(dO o O) and the saved log-sum-exp for this query row (overlaps the TMA + MMAs above)
   float Dsum = 0.0f, lse = 0.0f;
   const bool valid = t < p.S;
   if (valid) {
     const uint4* po = reinterpret_cast<const uint4*>(p.ctx + (size_t)(row0 + t) * p.H + h * D_HEAD);
     const uint4* pd = reinterpret_cast<const uint4*>(p.dctx + (size_t)(row0 + t) * p.H + h * D_HEAD);
+    uint4 a[8], d[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) { a[g] = __ldg(po + g); d[g] = __ldg(pd + g); }
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
-      const uint4 a = po[g], d = pd[g];
-      const uint32_t aa[4] = {a.x, a.y, a.z, a.w}, dd[4] = {d.x, d.y, d.z, d.w};
+      const uint32_t aa[4] = {a[g].x, a[g].y, a[g].z, a[g].w}, dd[4] = {d[g].x, d[g].y, d[g].z, d[g].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) Dsum += bf16lo(aa[j]) * bf16lo(dd[j]) + bf16hi(aa[j]) * bf16hi(dd[j]);
     }
@@ -306,9 +305,10 @@ __global__ void __launch_bounds__(128) mhsa_bwd_kernel(const __grid_constant__ C
 
   mbar_wait(smem_u32(&bars[1]), 0);
   tc_fence_after();
-  const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
 #pragma unroll 1
-  for (int c = 0; c < NK / 32; ++c) {
+  for (int cc = 0; cc < NK / 64; ++cc) {
+    const int c = half * (NK / 64) + cc;  // this thread's 32-column chunks: [half*64, half*64 + 64)
     uint32_t vs[32], vd[32];
     float pr[32], ds[32];
     tmem_ld32(t_row + c * 32, vs);
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(128) mhsa_bwd_kernel(const __grid_constant__ C
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
-  if (t == 0) {
+  if (tid == 0) {
     tc_fence_after();
     constexpr uint32_t idesc_q = make_idesc_bf16(TQ, D_HEAD, 0, 1);   // dQ = dS K      (A K-major, B MN-major)
     constexpr uint32_t idesc_kv = make_idesc_bf16(NK, D_HEAD, 1, 1);  // dK = dS^T Q, dV = P^T dO (both MN-major)
@@ -348,10 +348,11 @@ __global__ void __launch_bounds__(128) mhsa_bwd_kernel(const __grid_constant__ C
   mbar_wait(smem_u32(&bars[2]), 0);
   tc_fence_after();
   {
-    __nv_bfloat16* base = valid ? p.dqkv + (size_t)(row0 + t) * (3 * p.H) + h * D_HEAD : nullptr;
-    store_row64(base, t_row + 256);
-    store_row64(valid ? base + p.H : nullptr, t_row + 320);
-    store_row64(valid ? base + 2 * p.H : nullptr, t_row + 384);
+    // each thread of the pair stores 32 of the 64 head-dim columns of dQ, dK, dV for row t
+    __nv_bfloat16* base = valid ? p.dqkv + (size_t)(row0 + t) * (3 * p.H) + h * D_HEAD + half * 32 : nullptr;
+    store_row32(base, t_row + 256 + half * 32);
+    store_row32(valid ? base + p.H : nullptr, t_row + 320 + half * 32);
+    store_row32(valid ? base + 2 * p.H : nullptr, t_row + 384 + half * 32);
   }
   tc_fence_before();
   __syncthreads();
@@ -412,7 +413,7 @@ int mhsa_backward(const void* qkv, const float* add_mask, const void* ctx, const
     attr = true;
   }
   ProfScope prof(PROF_MHSA_BWD, 8.0 * B * heads * (double)S * S * D_HEAD, stream);
-  mhsa_bwd_kernel<<<dim3(heads, B), 128, BWD_SMEM, stream>>>(tm, tmd, p);
+  mhsa_bwd_kernel<<<dim3(heads, B), BWD_THREADS, BWD_SMEM, stream>>>(tm, tmd, p);
   VLB_CHECK_LAUNCH();
   return VLB_OK;
 }

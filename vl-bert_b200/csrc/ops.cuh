@@ -34,7 +34,7 @@ int pack_forward(const int32_t* kind, const int32_t* src, const int32_t* pos_id,
                  int B, int T, int R, int S, int H, int vocab, int max_pos, int32_t* err, cudaStream_t stream);
 int pack_backward(const int32_t* kind, const int32_t* src, const int32_t* pos_id, const int32_t* type_id, const int64_t* ids,
                   const float* de, float* d_word, float* d_end, float* d_pos, float* d_type, float* d_text_vl, float* d_obj_vl,
-                  int B, int T, int R, int S, int H, int vocab, int max_pos, cudaStream_t stream);
+                  int B, int T, int R, int S, int H, int vocab, int max_pos, int pos_offset, cudaStream_t stream);
 int gather_rows(const void* in, int in_is_bf16, int ld_in, const int32_t* idx, void* out, int out_is_bf16, int ld_out, int n_out,
                 int H, cudaStream_t stream);
 int scatter_rows_add(const void* in, int in_is_bf16, int ld_in, const int32_t* idx, float* out, int ld_out, int n_in, int H,

@@ -2,6 +2,8 @@
 // external/pytorch_pretrained_bert/modeling.py:231-235 -- biased variance, eps INSIDE the sqrt, eps = 1e-12),
 // column sums for bias gradients, fp32 -> bf16 casts.  One warp per row, 128-bit loads, warp-shuffle
 // reductions, statistics in fp32.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vlb {
@@ -115,11 +117,15 @@ struct RowRawB {
   float4 xa[ITERS], xb[ITERS];
   uint4 d16[ITERS];
   float4 da[ITERS], db[ITERS];
+  float mu, rs;
 };
 
 template <int ITERS, bool HAS16, bool HAS32>
 __device__ __forceinline__ void load_row_bwd(RowRawB<ITERS>& r, const float* __restrict__ xr, const __nv_bfloat16* __restrict__ d16r,
-                                             const float* __restrict__ d32r, int lane, int nvec) {
+                                             const float* __restrict__ d32r, const float* __restrict__ mean_p,
+                                             const float* __restrict__ rstd_p, int lane, int nvec) {
+  r.mu = __ldg(mean_p);
+  r.rs = __ldg(rstd_p);
 #pragma unroll
   for (int i = 0; i < ITERS; ++i) {
     const int vi = lane + i * 32;
@@ -159,12 +165,15 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
   }
   int row = blockIdx.x * LN_WARPS + warp;
   RowRawB<ITERS> cur, nxt;
-  if (row < M) load_row_bwd<ITERS, HAS16, HAS32>(cur, x + (size_t)row * ldx, dy16 + (size_t)row * H, dy32 + (size_t)row * H, lane, nvec);
+  if (row < M)
+    load_row_bwd<ITERS, HAS16, HAS32>(cur, x + (size_t)row * ldx, dy16 + (size_t)row * H, dy32 + (size_t)row * H, mean + row,
+                                      rstd + row, lane, nvec);
   for (; row < M; row += wstride) {
     const int nrow = row + wstride;
     if (nrow < M)
-      load_row_bwd<ITERS, HAS16, HAS32>(nxt, x + (size_t)nrow * ldx, dy16 + (size_t)nrow * H, dy32 + (size_t)nrow * H, lane, nvec);
-    const float mu = mean[row], rs = rstd[row];
+      load_row_bwd<ITERS, HAS16, HAS32>(nxt, x + (size_t)nrow * ldx, dy16 + (size_t)nrow * H, dy32 + (size_t)nrow * H,
+                                        mean + nrow, rstd + nrow, lane, nvec);
+    const float mu = cur.mu, rs = cur.rs;
     float dy[ITERS][8], xh[ITERS][8];
     float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
@@ -378,7 +387,8 @@ int layernorm_backward(const void* dy_bf16, const float* dy_f32, const float* x,
   if (M <= 0) return VLB_OK;
   const int iters = (H + 255) / 256;
   int grid = (M + LN_WARPS - 1) / LN_WARPS;
-  const int cap = num_sms() * 3;
+  static const int per_sm = [] { const char* v = getenv("VLB_LN_BWD_BLOCKS_PER_SM"); return v ? atoi(v) : 2; }();
+  const int cap = num_sms() * per_sm;
   if (grid > cap) grid = cap;
   ProfScope prof(PROF_LN_BWD, (double)M * H * (4.0 + (dy_bf16 ? 2.0 : 0.0) + (dy_f32 ? 4.0 : 0.0) + (dx_bf16 ? 2.0 : 0.0) + (dx_f32 ? 4.0 : 0.0)), stream);
 #define VLB_LN_BWD(H16, H32)                                                                                    \

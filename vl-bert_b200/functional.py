@@ -322,6 +322,7 @@ class PackIndex(object):
         R = object_mask.shape[1]
         dev = text_mask.device
         self.B, self.T, self.R, self.S = B, T, R, S
+        self.pos_offset = int(pos_offset)
         i32 = torch.int32
         self.kind = torch.empty((B, S), dtype=i32, device=dev)
         self.src = torch.empty((B, S), dtype=i32, device=dev)
@@ -386,7 +387,7 @@ class EmbeddingFn(torch.autograd.Function):
         d_text_vl, d_obj_vl = z(B * T, H), z(B * R, H)
         _chk(lib.vlb_pack_backward(_p(pidx.kind), _p(pidx.src), _p(pidx.pos_id), _p(pidx.type_id), _p(ids), _p(de), _p(d_word),
                                    _p(d_end), _p(d_pos), _p(d_typ), _p(d_text_vl), _p(d_obj_vl), B, T, R, S, H, word.shape[0],
-                                   pos.shape[0], st))
+                                   pos.shape[0], pidx.pos_offset, st))
         _, d_tv = layernorm_backward(None, d_text_vl, tv.view(B * T, H), tv_mean, tv_rstd, vt_w, d_vt_w, d_vt_b,
                                      want_bf16=False, want_f32=True)
         d_ov = torch.empty((B * R, 2 * H), dtype=F32, device=dev)
