@@ -32,6 +32,14 @@ S_LEN = T_TEXT + R_REG + 1
 FLOP_PER_SAMPLE = 3 * LAYERS * (24 * S_LEN * HID * HID + 4 * S_LEN * S_LEN * HID)  # 52.60 GFLOP
 
 
+def set_shape(text, regions):
+    """--text/--regions: 64/36 = BASELINE config 2 (default, the metric's config); 20/100 = config 3 (VQA shape)."""
+    global T_TEXT, R_REG, S_LEN, FLOP_PER_SAMPLE
+    T_TEXT, R_REG = text, regions
+    S_LEN = T_TEXT + R_REG + 1
+    FLOP_PER_SAMPLE = 3 * LAYERS * (24 * S_LEN * HID * HID + 4 * S_LEN * S_LEN * HID)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -39,6 +47,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="samples per GPU")
+    ap.add_argument("--text", type=int, default=64, help="text tokens per sample")
+    ap.add_argument("--regions", type=int, default=36, help="region tokens per sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-input arm")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
@@ -126,7 +136,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "samples/sec VL-BERT-base fwd+bwd", "value": cb["value"], "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "VL-BERT-base 12L/768, 64 text + 36 region tokens (S=101), fwd+bwd, CPU fp32; bounded sample batch 8"},
+            "config": {"workload": "VL-BERT-base 12L/768, %d text + %d region tokens (S=%d), fwd+bwd, CPU fp32; bounded sample batch 8" % (T_TEXT, R_REG, S_LEN)},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -134,6 +144,7 @@ def run_reference(args):
 
 def main():
     args = parse()
+    set_shape(args.text, args.regions)
     if args.impl == "reference":
         return run_reference(args)
     rank = int(os.environ.get("RANK", "0"))
@@ -303,8 +314,10 @@ def main():
         "metric": "samples/sec VL-BERT-base fwd+bwd", "value": world * B / (ms * 1e-3), "unit": "samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "BASELINE config 2: VL-BERT-base 12L/768/12 heads, 64 text + 36 region tokens (S=101), "
-                               "batch %d per GPU, fwd+bwd (encoder + embedding/packing), loss=mean(out^2)" % B,
+        "config": {"workload": "%s: VL-BERT-base 12L/768/12 heads, %d text + %d region tokens (S=%d), "
+                               "batch %d per GPU, fwd+bwd (encoder + embedding/packing), loss=mean(out^2)"
+                               % ("BASELINE config 2" if (T_TEXT, R_REG) == (64, 36) else "BASELINE config 3 shape" if (T_TEXT, R_REG) == (20, 100) else "custom",
+                                  T_TEXT, R_REG, S_LEN, B),
                    "global_batch": world * B, "seq_len": S_LEN, "parallelism": "dp%d" % world,
                    "l2": "no flush needed: per-step working set (saved activations ~2.1 GB + 0.5 GB weights/grads) >> 126 MB L2",
                    "algorithmic_tflop_per_step_per_gpu": B * FLOP_PER_SAMPLE / 1e12},

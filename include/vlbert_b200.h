@@ -62,6 +62,18 @@ int vlb_gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const v
                   int resid_kind, int act, void* aux, int ld_aux, float alpha, int split_k,
                   int force_bn, void* stream);
 
+/* Grouped weight-gradient GEMM: out_i[M_i,N_i] (+)= A_i[K,M_i]^T B_i[K,N_i], i < count <= 4, same K, ONE launch
+ * (the four wgrad GEMMs of a BertLayer backward).  accumulate != 0: fp32 atomic "+=" (required for split_k > 1);
+ * bn = 128 or 256 (tile width). */
+typedef struct VlbGroupedProblem {
+  int M, N;
+  const void* A; int lda;
+  const void* B; int ldb;
+  float* out; int ldo;
+} VlbGroupedProblem;
+int vlb_gemm_grouped_tn(int count, const VlbGroupedProblem* problems, int K, int split_k, int accumulate, int bn,
+                        void* stream);
+
 /* bring-up aid: override the MN-major shared-memory descriptor geometry (0 = default). */
 void vlb_debug_gemm_desc(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t mn_kadv);
 

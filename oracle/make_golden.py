@@ -128,6 +128,33 @@ def golden_vlbert_c1():
     print("vlbert_c1_base: loss", float(loss), "S", layers[0].shape[1])
 
 
+def golden_pretrain_heads():
+    """VisualLinguisticBertForPretraining (rel / MLM / MVRC heads, common/visual_linguistic_bert.py:312-380) on the tiny config."""
+    from common.visual_linguistic_bert import VisualLinguisticBertForPretraining
+    cfg = ref_shim.vlbert_config(vocab_size=200, hidden_size=128, num_hidden_layers=2, num_attention_heads=2,
+                                 intermediate_size=256, max_position_embeddings=64, visual_size=128,
+                                 visual_region_classes=17, pos_embedding_frozen=False)
+    torch.manual_seed(0)
+    model = VisualLinguisticBertForPretraining(cfg, None, with_rel_head=True, with_mlm_head=True, with_mvrc_head=True).eval()
+    sd = seeded_state_dict(model, 61, std=0.05)
+    sd["mlm_head.predictions.decoder.weight"] = sd["word_embeddings.weight"]  # tied (modeling.py:463-466)
+    model.load_state_dict(sd)
+    inputs = synth_vlbert_inputs(B=3, T=9, R=5, H=128, vocab=200, seed=62)
+    rel, mlm, mvrc = model(*inputs)
+    g = torch.Generator().manual_seed(63)
+    loss = (rel * torch.randn(rel.shape, generator=g)).sum() + (mlm * torch.randn(mlm.shape, generator=g)).sum() * 0.1 \
+        + (mvrc * torch.randn(mvrc.shape, generator=g)).sum()
+    model.zero_grad()
+    loss.backward()
+    out = {"sd." + k: v.numpy() for k, v in sd.items()}
+    out.update(rel=rel.detach().numpy(), mlm=mlm.detach().numpy(), mvrc=mvrc.detach().numpy(), loss=loss.detach().numpy())
+    for k, p_ in model.named_parameters():
+        if p_.grad is not None and (p_.numel() <= 40000):
+            out["grad." + k] = p_.grad.numpy()
+    np.savez_compressed(os.path.join(GOLD, "vlbert_tiny_pretrain_heads.npz"), **out)
+    print("vlbert_tiny_pretrain_heads: rel", tuple(rel.shape), "mlm", tuple(mlm.shape), "mvrc", tuple(mvrc.shape))
+
+
 def golden_fastrcnn():
     from easydict import EasyDict
     from common.fast_rcnn import FastRCNN
@@ -199,6 +226,7 @@ if __name__ == "__main__":
     torch.set_num_threads(8)
     golden_vlbert_tiny()
     golden_vlbert_c1()
+    golden_pretrain_heads()
     golden_fastrcnn()
     golden_roi_align()
     for f in sorted(os.listdir(GOLD)):

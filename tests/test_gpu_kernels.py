@@ -84,6 +84,29 @@ def test_gemm_cta_pair_mode(VF, mode, shape, bn):
         assert rel(acc, ref) <= 2e-5
 
 
+@pytest.mark.parametrize("bn,split,acc", [(128, 1, False), (256, 1, False), (256, 2, True), (128, 3, True)])
+def test_gemm_grouped_wgrad(VF, bn, split, acc):
+    """Four weight-gradient problems of a BertLayer in one grouped launch (vlb_gemm_grouped_tn)."""
+    import ctypes
+    import vlbert_b200
+    L = vlbert_b200._lib
+    Mtok, H, I = 1384, 256, 512
+    g = torch.Generator().manual_seed(bn + split)
+    mk = lambda n: bf(torch.randn(Mtok, n, generator=g))  # noqa: E731
+    d_y0, u, dz, h, dqkv, x, d_a, ctx = mk(H), mk(I), mk(I), mk(H), mk(3 * H), mk(H), mk(H), mk(H)
+    probs = [(d_y0, u), (dz, h), (dqkv, x), (d_a, ctx)]
+    dev = [(a.to(DEV, BF16), b.to(DEV, BF16)) for a, b in probs]
+    outs = [torch.full((a.shape[1], b.shape[1]), 1.0 if acc else float("nan"), device=DEV) for a, b in probs]
+    arr = (L.GroupedProblem * 4)()
+    for i, ((a, b), o) in enumerate(zip(dev, outs)):
+        arr[i].M, arr[i].N, arr[i].A, arr[i].lda = a.shape[1], b.shape[1], a.data_ptr(), a.stride(0)
+        arr[i].B, arr[i].ldb, arr[i].out, arr[i].ldo = b.data_ptr(), b.stride(0), o.data_ptr(), o.stride(0)
+    L.check(L.lib().vlb_gemm_grouped_tn(4, arr, Mtok, split, int(acc), bn, torch.cuda.current_stream().cuda_stream))
+    for (a, b), o in zip(probs, outs):
+        ref = a.t() @ b + (1.0 if acc else 0.0)
+        assert rel(o, ref) <= 2e-5
+
+
 def test_gemm_epilogues(VF):
     M, N, K = 777, 1536, 512
     g = torch.Generator().manual_seed(5)

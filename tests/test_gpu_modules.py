@@ -114,6 +114,46 @@ def test_config2_shape_single_layer_against_oracle():
     _compare(_run(model, inputs, 33, DEV), _run(ora, inputs, 33, "cpu"))
 
 
+def test_config3_vqa_shape_single_layer_against_oracle():
+    """BASELINE config 3 token shape (VQA: 20 text + 100 region tokens, S = 121), batch 4, one layer, ragged."""
+    import vlbert_b200
+    cfg = vo.default_config(num_hidden_layers=1)
+    ora = vo.VisualLinguisticBertOracle(cfg)
+    sd = seeded_state_dict(ora, 14)
+    ora.load_state_dict(sd)
+    model = vlbert_b200.VisualLinguisticBert(cfg).to(DEV)
+    model.load_state_dict(sd, strict=True)
+    inputs = synth_vlbert_inputs(B=4, T=20, R=100, H=768, vocab=30522, seed=24, ragged=True)
+    _compare(_run(model, inputs, 34, DEV), _run(ora, inputs, 34, "cpu"))
+
+
+def test_pretraining_heads_against_reference_fixture(golden_dir):
+    """VisualLinguisticBertForPretraining (rel / MLM with tied decoder / MVRC heads) vs the unmodified reference."""
+    import vlbert_b200
+    G = np.load(os.path.join(golden_dir, "vlbert_tiny_pretrain_heads.npz"))
+    cfg = vo.default_config(vocab_size=200, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256,
+                            max_position_embeddings=64, visual_size=128, visual_region_classes=17, pos_embedding_frozen=False)
+    model = vlbert_b200.VisualLinguisticBertForPretraining(cfg, None, True, True, True).to(DEV)
+    sd = {k[3:]: torch.from_numpy(G[k]) for k in G.files if k.startswith("sd.")}
+    assert set(sd.keys()) == set(model.state_dict().keys())
+    model.load_state_dict(sd, strict=True)
+    assert model.mlm_head.predictions.decoder.weight.data_ptr() == model.word_embeddings.weight.data_ptr()  # still tied
+    inputs = [t.to(DEV) for t in synth_vlbert_inputs(B=3, T=9, R=5, H=128, vocab=200, seed=62)]
+    rel_l, mlm_l, mvrc_l = model(*inputs)
+    assert rel(rel_l, torch.from_numpy(G["rel"])) <= TOL_OUT
+    assert rel(mlm_l, torch.from_numpy(G["mlm"])) <= TOL_OUT
+    assert rel(mvrc_l, torch.from_numpy(G["mvrc"])) <= TOL_OUT
+    g = torch.Generator().manual_seed(63)
+    loss = (rel_l * torch.randn(rel_l.shape, generator=g).to(DEV)).sum() + (mlm_l * torch.randn(mlm_l.shape, generator=g).to(DEV)).sum() * 0.1 \
+        + (mvrc_l * torch.randn(mvrc_l.shape, generator=g).to(DEV)).sum()
+    model.zero_grad()
+    loss.backward()
+    gref = {k[5:]: torch.from_numpy(G[k]) for k in G.files if k.startswith("grad.")}
+    grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    for k, gr in gref.items():
+        assert grad_ok(k, grads[k], gr, gref, TOL_GRAD), (k, rel(grads[k], gr))
+
+
 def test_max_length_hint_matches_synced_path():
     import vlbert_b200
     cfg = vo.default_config(num_hidden_layers=1)

@@ -49,3 +49,37 @@ def test_reference_cpu_roialign_equals_c_oracle():
         a = ref.roi_align_forward(f, rois, 1 / 16.0, 14, 14, sr).numpy()
         b = ro.roi_align_forward(f.numpy(), rois.numpy(), 1 / 16.0, 14, 14, sr)
         assert np.array_equal(a, b)
+
+
+def test_dropin_classes_have_the_reference_checkpoint_abi():
+    """state_dict keys + shapes of the drop-in modules == the live reference modules."""
+    ref_shim.install()
+    import vlbert_b200
+    from common.visual_linguistic_bert import VisualLinguisticBert, VisualLinguisticBertForPretraining
+    kw = dict(vocab_size=300, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=512,
+              max_position_embeddings=80, visual_size=128, visual_region_classes=11, pos_embedding_frozen=False)
+    for ref_cls, our_cls, args in ((VisualLinguisticBert, vlbert_b200.VisualLinguisticBert, ()),
+                                   (VisualLinguisticBertForPretraining, vlbert_b200.VisualLinguisticBertForPretraining, (None, True, True, True))):
+        a = ref_cls(ref_shim.vlbert_config(**kw), *args).state_dict()
+        b = our_cls(vo.default_config(**kw), *args).state_dict()
+        assert list(a.keys()) == list(b.keys())
+        assert all(a[k].shape == b[k].shape for k in a)
+
+
+def test_dropin_install_patches_the_reference_modules():
+    ref_shim.install()
+    import vlbert_b200
+    assert vlbert_b200.dropin.install()
+    import common.fast_rcnn
+    import common.visual_linguistic_bert as m
+    assert m.VisualLinguisticBert is vlbert_b200.VisualLinguisticBert
+    assert m.VisualLinguisticBertForPretraining is vlbert_b200.VisualLinguisticBertForPretraining
+    from easydict import EasyDict
+    frcnn = common.fast_rcnn.FastRCNN(EasyDict({"NETWORK": {"IMAGE_FEAT_PRECOMPUTED": True, "IMAGE_SEMANTIC": False}}), True, 768)
+    assert isinstance(frcnn, vlbert_b200.FastRCNN)
+    assert list(frcnn.state_dict().keys()) == ["obj_downsample.1.weight", "obj_downsample.1.bias"]
+    # the task module builds on the patched classes (construction only: forward needs a GPU)
+    import importlib
+    import pretrain.modules.resnet_vlbert_for_pretraining as tm
+    importlib.reload(tm)
+    assert tm.VisualLinguisticBertForPretraining is vlbert_b200.VisualLinguisticBertForPretraining

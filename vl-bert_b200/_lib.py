@@ -40,6 +40,7 @@ def _declare(lib):
         fn.restype = res
         fn.argtypes = args
 
+    decl("vlb_gemm_grouped_tn", [P, P, I, I, I, I, P])
     decl("vlb_profile_enable", [I], None)
     decl("vlb_profile_collect", [P, P, P])
     decl("vlb_mhsa_forward", [P, P, P, P, I, I, I, I, P])
@@ -79,6 +80,12 @@ class LayerGrads(ctypes.Structure):
     """VlbLayerGrads"""
     _fields_ = [(n, c_void_p) for n in ("dw_qkv", "db_qkv", "dw_o", "db_o", "dln1_g", "dln1_b", "dw_1", "db_1", "dw_2",
                                         "db_2", "dln2_g", "dln2_b")]
+
+
+class GroupedProblem(ctypes.Structure):
+    """VlbGroupedProblem"""
+    _fields_ = [("M", c_int), ("N", c_int), ("A", c_void_p), ("lda", c_int), ("B", c_void_p), ("ldb", c_int),
+                ("out", c_void_p), ("ldo", c_int)]
 
 
 class CastDesc(ctypes.Structure):

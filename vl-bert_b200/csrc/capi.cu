@@ -93,6 +93,18 @@ int vlb_gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const v
   return rc;
 }
 
+int vlb_gemm_grouped_tn(int count, const VlbGroupedProblem* problems, int K, int split_k, int accumulate, int bn, void* stream) {
+  if (count < 1 || count > 4 || !problems) { set_last_error("vlb_gemm_grouped_tn: bad arguments"); return VLB_ERR_INVALID; }
+  GroupedProblem q[4];
+  for (int i = 0; i < count; ++i) {
+    q[i].M = problems[i].M; q[i].N = problems[i].N; q[i].A = problems[i].A; q[i].lda = problems[i].lda;
+    q[i].B = problems[i].B; q[i].ldb = problems[i].ldb; q[i].out = problems[i].out; q[i].ldo = problems[i].ldo;
+  }
+  int rc = gemm_grouped_tn(count, q, K, split_k, accumulate != 0, bn, static_cast<cudaStream_t>(stream));
+  if (rc == VLB_OK) count_launch(1);
+  return rc;
+}
+
 void vlb_debug_gemm_desc(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t mn_kadv) {
   gemm_debug_override(mn_lbo, mn_sbo, mn_kadv);
 }

@@ -1,6 +1,8 @@
 // One BertLayer forward / backward as a fixed kernel sequence on one stream.
 // Reference: external/pytorch_pretrained_bert/modeling.py:388-397 (BertLayer) =
 //   BertSelfAttention :290-315, BertSelfOutput :329-333, BertIntermediate :361-364, BertOutput :374-378.
+#include <cstdlib>
+
 #include "ops.cuh"
 
 namespace vlb {
@@ -56,7 +58,7 @@ int64_t bert_layer_backward_workspace(int M, int H, int I) {
   return al((int64_t)M * H * 2) * 4 + al((int64_t)M * I * 2) + al((int64_t)M * 3 * H * 2);
 }
 
-// Backward: 12 launches.
+// Backward: 9 launches.
 int bert_layer_backward(const VlbLayerWeights& w, const VlbLayerActs& a, const void* x, const float* add_mask, const void* dy16,
                         const float* dy32, void* dx, const VlbLayerGrads& g, void* workspace, int64_t ws_bytes, int B, int S,
                         int H, int heads, int I, cudaStream_t st) {
@@ -76,36 +78,39 @@ int bert_layer_backward(const VlbLayerWeights& w, const VlbLayerActs& a, const v
   // LayerNorm 2 backward: d_y0 (bf16), dgamma2/dbeta2, db_2 = colsum(d_y0)
   if ((rc = layernorm_backward(dy16, dy32, a.y0, H, a.ln2_mean, a.ln2_rstd, w.ln2_g, d_y0, nullptr, 0, g.dln2_g, g.dln2_b,
                                g.db_2, M, H, st))) return rc;
-  // dW2 += d_y0^T u
-  e = GemmEpilogue(); e.out = g.dw_2; e.ldo = I; e.out_kind = OUT_F32_ATOMIC;
-  if ((rc = gemm_bf16(GEMM_TN, H, I, M, d_y0, H, a.u, I, e, wgrad_split(H, I, M), 0, st))) return rc;
   // dz = (d_y0 W2) o gelu'(z) ; db_1 += colsum(dz) fused into the same epilogue
   e = GemmEpilogue(); e.out = dz; e.ldo = I; e.out_kind = OUT_BF16; e.act = ACT_DGELU_MUL; e.aux = a.z; e.ld_aux = I;
   e.colsum = g.db_1;
   if ((rc = gemm_bf16(GEMM_NN, M, I, H, d_y0, H, w.w_2, I, e, 1, 0, st))) return rc;
-  // dW1 += dz^T h
-  e = GemmEpilogue(); e.out = g.dw_1; e.ldo = H; e.out_kind = OUT_F32_ATOMIC;
-  if ((rc = gemm_bf16(GEMM_TN, I, H, M, dz, I, a.h, H, e, wgrad_split(I, H, M), 0, st))) return rc;
   // dh = dz W1 + d_y0 (residual)
   e = GemmEpilogue(); e.out = dh; e.ldo = H; e.out_kind = OUT_BF16; e.resid = d_y0; e.ldr = H; e.resid_kind = RESID_BF16;
   if ((rc = gemm_bf16(GEMM_NN, M, H, I, dz, I, w.w_1, H, e, 1, 0, st))) return rc;
   // LayerNorm 1 backward: d_a, dgamma1/dbeta1, db_o = colsum(d_a)
   if ((rc = layernorm_backward(dh, nullptr, a.a, H, a.ln1_mean, a.ln1_rstd, w.ln1_g, d_a, nullptr, 0, g.dln1_g, g.dln1_b,
                                g.db_o, M, H, st))) return rc;
-  // dWo += d_a^T ctx ; dctx = d_a Wo
-  e = GemmEpilogue(); e.out = g.dw_o; e.ldo = H; e.out_kind = OUT_F32_ATOMIC;
-  if ((rc = gemm_bf16(GEMM_TN, H, H, M, d_a, H, a.ctx, H, e, wgrad_split(H, H, M), 0, st))) return rc;
+  // dctx = d_a Wo
   e = GemmEpilogue(); e.out = dctx; e.ldo = H; e.out_kind = OUT_BF16;
   if ((rc = gemm_bf16(GEMM_NN, M, H, H, d_a, H, w.w_o, H, e, 1, 0, st))) return rc;
   // attention backward
   if ((rc = mhsa_backward(a.qkv, add_mask, a.ctx, a.lse, dctx, dqkv, B, S, H, heads, st))) return rc;
-  // db_qkv += colsum(dqkv) ; dWqkv += dqkv^T x ; dx = dqkv Wqkv + d_a (residual)
+  // db_qkv += colsum(dqkv) ; dx = dqkv Wqkv + d_a (residual)
   if ((rc = colsum_bf16(dqkv, 3 * H, g.db_qkv, M, 3 * H, st))) return rc;
-  e = GemmEpilogue(); e.out = g.dw_qkv; e.ldo = H; e.out_kind = OUT_F32_ATOMIC;
-  if ((rc = gemm_bf16(GEMM_TN, 3 * H, H, M, dqkv, 3 * H, x, H, e, wgrad_split(3 * H, H, M), 0, st))) return rc;
   e = GemmEpilogue(); e.out = dx; e.ldo = H; e.out_kind = OUT_BF16; e.resid = d_a; e.ldr = H; e.resid_kind = RESID_BF16;
   if ((rc = gemm_bf16(GEMM_NN, M, H, 3 * H, dqkv, 3 * H, w.w_qkv, H, e, 1, 0, st))) return rc;
-  count_launch(12);
+  // all four weight gradients of the layer in ONE grouped launch (every operand is still live in the workspace):
+  //   dW2 += d_y0^T u ; dW1 += dz^T h ; dWo += d_a^T ctx ; dWqkv += dqkv^T x     (reduction over the M token rows)
+  {
+    GroupedProblem q[4] = {
+        {H, I, d_y0, H, a.u, I, g.dw_2, I},
+        {I, H, dz, I, a.h, H, g.dw_1, H},
+        {3 * H, H, dqkv, 3 * H, x, H, g.dw_qkv, H},
+        {H, H, d_a, H, a.ctx, H, g.dw_o, H},
+    };
+    static const int env_bn = [] { const char* v = getenv("VLB_WGRAD_BN"); return v ? atoi(v) : 256; }();
+    static const int env_split = [] { const char* v = getenv("VLB_WGRAD_SPLIT"); return v ? atoi(v) : 2; }();
+    if ((rc = gemm_grouped_tn(4, q, M, env_split, true, env_bn, st))) return rc;
+  }
+  count_launch(9);
   return VLB_OK;
 }
 

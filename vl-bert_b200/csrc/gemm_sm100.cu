@@ -46,6 +46,44 @@ struct GemmParams {
 
 // CG2 = CTA-pair mode (tcgen05 cta_group::2): a cluster of two CTAs computes a 256 x BN tile; each CTA stages its own 128
 // rows of A and one HALF of the B tile, so the B operand crosses the L2->SM fabric once per pair instead of once per CTA.
+// Grouped launch: up to MAX_GROUP independent problems with the same reduction length K share one persistent grid
+// (the four weight-gradient GEMMs of a layer: 432 equal tiles -> 3 full rounds instead of 4 launches of 1-2 ragged rounds).
+constexpr int MAX_GROUP = 4;
+struct GroupTable {
+  CUtensorMap ta[MAX_GROUP];
+  CUtensorMap tb[MAX_GROUP];
+  int count;
+  int item_begin[MAX_GROUP + 1];   // prefix sums of per-problem items (= m_blocks * n_blocks * splits)
+  int m_blocks[MAX_GROUP], n_blocks[MAX_GROUP];
+  int M[MAX_GROUP], N[MAX_GROUP];
+  void* out[MAX_GROUP];
+  int ldo[MAX_GROUP];
+};
+
+struct ItemCoord {
+  int g, split, m_blk, n_blk;
+};
+template <bool GROUPED>
+__device__ __forceinline__ ItemCoord decode_item(int item, const GemmParams& p, const GroupTable& gt) {
+  ItemCoord c;
+  c.g = 0;
+  int local = item, mb = p.num_m_blocks, nb = p.num_n_blocks;
+  if (GROUPED) {
+#pragma unroll
+    for (int i = 1; i < MAX_GROUP; ++i)
+      if (i < gt.count && item >= gt.item_begin[i]) c.g = i;
+    local = item - gt.item_begin[c.g];
+    mb = gt.m_blocks[c.g];
+    nb = gt.n_blocks[c.g];
+  }
+  const int per_split = mb * nb;
+  c.split = local / per_split;
+  const int rem = local - c.split * per_split;
+  c.m_blk = rem / nb;
+  c.n_blk = rem - c.m_blk * nb;
+  return c;
+}
+
 template <int BN, bool CG2 = false>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
@@ -170,10 +208,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
   __syncwarp();
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, bool CG2>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-            const GemmParams p) {
+template <int BN, bool A_MN, bool B_MN, int EPI, bool CG2, bool GROUPED>
+__device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtensorMap& tma_b, const GemmParams& p,
+                                          const GroupTable& gt) {
   using C = Cfg<BN, CG2>;
   const uint32_t rank = CG2 ? cluster_ctarank() : 0u;       // CTA rank inside the pair
   const bool leader = rank == 0;                            // the leader issues the MMAs for both CTAs
@@ -193,8 +230,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tma_a);
-    tma_prefetch_desc(&tma_b);
+    if (!GROUPED) {
+      tma_prefetch_desc(&tma_a);
+      tma_prefetch_desc(&tma_b);
+    }
 #pragma unroll
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(smem_u32(&full_bar[s]), CG2 ? 2 : 1);   // pair mode: one arrive(+expect_tx) per CTA, on the leader's barrier
@@ -215,21 +254,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int items_per_split = p.num_m_blocks * p.num_n_blocks;
-
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int item = worker; item < p.num_items; item += nworkers) {
-        const int split = item / items_per_split;
-        const int rem = item - split * items_per_split;
-        const int m_blk = rem / p.num_n_blocks;
-        const int n_blk = rem - m_blk * p.num_n_blocks;
-        const int m0 = (m_blk * (CG2 ? 2 : 1) + (int)rank) * BM;          // this CTA's 128 rows of the (256-row) tile
-        const int n0 = n_blk * BN + (int)rank * (CG2 ? BN / 2 : 0);       // this CTA's half of the B tile
-        const int kb_begin = split * p.kb_per_split;
+        const ItemCoord ic = decode_item<GROUPED>(item, p, gt);
+        const CUtensorMap* pta = GROUPED ? &gt.ta[ic.g] : &tma_a;
+        const CUtensorMap* ptb = GROUPED ? &gt.tb[ic.g] : &tma_b;
+        const int m0 = (ic.m_blk * (CG2 ? 2 : 1) + (int)rank) * BM;          // this CTA's 128 rows of the (256-row) tile
+        const int n0 = ic.n_blk * BN + (int)rank * (CG2 ? BN / 2 : 0);       // this CTA's half of the B tile
+        const int kb_begin = ic.split * p.kb_per_split;
         const int kb_end = min(p.num_k_blocks, kb_begin + p.kb_per_split);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
@@ -245,16 +281,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             if (CG2) tma_load_2d_cg2(dst, tm, fb, c0, c1); else tma_load_2d(dst, tm, fb, c0, c1);
           };
           if (!A_MN) {
-            load(sa, &tma_a, k0, m0);  // box {64 k, 128 rows}
+            load(sa, pta, k0, m0);  // box {64 k, 128 rows}
           } else {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c) load(sa + c * 8192, &tma_a, m0 + c * 64, k0);
+            for (int c = 0; c < BM / 64; ++c) load(sa + c * 8192, pta, m0 + c * 64, k0);
           }
           if (!B_MN) {
-            load(sb, &tma_b, k0, n0);  // box {64 k, B_ROWS rows}
+            load(sb, ptb, k0, n0);  // box {64 k, B_ROWS rows}
           } else {
 #pragma unroll
-            for (int c = 0; c < C::B_ROWS / 64; ++c) load(sb + c * 8192, &tma_b, n0 + c * 64, k0);
+            for (int c = 0; c < C::B_ROWS / 64; ++c) load(sb + c * 8192, ptb, n0 + c * 64, k0);
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -268,8 +304,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       uint32_t phase = 0;
       int it = 0;
       for (int item = worker; item < p.num_items; item += nworkers, ++it) {
-        const int split = item / items_per_split;
-        const int kb_begin = split * p.kb_per_split;
+        const ItemCoord ic = decode_item<GROUPED>(item, p, gt);
+        const int kb_begin = ic.split * p.kb_per_split;
         const int kb_end = min(p.num_k_blocks, kb_begin + p.kb_per_split);
         const int buf = it & 1;
         const uint32_t use = static_cast<uint32_t>(it >> 1);
@@ -303,9 +339,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     float* stage = epi_stage + (warp - 2) * STAGE_F32_PER_WARP;
     int it = 0;
     for (int item = worker; item < p.num_items; item += nworkers, ++it) {
-      const int rem = item % items_per_split;
-      const int m_blk = rem / p.num_n_blocks;
-      const int n_blk = rem - m_blk * p.num_n_blocks;
+      const ItemCoord ic = decode_item<GROUPED>(item, p, gt);
+      const int m_blk = ic.m_blk, n_blk = ic.n_blk;
+      GemmEpilogue eg = p.e;
+      int Mg = p.M, Ng = p.N;
+      if (GROUPED) { eg.out = gt.out[ic.g]; eg.ldo = gt.ldo[ic.g]; Mg = gt.M[ic.g]; Ng = gt.N[ic.g]; }
       const int buf = it & 1;
       const uint32_t use = static_cast<uint32_t>(it >> 1);
       mbar_wait(smem_u32(&tfull_bar[buf]), use & 1u);
@@ -318,7 +356,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         tmem_ld32(t_row + c * 32, v);
         tmem_ld_wait();
         const int col0 = n_blk * BN + c * 32;
-        if (row_base < p.M && col0 < p.N) epilogue_chunk<EPI>(p.e, v, stage, lane, row_base, col0, p.M, p.N);
+        if (row_base < Mg && col0 < Ng) epilogue_chunk<EPI>(eg, v, stage, lane, row_base, col0, Mg, Ng);
       }
       tc_fence_before();
       __syncwarp();
@@ -335,6 +373,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     tc_fence_after();
     if (CG2) tmem_dealloc_cg2(tmem_base, C::TMEM_COLS); else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI, bool CG2>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+  gemm_body<BN, A_MN, B_MN, EPI, CG2, false>(tma_a, tma_b, p, *reinterpret_cast<const GroupTable*>(&tma_a));  // table unused
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_grouped_tn_kernel(const __grid_constant__ GroupTable gt, const GemmParams p) {
+  gemm_body<BN, true, true, EPI, false, true>(gt.ta[0], gt.tb[0], p, gt);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -592,6 +642,68 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
   if (bn == 64) { VLB_GEMM_DISPATCH(64, false) }
   VLB_GEMM_DISPATCH(128, false)
 #undef VLB_GEMM_DISPATCH
+}
+
+namespace {
+template <int BN, int EPI>
+int launch_grouped(const GroupTable& gt, const GemmParams& p, cudaStream_t stream) {
+  using C = Cfg<BN, false>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VLB_CHECK_CUDA(cudaFuncSetAttribute(gemm_grouped_tn_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = p.num_items < num_sms() ? p.num_items : num_sms();
+  gemm_grouped_tn_kernel<BN, EPI><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(gt, p);
+  VLB_CHECK_LAUNCH();
+  return VLB_OK;
+}
+}  // namespace
+
+int gemm_grouped_tn(int count, const GroupedProblem* probs, int K, int split_k, bool accumulate, int bn, cudaStream_t stream) {
+  VLB_REQUIRE(count >= 1 && count <= MAX_GROUP && probs != nullptr, "gemm_grouped_tn: 1..%d problems", MAX_GROUP);
+  VLB_REQUIRE(bn == 128 || bn == 256, "gemm_grouped_tn: bn must be 128 or 256");
+  VLB_REQUIRE(K > 0, "gemm_grouped_tn: K");
+  GemmParams p;
+  p.M = p.N = 0; p.K = K;
+  p.num_m_blocks = p.num_n_blocks = 0;
+  p.num_k_blocks = (K + BK - 1) / BK;
+  int sk = split_k < 1 ? 1 : split_k;
+  if (sk > p.num_k_blocks) sk = p.num_k_blocks;
+  p.kb_per_split = (p.num_k_blocks + sk - 1) / sk;
+  sk = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+  p.split_k = sk;
+  VLB_REQUIRE(sk == 1 || accumulate, "gemm_grouped_tn: split-K needs accumulate");
+  p.e = GemmEpilogue();
+  p.e.out_kind = accumulate ? OUT_F32_ATOMIC : OUT_F32;
+  p.a_lbo = p.b_lbo = g_dbg_mn_lbo ? g_dbg_mn_lbo : 8192u;
+  p.a_sbo = p.b_sbo = g_dbg_mn_sbo ? g_dbg_mn_sbo : 1024u;
+  p.a_kadv = p.b_kadv = g_dbg_mn_kadv ? g_dbg_mn_kadv : 2048u;
+  GroupTable gt;
+  gt.count = count;
+  int items = 0;
+  double flops = 0;
+  for (int i = 0; i < count; ++i) {
+    const GroupedProblem& q = probs[i];
+    VLB_REQUIRE(q.M > 0 && q.N > 0 && q.N % 8 == 0 && q.M % 8 == 0 && q.A && q.B && q.out && q.ldo % 4 == 0, "gemm_grouped_tn: bad problem %d", i);
+    int rc = make_tmap_bf16_2d(&gt.ta[i], q.A, K, q.M, q.lda, 64, 64);
+    if (rc != VLB_OK) return rc;
+    rc = make_tmap_bf16_2d(&gt.tb[i], q.B, K, q.N, q.ldb, 64, 64);
+    if (rc != VLB_OK) return rc;
+    gt.m_blocks[i] = (q.M + BM - 1) / BM;
+    gt.n_blocks[i] = (q.N + bn - 1) / bn;
+    gt.M[i] = q.M; gt.N[i] = q.N;
+    gt.out[i] = q.out; gt.ldo[i] = q.ldo;
+    gt.item_begin[i] = items;
+    items += gt.m_blocks[i] * gt.n_blocks[i] * sk;
+    flops += 2.0 * q.M * q.N * K;
+  }
+  for (int i = count; i <= MAX_GROUP; ++i) gt.item_begin[i] = items;
+  for (int i = count; i < MAX_GROUP; ++i) { gt.m_blocks[i] = gt.n_blocks[i] = 1; gt.M[i] = gt.N[i] = 0; gt.out[i] = nullptr; gt.ldo[i] = 0; gt.ta[i] = gt.ta[0]; gt.tb[i] = gt.tb[0]; }
+  p.num_items = items;
+  ProfScope prof(PROF_GEMM_TN, flops, stream);
+  if (bn == 256) return accumulate ? launch_grouped<256, EPI_ATOMIC_F32>(gt, p, stream) : launch_grouped<256, EPI_GENERIC>(gt, p, stream);
+  return accumulate ? launch_grouped<128, EPI_ATOMIC_F32>(gt, p, stream) : launch_grouped<128, EPI_GENERIC>(gt, p, stream);
 }
 
 }  // namespace vlb

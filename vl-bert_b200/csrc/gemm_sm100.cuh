@@ -38,6 +38,17 @@ struct GemmEpilogue {
 int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
               const GemmEpilogue& epi, int split_k, int force_bn, cudaStream_t stream);
 
+// Grouped weight-gradient launch: out_i[M_i, N_i] (+)= A_i[K, M_i]^T B_i[K, N_i] for up to 4 problems sharing K, in ONE
+// persistent grid (equal-cost tiles of all problems are interleaved -> full rounds).  accumulate: fp32 atomic "+="
+// (required when split_k > 1), else plain fp32 stores.
+struct GroupedProblem {
+  int M, N;
+  const void* A; int lda;
+  const void* B; int ldb;
+  float* out; int ldo;
+};
+int gemm_grouped_tn(int count, const GroupedProblem* probs, int K, int split_k, bool accumulate, int bn, cudaStream_t stream);
+
 // TMA descriptor helper shared with the attention kernels: 2D bf16 row-major [rows, cols] with
 // 128B swizzle; box = {box_cols (<=64), box_rows (<=256)}.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,

@@ -362,6 +362,9 @@ class VisualLinguisticBertForPretraining(VisualLinguisticBert):
         self.visual_ln_object.weight.data.fill_(config.visual_scale_object_init)
         if language_pretrained_model_path is not None:
             self.load_language_pretrained_model(language_pretrained_model_path)
+        if getattr(config, "pos_embedding_frozen", False):  # common/visual_linguistic_bert.py:341-343
+            for p in self.position_embeddings.parameters():
+                p.requires_grad = False
 
     def forward(self, text_input_ids, text_token_type_ids, text_visual_embeddings, text_mask, object_vl_embeddings,
                 object_mask, output_all_encoded_layers=True, output_text_and_object_separately=False):
