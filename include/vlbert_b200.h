@@ -54,8 +54,8 @@ int vlb_profile_collect(double* ms, double* work, int64_t* launches);
  * Epilogue: x = alpha*acc; x += bias[col]; activation; x += resid[row,col]; store.
  *   out_kind   0 bf16, 1 f32, 2 f32 atomic accumulate (required when split_k > 1)
  *   resid_kind 0 none, 1 bf16, 2 f32
- *   act        0 none, 1 erf-GELU (pre-activation stored to aux if non-null), 2 ReLU,
- *              3 multiply by GELU'(aux), 4 multiply by [aux > 0]
+ *   act        0 none, 1 erf-GELU (GELU'(pre-activation) stored to aux as bf16 if non-null, for backward), 2 ReLU,
+ *              3 multiply by aux (the saved GELU'), 4 multiply by [aux > 0]
  */
 int vlb_gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
                   void* out, int ldo, int out_kind, const float* bias, const void* resid, int ldr,
@@ -204,7 +204,7 @@ typedef struct VlbLayerActs { /* saved activations of one layer, caller-allocate
   float* ln1_mean; /* f32 [M] */
   float* ln1_rstd;
   void* h;         /* bf16 [M, H]  attention output */
-  void* z;         /* bf16 [M, I]  pre-GELU */
+  void* z;         /* bf16 [M, I]  GELU'(pre-activation), saved for backward */
   void* u;         /* bf16 [M, I]  GELU output */
   float* y0;       /* f32 [M, H]   dense(u) + h, input of LayerNorm 2 */
   float* ln2_mean;

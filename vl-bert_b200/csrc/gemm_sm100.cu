@@ -155,21 +155,29 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
     if (row < M && col_ok) {
       float x[4] = {fmaf(a.x, e.alpha, bias4.x), fmaf(a.y, e.alpha, bias4.y), fmaf(a.z, e.alpha, bias4.z), fmaf(a.w, e.alpha, bias4.w)};
       if (act == ACT_GELU) {
+        // x = gelu(z); aux receives gelu'(z) (bf16), computed from the same erf / exp -- the backward dgrad epilogue then only
+        // multiplies (ACT_DGELU_MUL) instead of re-evaluating erf and exp for every element.
+        float gp[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float cdf, pdf;
+          gelu_parts(x[j], cdf, pdf);
+          gp[j] = fmaf(x[j], pdf, cdf);
+          x[j] *= cdf;
+        }
         if (e.aux != nullptr) {
           uint2 z;
-          z.x = pack_bf16x2(x[0], x[1]);
-          z.y = pack_bf16x2(x[2], x[3]);
+          z.x = pack_bf16x2(gp[0], gp[1]);
+          z.y = pack_bf16x2(gp[2], gp[3]);
           *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.aux) + (size_t)row * e.ld_aux + col) = z;
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) x[j] = gelu_fast(x[j]);
       } else if (act == ACT_RELU) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.0f);
       } else if (need_aux_in) {
         const float zz[4] = {bf16lo(in16[i].x), bf16hi(in16[i].x), bf16lo(in16[i].y), bf16hi(in16[i].y)};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) x[j] = (act == ACT_DGELU_MUL) ? x[j] * gelu_grad_fast(zz[j]) : (zz[j] > 0.0f ? x[j] : 0.0f);
+        for (int j = 0; j < 4; ++j) x[j] = (act == ACT_DGELU_MUL) ? x[j] * zz[j] : (zz[j] > 0.0f ? x[j] : 0.0f);
       }
       if (resid_kind == RESID_BF16) {
         x[0] += bf16lo(in16[i].x); x[1] += bf16hi(in16[i].x); x[2] += bf16lo(in16[i].y); x[3] += bf16hi(in16[i].y);

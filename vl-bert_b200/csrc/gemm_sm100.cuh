@@ -8,9 +8,9 @@ enum GemmOutKind : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_ATOMIC = 2 };
 enum GemmResidKind : int { RESID_NONE = 0, RESID_BF16 = 1, RESID_F32 = 2 };
 enum GemmAct : int {
   ACT_NONE = 0,
-  ACT_GELU = 1,       // x = gelu_erf(x); if aux != null the pre-activation is stored there (bf16)
+  ACT_GELU = 1,       // x = gelu_erf(x); if aux != null gelu_erf'(pre-activation) is stored there (bf16) for backward
   ACT_RELU = 2,
-  ACT_DGELU_MUL = 3,  // x = x * gelu_erf'(aux[row, col])      (aux: bf16 pre-activation)
+  ACT_DGELU_MUL = 3,  // x = x * aux[row, col]                 (aux: the bf16 gelu' saved by ACT_GELU)
   ACT_DRELU_MUL = 4,  // x = aux[row, col] > 0 ? x : 0         (aux: bf16 post-activation)
 };
 // Operand layout modes.  "K-major" = reduction dimension contiguous in memory.

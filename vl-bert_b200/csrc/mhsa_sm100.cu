@@ -36,20 +36,30 @@ struct MhsaParams {
   __nv_bfloat16* dqkv;        // [B*S, 3H]
 };
 
-// shared memory map (bytes, from a 1024-aligned base)
+// Shared memory maps (bytes from the 1024-aligned dynamic shared memory base).  Regions are re-used once their first
+// consumer is done so that more CTAs fit an SM (the kernels are latency-bound chains, occupancy is what hides them):
+//   forward : Q | K | V | mask | barriers ; P (32 KB) overwrites Q|K after S = QK^T has completed   -> 4 CTAs / SM
+//   backward: Q | K | dO | V | X | dS | barriers ; P (32 KB) = V|X, written after dP = dO V^T completed -> 2 CTAs / SM
 constexpr int SM_Q = 0;
 constexpr int SM_K = SM_Q + TQ * 128;
-constexpr int SM_V = SM_K + NK * 128;
-constexpr int SM_P = SM_V + NK * 128;             // [TQ x NK] bf16, two 64-key atoms of 16 KB
-constexpr int FWD_SM_MASK = SM_P + TQ * NK * 2;   // NK floats
+constexpr int FWD_SM_V = SM_K + NK * 128;
+constexpr int FWD_SM_P = SM_Q;                       // aliases Q | K
+constexpr int FWD_SM_MASK = FWD_SM_V + NK * 128;     // NK floats
 constexpr int FWD_SM_BAR = FWD_SM_MASK + NK * 4;
-constexpr int FWD_SMEM = FWD_SM_BAR + 64 + 1024;
+constexpr int FWD_SMEM = FWD_SM_BAR + 64;
 
-constexpr int SM_DO = SM_P + TQ * NK * 2;
-constexpr int SM_DS = SM_DO + TQ * 128;
-constexpr int BWD_SM_MASK = SM_DS + TQ * NK * 2;
-constexpr int BWD_SM_BAR = BWD_SM_MASK + NK * 4;
-constexpr int BWD_SMEM = BWD_SM_BAR + 64 + 1024;
+constexpr int SM_DO = SM_K + NK * 128;
+constexpr int BWD_SM_V = SM_DO + TQ * 128;
+constexpr int BWD_SM_P = BWD_SM_V;                   // aliases V | X
+constexpr int SM_DS = BWD_SM_V + 2 * NK * 128;
+constexpr int BWD_SM_BAR = SM_DS + TQ * NK * 2;
+constexpr int BWD_SMEM = BWD_SM_BAR + 128;
+static_assert(BWD_SMEM <= 113 * 1024, "two backward CTAs must fit one SM");
+
+__device__ __forceinline__ uint8_t* aligned_smem(uint8_t* raw) {
+  if ((smem_u32(raw) & 1023u) != 0) __trap();  // 128B-swizzled tiles need a 1024-byte aligned base
+  return raw;
+}
 
 // Write 32 consecutive keys (c0 .. c0+31) of row r into a K-major 128B-swizzled [128 x NK] bf16 tile.
 __device__ __forceinline__ void store_tile_row32(uint8_t* tile, int r, int c0, const float (&x)[32]) {
@@ -77,9 +87,9 @@ __device__ __forceinline__ void load_mask_to_smem(float* smask, const MhsaParams
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const MhsaParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+__global__ void __launch_bounds__(128, 4) mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const MhsaParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = aligned_smem(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FWD_SM_BAR);  // [0] load, [1] S ready, [2] O ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
   float* smask = reinterpret_cast<float*>(smem + FWD_SM_MASK);
@@ -87,7 +97,7 @@ __global__ void __launch_bounds__(128) mhsa_fwd_kernel(const __grid_constant__ C
   const int t = threadIdx.x, warp = t >> 5;
   const int h = blockIdx.x, b = blockIdx.y;
   const int row0 = b * p.S;
-  constexpr uint32_t TMEM_COLS = 256;  // S: [0,128)  O: [128,192)
+  constexpr uint32_t TMEM_COLS = 128;  // S: [0,128) ; O re-uses [0,64) once every thread has consumed S
 
   if (t == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -111,7 +121,7 @@ __global__ void __launch_bounds__(128) mhsa_fwd_kernel(const __grid_constant__ C
     mbar_arrive_expect_tx(bl, (TQ + 2 * NK) * 128);
     tma_load_2d(smem_u32(smem + SM_Q), &tm_qkv, bl, h * D_HEAD, row0);
     tma_load_2d(smem_u32(smem + SM_K), &tm_qkv, bl, p.H + h * D_HEAD, row0);
-    tma_load_2d(smem_u32(smem + SM_V), &tm_qkv, bl, 2 * p.H + h * D_HEAD, row0);
+    tma_load_2d(smem_u32(smem + FWD_SM_V), &tm_qkv, bl, 2 * p.H + h * D_HEAD, row0);
     mbar_wait(bl, 0);
     tc_fence_after();
     constexpr uint32_t idesc_s = make_idesc_bf16(TQ, NK, 0, 0);
@@ -136,7 +146,8 @@ __global__ void __launch_bounds__(128) mhsa_fwd_kernel(const __grid_constant__ C
 #pragma unroll
     for (int j = 0; j < 32; ++j) m = fmaxf(m, fmaf(__uint_as_float(v[j]), p.scale, smask[c * 32 + j]));
   }
-  // pass 2: p = exp(x - m), row sum, stage P (bf16) for the second product
+  // pass 2: p = exp(x - m), row sum, stage P (bf16) for the second product.  P overwrites the Q|K tiles (the S MMAs
+  // that read them completed before bars[1] fired).
   float l = 0.0f;
 #pragma unroll 1
   for (int c = 0; c < NK / 32; ++c) {
@@ -149,7 +160,7 @@ __global__ void __launch_bounds__(128) mhsa_fwd_kernel(const __grid_constant__ C
       x[j] = __expf(fmaf(__uint_as_float(v[j]), p.scale, smask[c * 32 + j]) - m);
       l += x[j];
     }
-    store_tile_row32(smem + SM_P, t, c * 32, x);
+    store_tile_row32(smem + FWD_SM_P, t, c * 32, x);
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -157,10 +168,10 @@ __global__ void __launch_bounds__(128) mhsa_fwd_kernel(const __grid_constant__ C
   if (t == 0) {
     tc_fence_after();
     constexpr uint32_t idesc_o = make_idesc_bf16(TQ, D_HEAD, 0, 1);
-    const uint32_t sp = smem_u32(smem + SM_P), sv = smem_u32(smem + SM_V);
+    const uint32_t sp = smem_u32(smem + FWD_SM_P), sv = smem_u32(smem + FWD_SM_V);
 #pragma unroll
     for (int j = 0; j < NK / 16; ++j)
-      umma_bf16_ss(tmem + 128, make_smem_desc_sw128(sp + (j >> 2) * (TQ * 128) + (j & 3) * 32, 16, 1024),
+      umma_bf16_ss(tmem, make_smem_desc_sw128(sp + (j >> 2) * (TQ * 128) + (j & 3) * 32, 16, 1024),
                    make_smem_desc_sw128(sv + j * 2048, 8192, 1024), idesc_o, j > 0);
     umma_commit(smem_u32(&bars[2]));
   }
@@ -169,8 +180,8 @@ __global__ void __launch_bounds__(128) mhsa_fwd_kernel(const __grid_constant__ C
   {
     const float inv = 1.0f / l;
     uint32_t v0[32], v1[32];
-    tmem_ld32(t_row + 128, v0);
-    tmem_ld32(t_row + 160, v1);
+    tmem_ld32(t_row, v0);
+    tmem_ld32(t_row + 32, v1);
     tmem_ld_wait();
     if (t < p.S) {
       __nv_bfloat16* dst = p.ctx + (size_t)(row0 + t) * p.H + h * D_HEAD;
@@ -228,20 +239,21 @@ __device__ __forceinline__ void store_row32(__nv_bfloat16* dst, uint32_t tcol_ad
 // splits the 128 key columns (softmax / dS phase) resp. the 64 head-dim columns (store phase) in halves.
 constexpr int BWD_THREADS = 256;
 
-__global__ void __launch_bounds__(BWD_THREADS) mhsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv,
-                                                               const __grid_constant__ CUtensorMap tm_dctx, const MhsaParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+__global__ void __launch_bounds__(BWD_THREADS, 2) mhsa_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv,
+                                                                  const __grid_constant__ CUtensorMap tm_dctx, const MhsaParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = aligned_smem(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BWD_SM_BAR);  // [0] load, [1] S & dP ready, [2] grads ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
-  float* smask = reinterpret_cast<float*>(smem + BWD_SM_MASK);
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int t = tid & 127;        // row owned by this thread
   const int half = tid >> 7;      // which half of the columns
   const int h = blockIdx.x, b = blockIdx.y;
   const int row0 = b * p.S;
-  constexpr uint32_t TMEM_COLS = 512;  // S [0,128) dP [128,256) dQ [256,320) dK [320,384) dV [384,448)
+  // S [0,128) dP [128,256); once every thread has consumed them: dQ [0,64) dK [64,128) dV [128,192)
+  constexpr uint32_t TMEM_COLS = 256;
+  constexpr uint32_t T_DQ = 0, T_DK = 64, T_DV = 128;
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -255,14 +267,15 @@ __global__ void __launch_bounds__(BWD_THREADS) mhsa_bwd_kernel(const __grid_cons
     tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     tmem_relinquish();
   }
-  load_mask_to_smem(smask, p, b);
+  
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  const uint32_t sq = smem_u32(smem + SM_Q), sk = smem_u32(smem + SM_K), sv = smem_u32(smem + SM_V);
-  const uint32_t sp = smem_u32(smem + SM_P), sdo = smem_u32(smem + SM_DO), sds = smem_u32(smem + SM_DS);
+  const uint32_t sq = smem_u32(smem + SM_Q), sk = smem_u32(smem + SM_K), sv = smem_u32(smem + BWD_SM_V);
+  const uint32_t sp = smem_u32(smem + BWD_SM_P), sdo = smem_u32(smem + SM_DO), sds = smem_u32(smem + SM_DS);
+  const float* __restrict__ gmask = p.add_mask ? p.add_mask + (size_t)b * p.S : nullptr;
 
   if (tid == 0) {
     const uint32_t bl = smem_u32(&bars[0]);
@@ -316,12 +329,14 @@ __global__ void __launch_bounds__(BWD_THREADS) mhsa_bwd_kernel(const __grid_cons
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      // query rows beyond this sample's sequence must contribute nothing to dK / dV
-      const float pj = valid ? __expf(fmaf(__uint_as_float(vs[j]), p.scale, smask[c * 32 + j]) - lse) : 0.0f;
+      // query rows beyond this sample's sequence must contribute nothing to dK / dV; keys beyond it are masked out
+      const int col = c * 32 + j;
+      const float mk = col < p.S ? (gmask ? __ldg(gmask + col) : 0.0f) : -INFINITY;
+      const float pj = valid ? __expf(fmaf(__uint_as_float(vs[j]), p.scale, mk) - lse) : 0.0f;
       pr[j] = pj;
       ds[j] = pj * (__uint_as_float(vd[j]) - Dsum) * p.scale;
     }
-    store_tile_row32(smem + SM_P, t, c * 32, pr);
+    store_tile_row32(smem + BWD_SM_P, t, c * 32, pr);   // P overwrites V (+ spare): dP = dO V^T completed before bars[1]
     store_tile_row32(smem + SM_DS, t, c * 32, ds);
   }
   fence_proxy_async_smem();
@@ -333,15 +348,15 @@ __global__ void __launch_bounds__(BWD_THREADS) mhsa_bwd_kernel(const __grid_cons
     constexpr uint32_t idesc_kv = make_idesc_bf16(NK, D_HEAD, 1, 1);  // dK = dS^T Q, dV = P^T dO (both MN-major)
 #pragma unroll
     for (int j = 0; j < NK / 16; ++j)
-      umma_bf16_ss(tmem + 256, make_smem_desc_sw128(sds + (j >> 2) * (TQ * 128) + (j & 3) * 32, 16, 1024),
+      umma_bf16_ss(tmem + T_DQ, make_smem_desc_sw128(sds + (j >> 2) * (TQ * 128) + (j & 3) * 32, 16, 1024),
                    make_smem_desc_sw128(sk + j * 2048, 8192, 1024), idesc_q, j > 0);
 #pragma unroll
     for (int j = 0; j < TQ / 16; ++j)
-      umma_bf16_ss(tmem + 320, make_smem_desc_sw128(sds + j * 2048, TQ * 128, 1024),
+      umma_bf16_ss(tmem + T_DK, make_smem_desc_sw128(sds + j * 2048, TQ * 128, 1024),
                    make_smem_desc_sw128(sq + j * 2048, 8192, 1024), idesc_kv, j > 0);
 #pragma unroll
     for (int j = 0; j < TQ / 16; ++j)
-      umma_bf16_ss(tmem + 384, make_smem_desc_sw128(sp + j * 2048, TQ * 128, 1024),
+      umma_bf16_ss(tmem + T_DV, make_smem_desc_sw128(sp + j * 2048, TQ * 128, 1024),
                    make_smem_desc_sw128(sdo + j * 2048, 8192, 1024), idesc_kv, j > 0);
     umma_commit(smem_u32(&bars[2]));
   }
@@ -350,9 +365,9 @@ __global__ void __launch_bounds__(BWD_THREADS) mhsa_bwd_kernel(const __grid_cons
   {
     // each thread of the pair stores 32 of the 64 head-dim columns of dQ, dK, dV for row t
     __nv_bfloat16* base = valid ? p.dqkv + (size_t)(row0 + t) * (3 * p.H) + h * D_HEAD + half * 32 : nullptr;
-    store_row32(base, t_row + 256 + half * 32);
-    store_row32(valid ? base + p.H : nullptr, t_row + 320 + half * 32);
-    store_row32(valid ? base + 2 * p.H : nullptr, t_row + 384 + half * 32);
+    store_row32(base, t_row + T_DQ + half * 32);
+    store_row32(valid ? base + p.H : nullptr, t_row + T_DK + half * 32);
+    store_row32(valid ? base + 2 * p.H : nullptr, t_row + T_DV + half * 32);
   }
   tc_fence_before();
   __syncthreads();
