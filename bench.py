@@ -142,6 +142,20 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def _bounded_teardown(dist):
+    """destroy_process_group() with a watchdog: a teardown hang must not eat the GPU lease (seen once with NCCL work captured
+    in a CUDA graph)."""
+    def _bye():
+        time.sleep(20)
+        sys.stdout.flush()
+        os._exit(0)
+    threading.Thread(target=_bye, daemon=True).start()
+    try:
+        dist.destroy_process_group()
+    except Exception:
+        pass
+
+
 def main():
     args = parse()
     set_shape(args.text, args.regions)
@@ -301,7 +315,8 @@ def main():
 
     if rank != 0:
         if dist is not None:
-            dist.destroy_process_group()
+            graphed = None
+            _bounded_teardown(dist)
         return
     pk, pk_kind = peaks()
     gemm_ms = pms[0] + pms[1] + pms[2]
@@ -337,8 +352,10 @@ def main():
         cb = cpu_baseline()
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))
+    sys.stdout.flush()
     if dist is not None:
-        dist.destroy_process_group()
+        graphed = None
+        _bounded_teardown(dist)
 
 
 if __name__ == "__main__":

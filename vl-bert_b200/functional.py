@@ -50,6 +50,11 @@ class _Carver(object):
             off += _align(n * torch.empty((), dtype=dtype).element_size())
         self.nbytes = off
         self.buf = torch.empty(max(off, 256), dtype=torch.uint8, device=device)
+        self.base = self.buf.data_ptr()
+
+    def ptr(self, name):
+        """device pointer of a carved region (no tensor view is created: the hot loops only need addresses)"""
+        return self.base + self.offsets[name][0]
 
     def get(self, name):
         off, shape, dtype, n = self.offsets[name]
@@ -179,6 +184,14 @@ class EncoderWeights(object):
         _chk(_lib.lib().vlb_multi_cast(_p(self._table), self._count, 24, _stream()))
 
     def layer_struct(self, l, params):
+        cache = getattr(self, "_structs", None)
+        if cache is not None and cache[0] == self._key:
+            return cache[1][l]
+        structs = [self._layer_struct(i, params) for i in range(self.L)]
+        self._structs = (self._key, structs)
+        return structs[l]
+
+    def _layer_struct(self, l, params):
         q = params[16 * l: 16 * l + 16]
         w = _lib.LayerWeights()
         w.w_qkv, w.b_qkv = self.w_qkv[l].data_ptr(), self.b_qkv[l].data_ptr()
@@ -201,7 +214,7 @@ def _act_specs(l, B, S, H, heads, I, want_f32):
 
 def _acts_struct(car, l, y_f32):
     a = _lib.LayerActs()
-    g = lambda n: car.get(n % l).data_ptr()  # noqa: E731
+    g = lambda n: car.ptr(n % l)  # noqa: E731
     a.qkv, a.ctx, a.lse, a.a = g("qkv%d"), g("ctx%d"), g("lse%d"), g("a%d")
     a.ln1_mean, a.ln1_rstd, a.h, a.z, a.u = g("m1_%d"), g("r1_%d"), g("h%d"), g("z%d"), g("u%d")
     a.y0, a.ln2_mean, a.ln2_rstd, a.y = g("y0_%d"), g("m2_%d"), g("r2_%d"), g("y%d")
@@ -228,15 +241,15 @@ class EncoderFn(torch.autograd.Function):
             specs += _act_specs(l, B, S, H, heads, I, False)
         car = _Carver(specs, emb.device)
         outs = []
-        x = emb.contiguous().view(B * S, H)
+        x_ptr = emb.contiguous().data_ptr()
         for l in range(L):
             want = meta.all_layers or l == L - 1
             y32 = torch.empty((B, S, H), dtype=F32, device=emb.device) if want else None
             w = meta.weights.layer_struct(l, params)
             a = _acts_struct(car, l, y32)
-            _chk(lib.vlb_bert_layer_forward(ctypes.byref(w), x.data_ptr(), _p(add_mask), ctypes.byref(a), B, S, H, heads, I,
+            _chk(lib.vlb_bert_layer_forward(ctypes.byref(w), x_ptr, _p(add_mask), ctypes.byref(a), B, S, H, heads, I,
                                             float(meta.eps), st))
-            x = car.get("y%d" % l)
+            x_ptr = car.ptr("y%d" % l)
             if want:
                 outs.append(y32)
         ctx.meta = meta
@@ -267,6 +280,8 @@ class EncoderFn(torch.autograd.Function):
             gouts = [None] * (L - 1) + gouts
         dy16 = None
         grads = [None] * (16 * L)
+        sizes = [3 * H * H, 3 * H, H * H, H, H, H, I * H, I, H * I, H, H, H]
+        emb_ptr = ctx.emb.data_ptr()
         for l in range(L - 1, -1, -1):
             dy32 = gouts[l]
             if dy32 is not None:
@@ -274,28 +289,20 @@ class EncoderFn(torch.autograd.Function):
             if dy16 is None and dy32 is None:
                 dy32 = torch.zeros((M, H), dtype=F32, device=dev)
             f = flat[l]
-            o = 0
-
-            def take(n, shape):
-                nonlocal o
-                t = f[o: o + n].view(*shape)
-                o += n
-                return t
-            dw_qkv, db_qkv = take(3 * H * H, (3 * H, H)), take(3 * H, (3 * H,))
-            dw_o, db_o = take(H * H, (H, H)), take(H, (H,))
-            dg1, dbt1 = take(H, (H,)), take(H, (H,))
-            dw_1, db_1 = take(I * H, (I, H)), take(I, (I,))
-            dw_2, db_2 = take(H * I, (H, I)), take(H, (H,))
-            dg2, dbt2 = take(H, (H,)), take(H, (H,))
+            parts = f.split(sizes)
+            dw_qkv, db_qkv = parts[0].view(3 * H, H), parts[1]
+            dw_o, db_o, dg1, dbt1 = parts[2].view(H, H), parts[3], parts[4], parts[5]
+            dw_1, db_1 = parts[6].view(I, H), parts[7]
+            dw_2, db_2, dg2, dbt2 = parts[8].view(H, I), parts[9], parts[10], parts[11]
             g = _lib.LayerGrads()
             g.dw_qkv, g.db_qkv, g.dw_o, g.db_o = dw_qkv.data_ptr(), db_qkv.data_ptr(), dw_o.data_ptr(), db_o.data_ptr()
             g.dln1_g, g.dln1_b, g.dw_1, g.db_1 = dg1.data_ptr(), dbt1.data_ptr(), dw_1.data_ptr(), db_1.data_ptr()
             g.dw_2, g.db_2, g.dln2_g, g.dln2_b = dw_2.data_ptr(), db_2.data_ptr(), dg2.data_ptr(), dbt2.data_ptr()
             w = meta.weights.layer_struct(l, params)
             a = _acts_struct(car, l, None)
-            x = ctx.emb.view(M, H) if l == 0 else car.get("y%d" % (l - 1))
+            x_ptr = emb_ptr if l == 0 else car.ptr("y%d" % (l - 1))
             out_dx = dx[l & 1]
-            _chk(lib.vlb_bert_layer_backward(ctypes.byref(w), ctypes.byref(a), x.data_ptr(), _p(ctx.add_mask), _p(dy16),
+            _chk(lib.vlb_bert_layer_backward(ctypes.byref(w), ctypes.byref(a), x_ptr, _p(ctx.add_mask), _p(dy16),
                                              _p(dy32), out_dx.data_ptr(), ctypes.byref(g), ws.data_ptr(), ws_bytes, B, S, H,
                                              heads, I, st))
             dy16 = out_dx
