@@ -79,7 +79,9 @@ void vlb_debug_gemm_desc(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t mn_kadv);
 
 /* ---- fused multi-head self-attention ---------------------------------------------------------
  * Replaces BertSelfAttention.forward after the three Linear layers (modeling.py:295-315):
- *   ctx[b*S+s, h*64:(h+1)*64] = softmax(q k^T / 8 + add_mask[b, :]) v        head size 64, S <= 128
+ *   ctx[b*S+s, h*64:(h+1)*64] = softmax(q k^T / 8 + add_mask[b, :]) v        head size 64, S <= 256
+ * (S <= 128: one tile per (batch, head); 128 < S <= 256: two query tiles x two key tiles, the backward then
+ * accumulates partial dQ/dK/dV in scratch_f32 [B*S, 3H] (fp32, required only in that case) before converting).
  * qkv: bf16 [B*S, 3H] (q | k | v column blocks, the output of one fused QKV GEMM); add_mask: f32 [B,S]
  * additive (0 / -10000, common/visual_linguistic_bert.py:119-127) or NULL; ctx: bf16 [B*S, H];
  * lse: f32 [B, heads, S] log-sum-exp of the masked scaled scores (saved for backward; may be NULL
@@ -88,7 +90,8 @@ void vlb_debug_gemm_desc(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t mn_kadv);
 int vlb_mhsa_forward(const void* qkv, const float* add_mask, void* ctx, float* lse, int B, int S, int H,
                      int heads, void* stream);
 int vlb_mhsa_backward(const void* qkv, const float* add_mask, const void* ctx, const float* lse,
-                      const void* dctx, void* dqkv, int B, int S, int H, int heads, void* stream);
+                      const void* dctx, void* dqkv, float* scratch_f32, int B, int S, int H, int heads,
+                      void* stream);
 
 /* ---- LayerNorm (TF style, eps inside the sqrt) -----------------------------------------------
  * Replaces BertLayerNorm.forward (modeling.py:231-235) and its autograd backward.

@@ -176,7 +176,7 @@ def _attn_oracle(qkv, add_mask, B, S, H, heads):
     return (p @ v).permute(0, 2, 1, 3).reshape(B * S, H)
 
 
-@pytest.mark.parametrize("B,S,heads", [(64, 101, 12), (3, 13, 2), (5, 128, 4), (2, 1, 2), (4, 121, 12)])
+@pytest.mark.parametrize("B,S,heads", [(64, 101, 12), (3, 13, 2), (5, 128, 4), (2, 1, 2), (4, 121, 12), (3, 165, 16), (2, 256, 4), (5, 129, 2)])
 def test_mhsa_forward_backward(VF, B, S, heads):
     H = heads * 64
     g = torch.Generator().manual_seed(B * 1000 + S)

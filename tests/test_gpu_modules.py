@@ -127,6 +127,21 @@ def test_config3_vqa_shape_single_layer_against_oracle():
     _compare(_run(model, inputs, 34, DEV), _run(ora, inputs, 34, "cpu"))
 
 
+def test_config4_large_shape_single_layer_against_oracle():
+    """BASELINE config 4 shape (VL-BERT-large: H = 1024, 16 heads, I = 4096; 128 text + 36 region tokens, S = 165 > 128 ->
+    two query tiles x two key tiles in the attention kernels), batch 3, one layer, ragged."""
+    import vlbert_b200
+    kw = dict(num_hidden_layers=1, hidden_size=1024, num_attention_heads=16, intermediate_size=4096, visual_size=1024)
+    cfg = vo.default_config(**kw)
+    ora = vo.VisualLinguisticBertOracle(cfg)
+    sd = seeded_state_dict(ora, 15)
+    ora.load_state_dict(sd)
+    model = vlbert_b200.VisualLinguisticBert(cfg).to(DEV)
+    model.load_state_dict(sd, strict=True)
+    inputs = synth_vlbert_inputs(B=3, T=128, R=36, H=1024, vocab=30522, seed=25, ragged=True)
+    _compare(_run(model, inputs, 35, DEV), _run(ora, inputs, 35, "cpu"))
+
+
 def test_pretraining_heads_against_reference_fixture(golden_dir):
     """VisualLinguisticBertForPretraining (rel / MLM with tied decoder / MVRC heads) vs the unmodified reference."""
     import vlbert_b200

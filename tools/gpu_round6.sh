@@ -1,0 +1,21 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+L=gpurun_out/gpu_round6.log
+: > $L
+run() { echo "=== $*" >> $L; timeout "$1" "${@:2}" >> $L 2>&1; echo "--- exit $?" >> $L; }
+run 600 python -m pytest tests/test_gpu_kernels.py -q -x -k "mhsa"
+run 900 python -m pytest tests/test_gpu_modules.py -q -x
+run 300 python -c "import __graft_entry__ as g; g.smoke()"
+run 400 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-graph --skip-e2e
+run 400 python bench.py --steps 20 --warmup 5 --no-cpu-baseline
+grep -E "^===|^---|passed|failed|rror|smoke" $L | head -40
+python - <<'PY'
+import json
+for line in open('gpurun_out/gpu_round6.log'):
+    if line.startswith('==='): hdr=line.strip()
+    if line.startswith('{"metric"'):
+        d=json.loads(line)
+        if d['ms_per_step']<1000:
+            print(hdr[:90]); print('  ms/step %.3f value %.0f e2e %.0f graph %s gemm frac %.3f ' % (d['ms_per_step'], d['value'], d['e2e']['value'], d.get('cuda_graph'), d['roofline']['frac']), {k:round(v['ms_per_step'],3) for k,v in d['kernel_profile'].items()})
+PY

@@ -44,7 +44,7 @@ def _declare(lib):
     decl("vlb_profile_enable", [I], None)
     decl("vlb_profile_collect", [P, P, P])
     decl("vlb_mhsa_forward", [P, P, P, P, I, I, I, I, P])
-    decl("vlb_mhsa_backward", [P, P, P, P, P, P, I, I, I, I, P])
+    decl("vlb_mhsa_backward", [P, P, P, P, P, P, P, I, I, I, I, P])
     decl("vlb_layernorm_forward", [P, I, P, P, P, P, P, P, I, I, F, P])
     decl("vlb_layernorm_backward", [P, P, P, I, P, P, P, P, P, I, P, P, P, I, I, P])
     decl("vlb_colsum_bf16", [P, I, P, I, I, P])

@@ -133,8 +133,8 @@ int vlb_mhsa_forward(const void* qkv, const float* add_mask, void* ctx, float* l
   COUNTED(1, mhsa_forward(qkv, add_mask, ctx, lse, B, S, H, heads, ST));
 }
 int vlb_mhsa_backward(const void* qkv, const float* add_mask, const void* ctx, const float* lse, const void* dctx, void* dqkv,
-                      int B, int S, int H, int heads, void* stream) {
-  COUNTED(1, mhsa_backward(qkv, add_mask, ctx, lse, dctx, dqkv, B, S, H, heads, ST));
+                      float* scratch_f32, int B, int S, int H, int heads, void* stream) {
+  COUNTED(1, mhsa_backward(qkv, add_mask, ctx, lse, dctx, dqkv, scratch_f32, B, S, H, heads, ST));
 }
 int vlb_layernorm_forward(const float* x, int ldx, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
                           float* mean, float* rstd, int M, int H, float eps, void* stream) {

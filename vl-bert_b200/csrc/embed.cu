@@ -139,11 +139,12 @@ pack_bwd_kernel(const int32_t* __restrict__ kind, const int32_t* __restrict__ sr
                 float* __restrict__ d_word, float* __restrict__ d_end, float* __restrict__ d_pos, float* __restrict__ d_type,
                 float* __restrict__ d_text_vl, float* __restrict__ d_obj_vl, int T, int R, int S, int H, int vocab,
                 int max_pos, int pos_offset) {
-  extern __shared__ float pos_acc[];  // [S + 2][256]
+  extern __shared__ float pos_acc[];  // [S + 2][W], W = blockDim.x columns per block
+  const int W = blockDim.x;
   const int b = blockIdx.x;
-  const int c = blockIdx.y * 256 + threadIdx.x;
+  const int c = blockIdx.y * W + threadIdx.x;
   const bool col_ok = c < H;
-  for (int i = threadIdx.x; i < (S + 2) * 256; i += 256) pos_acc[i] = 0.0f;
+  for (int i = threadIdx.x; i < (S + 2) * W; i += W) pos_acc[i] = 0.0f;
   __syncthreads();
   float ty0 = 0.0f, ty1 = 0.0f, ty2 = 0.0f;
   for (int s = 0; s < S; ++s) {
@@ -152,7 +153,7 @@ pack_bwd_kernel(const int32_t* __restrict__ kind, const int32_t* __restrict__ sr
     const float v = col_ok ? __ldg(de + (size_t)row * H + c) : 0.0f;
     int li = pos_id[row] - pos_offset;
     li = li < 0 ? 0 : (li > S + 1 ? S + 1 : li);
-    pos_acc[li * 256 + threadIdx.x] += v;
+    pos_acc[li * W + threadIdx.x] += v;
     const int ty = type_id[row];
     ty0 += (ty == 0) ? v : 0.0f;
     ty1 += (ty == 1) ? v : 0.0f;
@@ -177,7 +178,7 @@ pack_bwd_kernel(const int32_t* __restrict__ kind, const int32_t* __restrict__ sr
   }
   if (d_pos) {
     for (int li = 0; li < S + 2; ++li) {
-      const float v = pos_acc[li * 256 + threadIdx.x];
+      const float v = pos_acc[li * W + threadIdx.x];
       const int pid = li + pos_offset;
       if (v != 0.0f && pid >= 0 && pid < max_pos) atomicAdd(d_pos + (size_t)pid * H + c, v);
     }
@@ -281,14 +282,15 @@ int pack_backward(const int32_t* kind, const int32_t* src, const int32_t* pos_id
                   const float* de, float* d_word, float* d_end, float* d_pos, float* d_type, float* d_text_vl, float* d_obj_vl,
                   int B, int T, int R, int S, int H, int vocab, int max_pos, int pos_offset, cudaStream_t stream) {
   VLB_REQUIRE(kind && src && pos_id && type_id && ids && de, "pack_backward: null pointer");
-  const int smem = (S + 2) * 256 * (int)sizeof(float);
+  const int W = ((S + 2) * 256 * (int)sizeof(float) <= 160 * 1024) ? 256 : 128;   // columns per block
+  const int smem = (S + 2) * W * (int)sizeof(float);
   VLB_REQUIRE(smem <= 200 * 1024, "pack_backward: packed length %d too large", S);
   static int attr_smem = 0;
   if (smem > attr_smem) {
     VLB_CHECK_CUDA(cudaFuncSetAttribute(pack_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
   }
-  pack_bwd_kernel<<<dim3(B, (H + 255) / 256), 256, smem, stream>>>(kind, src, pos_id, type_id, ids, de, d_word, d_end, d_pos,
+  pack_bwd_kernel<<<dim3(B, (H + W - 1) / W), W, smem, stream>>>(kind, src, pos_id, type_id, ids, de, d_word, d_end, d_pos,
                                                                 d_type, d_text_vl, d_obj_vl, T, R, S, H, vocab, max_pos, pos_offset);
   VLB_CHECK_LAUNCH();
   return VLB_OK;

@@ -53,9 +53,10 @@ int bert_layer_forward(const VlbLayerWeights& w, const void* x, const float* add
 }
 
 int64_t bert_layer_backward_workspace(int M, int H, int I) {
-  // d_y0 [M,H] | dz [M,I] | dh [M,H] | d_a [M,H] | dctx [M,H] | dqkv [M,3H]   (bf16), each 256B-aligned
+  // d_y0 [M,H] | dz [M,I] | dh [M,H] | d_a [M,H] | dctx [M,H] | dqkv [M,3H]   (bf16), each 256B-aligned,
+  // + fp32 [M,3H] scratch for the multi-block attention backward (used when S > 128)
   auto al = [](int64_t v) { return (v + 255) & ~int64_t(255); };
-  return al((int64_t)M * H * 2) * 4 + al((int64_t)M * I * 2) + al((int64_t)M * 3 * H * 2);
+  return al((int64_t)M * H * 2) * 4 + al((int64_t)M * I * 2) + al((int64_t)M * 3 * H * 2) + al((int64_t)M * 3 * H * 4);
 }
 
 // Backward: 9 launches.
@@ -72,7 +73,8 @@ int bert_layer_backward(const VlbLayerWeights& w, const VlbLayerActs& a, const v
   void* dh = p;   p += al((int64_t)M * H * 2);
   void* d_a = p;  p += al((int64_t)M * H * 2);
   void* dctx = p; p += al((int64_t)M * H * 2);
-  void* dqkv = p;
+  void* dqkv = p; p += al((int64_t)M * 3 * H * 2);
+  float* attn_scratch = reinterpret_cast<float*>(p);
   int rc;
   GemmEpilogue e;
   // LayerNorm 2 backward: d_y0 (bf16), dgamma2/dbeta2, db_2 = colsum(d_y0)
@@ -92,7 +94,7 @@ int bert_layer_backward(const VlbLayerWeights& w, const VlbLayerActs& a, const v
   e = GemmEpilogue(); e.out = dctx; e.ldo = H; e.out_kind = OUT_BF16;
   if ((rc = gemm_bf16(GEMM_NN, M, H, H, d_a, H, w.w_o, H, e, 1, 0, st))) return rc;
   // attention backward
-  if ((rc = mhsa_backward(a.qkv, add_mask, a.ctx, a.lse, dctx, dqkv, B, S, H, heads, st))) return rc;
+  if ((rc = mhsa_backward(a.qkv, add_mask, a.ctx, a.lse, dctx, dqkv, attn_scratch, B, S, H, heads, st))) return rc;
   // db_qkv += colsum(dqkv) ; dx = dqkv Wqkv + d_a (residual)
   if ((rc = colsum_bf16(dqkv, 3 * H, g.db_qkv, M, 3 * H, st))) return rc;
   e = GemmEpilogue(); e.out = dx; e.ldo = H; e.out_kind = OUT_BF16; e.resid = d_a; e.ldr = H; e.resid_kind = RESID_BF16;

@@ -34,6 +34,8 @@ struct MhsaParams {
   // backward
   const __nv_bfloat16* dctx;  // [B*S, H]
   __nv_bfloat16* dqkv;        // [B*S, 3H]
+  float* dqkv_f32;            // [B*S, 3H] fp32 accumulation buffer, only for S > 128 (several (q-tile, k-tile) blocks)
+  int ktiles;                 // number of 128-key tiles (blockIdx.z = q_tile * ktiles + k_tile)
 };
 
 // Shared memory maps (bytes from the 1024-aligned dynamic shared memory base).  Regions are re-used once their first
@@ -42,11 +44,6 @@ struct MhsaParams {
 //   backward: Q | K | dO | V | X | dS | barriers ; P (32 KB) = V|X, written after dP = dO V^T completed -> 2 CTAs / SM
 constexpr int SM_Q = 0;
 constexpr int SM_K = SM_Q + TQ * 128;
-constexpr int FWD_SM_V = SM_K + NK * 128;
-constexpr int FWD_SM_P = SM_Q;                       // aliases Q | K
-constexpr int FWD_SM_MASK = FWD_SM_V + NK * 128;     // NK floats
-constexpr int FWD_SM_BAR = FWD_SM_MASK + NK * 4;
-constexpr int FWD_SMEM = FWD_SM_BAR + 64;
 
 constexpr int SM_DO = SM_K + NK * 128;
 constexpr int BWD_SM_V = SM_DO + TQ * 128;
@@ -76,41 +73,55 @@ __device__ __forceinline__ void store_tile_row32(uint8_t* tile, int r, int c0, c
   }
 }
 
-__device__ __forceinline__ void load_mask_to_smem(float* smask, const MhsaParams& p, int b) {
-  for (int c = threadIdx.x; c < NK; c += blockDim.x) {
-    float m = -INFINITY;
-    if (c < p.S) m = p.add_mask ? p.add_mask[(size_t)b * p.S + c] : 0.0f;
-    smask[c] = m;
-  }
-}
+// ------------------------------------------------------------------------------------------------
+// forward.  NKT = number of 128-key tiles (1: S <= 128, four CTAs per SM; 2: S <= 256, two CTAs per SM).
+// grid = (heads, batch, ceil(S / 128) query tiles).
+// shared memory: Q (16 KB) | K (NKT x 16 KB) | pad (P needs NKT x 32 KB and overwrites Q | K | pad) | V | mask | barriers
+// ------------------------------------------------------------------------------------------------
+template <int NKT>
+struct FwdCfg {
+  static constexpr int NKEYS = 128 * NKT;
+  static constexpr int P_BYTES = TQ * NKEYS * 2;
+  static constexpr int QK_BYTES = TQ * 128 + NKEYS * 128;
+  static constexpr int SM_V = P_BYTES > QK_BYTES ? P_BYTES : QK_BYTES;
+  static constexpr int SM_MASK = SM_V + NKEYS * 128;
+  static constexpr int SM_BAR = SM_MASK + NKEYS * 4;
+  static constexpr int SMEM = SM_BAR + 64;
+  static constexpr uint32_t TMEM_COLS = NKEYS;  // S: [0, NKEYS) ; O re-uses [0,64) once every thread has consumed S
+};
 
-// ------------------------------------------------------------------------------------------------
-// forward
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 4) mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const MhsaParams p) {
+template <int NKT>
+__global__ void __launch_bounds__(128, NKT == 1 ? 4 : 2)
+mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const MhsaParams p) {
+  using C = FwdCfg<NKT>;
+  constexpr int NKEYS = C::NKEYS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = aligned_smem(smem_raw);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FWD_SM_BAR);  // [0] load, [1] S ready, [2] O ready
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::SM_BAR);  // [0] load, [1] S ready, [2] O ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
-  float* smask = reinterpret_cast<float*>(smem + FWD_SM_MASK);
+  float* smask = reinterpret_cast<float*>(smem + C::SM_MASK);
 
   const int t = threadIdx.x, warp = t >> 5;
-  const int h = blockIdx.x, b = blockIdx.y;
+  const int h = blockIdx.x, b = blockIdx.y, q0 = blockIdx.z * TQ;
   const int row0 = b * p.S;
-  constexpr uint32_t TMEM_COLS = 128;  // S: [0,128) ; O re-uses [0,64) once every thread has consumed S
 
   if (t == 0) {
-    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_kv);
     mbar_init(smem_u32(&bars[0]), 1);
     mbar_init(smem_u32(&bars[1]), 1);
     mbar_init(smem_u32(&bars[2]), 1);
     fence_mbar_init();
   }
   if (warp == 0) {
-    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
     tmem_relinquish();
   }
-  load_mask_to_smem(smask, p, b);
+  for (int c = t; c < NKEYS; c += 128) {
+    float m = -INFINITY;  // keys beyond this sample's sequence (neighbouring sample / out of bounds) never contribute
+    if (c < p.S) m = p.add_mask ? p.add_mask[(size_t)b * p.S + c] : 0.0f;
+    smask[c] = m;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -118,13 +129,13 @@ __global__ void __launch_bounds__(128, 4) mhsa_fwd_kernel(const __grid_constant_
 
   if (t == 0) {
     const uint32_t bl = smem_u32(&bars[0]);
-    mbar_arrive_expect_tx(bl, (TQ + 2 * NK) * 128);
-    tma_load_2d(smem_u32(smem + SM_Q), &tm_qkv, bl, h * D_HEAD, row0);
-    tma_load_2d(smem_u32(smem + SM_K), &tm_qkv, bl, p.H + h * D_HEAD, row0);
-    tma_load_2d(smem_u32(smem + FWD_SM_V), &tm_qkv, bl, 2 * p.H + h * D_HEAD, row0);
+    mbar_arrive_expect_tx(bl, (TQ + 2 * NKEYS) * 128);
+    tma_load_2d(smem_u32(smem + SM_Q), &tm_q, bl, h * D_HEAD, row0 + q0);
+    tma_load_2d(smem_u32(smem + SM_K), &tm_kv, bl, p.H + h * D_HEAD, row0);
+    tma_load_2d(smem_u32(smem + C::SM_V), &tm_kv, bl, 2 * p.H + h * D_HEAD, row0);
     mbar_wait(bl, 0);
     tc_fence_after();
-    constexpr uint32_t idesc_s = make_idesc_bf16(TQ, NK, 0, 0);
+    constexpr uint32_t idesc_s = make_idesc_bf16(TQ, NKEYS, 0, 0);
     const uint32_t sq = smem_u32(smem + SM_Q), sk = smem_u32(smem + SM_K);
 #pragma unroll
     for (int k = 0; k < D_HEAD / 16; ++k)
@@ -139,7 +150,7 @@ __global__ void __launch_bounds__(128, 4) mhsa_fwd_kernel(const __grid_constant_
   // pass 1: row maximum of scale * s + mask
   float m = -INFINITY;
 #pragma unroll 1
-  for (int c = 0; c < NK / 32; ++c) {
+  for (int c = 0; c < NKEYS / 32; ++c) {
     uint32_t v[32];
     tmem_ld32(t_row + c * 32, v);
     tmem_ld_wait();
@@ -150,7 +161,7 @@ __global__ void __launch_bounds__(128, 4) mhsa_fwd_kernel(const __grid_constant_
   // that read them completed before bars[1] fired).
   float l = 0.0f;
 #pragma unroll 1
-  for (int c = 0; c < NK / 32; ++c) {
+  for (int c = 0; c < NKEYS / 32; ++c) {
     uint32_t v[32];
     float x[32];
     tmem_ld32(t_row + c * 32, v);
@@ -160,7 +171,7 @@ __global__ void __launch_bounds__(128, 4) mhsa_fwd_kernel(const __grid_constant_
       x[j] = __expf(fmaf(__uint_as_float(v[j]), p.scale, smask[c * 32 + j]) - m);
       l += x[j];
     }
-    store_tile_row32(smem + FWD_SM_P, t, c * 32, x);
+    store_tile_row32(smem, t, c * 32, x);  // P tile starts at offset 0 (aliases Q | K)
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -168,9 +179,9 @@ __global__ void __launch_bounds__(128, 4) mhsa_fwd_kernel(const __grid_constant_
   if (t == 0) {
     tc_fence_after();
     constexpr uint32_t idesc_o = make_idesc_bf16(TQ, D_HEAD, 0, 1);
-    const uint32_t sp = smem_u32(smem + FWD_SM_P), sv = smem_u32(smem + FWD_SM_V);
+    const uint32_t sp = smem_u32(smem), sv = smem_u32(smem + C::SM_V);
 #pragma unroll
-    for (int j = 0; j < NK / 16; ++j)
+    for (int j = 0; j < NKEYS / 16; ++j)
       umma_bf16_ss(tmem, make_smem_desc_sw128(sp + (j >> 2) * (TQ * 128) + (j & 3) * 32, 16, 1024),
                    make_smem_desc_sw128(sv + j * 2048, 8192, 1024), idesc_o, j > 0);
     umma_commit(smem_u32(&bars[2]));
@@ -183,8 +194,8 @@ __global__ void __launch_bounds__(128, 4) mhsa_fwd_kernel(const __grid_constant_
     tmem_ld32(t_row, v0);
     tmem_ld32(t_row + 32, v1);
     tmem_ld_wait();
-    if (t < p.S) {
-      __nv_bfloat16* dst = p.ctx + (size_t)(row0 + t) * p.H + h * D_HEAD;
+    if (q0 + t < p.S) {
+      __nv_bfloat16* dst = p.ctx + (size_t)(row0 + q0 + t) * p.H + h * D_HEAD;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         uint4 o;
@@ -203,14 +214,14 @@ __global__ void __launch_bounds__(128, 4) mhsa_fwd_kernel(const __grid_constant_
         o.w = pack_bf16x2(__uint_as_float(v1[g * 8 + 6]) * inv, __uint_as_float(v1[g * 8 + 7]) * inv);
         *reinterpret_cast<uint4*>(dst + 32 + g * 8) = o;
       }
-      if (p.lse) p.lse[((size_t)b * p.heads + h) * p.S + t] = m + __logf(l);
+      if (p.lse) p.lse[((size_t)b * p.heads + h) * p.S + q0 + t] = m + __logf(l);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem, TMEM_COLS);
+    tmem_dealloc(tmem, C::TMEM_COLS);
   }
 }
 
@@ -235,6 +246,20 @@ __device__ __forceinline__ void store_row32(__nv_bfloat16* dst, uint32_t tcol_ad
   }
 }
 
+// 32 accumulator columns of one row -> fp32 atomic accumulation (multi-block backward, S > 128)
+__device__ __forceinline__ void add_row32(float* dst, uint32_t tcol_addr) {
+  uint32_t v0[32];
+  tmem_ld32(tcol_addr, v0);
+  tmem_ld_wait();
+  if (dst != nullptr) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4), "f"(__uint_as_float(v0[g * 4])),
+                   "f"(__uint_as_float(v0[g * 4 + 1])), "f"(__uint_as_float(v0[g * 4 + 2])), "f"(__uint_as_float(v0[g * 4 + 3]))
+                   : "memory");
+  }
+}
+
 // 256 threads: warps w and w+4 share TMEM lane quarter (w % 4); thread pair (t, t+128) owns query/key row t % 128 and
 // splits the 128 key columns (softmax / dS phase) resp. the 64 head-dim columns (store phase) in halves.
 constexpr int BWD_THREADS = 256;
@@ -250,6 +275,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) mhsa_bwd_kernel(const __grid_c
   const int t = tid & 127;        // row owned by this thread
   const int half = tid >> 7;      // which half of the columns
   const int h = blockIdx.x, b = blockIdx.y;
+  const int q0 = (blockIdx.z / p.ktiles) * TQ, k0 = (blockIdx.z % p.ktiles) * NK;  // this CTA's (query tile, key tile) block
   const int row0 = b * p.S;
   // S [0,128) dP [128,256); once every thread has consumed them: dQ [0,64) dK [64,128) dV [128,192)
   constexpr uint32_t TMEM_COLS = 256;
@@ -280,10 +306,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) mhsa_bwd_kernel(const __grid_c
   if (tid == 0) {
     const uint32_t bl = smem_u32(&bars[0]);
     mbar_arrive_expect_tx(bl, (2 * TQ + 2 * NK) * 128);
-    tma_load_2d(sq, &tm_qkv, bl, h * D_HEAD, row0);
-    tma_load_2d(sk, &tm_qkv, bl, p.H + h * D_HEAD, row0);
-    tma_load_2d(sv, &tm_qkv, bl, 2 * p.H + h * D_HEAD, row0);
-    tma_load_2d(sdo, &tm_dctx, bl, h * D_HEAD, row0);
+    tma_load_2d(sq, &tm_qkv, bl, h * D_HEAD, row0 + q0);
+    tma_load_2d(sk, &tm_qkv, bl, p.H + h * D_HEAD, row0 + k0);
+    tma_load_2d(sv, &tm_qkv, bl, 2 * p.H + h * D_HEAD, row0 + k0);
+    tma_load_2d(sdo, &tm_dctx, bl, h * D_HEAD, row0 + q0);
     mbar_wait(bl, 0);
     tc_fence_after();
     constexpr uint32_t idesc = make_idesc_bf16(TQ, NK, 0, 0);
@@ -300,10 +326,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) mhsa_bwd_kernel(const __grid_c
 
   // D = rowsum(dO o O) and the saved log-sum-exp for this query row (overlaps the TMA + MMAs above)
   float Dsum = 0.0f, lse = 0.0f;
-  const bool valid = t < p.S;
+  const bool valid = q0 + t < p.S;     // this thread's QUERY row exists
+  const bool kvalid = k0 + t < p.S;    // this thread's KEY row exists (dK / dV rows)
   if (valid) {
-    const uint4* po = reinterpret_cast<const uint4*>(p.ctx + (size_t)(row0 + t) * p.H + h * D_HEAD);
-    const uint4* pd = reinterpret_cast<const uint4*>(p.dctx + (size_t)(row0 + t) * p.H + h * D_HEAD);
+    const uint4* po = reinterpret_cast<const uint4*>(p.ctx + (size_t)(row0 + q0 + t) * p.H + h * D_HEAD);
+    const uint4* pd = reinterpret_cast<const uint4*>(p.dctx + (size_t)(row0 + q0 + t) * p.H + h * D_HEAD);
     uint4 a[8], d[8];
 #pragma unroll
     for (int g = 0; g < 8; ++g) { a[g] = __ldg(po + g); d[g] = __ldg(pd + g); }
@@ -313,7 +340,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) mhsa_bwd_kernel(const __grid_c
 #pragma unroll
       for (int j = 0; j < 4; ++j) Dsum += bf16lo(aa[j]) * bf16lo(dd[j]) + bf16hi(aa[j]) * bf16hi(dd[j]);
     }
-    lse = p.lse[((size_t)b * p.heads + h) * p.S + t];
+    lse = p.lse[((size_t)b * p.heads + h) * p.S + q0 + t];
   }
 
   mbar_wait(smem_u32(&bars[1]), 0);
@@ -330,7 +357,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) mhsa_bwd_kernel(const __grid_c
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       // query rows beyond this sample's sequence must contribute nothing to dK / dV; keys beyond it are masked out
-      const int col = c * 32 + j;
+      const int col = k0 + c * 32 + j;
       const float mk = col < p.S ? (gmask ? __ldg(gmask + col) : 0.0f) : -INFINITY;
       const float pj = valid ? __expf(fmaf(__uint_as_float(vs[j]), p.scale, mk) - lse) : 0.0f;
       pr[j] = pj;
@@ -363,11 +390,17 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) mhsa_bwd_kernel(const __grid_c
   mbar_wait(smem_u32(&bars[2]), 0);
   tc_fence_after();
   {
-    // each thread of the pair stores 32 of the 64 head-dim columns of dQ, dK, dV for row t
-    __nv_bfloat16* base = valid ? p.dqkv + (size_t)(row0 + t) * (3 * p.H) + h * D_HEAD + half * 32 : nullptr;
-    store_row32(base, t_row + T_DQ + half * 32);
-    store_row32(valid ? base + p.H : nullptr, t_row + T_DK + half * 32);
-    store_row32(valid ? base + 2 * p.H : nullptr, t_row + T_DV + half * 32);
+    // each thread of the pair handles 32 of the 64 head-dim columns: dQ of query row q0+t, dK / dV of key row k0+t
+    const size_t col = (size_t)h * D_HEAD + half * 32;
+    if (p.dqkv_f32 == nullptr) {  // single block: final values, bf16
+      store_row32(valid ? p.dqkv + (size_t)(row0 + q0 + t) * (3 * p.H) + col : nullptr, t_row + T_DQ + half * 32);
+      store_row32(kvalid ? p.dqkv + (size_t)(row0 + k0 + t) * (3 * p.H) + p.H + col : nullptr, t_row + T_DK + half * 32);
+      store_row32(kvalid ? p.dqkv + (size_t)(row0 + k0 + t) * (3 * p.H) + 2 * p.H + col : nullptr, t_row + T_DV + half * 32);
+    } else {                      // partial sums over the other tile dimension: fp32 atomics, converted afterwards
+      add_row32(valid ? p.dqkv_f32 + (size_t)(row0 + q0 + t) * (3 * p.H) + col : nullptr, t_row + T_DQ + half * 32);
+      add_row32(kvalid ? p.dqkv_f32 + (size_t)(row0 + k0 + t) * (3 * p.H) + p.H + col : nullptr, t_row + T_DK + half * 32);
+      add_row32(kvalid ? p.dqkv_f32 + (size_t)(row0 + k0 + t) * (3 * p.H) + 2 * p.H + col : nullptr, t_row + T_DV + half * 32);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -379,36 +412,50 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) mhsa_bwd_kernel(const __grid_c
 
 }  // namespace
 
+template <int NKT>
+static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tkv, const MhsaParams& p, int B, int heads, int qtiles, cudaStream_t stream) {
+  using C = FwdCfg<NKT>;
+  static bool attr = false;
+  if (!attr) {
+    VLB_CHECK_CUDA(cudaFuncSetAttribute(mhsa_fwd_kernel<NKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr = true;
+  }
+  mhsa_fwd_kernel<NKT><<<dim3(heads, B, qtiles), 128, C::SMEM, stream>>>(tq, tkv, p);
+  VLB_CHECK_LAUNCH();
+  return VLB_OK;
+}
+
 int mhsa_forward(const void* qkv, const float* add_mask, void* ctx, float* lse, int B, int S, int H, int heads,
                  cudaStream_t stream) {
   VLB_REQUIRE(qkv && ctx, "mhsa_forward: null pointer");
   VLB_REQUIRE(H == heads * D_HEAD, "mhsa: head size must be 64 (H=%d heads=%d)", H, heads);
-  VLB_REQUIRE(S >= 1 && S <= NK, "mhsa: sequence length %d not supported (1..%d)", S, NK);
+  VLB_REQUIRE(S >= 1 && S <= 256, "mhsa: sequence length %d not supported (1..256)", S);
   MhsaParams p{};
   p.B = B; p.S = S; p.H = H; p.heads = heads;
   p.scale = 0.125f;
   p.add_mask = add_mask;
   p.ctx = static_cast<__nv_bfloat16*>(ctx);
   p.lse = lse;
-  CUtensorMap tm;
-  int rc = make_tmap_bf16_2d(&tm, qkv, (uint64_t)B * S, 3 * H, 3 * H, 64, 128);
+  const int nkt = S <= 128 ? 1 : 2;
+  CUtensorMap tq, tkv;
+  int rc = make_tmap_bf16_2d(&tq, qkv, (uint64_t)B * S, 3 * H, 3 * H, 64, 128);
   if (rc != VLB_OK) return rc;
-  static bool attr = false;
-  if (!attr) {
-    VLB_CHECK_CUDA(cudaFuncSetAttribute(mhsa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
-    attr = true;
-  }
+  rc = make_tmap_bf16_2d(&tkv, qkv, (uint64_t)B * S, 3 * H, 3 * H, 64, 128 * nkt);
+  if (rc != VLB_OK) return rc;
   ProfScope prof(PROF_MHSA_FWD, 4.0 * B * heads * (double)S * S * D_HEAD, stream);
-  mhsa_fwd_kernel<<<dim3(heads, B), 128, FWD_SMEM, stream>>>(tm, p);
-  VLB_CHECK_LAUNCH();
-  return VLB_OK;
+  const int qtiles = (S + TQ - 1) / TQ;
+  return nkt == 1 ? launch_fwd<1>(tq, tkv, p, B, heads, qtiles, stream) : launch_fwd<2>(tq, tkv, p, B, heads, qtiles, stream);
 }
 
+int cast_f32_to_bf16(const float* in, void* out, size_t n, cudaStream_t stream);
+
 int mhsa_backward(const void* qkv, const float* add_mask, const void* ctx, const float* lse, const void* dctx, void* dqkv,
-                  int B, int S, int H, int heads, cudaStream_t stream) {
+                  float* scratch_f32, int B, int S, int H, int heads, cudaStream_t stream) {
   VLB_REQUIRE(qkv && ctx && lse && dctx && dqkv, "mhsa_backward: null pointer");
   VLB_REQUIRE(H == heads * D_HEAD, "mhsa: head size must be 64 (H=%d heads=%d)", H, heads);
-  VLB_REQUIRE(S >= 1 && S <= NK, "mhsa: sequence length %d not supported (1..%d)", S, NK);
+  VLB_REQUIRE(S >= 1 && S <= 256, "mhsa: sequence length %d not supported (1..256)", S);
+  const int tiles = (S + TQ - 1) / TQ;
+  VLB_REQUIRE(tiles == 1 || scratch_f32 != nullptr, "mhsa_backward: S > 128 needs the fp32 scratch buffer [B*S, 3H]");
   MhsaParams p{};
   p.B = B; p.S = S; p.H = H; p.heads = heads;
   p.scale = 0.125f;
@@ -417,6 +464,8 @@ int mhsa_backward(const void* qkv, const float* add_mask, const void* ctx, const
   p.lse = const_cast<float*>(lse);
   p.dctx = static_cast<const __nv_bfloat16*>(dctx);
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  p.dqkv_f32 = tiles == 1 ? nullptr : scratch_f32;
+  p.ktiles = tiles;
   CUtensorMap tm, tmd;
   int rc = make_tmap_bf16_2d(&tm, qkv, (uint64_t)B * S, 3 * H, 3 * H, 64, 128);
   if (rc != VLB_OK) return rc;
@@ -427,9 +476,14 @@ int mhsa_backward(const void* qkv, const float* add_mask, const void* ctx, const
     VLB_CHECK_CUDA(cudaFuncSetAttribute(mhsa_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     attr = true;
   }
-  ProfScope prof(PROF_MHSA_BWD, 8.0 * B * heads * (double)S * S * D_HEAD, stream);
-  mhsa_bwd_kernel<<<dim3(heads, B), BWD_THREADS, BWD_SMEM, stream>>>(tm, tmd, p);
-  VLB_CHECK_LAUNCH();
+  const size_t n = (size_t)B * S * 3 * H;
+  if (tiles > 1) VLB_CHECK_CUDA(cudaMemsetAsync(scratch_f32, 0, n * sizeof(float), stream));
+  {
+    ProfScope prof(PROF_MHSA_BWD, 8.0 * B * heads * (double)S * S * D_HEAD, stream);
+    mhsa_bwd_kernel<<<dim3(heads, B, tiles * tiles), BWD_THREADS, BWD_SMEM, stream>>>(tm, tmd, p);
+    VLB_CHECK_LAUNCH();
+  }
+  if (tiles > 1) return cast_f32_to_bf16(scratch_f32, dqkv, n, stream);
   return VLB_OK;
 }
 

@@ -11,7 +11,7 @@ void count_launch(int n);
 int mhsa_forward(const void* qkv, const float* add_mask, void* ctx, float* lse, int B, int S, int H, int heads,
                  cudaStream_t stream);
 int mhsa_backward(const void* qkv, const float* add_mask, const void* ctx, const float* lse, const void* dctx, void* dqkv,
-                  int B, int S, int H, int heads, cudaStream_t stream);
+                  float* scratch_f32, int B, int S, int H, int heads, cudaStream_t stream);
 
 // rowops.cu
 int layernorm_forward(const float* x, int ldx, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean,

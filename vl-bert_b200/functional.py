@@ -121,7 +121,9 @@ def mhsa_forward(qkv, add_mask, B, S, H, heads):
 
 def mhsa_backward(qkv, add_mask, ctx, lse, dctx, B, S, H, heads):
     dqkv = torch.empty((B * S, 3 * H), dtype=BF16, device=qkv.device)
-    _chk(_lib.lib().vlb_mhsa_backward(_p(qkv), _p(add_mask), _p(ctx), _p(lse), _p(dctx), _p(dqkv), B, S, H, heads, _stream()))
+    scratch = torch.empty((B * S, 3 * H), dtype=F32, device=qkv.device) if S > 128 else None
+    _chk(_lib.lib().vlb_mhsa_backward(_p(qkv), _p(add_mask), _p(ctx), _p(lse), _p(dctx), _p(dqkv), _p(scratch), B, S, H, heads,
+                                      _stream()))
     return dqkv
 
 

@@ -177,7 +177,10 @@ class VisualLinguisticBert(BaseModel):
         T, R = text_mask.shape[1], object_mask.shape[1]
         if self.max_length_hint is not None:
             return min(int(self.max_length_hint), T + R + 1)
-        return int((text_mask.sum(1) + object_mask.sum(1)).max().item()) + 1
+        S = int((text_mask.sum(1) + object_mask.sum(1)).max().item()) + 1
+        if S > 256:
+            raise ValueError("vlbert_b200: packed sequence length %d > 256 is not supported by the fused attention" % S)
+        return S
 
     def embedding(self, text_input_ids, text_token_type_ids, text_visual_embeddings, text_mask, object_vl_embeddings,
                   object_mask):
