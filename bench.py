@@ -77,31 +77,52 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons DURING the timed region (NVML, ~10 ms period; nvidia-smi as a fallback)."""
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.rows, self.stop_flag, self.index = [], False, index
+        self.max_mhz = None
 
     def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            while not self.stop_flag:
+                mhz = int(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.rows.append((mhz, [n for b, n in names.items() if mask & b]))
+                time.sleep(0.01)
+            return
+        except Exception:
+            pass
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                c = [x.strip() for x in out.split(",")]
+                if c and c[0].isdigit():
+                    self.max_mhz = int(c[1]) if c[1].isdigit() else self.max_mhz
+                    self.rows.append((int(c[0]), [n for i, n in enumerate(names) if c[2 + i].lower().startswith("active")]))
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"], "samples": 0}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = sorted(set(n for r in self.rows for n in r[1]))
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.rows)}
 
 
 def cpu_baseline(steps=2, warmup=1, batch=8, threads=None):

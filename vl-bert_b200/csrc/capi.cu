@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/vlbert_b200.h"
@@ -59,6 +60,11 @@ ProfScope::ProfScope(int cat, double work, cudaStream_t stream) : idx_(-1), stre
 }
 ProfScope::~ProfScope() {
   if (idx_ >= 0) cudaEventRecord(g_prof[idx_].b, stream_);
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* v = getenv("VLB_PDL"); return v ? atoi(v) != 0 : true; }();
+  return on;
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }

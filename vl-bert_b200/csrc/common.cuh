@@ -37,6 +37,27 @@ int cuda_fail(cudaError_t e, const char* what);
 
 int num_sms();
 
+// Programmatic dependent launch (PDL): kernels of the layer sequence are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization; each kernel calls pdl_trigger() at its very start (the next kernel
+// of the stream may then be scheduled as soon as resources free up and run its prologue: barrier init, TMEM allocation,
+// descriptor prefetch) and pdl_wait() before its first access to global memory (which blocks until the preceding grid has
+// fully completed and flushed).  VLB_PDL=0 disables the attribute (the device-side instructions are then no-ops).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Optional per-launch timing (bench.py's roofline): when enabled through vlb_profile_enable(), launchers bracket their
 // kernel with CUDA events on the launch stream; vlb_profile_collect() sums elapsed time / work per category.
 enum ProfCat : int { PROF_GEMM_NT = 0, PROF_GEMM_NN, PROF_GEMM_TN, PROF_MHSA_FWD, PROF_MHSA_BWD, PROF_LN_FWD, PROF_LN_BWD,
@@ -52,6 +73,9 @@ struct ProfScope {
 // device helpers
 // ----------------------------------------------------------------------------------------------
 #if defined(__CUDACC__)
+
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -236,6 +236,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     if (!GROUPED) {
@@ -261,6 +262,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
   if (CG2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -446,8 +448,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
   }
   if (!CG2) {
     const int grid = p.num_items < num_sms() ? p.num_items : num_sms();
-    gemm_kernel<BN, A_MN, B_MN, EPI, CG2><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
-    VLB_CHECK_LAUNCH();
+    VLB_CHECK_CUDA(launch_pdl(gemm_kernel<BN, A_MN, B_MN, EPI, CG2>, dim3(grid), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, ta, tb, p));
     return VLB_OK;
   }
   const int pairs = num_sms() / 2;
@@ -662,8 +663,7 @@ int launch_grouped(const GroupTable& gt, const GemmParams& p, cudaStream_t strea
     attr_set = true;
   }
   const int grid = p.num_items < num_sms() ? p.num_items : num_sms();
-  gemm_grouped_tn_kernel<BN, EPI><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(gt, p);
-  VLB_CHECK_LAUNCH();
+  VLB_CHECK_CUDA(launch_pdl(gemm_grouped_tn_kernel<BN, EPI>, dim3(grid), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, gt, p));
   return VLB_OK;
 }
 }  // namespace

@@ -104,6 +104,7 @@ mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int t = threadIdx.x, warp = t >> 5;
   const int h = blockIdx.x, b = blockIdx.y, q0 = blockIdx.z * TQ;
   const int row0 = b * p.S;
+  pdl_trigger();
 
   if (t == 0) {
     tma_prefetch_desc(&tm_q);
@@ -117,6 +118,7 @@ mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
     tmem_relinquish();
   }
+  pdl_wait();
   for (int c = t; c < NKEYS; c += 128) {
     float m = -INFINITY;  // keys beyond this sample's sequence (neighbouring sample / out of bounds) never contribute
     if (c < p.S) m = p.add_mask ? p.add_mask[(size_t)b * p.S + c] : 0.0f;
@@ -277,6 +279,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) mhsa_bwd_kernel(const __grid_c
   const int h = blockIdx.x, b = blockIdx.y;
   const int q0 = (blockIdx.z / p.ktiles) * TQ, k0 = (blockIdx.z % p.ktiles) * NK;  // this CTA's (query tile, key tile) block
   const int row0 = b * p.S;
+  pdl_trigger();
   // S [0,128) dP [128,256); once every thread has consumed them: dQ [0,64) dK [64,128) dV [128,192)
   constexpr uint32_t TMEM_COLS = 256;
   constexpr uint32_t T_DQ = 0, T_DK = 64, T_DV = 128;
@@ -293,7 +296,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) mhsa_bwd_kernel(const __grid_c
     tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     tmem_relinquish();
   }
-  
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -420,8 +423,7 @@ static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tkv, const MhsaP
     VLB_CHECK_CUDA(cudaFuncSetAttribute(mhsa_fwd_kernel<NKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr = true;
   }
-  mhsa_fwd_kernel<NKT><<<dim3(heads, B, qtiles), 128, C::SMEM, stream>>>(tq, tkv, p);
-  VLB_CHECK_LAUNCH();
+  VLB_CHECK_CUDA(launch_pdl(mhsa_fwd_kernel<NKT>, dim3(heads, B, qtiles), dim3(128), C::SMEM, stream, tq, tkv, p));
   return VLB_OK;
 }
 
@@ -480,8 +482,7 @@ int mhsa_backward(const void* qkv, const float* add_mask, const void* ctx, const
   if (tiles > 1) VLB_CHECK_CUDA(cudaMemsetAsync(scratch_f32, 0, n * sizeof(float), stream));
   {
     ProfScope prof(PROF_MHSA_BWD, 8.0 * B * heads * (double)S * S * D_HEAD, stream);
-    mhsa_bwd_kernel<<<dim3(heads, B, tiles * tiles), BWD_THREADS, BWD_SMEM, stream>>>(tm, tmd, p);
-    VLB_CHECK_LAUNCH();
+    VLB_CHECK_CUDA(launch_pdl(mhsa_bwd_kernel, dim3(heads, B, tiles * tiles), dim3(BWD_THREADS), BWD_SMEM, stream, tm, tmd, p));
   }
   if (tiles > 1) return cast_f32_to_bf16(scratch_f32, dqkv, n, stream);
   return VLB_OK;

@@ -45,6 +45,8 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   const int nvec = H >> 3;
   const int wstride = gridDim.x * LN_WARPS;
   int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  pdl_trigger();
+  pdl_wait();
   if (row >= M) return;
   RowRaw<ITERS> cur, nxt;
   load_row_f32<ITERS>(cur, x + (size_t)row * ldx, lane, nvec);
@@ -152,6 +154,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = H >> 3;
   const int wstride = gridDim.x * LN_WARPS;
+  pdl_trigger();
+  pdl_wait();
   float gam[ITERS][8];
   float acc_g[ITERS][8], acc_b[ITERS][8], acc_c[ITERS][8];
 #pragma unroll
@@ -271,6 +275,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int ld, float* __restrict__ out, int M, int N, int rows_per_block) {
   __shared__ float red[8][256 + 8];
+  pdl_trigger();
+  pdl_wait();
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + cg * 8;
   const int r0 = blockIdx.y * rows_per_block;
@@ -320,6 +326,8 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float
 
 // many tensors, one launch: descriptor table lives in device memory (grid.y = tensor)
 __global__ void multi_cast_kernel(const VlbCastDesc* __restrict__ descs) {
+  pdl_trigger();
+  pdl_wait();
   const VlbCastDesc d = descs[blockIdx.y];
   const float* in = static_cast<const float*>(d.src);
   const size_t n = (size_t)d.n;
@@ -347,8 +355,7 @@ __global__ void multi_cast_kernel(const VlbCastDesc* __restrict__ descs) {
 int multi_cast(const VlbCastDesc* descs_device, int count, int blocks_per_tensor, cudaStream_t stream) {
   VLB_REQUIRE(descs_device && count > 0, "multi_cast: bad arguments");
   if (blocks_per_tensor < 1) blocks_per_tensor = 16;
-  multi_cast_kernel<<<dim3(blocks_per_tensor, count), 256, 0, stream>>>(descs_device);
-  VLB_CHECK_LAUNCH();
+  VLB_CHECK_CUDA(launch_pdl(multi_cast_kernel, dim3(blocks_per_tensor, count), dim3(256), 0, stream, descs_device));
   return VLB_OK;
 }
 
@@ -372,9 +379,10 @@ int layernorm_forward(const float* x, int ldx, const float* gamma, const float* 
   int grid = (M + LN_WARPS - 1) / LN_WARPS;
   if (grid > num_sms() * 8) grid = num_sms() * 8;
   ProfScope prof(PROF_LN_FWD, (double)M * H * (4.0 + (y_bf16 ? 2.0 : 0.0) + (y_f32 ? 4.0 : 0.0)), stream);
-  VLB_LN_DISPATCH(iters, (layernorm_fwd_kernel<IT><<<grid, LN_WARPS * 32, 0, stream>>>(
-                             x, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, M, H, ldx, eps)));
-  VLB_CHECK_LAUNCH();
+  cudaError_t lerr = cudaSuccess;
+  VLB_LN_DISPATCH(iters, (lerr = launch_pdl(layernorm_fwd_kernel<IT>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, x, gamma, beta,
+                                            static_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, M, H, ldx, eps)));
+  VLB_CHECK_CUDA(lerr);
   return VLB_OK;
 }
 
@@ -392,14 +400,15 @@ int layernorm_backward(const void* dy_bf16, const float* dy_f32, const float* x,
   if (grid > cap) grid = cap;
   ProfScope prof(PROF_LN_BWD, (double)M * H * (4.0 + (dy_bf16 ? 2.0 : 0.0) + (dy_f32 ? 4.0 : 0.0) + (dx_bf16 ? 2.0 : 0.0) + (dx_f32 ? 4.0 : 0.0)), stream);
 #define VLB_LN_BWD(H16, H32)                                                                                    \
-  VLB_LN_DISPATCH(iters, (layernorm_bwd_kernel<IT, H16, H32><<<grid, LN_WARPS * 32, 0, stream>>>(                  \
+  VLB_LN_DISPATCH(iters, (lerr = launch_pdl(layernorm_bwd_kernel<IT, H16, H32>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, \
                              static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, mean, rstd, gamma,             \
                              static_cast<__nv_bfloat16*>(dx_bf16), dx_f32, dgamma, dbeta, dcolsum, M, H, ldx, ld_dx)))
+  cudaError_t lerr = cudaSuccess;
   if (dy_bf16 && dy_f32) { VLB_LN_BWD(true, true) }
   else if (dy_bf16) { VLB_LN_BWD(true, false) }
   else { VLB_LN_BWD(false, true) }
 #undef VLB_LN_BWD
-  VLB_CHECK_LAUNCH();
+  VLB_CHECK_CUDA(lerr);
   return VLB_OK;
 }
 
@@ -412,9 +421,8 @@ int colsum_bf16(const void* x, int ld, float* out, int M, int N, cudaStream_t st
   int rows_per = (M + slabs - 1) / slabs;
   if (rows_per < 32) rows_per = 32;
   slabs = (M + rows_per - 1) / rows_per;
-  colsum_bf16_kernel<<<dim3(col_blocks, slabs), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ld, out, M, N,
-                                                                  rows_per);
-  VLB_CHECK_LAUNCH();
+  VLB_CHECK_CUDA(launch_pdl(colsum_bf16_kernel, dim3(col_blocks, slabs), dim3(256), 0, stream, static_cast<const __nv_bfloat16*>(x), ld,
+                            out, M, N, rows_per));
   return VLB_OK;
 }
 
