@@ -37,7 +37,11 @@ def _worker(rank, world, port, ret):
         ps = [torch.nn.Parameter(torch.zeros(7, 3)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2))]
         ps[0].grad = torch.full((7, 3), float(rank))
         ps[1].grad = torch.full((5,), 10.0 * rank)
+        big = torch.nn.Parameter(torch.zeros(1200, 1000))  # >= 1M elements: reduced in place, not coalesced
+        big.grad = torch.full((1200, 1000), 3.0 * rank)
+        ps.append(big)
         red.reduce_params(ps)  # ps[2] has no grad: skipped
+        ok = ok and torch.allclose(big.grad, torch.full((1200, 1000), 1.5 * (world - 1)))
         ok = ok and torch.allclose(ps[0].grad, torch.full((7, 3), (world - 1) / 2)) and torch.allclose(ps[1].grad, torch.full((5,), 5.0 * (world - 1)))
         ok = ok and ps[2].grad is None
         # gradient equivalence: mean of per-shard gradients == gradient of the mean loss over the concatenated batch

@@ -29,18 +29,27 @@ class LayerGradReducer(object):
                 flat.mul_(1.0 / self.world)
         self.pending = []
 
-    def reduce_params(self, params):
-        """Average the .grad of parameters that are not covered by launch() (embeddings, pooler, heads)."""
+    def reduce_params(self, params, coalesce_below=1 << 20):
+        """Average the .grad of parameters that are not covered by launch() (embeddings, pooler, heads).
+        Large gradients (the dense [vocab, H] word-embedding gradient) are reduced in place; the many small ones are
+        coalesced into one flat buffer (one collective instead of dozens)."""
         gs = [p.grad for p in params if p.grad is not None]
         if not gs:
             return
-        flat = torch.cat([g.reshape(-1) for g in gs])
-        self.launch(flat)
-        self.drain()
-        o = 0
+        small = [g for g in gs if g.numel() < coalesce_below or not g.is_contiguous()]
         for g in gs:
-            g.copy_(flat[o:o + g.numel()].view_as(g))
-            o += g.numel()
+            if g.numel() >= coalesce_below and g.is_contiguous():
+                self.launch(g)
+        flat = None
+        if small:
+            flat = torch.cat([g.reshape(-1) for g in small])
+            self.launch(flat)
+        self.drain()
+        if flat is not None:
+            o = 0
+            for g in small:
+                g.copy_(flat[o:o + g.numel()].view_as(g))
+                o += g.numel()
 
 
 def attach(model, group=None):
