@@ -63,9 +63,10 @@ def test_gemm_modes_against_fp32_matmul(VF, mode, shape, bn):
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("shape", [(256, 256, 64), (6464, 768, 768), (6464, 2304, 768), (264, 3072, 768), (3072, 768, 6464), (1000, 1608, 200)])
-@pytest.mark.parametrize("bn", [1128, 1256])
+@pytest.mark.parametrize("bn", [1128, 1256, 2128, 2256])
 def test_gemm_cta_pair_mode(VF, mode, shape, bn):
-    """cta_group::2: a cluster of two CTAs computes 256 x BN tiles (force_bn = 1000 + BN)."""
+    """Two-CTA cluster modes: force_bn = 1000 + BN -> cta_group::2 pair MMA on 256 x BN tiles; 2000 + BN -> two independent
+    128 x BN tiles sharing a TMA-multicast B tile."""
     M, N, K = shape
     if mode == 2 and M % 8:
         pytest.skip("TN stores A as [K, M]: M must be a multiple of 8")

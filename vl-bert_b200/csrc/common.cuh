@@ -271,6 +271,22 @@ __device__ __forceinline__ void tma_load_2d_cg2(uint32_t smem_dst, const CUtenso
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// TMA load multicast to every CTA of `cta_mask` in the cluster: the tile lands at the same shared-memory offset in each
+// destination CTA and complete_tx is signalled on the mbarrier at the same offset in each of them.
+__device__ __forceinline__ void tma_load_2d_multicast(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,
+                                                      uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+// single-CTA MMA commit that arrives on the mbarrier at the same offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_cg2(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
 }

@@ -84,10 +84,14 @@ __device__ __forceinline__ ItemCoord decode_item(int item, const GemmParams& p, 
   return c;
 }
 
-template <int BN, bool CG2 = false>
+// Cluster modes (CM): 0 = independent CTAs; 1 = CG2 pair MMA (above); 2 = MC2: a cluster of two CTAs works on two
+// vertically adjacent 128 x BN tiles that need the SAME B tile; each CTA fetches one half of it and TMA-multicasts it into
+// both CTAs' shared memory (B crosses the L2->SM fabric once per cluster), the MMAs stay independent cta_group::1.
+template <int BN, int CM = 0>
 struct Cfg {
+  static constexpr bool CG2 = CM == 1;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_ROWS = CG2 ? BN / 2 : BN;   // rows (n) of the B tile this CTA stages
+  static constexpr int B_ROWS = CG2 ? BN / 2 : BN;   // rows (n) of the B tile present in this CTA's shared memory
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = CG2 ? (BN == 256 ? 6 : 8) : ((BN == 256) ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8)));
@@ -216,14 +220,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
   __syncwarp();
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, bool CG2, bool GROUPED>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CM, bool GROUPED>
 __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtensorMap& tma_b, const GemmParams& p,
                                           const GroupTable& gt) {
-  using C = Cfg<BN, CG2>;
-  const uint32_t rank = CG2 ? cluster_ctarank() : 0u;       // CTA rank inside the pair
-  const bool leader = rank == 0;                            // the leader issues the MMAs for both CTAs
-  const int worker = CG2 ? (blockIdx.x >> 1) : blockIdx.x;  // persistent work-loop index (a pair shares it)
-  const int nworkers = CG2 ? (gridDim.x >> 1) : gridDim.x;
+  using C = Cfg<BN, CM>;
+  constexpr bool CG2 = CM == 1;   // pair MMA
+  constexpr bool MC2 = CM == 2;   // independent MMAs, B tile multicast
+  constexpr bool CL = CM != 0;    // any 2-CTA cluster mode
+  const uint32_t rank = CL ? cluster_ctarank() : 0u;        // CTA rank inside the cluster
+  const bool leader = MC2 || rank == 0;                     // CG2: the leader issues the MMAs for both CTAs
+  const int worker = CL ? (blockIdx.x >> 1) : blockIdx.x;   // persistent work-loop index (a cluster shares it)
+  const int nworkers = CL ? (gridDim.x >> 1) : gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* epi_stage = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -246,7 +253,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
 #pragma unroll
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(smem_u32(&full_bar[s]), CG2 ? 2 : 1);   // pair mode: one arrive(+expect_tx) per CTA, on the leader's barrier
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), MC2 ? 2 : 1);  // MC2: the slot is written by both CTAs' multicasts -> both MMAs must release it
     }
     mbar_init(smem_u32(&tfull_bar[0]), 1);
     mbar_init(smem_u32(&tfull_bar[1]), 1);
@@ -259,7 +266,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
     else     { tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
-  if (CG2) cluster_sync_all(); else __syncthreads();
+  if (CL) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only from here on
@@ -273,8 +280,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
         const ItemCoord ic = decode_item<GROUPED>(item, p, gt);
         const CUtensorMap* pta = GROUPED ? &gt.ta[ic.g] : &tma_a;
         const CUtensorMap* ptb = GROUPED ? &gt.tb[ic.g] : &tma_b;
-        const int m0 = (ic.m_blk * (CG2 ? 2 : 1) + (int)rank) * BM;          // this CTA's 128 rows of the (256-row) tile
-        const int n0 = ic.n_blk * BN + (int)rank * (CG2 ? BN / 2 : 0);       // this CTA's half of the B tile
+        const int m0 = (ic.m_blk * (CL ? 2 : 1) + (int)rank) * BM;           // this CTA's 128 rows of the (256-row) super-tile
+        const int n0 = ic.n_blk * BN + (int)rank * (CG2 ? BN / 2 : 0);       // CG2: this CTA's half of the B tile
         const int kb_begin = ic.split * p.kb_per_split;
         const int kb_end = min(p.num_k_blocks, kb_begin + p.kb_per_split);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -296,7 +303,18 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
 #pragma unroll
             for (int c = 0; c < BM / 64; ++c) load(sa + c * 8192, pta, m0 + c * 64, k0);
           }
-          if (!B_MN) {
+          if (MC2) {
+            // this CTA fetches half of the B tile and multicasts it to both CTAs (same smem offset, same barrier offset)
+            if (!B_MN) {
+              tma_load_2d_multicast(sb + rank * (BN / 2) * 128, ptb, fb, k0, n0 + (int)rank * (BN / 2), 3);  // box {64 k, BN/2 rows}
+            } else {
+#pragma unroll
+              for (int c = 0; c < BN / 128; ++c) {
+                const int cc = (int)rank * (BN / 128) + c;
+                tma_load_2d_multicast(sb + cc * 8192, ptb, fb, n0 + cc * 64, k0, 3);
+              }
+            }
+          } else if (!B_MN) {
             load(sb, ptb, k0, n0);  // box {64 k, B_ROWS rows}
           } else {
 #pragma unroll
@@ -335,7 +353,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
             else umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
           }
           // frees the smem slot (in both CTAs of a pair) once these MMAs retire
-          if (CG2) umma_commit_cg2_mc(smem_u32(&empty_bar[stage]), 3); else umma_commit(smem_u32(&empty_bar[stage]));
+          if (CG2) umma_commit_cg2_mc(smem_u32(&empty_bar[stage]), 3);
+          else if (MC2) umma_commit_mc(smem_u32(&empty_bar[stage]), 3);
+          else umma_commit(smem_u32(&empty_bar[stage]));
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
         // accumulator ready for the epilogue warps (of both CTAs)
@@ -358,7 +378,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
       const uint32_t use = static_cast<uint32_t>(it >> 1);
       mbar_wait(smem_u32(&tfull_bar[buf]), use & 1u);
       tc_fence_after();
-      const int row_base = (m_blk * (CG2 ? 2 : 1) + (int)rank) * BM + q * 32;
+      const int row_base = (m_blk * (CL ? 2 : 1) + (int)rank) * BM + q * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
@@ -378,23 +398,23 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
   }
 
   tc_fence_before();
-  if (CG2) cluster_sync_all(); else __syncthreads();   // the peer's shared memory / TMEM must outlive the leader's MMAs
+  if (CL) cluster_sync_all(); else __syncthreads();   // the peer's shared memory / TMEM must outlive everything that targets it
   if (warp == 1) {
     tc_fence_after();
     if (CG2) tmem_dealloc_cg2(tmem_base, C::TMEM_COLS); else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, bool CG2>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CM>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
-  gemm_body<BN, A_MN, B_MN, EPI, CG2, false>(tma_a, tma_b, p, *reinterpret_cast<const GroupTable*>(&tma_a));  // table unused
+  gemm_body<BN, A_MN, B_MN, EPI, CM, false>(tma_a, tma_b, p, *reinterpret_cast<const GroupTable*>(&tma_a));  // table unused
 }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_grouped_tn_kernel(const __grid_constant__ GroupTable gt, const GemmParams p) {
-  gemm_body<BN, true, true, EPI, false, true>(gt.ta[0], gt.tb[0], p, gt);
+  gemm_body<BN, true, true, EPI, 0, true>(gt.ta[0], gt.tb[0], p, gt);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -437,18 +457,18 @@ struct TmapKeyHash {
   }
 };
 
-template <int BN, bool A_MN, bool B_MN, int EPI, bool CG2>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CM>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  using C = Cfg<BN, CG2>;
+  using C = Cfg<BN, CM>;
   static bool attr_set = false;
   if (!attr_set) {
-    VLB_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, A_MN, B_MN, EPI, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VLB_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, A_MN, B_MN, EPI, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         C::SMEM_BYTES));
     attr_set = true;
   }
-  if (!CG2) {
+  if (CM == 0) {
     const int grid = p.num_items < num_sms() ? p.num_items : num_sms();
-    VLB_CHECK_CUDA(launch_pdl(gemm_kernel<BN, A_MN, B_MN, EPI, CG2>, dim3(grid), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, ta, tb, p));
+    VLB_CHECK_CUDA(launch_pdl(gemm_kernel<BN, A_MN, B_MN, EPI, CM>, dim3(grid), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, ta, tb, p));
     return VLB_OK;
   }
   const int pairs = num_sms() / 2;
@@ -458,14 +478,16 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  VLB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, A_MN, B_MN, EPI, CG2>, ta, tb, p));
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  VLB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, A_MN, B_MN, EPI, CM>, ta, tb, p));
   return VLB_OK;
 }
 
@@ -555,14 +577,21 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
   const bool b_mn = (mode != GEMM_NT);
 
   // Tile-N choice: fewest "rounds" of the persistent grid weighted by tile cost.
-  // force_bn: 0 = heuristic; 64/128/192/256 = single-CTA tile width; 1128/1256 = CTA-pair (cta_group::2) 256 x {128,256} tiles.
+  // force_bn: 0 = heuristic; 64/128/192/256 = single-CTA tile width; 1128/1256 = CTA-pair (cta_group::2) 256 x {128,256} tiles;
+  // 2128/2256 = two-CTA clusters with the B tile TMA-multicast (independent 128 x {128,256} MMAs).
   static const int env_bn = [] { const char* v = getenv("VLB_FORCE_BN"); return v ? atoi(v) : 0; }();  // tuning aids
   static const int env_cg2 = [] { const char* v = getenv("VLB_CG2"); return v ? atoi(v) : 0; }();  // 0 off (default: measured ~5% slower in situ), 1 force, -1 auto
+  static const int env_mc2 = [] { const char* v = getenv("VLB_MC2"); return v ? atoi(v) : 0; }();  // 1: B-multicast clusters wherever the tile is 128/256 wide
   if (force_bn == 0 && env_bn != 0 && (N >= (env_bn % 1000) || env_bn == 64)) force_bn = env_bn;
   int bn = 128;
   bool cg2 = false;
+  int cm = 0;
   const int sms = num_sms();
-  if (force_bn >= 1000) {
+  if (force_bn >= 2000) {
+    cm = 2;
+    bn = force_bn - 2000;
+    VLB_REQUIRE(bn == 128 || bn == 256, "gemm: cluster modes support BN 128 / 256");
+  } else if (force_bn >= 1000) {
     cg2 = true;
     bn = force_bn - 1000;
     VLB_REQUIRE(bn == 128 || bn == 256, "gemm: pair mode supports BN 128 / 256");
@@ -595,9 +624,11 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
     }
   }
 
+  if (cg2) cm = 1;
+  if (cm == 0 && env_mc2 == 1 && force_bn == 0 && (bn == 128 || bn == 256)) cm = 2;
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
-  p.num_m_blocks = cg2 ? (M + 2 * BM - 1) / (2 * BM) : (M + BM - 1) / BM;
+  p.num_m_blocks = cm != 0 ? (M + 2 * BM - 1) / (2 * BM) : (M + BM - 1) / BM;
   p.num_n_blocks = (N + bn - 1) / bn;
   p.num_k_blocks = (K + BK - 1) / BK;
   int sk = split_k < 1 ? 1 : split_k;
@@ -622,7 +653,7 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
   if (!a_mn) rc = make_tmap_bf16_2d(&ta, A, M, K, lda, 64, BM);       // A [M, K]
   else       rc = make_tmap_bf16_2d(&ta, A, K, M, lda, 64, 64);       // A stored [K, M]
   if (rc != VLB_OK) return rc;
-  if (!b_mn) rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, 64, cg2 ? bn / 2 : bn);  // B [N, K]
+  if (!b_mn) rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, 64, cm != 0 ? bn / 2 : bn);  // B [N, K]; cluster modes fetch it in halves
   else       rc = make_tmap_bf16_2d(&tb, B, K, N, ldb, 64, 64);       // B stored [K, N]
   if (rc != VLB_OK) return rc;
 
@@ -642,21 +673,25 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
   if (epi_id == EPI_ATOMIC_F32) return launch<BN_, true, true, EPI_ATOMIC_F32, CG_>(ta, tb, p, stream);       \
   return launch<BN_, true, true, EPI_GENERIC, CG_>(ta, tb, p, stream);
   const int epi_id = classify_epilogue(mode, epi_in);
-  if (cg2) {
-    if (bn == 256) { VLB_GEMM_DISPATCH(256, true) }
-    VLB_GEMM_DISPATCH(128, true)
+  if (cm == 1) {
+    if (bn == 256) { VLB_GEMM_DISPATCH(256, 1) }
+    VLB_GEMM_DISPATCH(128, 1)
   }
-  if (bn == 256) { VLB_GEMM_DISPATCH(256, false) }
-  if (bn == 192) { VLB_GEMM_DISPATCH(192, false) }
-  if (bn == 64) { VLB_GEMM_DISPATCH(64, false) }
-  VLB_GEMM_DISPATCH(128, false)
+  if (cm == 2) {
+    if (bn == 256) { VLB_GEMM_DISPATCH(256, 2) }
+    VLB_GEMM_DISPATCH(128, 2)
+  }
+  if (bn == 256) { VLB_GEMM_DISPATCH(256, 0) }
+  if (bn == 192) { VLB_GEMM_DISPATCH(192, 0) }
+  if (bn == 64) { VLB_GEMM_DISPATCH(64, 0) }
+  VLB_GEMM_DISPATCH(128, 0)
 #undef VLB_GEMM_DISPATCH
 }
 
 namespace {
 template <int BN, int EPI>
 int launch_grouped(const GroupTable& gt, const GemmParams& p, cudaStream_t stream) {
-  using C = Cfg<BN, false>;
+  using C = Cfg<BN, 0>;
   static bool attr_set = false;
   if (!attr_set) {
     VLB_CHECK_CUDA(cudaFuncSetAttribute(gemm_grouped_tn_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
