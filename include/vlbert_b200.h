@@ -179,6 +179,36 @@ int vlb_region_operand(const float* boxes, int ld_box, const uint8_t* box_mask, 
                        int ld_info, const int64_t* mvrc_ops, const float* mask_visual_embed, void* A,
                        int32_t* gather_idx, int B, int R, int feat_dim, void* stream);
 
+/* ---- convolution front end (ResNet-101 C4 + res5 RoI head), NHWC bf16 ------------------------------
+ * Replaces the nn.Conv2d / BatchNorm2d(eval, frozen) / ReLU / residual stack of Bottleneck.forward
+ * (common/backbone/resnet/resnet.py:98-118) and the stem (:175-179): a convolution is lowered to vlb_conv_gemm (the
+ * tcgen05 GEMM with the BN scale/shift, residual add and ReLU in its epilogue) on an im2col matrix; 1x1 stride-1
+ * convolutions need no lowering.  col rows are output pixels (n, ho, wo), columns (r, s, c) tap-major, padded to Kp.
+ */
+int vlb_im2col_nhwc(const void* x_bf16, void* col_bf16, int N, int H, int W, int C, int kh, int kw, int stride,
+                    int pad, int dil, int Ho, int Wo, int Kp, void* stream);
+/* adjoint of im2col in gather form (no atomics): dx = col2im(dcol) (+ add, optional bf16 [N,H,W,C]) */
+int vlb_col2im_nhwc(const void* dcol_bf16, const void* add_bf16, void* dx_bf16, int N, int H, int W, int C, int kh,
+                    int kw, int stride, int pad, int dil, int Ho, int Wo, int Kp, void* stream);
+/* y[P,Cout] = act(col[P,K] W[Cout,K]^T * scale[co] + shift[co] (+ resid[P,Cout])); relu_mode 0 none, 1 ReLU,
+ * 2 ReLU after the residual add.  All matrices bf16 row-major; scale/shift f32 [Cout] (shift may be NULL). */
+int vlb_conv_gemm(const void* col, int ld_col, const void* w, int ld_w, void* y, int P, int Cout, int K,
+                  const float* scale, const float* shift, const void* resid, int relu_mode, void* stream);
+/* d_pre = (dy (+ dy2)) * [y_mask > 0] ; d_conv = d_pre * scale[c]  (either output may be NULL; y_mask NULL = no ReLU) */
+int vlb_relu_bn_backward(const void* dy, const void* dy2, const void* y_mask, const float* scale, void* d_pre,
+                         void* d_conv, int64_t rows, int C, void* stream);
+int vlb_maxpool3x3s2_nhwc(const void* x, void* y, int N, int H, int W, int C, void* stream);
+int vlb_avgpool_forward(const void* x_bf16, float* y, int K, int HW, int C, void* stream);
+int vlb_avgpool_backward(const float* dy, void* dx_bf16, int K, int HW, int C, void* stream);
+int vlb_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W, void* stream);
+int vlb_nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, int H, int W, void* stream);
+/* RoIAlign on an NHWC bf16 feature map [N,H,W,C] -> [K,ph,pw,C] bf16 (same sampling rules as vlb_roi_align_forward);
+ * backward accumulates into grad_feat f32 [N,H,W,C] (zero-filled here). */
+int vlb_roi_align_nhwc_forward(const void* feat, const float* rois, void* out, int K, int C, int H, int W, int ph,
+                               int pw, float spatial_scale, int sampling_ratio, void* stream);
+int vlb_roi_align_nhwc_backward(const void* grad_out, const float* rois, float* grad_feat, int K, int N, int C, int H,
+                                int W, int ph, int pw, float spatial_scale, int sampling_ratio, void* stream);
+
 /* ---- one BertLayer, forward and backward -------------------------------------------------------
  * Replaces BertLayer.forward (modeling.py:388-397) = BertAttention + BertIntermediate + BertOutput and
  * its autograd backward, as a fixed sequence of the kernels above on `stream`

@@ -10,6 +10,9 @@ Fixtures (kept small enough to commit):
                          weights are re-generated from a seed by the test (too big to commit);
                          outputs + small gradients + norms of the big gradients are stored.
   fastrcnn_prec.npz      FastRCNN precomputed-feature path (final_dim=32) incl. coordinate embeddings.
+  fastrcnn_e2e.npz       FastRCNN end to end (ResNet-101 C4 + RoIAlign + dilated res5 head, final_dim=64) on 2 images of
+                         128x160: weights are re-generated from a seed (oracle/frontend_oracle.py:synth_frontend_state);
+                         outputs, a slice of body4 and slices + norms of the conv-weight gradients are stored.
   roi_align_debug.npz    common/lib/roi_pooling/debug.py inputs + a 38x63 realistic case through the
                          reference's own CPU kernel (oracle/_ref, built by oracle/build_ref.py).
 """
@@ -193,6 +196,62 @@ def golden_fastrcnn():
     print("fastrcnn_prec: obj_reps", tuple(out["obj_reps"].shape))
 
 
+E2E_GRAD_SLICES = (("obj_downsample.1.bias", None), ("obj_downsample.1.weight", 8),
+                   ("roi_head_feature_extractor.2.conv3.weight", 32), ("roi_head_feature_extractor.0.conv2.weight", 4),
+                   ("roi_head_feature_extractor.0.downsample.0.weight", 16), ("backbone.layer3.22.conv3.weight", 32),
+                   ("backbone.layer3.0.conv2.weight", 8), ("backbone.layer2.0.conv1.weight", None),
+                   ("backbone.layer2.0.conv2.weight", 8), ("backbone.layer2.0.downsample.0.weight", 16))
+
+
+def synth_frontend_inputs(seed, B=2, R=4, H=128, W=160):
+    """Shared with the tests (tests/synth.py:synth_frontend_inputs is call-for-call identical)."""
+    g = torch.Generator().manual_seed(seed)
+    images = torch.randn(B, 3, H, W, generator=g)
+    im_info = torch.tensor([[float(W), float(H), 1.0, 1.0]] * B)
+    x1 = torch.rand(B, R, generator=g) * W * 0.55
+    y1 = torch.rand(B, R, generator=g) * H * 0.55
+    x2 = x1 + 12 + torch.rand(B, R, generator=g) * W * 0.4
+    y2 = y1 + 12 + torch.rand(B, R, generator=g) * H * 0.4
+    boxes = torch.stack((x1, y1, x2.clamp(max=W - 1), y2.clamp(max=H - 1)), -1)
+    box_mask = torch.ones(B, R, dtype=torch.bool)
+    box_mask[1, R - 1:] = False
+    boxes[~box_mask] = -2.0
+    grad_out = torch.randn(B, R, 64, generator=g)
+    return images, boxes, box_mask, im_info, grad_out
+
+
+def golden_fastrcnn_e2e():
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from oracle.frontend_oracle import synth_frontend_state
+    import warnings
+    import torch.utils.model_zoo as model_zoo
+    from easydict import EasyDict
+    model_zoo.load_url = lambda *a, **k: {}          # no network; every tensor is overwritten below
+    from common.fast_rcnn import FastRCNN
+    cfg = EasyDict({"NETWORK": dict(IMAGE_FEAT_PRECOMPUTED=False, IMAGE_SEMANTIC=False, IMAGE_STRIDE_IN_1x1=True, IMAGE_C5_DILATED=True,
+                                    IMAGE_NUM_LAYERS=101, IMAGE_PRETRAINED="", IMAGE_PRETRAINED_EPOCH=0, OUTPUT_CONV5=False,
+                                    IMAGE_FROZEN_BN=True, IMAGE_FROZEN_BACKBONE_STAGES=[1, 2])})
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = FastRCNN(cfg, average_pool=True, final_dim=64, enable_cnn_reg_loss=False)
+    m.load_state_dict(synth_frontend_state({k: v.shape for k, v in m.state_dict().items()}, 77), strict=True)
+    m.eval()                                          # dropout off; BN on its frozen statistics (FastRCNN.bn_eval)
+    images, boxes, box_mask, im_info, gw = synth_frontend_inputs(78)
+    body4 = m.backbone(images)["body4"]
+    out = m(images=images, boxes=boxes, box_mask=box_mask, im_info=im_info)
+    (out["obj_reps"] * gw).sum().backward()
+    params = dict(m.named_parameters())
+    res = dict(obj_reps=out["obj_reps"].detach().numpy(), obj_reps_raw=out["obj_reps_raw"].detach().numpy(),
+               body4_slice=body4.detach()[:, ::8].numpy())
+    for name, rows in E2E_GRAD_SLICES:
+        gfull = params[name].grad
+        res["grad:" + name] = (gfull if rows is None else gfull[:rows]).numpy()
+        res["gnorm:" + name] = np.float64(gfull.double().norm())
+    np.savez_compressed(os.path.join(GOLD, "fastrcnn_e2e.npz"), **res)
+    print("fastrcnn_e2e: obj_reps", tuple(out["obj_reps"].shape), "|raw|", float(out["obj_reps_raw"].abs().mean()),
+          "|body4|", float(body4.abs().mean()))
+
+
 def golden_roi_align():
     import build_ref
     ref = build_ref.load()
@@ -228,6 +287,7 @@ if __name__ == "__main__":
     golden_vlbert_c1()
     golden_pretrain_heads()
     golden_fastrcnn()
+    golden_fastrcnn_e2e()
     golden_roi_align()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)) // 1024, "KiB")

@@ -10,7 +10,8 @@ import torch
 
 import roi_align as roi_oracle
 import vlbert_oracle as vo
-from synth import seeded_state_dict, synth_vlbert_inputs, vlbert_loss
+import frontend_oracle as fo
+from synth import (E2E_GRAD_SLICES, frontend_shapes, seeded_state_dict, synth_frontend_inputs, synth_vlbert_inputs, vlbert_loss)
 
 
 def _close(a, b, rel=2e-5, name=""):
@@ -102,6 +103,28 @@ def test_fastrcnn_precomputed_matches_reference_fixture(golden_dir):
     idx = box_mask.nonzero()
     ce = vo.coordinate_embeddings(torch.cat((boxes.detach()[idx[:, 0], idx[:, 1]][:, :4], im_info[idx[:, 0], :2]), 1))
     _close(ce.numpy(), G["coord_embed"], rel=1e-5)
+
+
+def test_frontend_oracle_matches_reference_fixture(golden_dir):
+    """ResNet-101 C4 + RoIAlign + res5 + projection, forward and backward, against the reference's own run
+    (oracle/make_golden.py:golden_fastrcnn_e2e).  fp32 both sides: 1e-4 of the tensor's max (conv re-association)."""
+    torch.set_num_threads(8)
+    G = np.load(os.path.join(golden_dir, "fastrcnn_e2e.npz"))
+    sd = fo.synth_frontend_state(frontend_shapes(), 77)
+    names = [n for n, _ in E2E_GRAD_SLICES]
+    for n in names:
+        sd[n] = sd[n].clone().requires_grad_(True)
+    images, boxes, box_mask, im_info, gw = synth_frontend_inputs(78)
+    body4 = fo.resnet_c4(sd, images)
+    _close(body4.detach()[:, ::8].numpy(), G["body4_slice"], rel=1e-4, name="body4")
+    obj, raw = fo.fast_rcnn_end2end(sd, images, boxes, box_mask, im_info)
+    _close(obj.detach().numpy(), G["obj_reps"], rel=1e-4, name="obj_reps")
+    _close(raw.detach().numpy(), G["obj_reps_raw"], rel=1e-4, name="raw")
+    (obj * gw).sum().backward()
+    for n, rows in E2E_GRAD_SLICES:
+        g = sd[n].grad
+        _close((g if rows is None else g[:rows]).numpy(), G["grad:" + n], rel=2e-4, name=n)
+        assert abs(float(g.double().norm()) / float(G["gnorm:" + n]) - 1) < 1e-4, n
 
 
 def test_roi_align_c_oracle_matches_reference_cpu_kernel_fixture(golden_dir):

@@ -83,3 +83,36 @@ def test_dropin_install_patches_the_reference_modules():
     import pretrain.modules.resnet_vlbert_for_pretraining as tm
     importlib.reload(tm)
     assert tm.VisualLinguisticBertForPretraining is vlbert_b200.VisualLinguisticBertForPretraining
+
+
+def test_end_to_end_fastrcnn_has_the_reference_checkpoint_abi(monkeypatch):
+    """ResNet-101 C4 + res5 head (common/fast_rcnn.py:36-102): same state_dict keys/shapes and the same trainable set."""
+    ref_shim.install()
+    import vlbert_b200
+    import torch.utils.model_zoo as model_zoo
+    monkeypatch.setattr(model_zoo, "load_url", lambda *a, **k: {})       # no network: the zoo download returns no tensors
+    import warnings
+    import common.backbone.resnet.resnet as ref_resnet
+    import common.fast_rcnn
+    ref_cls = getattr(common.fast_rcnn.FastRCNN, "__wrapped__", None) or _unpatched_fastrcnn()
+    from easydict import EasyDict
+    cfg = EasyDict({"NETWORK": dict(IMAGE_FEAT_PRECOMPUTED=False, IMAGE_SEMANTIC=False, IMAGE_STRIDE_IN_1x1=True, IMAGE_C5_DILATED=True,
+                                    IMAGE_NUM_LAYERS=101, IMAGE_PRETRAINED="", IMAGE_PRETRAINED_EPOCH=0, OUTPUT_CONV5=False,
+                                    IMAGE_FROZEN_BN=True, IMAGE_FROZEN_BACKBONE_STAGES=[1, 2])})
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = ref_cls(cfg, True, 768, True)
+    ours = vlbert_b200.FastRCNN(cfg, True, 768, True)
+    a, b = ref.state_dict(), ours.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(a[k].shape == b[k].shape for k in a)
+    ta = [n for n, p in ref.named_parameters() if p.requires_grad]
+    tb = [n for n, p in ours.named_parameters() if p.requires_grad]
+    assert ta == tb and len(ta) > 0
+    ours.load_state_dict(a, strict=True)
+
+
+def _unpatched_fastrcnn():
+    import importlib
+    import common.fast_rcnn as m
+    return importlib.reload(m).FastRCNN

@@ -59,6 +59,17 @@ def _declare(lib):
     decl("vlb_roi_align_forward", [P, P, P, I, I, I, I, I, I, F, I, P])
     decl("vlb_roi_align_backward", [P, P, P, I, I, I, I, I, I, I, F, I, P])
     decl("vlb_region_operand", [P, I, P, P, I, P, P, P, P, I, I, I, P])
+    decl("vlb_im2col_nhwc", [P, P] + [I] * 12 + [P])
+    decl("vlb_col2im_nhwc", [P, P, P] + [I] * 12 + [P])
+    decl("vlb_conv_gemm", [P, I, P, I, P, I, I, I, P, P, P, I, P])
+    decl("vlb_relu_bn_backward", [P, P, P, P, P, P, L, I, P])
+    decl("vlb_maxpool3x3s2_nhwc", [P, P, I, I, I, I, P])
+    decl("vlb_avgpool_forward", [P, P, I, I, I, P])
+    decl("vlb_avgpool_backward", [P, P, I, I, I, P])
+    decl("vlb_nchw_f32_to_nhwc_bf16", [P, P, I, I, I, I, P])
+    decl("vlb_nhwc_bf16_to_nchw_f32", [P, P, I, I, I, I, P])
+    decl("vlb_roi_align_nhwc_forward", [P, P, P, I, I, I, I, I, I, F, I, P])
+    decl("vlb_roi_align_nhwc_backward", [P, P, P, I, I, I, I, I, I, I, F, I, P])
     decl("vlb_bert_layer_forward", [P, P, P, P, I, I, I, I, I, F, P])
     decl("vlb_bert_layer_backward_workspace", [I, I, I], L)
     decl("vlb_bert_layer_backward", [P, P, P, P, P, P, P, P, P, L, I, I, I, I, I, P])

@@ -204,6 +204,46 @@ int vlb_region_operand(const float* boxes, int ld_box, const uint8_t* box_mask, 
   COUNTED(2, region_operand(boxes, ld_box, box_mask, im_info, ld_info, mvrc_ops, mask_visual_embed, A, gather_idx, B, R,
                             feat_dim, ST));
 }
+int vlb_im2col_nhwc(const void* x, void* col, int N, int H, int W, int C, int kh, int kw, int stride, int pad, int dil, int Ho,
+                    int Wo, int Kp, void* stream) {
+  COUNTED(1, im2col_nhwc(x, col, N, H, W, C, kh, kw, stride, pad, dil, Ho, Wo, Kp, ST));
+}
+int vlb_col2im_nhwc(const void* dcol, const void* add, void* dx, int N, int H, int W, int C, int kh, int kw, int stride, int pad,
+                    int dil, int Ho, int Wo, int Kp, void* stream) {
+  COUNTED(1, col2im_nhwc(dcol, add, dx, N, H, W, C, kh, kw, stride, pad, dil, Ho, Wo, Kp, ST));
+}
+int vlb_conv_gemm(const void* col, int ld_col, const void* w, int ld_w, void* y, int P, int Cout, int K, const float* scale,
+                  const float* shift, const void* resid, int relu_mode, void* stream) {
+  GemmEpilogue e;
+  e.out = y; e.ldo = Cout; e.out_kind = OUT_BF16;
+  e.colscale = scale; e.bias = shift;
+  if (resid) { e.resid = resid; e.ldr = Cout; e.resid_kind = RESID_BF16; }
+  e.act = relu_mode == 1 ? ACT_RELU : (relu_mode == 2 ? ACT_RELU_POST : ACT_NONE);
+  COUNTED(1, gemm_bf16(GEMM_NT, P, Cout, K, col, ld_col, w, ld_w, e, 1, 0, ST));
+}
+int vlb_relu_bn_backward(const void* dy, const void* dy2, const void* y_mask, const float* scale, void* d_pre, void* d_conv,
+                         int64_t rows, int C, void* stream) {
+  COUNTED(1, relu_bn_backward(dy, dy2, y_mask, scale, d_pre, d_conv, rows, C, ST));
+}
+int vlb_maxpool3x3s2_nhwc(const void* x, void* y, int N, int H, int W, int C, void* stream) {
+  COUNTED(1, maxpool3x3s2_nhwc(x, y, N, H, W, C, ST));
+}
+int vlb_avgpool_forward(const void* x, float* y, int K, int HW, int C, void* stream) { COUNTED(1, avgpool_forward(x, y, K, HW, C, ST)); }
+int vlb_avgpool_backward(const float* dy, void* dx, int K, int HW, int C, void* stream) { COUNTED(1, avgpool_backward(dy, dx, K, HW, C, ST)); }
+int vlb_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W, void* stream) {
+  COUNTED(1, nchw_f32_to_nhwc_bf16(x, y, N, C, H, W, ST));
+}
+int vlb_nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, int H, int W, void* stream) {
+  COUNTED(1, nhwc_bf16_to_nchw_f32(x, y, N, C, H, W, ST));
+}
+int vlb_roi_align_nhwc_forward(const void* feat, const float* rois, void* out, int K, int C, int H, int W, int ph, int pw,
+                               float spatial_scale, int sampling_ratio, void* stream) {
+  COUNTED(1, roi_align_nhwc_forward(feat, rois, out, K, C, H, W, ph, pw, spatial_scale, sampling_ratio, ST));
+}
+int vlb_roi_align_nhwc_backward(const void* grad_out, const float* rois, float* grad_feat, int K, int N, int C, int H, int W, int ph,
+                                int pw, float spatial_scale, int sampling_ratio, void* stream) {
+  COUNTED(1, roi_align_nhwc_backward(grad_out, rois, grad_feat, K, N, C, H, W, ph, pw, spatial_scale, sampling_ratio, ST));
+}
 int vlb_bert_layer_forward(const VlbLayerWeights* w, const void* x_bf16, const float* add_mask, const VlbLayerActs* acts, int B,
                            int S, int H, int heads, int I, float eps, void* stream) {
   if (!w || !acts || !x_bf16) { set_last_error("vlb_bert_layer_forward: null pointer"); return VLB_ERR_INVALID; }

@@ -121,6 +121,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
   // ---- phase 0: issue every global load of this chunk up front (8 independent requests per lane in flight) ----
   float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (has_bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+  float4 scale4 = make_float4(e.alpha, e.alpha, e.alpha, e.alpha);
+  if (!T::kStatic && e.colscale != nullptr && col_ok) {
+    const float4 cs = __ldg(reinterpret_cast<const float4*>(e.colscale + col));
+    scale4 = make_float4(cs.x * e.alpha, cs.y * e.alpha, cs.z * e.alpha, cs.w * e.alpha);
+  }
   uint2 in16[8];   // bf16 residual or saved pre-activation
   float4 in32[8];  // fp32 residual (generic path only)
   if (resid_kind == RESID_BF16 || need_aux_in) {
@@ -157,7 +162,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
     const int row = row_base + r;
     const float4 a = reinterpret_cast<const float4*>(stage + r * 32)[g ^ (r & 7)];
     if (row < M && col_ok) {
-      float x[4] = {fmaf(a.x, e.alpha, bias4.x), fmaf(a.y, e.alpha, bias4.y), fmaf(a.z, e.alpha, bias4.z), fmaf(a.w, e.alpha, bias4.w)};
+      float x[4] = {fmaf(a.x, scale4.x, bias4.x), fmaf(a.y, scale4.y, bias4.y), fmaf(a.z, scale4.z, bias4.z), fmaf(a.w, scale4.w, bias4.w)};
       if (act == ACT_GELU) {
         // x = gelu(z); aux receives gelu'(z) (bf16), computed from the same erf / exp -- the backward dgrad epilogue then only
         // multiplies (ACT_DGELU_MUL) instead of re-evaluating erf and exp for every element.
@@ -187,6 +192,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
         x[0] += bf16lo(in16[i].x); x[1] += bf16hi(in16[i].x); x[2] += bf16lo(in16[i].y); x[3] += bf16hi(in16[i].y);
       } else if (resid_kind == RESID_F32) {
         x[0] += in32[i].x; x[1] += in32[i].y; x[2] += in32[i].z; x[3] += in32[i].w;
+      }
+      if (!T::kStatic && act == ACT_RELU_POST) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.0f);
       }
       if (out_kind == OUT_BF16) {
         uint2 o;

@@ -12,6 +12,7 @@ enum GemmAct : int {
   ACT_RELU = 2,
   ACT_DGELU_MUL = 3,  // x = x * aux[row, col]                 (aux: the bf16 gelu' saved by ACT_GELU)
   ACT_DRELU_MUL = 4,  // x = aux[row, col] > 0 ? x : 0         (aux: bf16 post-activation)
+  ACT_RELU_POST = 5,  // ReLU applied AFTER the residual add   (ResNet bottleneck output: relu(bn3(conv3) + identity))
 };
 // Operand layout modes.  "K-major" = reduction dimension contiguous in memory.
 //   GEMM_NT : C[M,N] = A[M,K] * B[N,K]^T      (forward  y = x W^T ; A, B K-major)
@@ -32,6 +33,7 @@ struct GemmEpilogue {
   int ld_aux = 0;
   float alpha = 1.0f;            // scale applied to the accumulator before everything else
   float* colsum = nullptr;       // optional [N] fp32: += column sums of the stored values (bias gradient of the producer)
+  const float* colscale = nullptr;  // optional [N] fp32: x = acc * colscale[col] before the bias (frozen BatchNorm scale)
 };
 
 // All matrices are bf16 row-major with leading dimensions in elements (multiples of 8).

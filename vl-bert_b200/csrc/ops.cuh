@@ -49,4 +49,21 @@ int region_operand(const float* boxes, int ld_box, const uint8_t* box_mask, cons
                    const int64_t* mvrc_ops, const float* mask_visual_embed, void* A, int32_t* gather_idx, int B, int R,
                    int feat_dim, cudaStream_t stream);
 
+// conv.cu
+int im2col_nhwc(const void* x, void* col, int N, int H, int W, int C, int kh, int kw, int stride, int pad, int dil, int Ho, int Wo,
+                int Kp, cudaStream_t stream);
+int col2im_nhwc(const void* dcol, const void* add, void* dx, int N, int H, int W, int C, int kh, int kw, int stride, int pad, int dil,
+                int Ho, int Wo, int Kp, cudaStream_t stream);
+int relu_bn_backward(const void* dy, const void* dy2, const void* y_mask, const float* scale, void* d_pre, void* d_conv, int64_t rows,
+                     int C, cudaStream_t stream);
+int maxpool3x3s2_nhwc(const void* x, void* y, int N, int H, int W, int C, cudaStream_t stream);
+int avgpool_forward(const void* x, float* y, int K, int HW, int C, cudaStream_t stream);
+int avgpool_backward(const float* dy, void* dx, int K, int HW, int C, cudaStream_t stream);
+int nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W, cudaStream_t stream);
+int nhwc_bf16_to_nchw_f32(const void* x, float* y, int N, int C, int H, int W, cudaStream_t stream);
+int roi_align_nhwc_forward(const void* feat, const float* rois, void* out, int K, int C, int H, int W, int ph, int pw, float scale,
+                           int sampling_ratio, cudaStream_t stream);
+int roi_align_nhwc_backward(const void* grad_out, const float* rois, float* grad_feat, int K, int N, int C, int H, int W, int ph, int pw,
+                            float scale, int sampling_ratio, cudaStream_t stream);
+
 }  // namespace vlb

@@ -6,7 +6,7 @@
 
 What gets replaced (reference file:line):
   common.visual_linguistic_bert.VisualLinguisticBert / ...ForPretraining / ...MVRCHeadTransform  (:31, :312, :473)
-  common.fast_rcnn.FastRCNN when NETWORK.IMAGE_FEAT_PRECOMPUTED                                   (common/fast_rcnn.py:17)
+  common.fast_rcnn.FastRCNN (precomputed features, or a Bottleneck ResNet-C4 end to end)          (common/fast_rcnn.py:17)
   common.lib.roi_pooling.C_ROIPooling, common.lib.roi_pooling.roi_align.ROIAlign                  (vision.cpp:6-11)
 """
 import sys
@@ -35,9 +35,9 @@ def install(reference_root=None):
     ref_original = ref_frcnn.FastRCNN
 
     def fast_rcnn_factory(config, *a, **k):
-        if config.NETWORK.IMAGE_FEAT_PRECOMPUTED:
+        if config.NETWORK.IMAGE_FEAT_PRECOMPUTED or config.NETWORK.IMAGE_NUM_LAYERS in (50, 101, 152):
             return M.FastRCNN(config, *a, **k)
-        return ref_original(config, *a, **k)  # ResNet path: reference convs + library RoIAlign (patched above)
+        return ref_original(config, *a, **k)  # BasicBlock backbones: reference convs + library RoIAlign (patched above)
 
     ref_frcnn.FastRCNN = fast_rcnn_factory
     return True

@@ -478,6 +478,8 @@ class RegionFn(torch.autograd.Function):
         d_w._vlb_accumulate = True
         gemm(2, dY, A, d_w, split_k=max(1, min(16, (B * R) // 256)))
         # gradient wrt the feature half of boxes (the coordinate half is not propagated: the reference's boxes are data)
+        if not ctx.needs_input_grad[0]:
+            return None, d_w, d_bias, None, None
         d_boxes = torch.zeros((B * R, C), dtype=F32, device=dev)
         d_feat = torch.empty((B * R, Fd), dtype=BF16, device=dev)
         gemm(1, dY, w16[:, 2048:], d_feat, M=B * R, N=Fd, K=D)
@@ -523,3 +525,160 @@ def roi_align_backward(grad, rois, spatial_scale, pooled_h, pooled_w, batch_size
     _chk(_lib.lib().vlb_roi_align_backward(_p(g), _p(r), _p(gin), r.shape[0], batch_size, channels, height, width, pooled_h,
                                            pooled_w, float(spatial_scale), int(sampling_ratio), _stream()))
     return gin
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution front end (NHWC bf16): conv + frozen BatchNorm + ReLU (+ residual) on the tcgen05 GEMM
+# ------------------------------------------------------------------------------------------------
+def _conv_out(n, k, stride, pad, dil):
+    return (n + 2 * pad - dil * (k - 1) - 1) // stride + 1
+
+
+def weight_to_gemm(weight, Kp=None):
+    """[Cout, Cin, kh, kw] fp32 -> bf16 [Cout, Kp] with columns ordered (r, s, c) like the im2col rows."""
+    Cout = weight.shape[0]
+    w = weight.detach().permute(0, 2, 3, 1).reshape(Cout, -1)
+    K = w.shape[1]
+    Kp = Kp or _align(K, 8)
+    if Kp != K:
+        w = torch.nn.functional.pad(w, (0, Kp - K))
+    return w.to(BF16).contiguous()
+
+
+def _im2col(x, kh, kw, stride, pad, dil, Ho, Wo, Kp):
+    N, H, W, C = x.shape
+    col = torch.empty((N * Ho * Wo, Kp), dtype=BF16, device=x.device)
+    _chk(_lib.lib().vlb_im2col_nhwc(_p(x), _p(col), N, H, W, C, kh, kw, stride, pad, dil, Ho, Wo, Kp, _stream()))
+    return col
+
+
+class ConvBnActFn(torch.autograd.Function):
+    """y = act(conv(x, weight) * scale + shift (+ resid)) in NHWC bf16.
+    relu_mode: 0 none, 1 ReLU, 2 ReLU after the residual add (Bottleneck output, resnet.py:110-116).
+    scale/shift are the constants of a frozen eval-mode BatchNorm (no gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, scale, shift, resid, stride, pad, dil, relu_mode, w16):
+        _require_cuda(x, weight, scale)
+        N, H, W, C = x.shape
+        Cout, Cin, kh, kw = weight.shape
+        assert Cin == C and x.dtype == BF16 and x.is_contiguous()
+        Ho, Wo = _conv_out(H, kh, stride, pad, dil), _conv_out(W, kw, stride, pad, dil)
+        K = kh * kw * C
+        Kp = _align(K, 8)
+        if w16 is None:
+            w16 = weight_to_gemm(weight, Kp)
+        direct = (kh == 1 and kw == 1 and stride == 1 and pad == 0)
+        col = x.view(N * H * W, C) if direct else _im2col(x, kh, kw, stride, pad, dil, Ho, Wo, Kp)
+        P = N * Ho * Wo
+        y = torch.empty((N, Ho, Wo, Cout), dtype=BF16, device=x.device)
+        r = None if resid is None else resid.contiguous()
+        _chk(_lib.lib().vlb_conv_gemm(_p(col), col.stride(0), _p(w16), w16.stride(0), _p(y), P, Cout, Kp, _p(scale), _p(shift),
+                                      _p(r), int(relu_mode), _stream()))
+        ctx.save_for_backward(x, w16, y if relu_mode else None, scale)
+        ctx.geom = (N, H, W, C, Cout, kh, kw, stride, pad, dil, Ho, Wo, Kp, direct, relu_mode, resid is not None)
+        ctx.wshape = tuple(weight.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w16, y, scale = ctx.saved_tensors
+        N, H, W, C, Cout, kh, kw, stride, pad, dil, Ho, Wo, Kp, direct, relu_mode, has_resid = ctx.geom
+        lib = _lib.lib()
+        st = _stream()
+        dev = x.device
+        P = N * Ho * Wo
+        dy = dy.contiguous()
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        need_r = has_resid and ctx.needs_input_grad[4]
+        d_pre = torch.empty_like(dy) if need_r else None
+        d_conv = torch.empty_like(dy)
+        _chk(lib.vlb_relu_bn_backward(_p(dy), None, _p(y) if relu_mode else None, _p(scale), _p(d_pre), _p(d_conv), P, Cout, st))
+        dconv2 = d_conv.view(P, Cout)
+        dx = dw = None
+        if need_w:
+            col = x.view(P, C) if direct else _im2col(x, kh, kw, stride, pad, dil, Ho, Wo, Kp)
+            dwk = torch.zeros((Cout, Kp), dtype=F32, device=dev)
+            dwk._vlb_accumulate = True
+            tiles = ((Cout + 127) // 128) * ((Kp + 255) // 256)
+            split = max(1, min(16, 148 // max(1, tiles), (P + 63) // 64))
+            gemm(2, dconv2, col, dwk, split_k=split)
+            dw = dwk[:, :kh * kw * C].view(Cout, kh, kw, C).permute(0, 3, 1, 2).contiguous()
+        if need_x:
+            dcol = torch.empty((P, Kp), dtype=BF16, device=dev)
+            gemm(1, dconv2, w16, dcol)
+            if direct:
+                dx = dcol.view(N, H, W, C)
+            else:
+                dx = torch.empty((N, H, W, C), dtype=BF16, device=dev)
+                _chk(lib.vlb_col2im_nhwc(_p(dcol), None, _p(dx), N, H, W, C, kh, kw, stride, pad, dil, Ho, Wo, Kp, st))
+        return dx, dw, None, None, d_pre, None, None, None, None, None
+
+
+def conv_bn_act(x, weight, scale, shift, resid=None, stride=1, pad=0, dil=1, relu_mode=1, w16=None):
+    return ConvBnActFn.apply(x, weight, scale, shift, resid, stride, pad, dil, relu_mode, w16)
+
+
+def maxpool3x3s2(x):
+    N, H, W, C = x.shape
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    y = torch.empty((N, Ho, Wo, C), dtype=BF16, device=x.device)
+    _chk(_lib.lib().vlb_maxpool3x3s2_nhwc(_p(x), _p(y), N, H, W, C, _stream()))
+    return y
+
+
+def nchw_to_nhwc_bf16(x):
+    N, C, H, W = x.shape
+    y = torch.empty((N, H, W, C), dtype=BF16, device=x.device)
+    _chk(_lib.lib().vlb_nchw_f32_to_nhwc_bf16(_p(x.contiguous().float()), _p(y), N, C, H, W, _stream()))
+    return y
+
+
+def nhwc_to_nchw_f32(x):
+    N, H, W, C = x.shape
+    y = torch.empty((N, C, H, W), dtype=F32, device=x.device)
+    _chk(_lib.lib().vlb_nhwc_bf16_to_nchw_f32(_p(x.contiguous()), _p(y), N, C, H, W, _stream()))
+    return y
+
+
+class AvgPoolFn(torch.autograd.Function):
+    """mean over the spatial positions: bf16 [K, h, w, C] -> f32 [K, C]  (AvgPool2d + Flattener, common/fast_rcnn.py:80-84)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        K, h, w, C = x.shape
+        y = torch.empty((K, C), dtype=F32, device=x.device)
+        _chk(_lib.lib().vlb_avgpool_forward(_p(x.contiguous()), _p(y), K, h * w, C, _stream()))
+        ctx.shape = (K, h, w, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        K, h, w, C = ctx.shape
+        dx = torch.empty((K, h, w, C), dtype=BF16, device=dy.device)
+        _chk(_lib.lib().vlb_avgpool_backward(_p(dy.contiguous().float()), _p(dx), K, h * w, C, _stream()))
+        return dx
+
+
+class RoIAlignNHWCFn(torch.autograd.Function):
+    """RoIAlign on an NHWC bf16 feature map (same sampling rules as the reference op) -> bf16 [K, ph, pw, C]."""
+
+    @staticmethod
+    def forward(ctx, feat, rois, ph, pw, spatial_scale, sampling_ratio):
+        N, H, W, C = feat.shape
+        r = rois.contiguous().float()
+        K = r.shape[0]
+        out = torch.empty((K, ph, pw, C), dtype=BF16, device=feat.device)
+        _chk(_lib.lib().vlb_roi_align_nhwc_forward(_p(feat.contiguous()), _p(r), _p(out), K, C, H, W, ph, pw, float(spatial_scale),
+                                                   int(sampling_ratio), _stream()))
+        ctx.save_for_backward(r)
+        ctx.cfg = (N, H, W, C, ph, pw, float(spatial_scale), int(sampling_ratio))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (r,) = ctx.saved_tensors
+        N, H, W, C, ph, pw, scale, sr = ctx.cfg
+        gf = torch.empty((N, H, W, C), dtype=F32, device=g.device)
+        _chk(_lib.lib().vlb_roi_align_nhwc_backward(_p(g.contiguous()), _p(r), _p(gf), r.shape[0], N, C, H, W, ph, pw, scale, sr, _stream()))
+        return gf.to(BF16), None, None, None, None, None

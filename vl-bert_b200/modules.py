@@ -410,10 +410,24 @@ C_ROIPooling = types.SimpleNamespace(roi_align_forward=VF.roi_align_forward, roi
                                      roi_pool_forward=_roi_pool_unavailable, roi_pool_backward=_roi_pool_unavailable)
 
 
+class Flattener(nn.Module):
+    """common/utils/flatten.py:4-13 (parameter-free; kept so `head.*` state_dict keys match the reference)"""
+
+    def forward(self, x):
+        return x.view(x.size(0), -1)
+
+
+_RESNET_LAYERS = {50: (3, 4, 6), 101: (3, 4, 23), 152: (3, 8, 36)}
+
+
 class FastRCNN(nn.Module):
-    """common/fast_rcnn.py:17-203.  The precomputed-feature path (IMAGE_FEAT_PRECOMPUTED, BASELINE configs 1-4) runs
-    entirely on the library; the end-to-end path keeps the ResNet-101 C4 / res5 convolutions on torch (cuDNN) for now and
-    uses the library's RoIAlign and region projection (conv rows K13/K14 are the next widening)."""
+    """common/fast_rcnn.py:17-203.  Both paths run on the library: the precomputed-feature path
+    (IMAGE_FEAT_PRECOMPUTED, BASELINE configs 1-4) is region-operand + one GEMM; the end-to-end path (config 5) is
+    ResNet-C4 (NHWC bf16, frozen BN folded into the conv GEMM epilogue) -> RoIAlign 14x14 @ 1/16 -> dilated res5 head ->
+    mean pool -> the same region projection.
+
+    `compact_rois` (default True) gathers the valid boxes with one host sync like the reference (`box_mask.nonzero()`,
+    :135); set it False to run every [B, R] slot with static shapes (no sync; padded slots are computed and discarded)."""
 
     def __init__(self, config, average_pool=True, final_dim=768, enable_cnn_reg_loss=False):
         super().__init__()
@@ -421,12 +435,54 @@ class FastRCNN(nn.Module):
         self.enable_cnn_reg_loss = enable_cnn_reg_loss
         self.final_dim = final_dim
         self.image_feat_precomputed = config.NETWORK.IMAGE_FEAT_PRECOMPUTED
+        self.compact_rois = True
         if config.NETWORK.IMAGE_SEMANTIC:
             raise ValueError("vlbert_b200: IMAGE_SEMANTIC (object class embedding) is not implemented")
         self.object_embed = None
         if not self.image_feat_precomputed:
-            raise NotImplementedError("vlbert_b200: the end-to-end ResNet path is assembled by vlbert_b200.dropin "
-                                      "(reference backbone + library RoIAlign); construct the reference FastRCNN there")
+            from .resnet import ResNetC4, make_layer
+            self.stride_in_1x1 = config.NETWORK.IMAGE_STRIDE_IN_1x1
+            self.c5_dilated = config.NETWORK.IMAGE_C5_DILATED
+            self.num_layers = config.NETWORK.IMAGE_NUM_LAYERS
+            self.pretrained_model_path = '{}-{:04d}.model'.format(
+                config.NETWORK.IMAGE_PRETRAINED, config.NETWORK.IMAGE_PRETRAINED_EPOCH) if config.NETWORK.IMAGE_PRETRAINED != '' else None
+            self.output_conv5 = config.NETWORK.OUTPUT_CONV5
+            if self.output_conv5:
+                raise NotImplementedError("vlbert_b200: OUTPUT_CONV5 is not implemented (false in every reference cfg)")
+            if self.num_layers not in _RESNET_LAYERS:
+                raise NotImplementedError("vlbert_b200: only Bottleneck backbones (50/101/152) are implemented")
+            if not average_pool:
+                raise NotImplementedError("vlbert_b200: average_pool=False is not implemented")
+            self.backbone = ResNetC4(_RESNET_LAYERS[self.num_layers], stride_in_1x1=self.stride_in_1x1)
+            if self.pretrained_model_path is not None:
+                import os
+                if os.path.exists(self.pretrained_model_path):
+                    sd = torch.load(self.pretrained_model_path, map_location="cpu")
+                    own = self.backbone.state_dict()
+                    self.backbone.load_state_dict({k: sd.get(k, v) for k, v in own.items()})
+            self.mask_upsample = None
+            self.roi_head_feature_extractor, _ = make_layer(self.backbone.inplanes, 512, 3,
+                                                            stride=2 if not self.c5_dilated else 1,
+                                                            dilation=1 if not self.c5_dilated else 2,
+                                                            stride_in_1x1=self.stride_in_1x1)
+            for m in self.roi_head_feature_extractor.modules():
+                if isinstance(m, nn.Conv2d):
+                    nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            self.head = torch.nn.Sequential(self.roi_head_feature_extractor,
+                                            nn.AvgPool2d(7 if not self.c5_dilated else 14, stride=1), Flattener())
+            if config.NETWORK.IMAGE_FROZEN_BN:
+                for m in self.roi_head_feature_extractor.modules():
+                    if isinstance(m, nn.BatchNorm2d):
+                        for p in m.parameters():
+                            p.requires_grad = False
+            frozen_stages = list(config.NETWORK.IMAGE_FROZEN_BACKBONE_STAGES)
+            if 5 in frozen_stages:
+                for p in self.roi_head_feature_extractor.parameters():
+                    p.requires_grad = False
+                frozen_stages = [s for s in frozen_stages if s != 5]
+            self.backbone.frozen_parameters(frozen_stages=frozen_stages, frozen_bn=config.NETWORK.IMAGE_FROZEN_BN)
+            if self.enable_cnn_reg_loss:
+                self.regularizing_predictor = torch.nn.Linear(2048, 81)
         self.obj_downsample = torch.nn.Sequential(
             torch.nn.Dropout(p=0.1),
             torch.nn.Linear(2 * 2048, final_dim),
@@ -434,22 +490,69 @@ class FastRCNN(nn.Module):
         )
 
     def init_weight(self):
-        pass
+        """common/fast_rcnn.py:111-120: the res5 head starts from the checkpoint's layer4.* (no model-zoo download here)."""
+        if not self.image_feat_precomputed and self.pretrained_model_path is not None:
+            sd = torch.load(self.pretrained_model_path, map_location="cpu")
+            self.roi_head_feature_extractor.load_state_dict({k[len("layer4."):]: v for k, v in sd.items() if k.startswith("layer4.")})
 
     def bn_eval(self):
-        pass
+        if not self.image_feat_precomputed:
+            for m in self.modules():
+                if isinstance(m, nn.BatchNorm2d):
+                    m.eval()
+
+    def _region_features(self, images, boxes, box_mask, segms):
+        """images -> per-slot res5 features f32 [B, R, 2048] (zeros in invalid slots); common/fast_rcnn.py:143-158"""
+        if segms is not None:
+            raise NotImplementedError("vlbert_b200: segms (mask-weighted pooling) is not implemented")
+        B, R = box_mask.shape
+        feat = self.backbone(images)["body4"]
+        b4 = boxes[:, :, :4].float()
+        if self.compact_rois:
+            inds = box_mask.nonzero()
+            assert inds.shape[0] > 0
+            rois = torch.cat((inds[:, 0, None].float(), b4[inds[:, 0], inds[:, 1]]), 1)
+        else:
+            inds = None
+            bidx = torch.arange(B, device=boxes.device, dtype=torch.float32).view(B, 1, 1).expand(B, R, 1)
+            rois = torch.cat((bidx, b4), 2).view(B * R, 5)
+        pooled = VF.RoIAlignNHWCFn.apply(feat, rois, 14, 14, 1.0 / 16, 1)          # ROIAlign(sampling_ratio=1), roi_align.py:51
+        x = self.roi_head_feature_extractor(pooled)
+        if x.shape[1] != (7 if not self.c5_dilated else 14):
+            raise NotImplementedError("vlbert_b200: AvgPool2d window must cover the whole res5 map")
+        post = VF.AvgPoolFn.apply(x)                                              # [K, 2048] f32
+        if inds is None:
+            return post.view(B, R, -1), post, None
+        full = post.new_zeros((B, R, post.shape[1]))
+        full = full.index_put((inds[:, 0], inds[:, 1]), post)
+        return full, post, inds
 
     def forward(self, images, boxes, box_mask, im_info, classes=None, segms=None, mvrc_ops=None, mask_visual_embed=None):
-        if classes is not None or segms is not None:
-            raise NotImplementedError("vlbert_b200: classes/segms inputs are not implemented on the precomputed path")
         if self.training and self.obj_downsample[0].p > 0 and not getattr(self, "_warned", False):
             import warnings
             warnings.warn("vlbert_b200: obj_downsample dropout is not implemented on the fused path; running with p = 0")
             self._warned = True
         lin = self.obj_downsample[1]
+        extra = {}
+        if self.image_feat_precomputed:
+            if segms is not None:
+                raise NotImplementedError("vlbert_b200: segms input is not implemented on the precomputed path")
+            feats = boxes[:, :, 4:]
+        else:
+            feats, post, inds = self._region_features(images, boxes, box_mask, segms)
+            if self.enable_cnn_reg_loss:
+                if inds is None:
+                    inds = box_mask.nonzero()
+                    post = feats[inds[:, 0], inds[:, 1]]
+                obj_labels = classes[inds[:, 0], inds[:, 1]].type(torch.long)
+                obj_logits = self.regularizing_predictor(post)
+                extra = {"obj_logits": obj_logits, "obj_labels": obj_labels,
+                         "cnn_regularization_loss": F.cross_entropy(obj_logits, obj_labels)[None]}
         if mvrc_ops is not None and mask_visual_embed is not None:
-            feats = boxes[:, :, 4:].clone()
+            feats = feats.clone()
             feats[mvrc_ops == 1] = mask_visual_embed
-            boxes = torch.cat((boxes[:, :, :4], feats), -1)
-        obj_reps, raw = VF.RegionFn.apply(boxes, lin.weight, lin.bias, box_mask, im_info)
-        return {"obj_reps_raw": raw, "obj_reps": obj_reps}
+        packed = torch.cat((boxes[:, :, :4].to(feats.dtype), feats), -1)
+        obj_reps, raw = VF.RegionFn.apply(packed, lin.weight, lin.bias, box_mask, im_info)
+        out = {"obj_reps_raw": raw, "obj_reps": obj_reps}
+        out.update(extra)
+        return out
