@@ -253,7 +253,7 @@ def main():
     barrier()
     lib.vlb_profile_enable(0)
     import ctypes
-    pms, pwork, pcnt = (ctypes.c_double * 8)(), (ctypes.c_double * 8)(), (ctypes.c_int64 * 8)()
+    pms, pwork, pcnt = (ctypes.c_double * 12)(), (ctypes.c_double * 12)(), (ctypes.c_int64 * 12)()
     vlbert_b200._lib.check(lib.vlb_profile_collect(pms, pwork, pcnt))
 
     # ---------------- device-resident arm ----------------

@@ -40,8 +40,10 @@ int64_t vlb_launch_count(void);
 
 /* Per-launch device timing for bench.py's roofline.  While enabled, GEMM / attention / LayerNorm launchers bracket
  * their kernel with CUDA events on the launch stream.  vlb_profile_collect() waits for the recorded events and
- * returns, per category (0 gemm NT, 1 gemm NN, 2 gemm TN, 3 mhsa fwd, 4 mhsa bwd, 5 LN fwd, 6 LN bwd, 7 other; arrays
- * of 8), the summed milliseconds, algorithmic work (FLOPs for 0-4, bytes for 5-6) and launch count, then resets. */
+ * returns, per category (0 gemm NT, 1 gemm NN, 2 gemm TN, 3 mhsa fwd, 4 mhsa bwd, 5 LN fwd, 6 LN bwd, 7 other, 8 im2col,
+ * 9 col2im, 10 conv elementwise backward, 11 NHWC RoIAlign; arrays of VLB_PROFILE_CATEGORIES = 12), the summed
+ * milliseconds, algorithmic work (FLOPs for 0-4, bytes for 5-6 and 8-11) and launch count, then resets. */
+#define VLB_PROFILE_CATEGORIES 12
 void vlb_profile_enable(int on);
 int vlb_profile_collect(double* ms, double* work, int64_t* launches);
 

@@ -13,6 +13,13 @@ It is a function of a reference-format state_dict (keys `backbone.*`, `roi_head_
 oracle/make_golden.py wrote from the reference.  BatchNorm is the eval-mode (frozen statistics) map, the
 only mode the reference runs the backbone in (common/fast_rcnn.py:122-126, FastRCNN.bn_eval).
 
+`storage="bf16"` evaluates the same fp32 graph but rounds every tensor the CUDA path keeps in bf16 (images, conv
+weights, each conv+BN(+ReLU) output, RoIAlign output, the region operand and the projection) to bf16, forward and
+backward (straight-through).  ReLU networks amplify forward rounding into gradient error (a pre-activation within
+rounding distance of 0 flips its mask and moves that element's gradient by 100%: relative L2 error ~ sqrt(fraction
+flipped)), so the fp32 graph bounds the CUDA path's gradients only loosely; the bf16-storage graph has the same masks
+and bounds them tightly.  tests/test_gpu_frontend.py uses both.
+
 Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this module.
 """
 import numpy as np
@@ -29,37 +36,55 @@ except ImportError:  # tests put oracle/ itself on sys.path
 LAYERS = {50: (3, 4, 6), 101: (3, 4, 23), 152: (3, 8, 36)}
 
 
+class _RoundBF16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).float()
+
+
+def _q(storage):
+    if storage is None:
+        return lambda t: t
+    assert storage == "bf16"
+    return _RoundBF16.apply
+
+
 def _bn(sd, prefix, x, eps=1e-5):
     return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"], sd[prefix + ".weight"], sd[prefix + ".bias"],
                         False, 0.0, eps)
 
 
-def bottleneck(sd, prefix, x, stride, dilation, stride_in_1x1):
+def bottleneck(sd, prefix, x, stride, dilation, stride_in_1x1, storage=None):
     """resnet.py:79-118.  `stride` applies to conv1 when stride_in_1x1 else to conv2; the downsample conv takes it too."""
+    q = _q(storage)
     s1, s2 = (stride, 1) if stride_in_1x1 else (1, stride)
-    o = torch.relu(_bn(sd, prefix + ".bn1", F.conv2d(x, sd[prefix + ".conv1.weight"], stride=s1)))
-    o = torch.relu(_bn(sd, prefix + ".bn2", F.conv2d(o, sd[prefix + ".conv2.weight"], stride=s2, padding=dilation, dilation=dilation)))
-    o = _bn(sd, prefix + ".bn3", F.conv2d(o, sd[prefix + ".conv3.weight"]))
+    o = q(torch.relu(_bn(sd, prefix + ".bn1", F.conv2d(x, q(sd[prefix + ".conv1.weight"]), stride=s1))))
+    o = q(torch.relu(_bn(sd, prefix + ".bn2", F.conv2d(o, q(sd[prefix + ".conv2.weight"]), stride=s2, padding=dilation, dilation=dilation))))
+    o = _bn(sd, prefix + ".bn3", F.conv2d(o, q(sd[prefix + ".conv3.weight"])))
     if prefix + ".downsample.0.weight" in sd:
-        x = _bn(sd, prefix + ".downsample.1", F.conv2d(x, sd[prefix + ".downsample.0.weight"], stride=stride))
-    return torch.relu(o + x)
+        x = q(_bn(sd, prefix + ".downsample.1", F.conv2d(x, q(sd[prefix + ".downsample.0.weight"]), stride=stride)))
+    return q(torch.relu(o + x))
 
 
-def res_layer(sd, prefix, x, blocks, stride, dilation, stride_in_1x1):
+def res_layer(sd, prefix, x, blocks, stride, dilation, stride_in_1x1, storage=None):
     """resnet.py:158-173: the first block carries the stride (and stride_in_1x1); the rest are stride 1."""
-    x = bottleneck(sd, prefix + ".0", x, stride, dilation, stride_in_1x1)
+    x = bottleneck(sd, prefix + ".0", x, stride, dilation, stride_in_1x1, storage)
     for i in range(1, blocks):
-        x = bottleneck(sd, "%s.%d" % (prefix, i), x, 1, dilation, False)
+        x = bottleneck(sd, "%s.%d" % (prefix, i), x, 1, dilation, False, storage)
     return x
 
 
-def resnet_c4(sd, images, layers=(3, 4, 23), stride_in_1x1=True, prefix="backbone", frozen_front=True):
-    """resnet.py:175-186 up to body4.  conv1/bn1/layer1 are frozen in every reference cfg (IMAGE_FROZEN_BACKBONE_STAGES
-    [1, 2]); `frozen_front` only detaches nothing -- gradients there are simply never requested."""
-    x = torch.relu(_bn(sd, prefix + ".bn1", F.conv2d(images, sd[prefix + ".conv1.weight"], stride=2, padding=3)))
+def resnet_c4(sd, images, layers=(3, 4, 23), stride_in_1x1=True, prefix="backbone", storage=None):
+    """resnet.py:175-186 up to body4."""
+    q = _q(storage)
+    x = q(torch.relu(_bn(sd, prefix + ".bn1", F.conv2d(q(images), q(sd[prefix + ".conv1.weight"]), stride=2, padding=3))))
     x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
     for i, (blocks, stride) in enumerate(zip(layers, (1, 2, 2))):
-        x = res_layer(sd, "%s.layer%d" % (prefix, i + 1), x, blocks, stride, 1, stride_in_1x1)
+        x = res_layer(sd, "%s.layer%d" % (prefix, i + 1), x, blocks, stride, 1, stride_in_1x1, storage)
     return x
 
 
@@ -81,21 +106,23 @@ class _RoIAlign(torch.autograd.Function):
 
 
 def fast_rcnn_end2end(sd, images, boxes, box_mask, im_info, layers=(3, 4, 23), stride_in_1x1=True, c5_dilated=True,
-                      mvrc_ops=None, mask_visual_embed=None):
+                      mvrc_ops=None, mask_visual_embed=None, storage=None):
     """common/fast_rcnn.py:128-193 (no classes / segms, dropout p = 0).  Returns obj_reps [B,R,D], obj_reps_raw [B,R,2048]."""
+    q = _q(storage)
     B, R = box_mask.shape
     idx = box_mask.nonzero()
-    feat = resnet_c4(sd, images, layers, stride_in_1x1)
+    feat = resnet_c4(sd, images, layers, stride_in_1x1, storage=storage)
     rois = torch.cat((idx[:, 0, None].to(boxes.dtype), boxes[idx[:, 0], idx[:, 1]][:, :4]), 1)
-    pooled = _RoIAlign.apply(feat, rois, 14, 14, 1.0 / 16, 1)
-    x = res_layer(sd, "roi_head_feature_extractor", pooled, 3, 1 if c5_dilated else 2, 2 if c5_dilated else 1, stride_in_1x1)
+    pooled = q(_RoIAlign.apply(feat, rois, 14, 14, 1.0 / 16, 1))
+    x = res_layer(sd, "roi_head_feature_extractor", pooled, 3, 1 if c5_dilated else 2, 2 if c5_dilated else 1, stride_in_1x1, storage)
     post = F.avg_pool2d(x, 14 if c5_dilated else 7, stride=1).flatten(1)
     feats = post
     if mvrc_ops is not None and mask_visual_embed is not None:
         feats = feats.clone()
         feats[(mvrc_ops == 1)[idx[:, 0], idx[:, 1]]] = mask_visual_embed
     ce = coordinate_embeddings(torch.cat((boxes[idx[:, 0], idx[:, 1]][:, :4], im_info[idx[:, 0], :2]), 1), 256)
-    final = torch.relu(F.linear(torch.cat((ce.reshape(ce.shape[0], -1), feats), -1), sd["obj_downsample.1.weight"], sd["obj_downsample.1.bias"]))
+    operand = q(torch.cat((ce.reshape(ce.shape[0], -1), feats), -1))
+    final = q(torch.relu(F.linear(operand, q(sd["obj_downsample.1.weight"]), sd["obj_downsample.1.bias"])))
     slot = torch.cumsum(box_mask.long(), 1) - 1
     obj_reps = final.new_zeros((B, R, final.shape[1]))
     raw = post.new_zeros((B, R, post.shape[1]))

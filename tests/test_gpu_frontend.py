@@ -5,9 +5,14 @@ the only differences are fp32 accumulation order and the final bf16 rounding of 
 max for bf16 outputs (half an ulp of bf16 is 2^-9 = 2e-3 of the value; the bound leaves room for cancellation in sums of
 ~5k products), relative L2 <= 3e-3.  Pure data movement (layout changes, max-pool, im2col/col2im round trip) is bit-exact.
 
-End to end (33 bottlenecks + head): against the fp32 oracle / the reference fixture the error is a random walk of bf16
-roundings, one per stored activation: relative L2 <= 3e-2 on outputs, <= 6e-2 on weight gradients (measured values are
-printed by the test and recorded in DESIGN.md)."""
+End to end (33 bottlenecks + head), two bounds (measured values are printed by the test and recorded in DESIGN.md):
+  * against the reference fixture (fp32): outputs relative L2 <= 3e-2 (random walk of one bf16 rounding per stored
+    activation).  Gradients: a ReLU whose pre-activation lies within rounding distance of 0 flips its mask and changes
+    that element's gradient by 100%, so forward error eps becomes gradient error ~ sqrt(eps) (10-20% at the bottom of a
+    100-layer bf16 network, for ANY bf16 implementation: oracle/frontend_oracle.py reproduces it in fp32 arithmetic with
+    bf16-rounded storage).  Asserted: gradient norm within 5%, relative L2 <= 0.3.
+  * against the oracle evaluated with the SAME storage points rounded to bf16 (`storage="bf16"`: same masks): outputs
+    <= 5e-3, gradients <= 3e-2 -- this is the bound that pins the backward kernels end to end."""
 import os
 
 import numpy as np
@@ -185,10 +190,28 @@ def test_state_dict_shapes_match_the_reference_layout():
     assert ours == {k: tuple(v) for k, v in frontend_shapes().items()}
 
 
+_E2E_ORACLE = {}
+
+
+def _bf16_storage_oracle(sd):
+    """the oracle with bf16 storage on the fixture's inputs (CPU, a few seconds); cached across the parametrised runs"""
+    if not _E2E_ORACLE:
+        torch.set_num_threads(min(16, os.cpu_count() or 1))
+        sd = dict(sd)
+        for n, _ in E2E_GRAD_SLICES:
+            sd[n] = sd[n].clone().requires_grad_(True)
+        images, boxes, box_mask, im_info, gw = synth_frontend_inputs(78)
+        obj, raw = fo.fast_rcnn_end2end(sd, images, boxes, box_mask, im_info, storage="bf16")
+        (obj * gw).sum().backward()
+        _E2E_ORACLE.update(obj=obj.detach(), raw=raw.detach(), grads={n: sd[n].grad for n, _ in E2E_GRAD_SLICES})
+    return _E2E_ORACLE
+
+
 @pytest.mark.parametrize("compact", [True, False])
 def test_fastrcnn_end_to_end_against_reference_fixture(golden_dir, compact):
     G = np.load(os.path.join(golden_dir, "fastrcnn_e2e.npz"))
-    m, _ = _load_e2e()
+    m, sd = _load_e2e()
+    O = _bf16_storage_oracle(sd)
     m.compact_rois = compact
     images, boxes, box_mask, im_info, gw = [t.to(DEV) for t in synth_frontend_inputs(78)]
     from vlbert_b200 import functional as VF
@@ -197,6 +220,7 @@ def test_fastrcnn_end_to_end_against_reference_fixture(golden_dir, compact):
     out = m(images=images, boxes=boxes, box_mask=box_mask, im_info=im_info)
     e["obj_reps"] = rel(out["obj_reps"], torch.from_numpy(G["obj_reps"]))
     e["obj_reps_raw"] = rel(out["obj_reps_raw"], torch.from_numpy(G["obj_reps_raw"]))
+    o = {"obj_reps": rel(out["obj_reps"], O["obj"]), "obj_reps_raw": rel(out["obj_reps_raw"], O["raw"])}
     pad = ~torch.from_numpy(G["obj_reps"]).abs().sum(-1).bool()
     assert bool((out["obj_reps"].cpu()[pad] == 0).all())
     m.zero_grad()
@@ -205,10 +229,14 @@ def test_fastrcnn_end_to_end_against_reference_fixture(golden_dir, compact):
     for name, rows in E2E_GRAD_SLICES:
         gfull = params[name].grad
         e["grad:" + name] = rel(gfull if rows is None else gfull[:rows], torch.from_numpy(G["grad:" + name]))
+        o["grad:" + name] = rel(gfull, O["grads"][name])
         assert abs(float(gfull.double().norm()) / float(G["gnorm:" + name]) - 1) < 5e-2, name
-    print("fastrcnn_e2e parity (relative L2):", {k: "%.2e" % v for k, v in e.items()})
+    print("fastrcnn_e2e vs reference fixture (fp32), relative L2:", {k: "%.2e" % v for k, v in e.items()})
+    print("fastrcnn_e2e vs bf16-storage oracle, relative L2:", {k: "%.2e" % v for k, v in o.items()})
     assert e["body4"] <= 3e-2 and e["obj_reps"] <= 3e-2 and e["obj_reps_raw"] <= 3e-2, e
-    assert all(v <= 6e-2 for k, v in e.items() if k.startswith("grad:")), e
+    assert all(v <= 0.3 for k, v in e.items() if k.startswith("grad:")), e
+    assert o["obj_reps"] <= 5e-3 and o["obj_reps_raw"] <= 5e-3, o
+    assert all(v <= 3e-2 for k, v in o.items() if k.startswith("grad:")), o
     # frozen parts get no gradient (IMAGE_FROZEN_BACKBONE_STAGES [1, 2], IMAGE_FROZEN_BN)
     assert all(p.grad is None for n, p in params.items() if n.startswith("backbone.layer1") or ".bn" in n or n.startswith("backbone.conv1"))
     assert all(p.grad is not None for n, p in params.items() if p.requires_grad)

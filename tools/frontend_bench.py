@@ -112,6 +112,20 @@ def main():
         res[name] = {"ms_per_step": round(ms, 3), "images_per_s": round(B / ms * 1e3, 2),
                      "launches_per_step": (_lib.lib().vlb_launch_count() - n0) // a.steps,
                      "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}
+    # per-category device time of one eager step (events around every library launch; serialises nothing)
+    import ctypes
+    lib = _lib.lib()
+    ours(); torch.cuda.synchronize()
+    lib.vlb_profile_enable(1)
+    ours(); torch.cuda.synchronize()
+    lib.vlb_profile_enable(0)
+    pms, pwork, pcnt = (ctypes.c_double * 12)(), (ctypes.c_double * 12)(), (ctypes.c_int64 * 12)()
+    _lib.check(lib.vlb_profile_collect(pms, pwork, pcnt))
+    names = ["gemm_nt", "gemm_nn", "gemm_tn", "mhsa_fwd", "mhsa_bwd", "ln_fwd", "ln_bwd", "other", "im2col", "col2im", "conv_elt", "roi_nhwc"]
+    res["profile"] = {n: {"ms": round(pms[i], 3), "launches": pcnt[i],
+                          ("tflops" if i < 5 else "gbps"): round(pwork[i] / max(pms[i], 1e-9) / (1e9 if i < 5 else 1e6), 1)}
+                      for i, n in enumerate(names) if pcnt[i]}
+    res["profile_sum_ms"] = round(sum(pms), 3)
     # analytic conv MACs (fwd) for the roofline note: backbone trainable part x3 (fwd + dgrad + wgrad), frozen part x1
     print(json.dumps(res))
 

@@ -61,7 +61,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 // Optional per-launch timing (bench.py's roofline): when enabled through vlb_profile_enable(), launchers bracket their
 // kernel with CUDA events on the launch stream; vlb_profile_collect() sums elapsed time / work per category.
 enum ProfCat : int { PROF_GEMM_NT = 0, PROF_GEMM_NN, PROF_GEMM_TN, PROF_MHSA_FWD, PROF_MHSA_BWD, PROF_LN_FWD, PROF_LN_BWD,
-                     PROF_OTHER, PROF_NUM };
+                     PROF_OTHER, PROF_IM2COL, PROF_COL2IM, PROF_CONV_ELT, PROF_ROI_NHWC, PROF_NUM };
 struct ProfScope {
   ProfScope(int cat, double work, cudaStream_t stream);
   ~ProfScope();

@@ -320,6 +320,7 @@ int im2col_nhwc(const void* x, void* col, int N, int H, int W, int C, int kh, in
   VLB_REQUIRE(x && col, "im2col: null pointer");
   VLB_REQUIRE(Kp >= kh * kw * C && Kp % 8 == 0, "im2col: bad padded K %d", Kp);
   ConvGeom g{N, H, W, C, Ho, Wo, kh, kw, stride, pad, dil, Kp};
+  ProfScope prof(PROF_IM2COL, 2.0 * N * Ho * Wo * Kp + 2.0 * N * H * W * C, stream);   // bytes: col written + x read once
   if (C % 8 == 0 && Kp == kh * kw * C) {
     const long total = (long)N * Ho * Wo * kh * kw * (C / 8);
     im2col_v8_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(col), g);
@@ -336,6 +337,7 @@ int col2im_nhwc(const void* dcol, const void* add, void* dx, int N, int H, int W
   VLB_REQUIRE(dcol && dx, "col2im: null pointer");
   VLB_REQUIRE(C % 8 == 0 && Kp == kh * kw * C, "col2im: channels must be a multiple of 8");
   ConvGeom g{N, H, W, C, Ho, Wo, kh, kw, stride, pad, dil, Kp};
+  ProfScope prof(PROF_COL2IM, 2.0 * N * Ho * Wo * Kp + 2.0 * N * H * W * C * (add ? 2 : 1), stream);
   const long total = (long)N * H * W * (C / 8);
   col2im_v8_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dcol), static_cast<const __nv_bfloat16*>(add),
                                                             static_cast<__nv_bfloat16*>(dx), g);
@@ -349,6 +351,7 @@ int relu_bn_backward(const void* dy, const void* dy2, const void* y_mask, const 
   VLB_REQUIRE(C % 8 == 0, "relu_bn_backward: channels must be a multiple of 8");
   const long total = rows * (C / 8);
   if (total <= 0) return VLB_OK;
+  ProfScope prof(PROF_CONV_ELT, 2.0 * rows * C * (1 + (dy2 ? 1 : 0) + (y_mask ? 1 : 0) + (d_pre ? 1 : 0) + (d_conv ? 1 : 0)), stream);
   relu_bn_bwd_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(dy2),
                                                               static_cast<const __nv_bfloat16*>(y_mask), scale,
                                                               static_cast<__nv_bfloat16*>(d_pre), static_cast<__nv_bfloat16*>(d_conv), rows, C);
@@ -401,6 +404,7 @@ int roi_align_nhwc_forward(const void* feat, const float* rois, void* out, int K
   if (K == 0) return VLB_OK;
   VLB_REQUIRE(feat && rois && out && C % 8 == 0, "roi_align_nhwc_forward: bad arguments");
   const int warps = K * ph * pw;
+  ProfScope prof(PROF_ROI_NHWC, 2.0 * K * ph * pw * C * 5, stream);      // 4 taps read + 1 write per output (sampling_ratio 1)
   roi_align_nhwc_kernel<false><<<(warps + 3) / 4, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(feat), rois,
                                                                    static_cast<__nv_bfloat16*>(out), nullptr, nullptr, K, C, H, W, ph, pw,
                                                                    scale, sampling_ratio);
@@ -410,6 +414,7 @@ int roi_align_nhwc_forward(const void* feat, const float* rois, void* out, int K
 int roi_align_nhwc_backward(const void* grad_out, const float* rois, float* grad_feat, int K, int N, int C, int H, int W, int ph, int pw,
                             float scale, int sampling_ratio, cudaStream_t stream) {
   VLB_REQUIRE(grad_feat, "roi_align_nhwc_backward: null pointer");
+  ProfScope prof(PROF_ROI_NHWC, 4.0 * N * C * H * W + 2.0 * K * ph * pw * C + 16.0 * K * ph * pw * C, stream);
   VLB_CHECK_CUDA(cudaMemsetAsync(grad_feat, 0, sizeof(float) * (size_t)N * C * H * W, stream));
   if (K == 0) return VLB_OK;
   VLB_REQUIRE(grad_out && rois && C % 8 == 0, "roi_align_nhwc_backward: bad arguments");

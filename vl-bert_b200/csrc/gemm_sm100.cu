@@ -503,6 +503,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
 // which compile-time epilogue matches this runtime description (EPI_GENERIC if none)
 int classify_epilogue(int mode, const GemmEpilogue& e) {
   const bool bias = e.bias != nullptr;
+  if (e.colscale != nullptr) return EPI_GENERIC;  // per-column scale lives in the generic epilogue only
   if (mode == GEMM_NT) {
     if (bias && e.act == ACT_NONE && e.resid_kind == RESID_NONE && e.out_kind == OUT_BF16) return EPI_BIAS_BF16;
     if (bias && e.act == ACT_NONE && e.resid_kind == RESID_BF16 && e.out_kind == OUT_F32) return EPI_BIAS_RESID16_F32;
