@@ -11,8 +11,12 @@ End to end (33 bottlenecks + head), two bounds (measured values are printed by t
     that element's gradient by 100%, so forward error eps becomes gradient error ~ sqrt(eps) (10-20% at the bottom of a
     100-layer bf16 network, for ANY bf16 implementation: oracle/frontend_oracle.py reproduces it in fp32 arithmetic with
     bf16-rounded storage).  Asserted: gradient norm within 5%, relative L2 <= 0.3.
-  * against the oracle evaluated with the SAME storage points rounded to bf16 (`storage="bf16"`: same masks): outputs
-    <= 5e-3, gradients <= 3e-2 -- this is the bound that pins the backward kernels end to end."""
+  * rounding to bf16 also makes a deep network diverge from ANY other evaluation of itself: a difference delta << ulp in a
+    layer's input flips a fraction ~delta/ulp of the output roundings, i.e. becomes sqrt(delta * ulp) >> delta one layer
+    later (measured with tools/frontend_diag.py against the oracle's bf16-storage graph: 2e-5 after the stem, 1e-3 after
+    7 blocks, 1e-2 after 33), so no oracle can pin the end-to-end gradients tighter than the bound above.  The backward
+    kernels are therefore pinned per Bottleneck with identical inputs (test_bottleneck_against_bf16_storage_oracle: same
+    masks, forward <= 2e-3, gradients <= 1e-2) and per operator (test_conv_bn_act_forward_backward)."""
 import os
 
 import numpy as np
@@ -190,28 +194,50 @@ def test_state_dict_shapes_match_the_reference_layout():
     assert ours == {k: tuple(v) for k, v in frontend_shapes().items()}
 
 
-_E2E_ORACLE = {}
+BLOCK_CASES = [
+    # (inplanes, planes, stride, dilation, stride_in_1x1, N, H, W)
+    (256, 128, 2, 1, True, 2, 18, 22),     # layer2.0 / layer3.0: stride 2 in conv1 + strided downsample
+    (512, 128, 1, 1, False, 2, 9, 11),     # identity block
+    (1024, 512, 1, 2, True, 3, 14, 14),    # res5 head block 0: dilation 2, 1x1 downsample, stride 1 (IMAGE_C5_DILATED)
+    (256, 64, 2, 1, False, 2, 12, 10),     # stride in the 3x3 (stride_in_1x1 = False)
+]
 
 
-def _bf16_storage_oracle(sd):
-    """the oracle with bf16 storage on the fixture's inputs (CPU, a few seconds); cached across the parametrised runs"""
-    if not _E2E_ORACLE:
-        torch.set_num_threads(min(16, os.cpu_count() or 1))
-        sd = dict(sd)
-        for n, _ in E2E_GRAD_SLICES:
-            sd[n] = sd[n].clone().requires_grad_(True)
-        images, boxes, box_mask, im_info, gw = synth_frontend_inputs(78)
-        obj, raw = fo.fast_rcnn_end2end(sd, images, boxes, box_mask, im_info, storage="bf16")
-        (obj * gw).sum().backward()
-        _E2E_ORACLE.update(obj=obj.detach(), raw=raw.detach(), grads={n: sd[n].grad for n, _ in E2E_GRAD_SLICES})
-    return _E2E_ORACLE
+@pytest.mark.parametrize("case", BLOCK_CASES)
+def test_bottleneck_against_bf16_storage_oracle(case):
+    """One Bottleneck (resnet.py:98-118), forward + backward, on identical bf16 inputs against the oracle graph with the
+    same bf16 storage points: the ReLU masks agree, so the comparison is tight."""
+    from vlbert_b200.resnet import Bottleneck, make_layer
+    inpl, planes, stride, dil, s11, N, H, W = case
+    torch.manual_seed(sum(case))
+    layer, _ = make_layer(inpl, planes, 1, stride=stride, dilation=dil, stride_in_1x1=s11)
+    blk = layer[0]
+    sd = fo.synth_frontend_state({"blk." + k: v.shape for k, v in blk.state_dict().items()}, 5)
+    blk.load_state_dict({k[4:]: v for k, v in sd.items()})
+    blk = blk.to(DEV).eval()
+    g = torch.Generator().manual_seed(1)
+    x = bf(torch.randn(N, inpl, H, W, generator=g))
+    names = [k for k in sd if k.endswith("conv1.weight") or k.endswith("conv2.weight") or k.endswith("conv3.weight") or k.endswith("downsample.0.weight")]
+    for k in names:
+        sd[k] = sd[k].clone().requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    y_ref = fo.bottleneck(sd, "blk", xr, stride, dil, s11, storage="bf16")
+    gy = bf(torch.randn(y_ref.shape, generator=g))
+    y_ref.backward(gy)
+    xo = nhwc(x.to(DEV)).requires_grad_(True)
+    y = blk(xo)
+    y.backward(nhwc(gy.to(DEV)))
+    assert rel(nchw(y), y_ref) <= 2e-3, rel(nchw(y), y_ref)
+    assert rel(nchw(xo.grad), xr.grad) <= 1e-2, rel(nchw(xo.grad), xr.grad)
+    for k in names:
+        mine = dict(blk.named_parameters())[k[4:]].grad
+        assert rel(mine, sd[k].grad) <= 1e-2, (k, rel(mine, sd[k].grad))
 
 
 @pytest.mark.parametrize("compact", [True, False])
 def test_fastrcnn_end_to_end_against_reference_fixture(golden_dir, compact):
     G = np.load(os.path.join(golden_dir, "fastrcnn_e2e.npz"))
     m, sd = _load_e2e()
-    O = _bf16_storage_oracle(sd)
     m.compact_rois = compact
     images, boxes, box_mask, im_info, gw = [t.to(DEV) for t in synth_frontend_inputs(78)]
     from vlbert_b200 import functional as VF
@@ -220,7 +246,6 @@ def test_fastrcnn_end_to_end_against_reference_fixture(golden_dir, compact):
     out = m(images=images, boxes=boxes, box_mask=box_mask, im_info=im_info)
     e["obj_reps"] = rel(out["obj_reps"], torch.from_numpy(G["obj_reps"]))
     e["obj_reps_raw"] = rel(out["obj_reps_raw"], torch.from_numpy(G["obj_reps_raw"]))
-    o = {"obj_reps": rel(out["obj_reps"], O["obj"]), "obj_reps_raw": rel(out["obj_reps_raw"], O["raw"])}
     pad = ~torch.from_numpy(G["obj_reps"]).abs().sum(-1).bool()
     assert bool((out["obj_reps"].cpu()[pad] == 0).all())
     m.zero_grad()
@@ -229,14 +254,13 @@ def test_fastrcnn_end_to_end_against_reference_fixture(golden_dir, compact):
     for name, rows in E2E_GRAD_SLICES:
         gfull = params[name].grad
         e["grad:" + name] = rel(gfull if rows is None else gfull[:rows], torch.from_numpy(G["grad:" + name]))
-        o["grad:" + name] = rel(gfull, O["grads"][name])
+        a, b = (gfull if rows is None else gfull[:rows]).double().cpu().flatten(), torch.from_numpy(G["grad:" + name]).double().flatten()
+        e["cos:" + name] = float(a @ b / (a.norm() * b.norm()))
         assert abs(float(gfull.double().norm()) / float(G["gnorm:" + name]) - 1) < 5e-2, name
     print("fastrcnn_e2e vs reference fixture (fp32), relative L2:", {k: "%.2e" % v for k, v in e.items()})
-    print("fastrcnn_e2e vs bf16-storage oracle, relative L2:", {k: "%.2e" % v for k, v in o.items()})
     assert e["body4"] <= 3e-2 and e["obj_reps"] <= 3e-2 and e["obj_reps_raw"] <= 3e-2, e
     assert all(v <= 0.3 for k, v in e.items() if k.startswith("grad:")), e
-    assert o["obj_reps"] <= 5e-3 and o["obj_reps_raw"] <= 5e-3, o
-    assert all(v <= 3e-2 for k, v in o.items() if k.startswith("grad:")), o
+    assert all(v >= 0.95 for k, v in e.items() if k.startswith("cos:")), e
     # frozen parts get no gradient (IMAGE_FROZEN_BACKBONE_STAGES [1, 2], IMAGE_FROZEN_BN)
     assert all(p.grad is None for n, p in params.items() if n.startswith("backbone.layer1") or ".bn" in n or n.startswith("backbone.conv1"))
     assert all(p.grad is not None for n, p in params.items() if p.requires_grad)
