@@ -196,6 +196,20 @@ int vlb_col2im_nhwc(const void* dcol_bf16, const void* add_bf16, void* dx_bf16, 
  * 2 ReLU after the residual add.  All matrices bf16 row-major; scale/shift f32 [Cout] (shift may be NULL). */
 int vlb_conv_gemm(const void* col, int ld_col, const void* w, int ld_w, void* y, int P, int Cout, int K,
                   const float* scale, const float* shift, const void* resid, int relu_mode, void* stream);
+/* Implicit-GEMM forms of the same convolution: the producer warp of the GEMM gathers the filter taps itself with TMA
+ * im2col-mode loads from the NHWC tensor (no col matrix in HBM).  Needs C % 64 == 0; w is bf16 [Cout, kh*kw*C] tap-major.
+ * vlb_conv_fprop also serves the data gradient of a stride-1 convolution: x := dY [N,Ho,Wo,Cout], w := the filter flipped
+ * and transposed to [C, kh*kw*Cout], pad := dil*(k-1) - pad, scale = shift = NULL. */
+typedef struct VlbConvGeom {
+  int N, H, W, C;   /* input tensor, NHWC */
+  int Ho, Wo;       /* output spatial size */
+  int kh, kw, stride, pad, dil;
+} VlbConvGeom;
+int vlb_conv_fprop(const void* x, const VlbConvGeom* g, const void* w, int ld_w, void* y, int Cout, const float* scale,
+                   const float* shift, const void* resid, int relu_mode, void* stream);
+/* dw[Cout, kh*kw*C] (f32, ld_dw) += dy[P, Cout]^T im2col(x)[P, kh*kw*C]   (split_k > 1 splits the pixel reduction) */
+int vlb_conv_wgrad(const void* x, const VlbConvGeom* g, const void* dy, int Cout, float* dw, int ld_dw, int split_k,
+                   void* stream);
 /* d_pre = (dy (+ dy2)) * [y_mask > 0] ; d_conv = d_pre * scale[c]  (either output may be NULL; y_mask NULL = no ReLU) */
 int vlb_relu_bn_backward(const void* dy, const void* dy2, const void* y_mask, const float* scale, void* d_pre,
                          void* d_conv, int64_t rows, int C, void* stream);

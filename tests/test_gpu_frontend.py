@@ -71,12 +71,18 @@ CONV_CASES = [
     (2, 37, 45, 3, 64, 7, 2, 3, 1, 1, False),       # stem 7x7/2, Cin = 3 (scalar im2col, K padded 147 -> 152)
     (2, 9, 11, 64, 256, 1, 1, 0, 1, 2, True),       # conv3 + residual + ReLU
     (1, 5, 7, 256, 64, 1, 1, 0, 1, 1, False),       # P = 35 rows (ragged tile)
+    (4, 19, 23, 64, 64, 3, 1, 1, 1, 1, False),      # P = 1748 (ragged last tile), tensor > 128 KiB
+    (2, 21, 17, 128, 64, 3, 1, 1, 1, 2, True),      # 3x3 + residual
+    (5, 14, 14, 512, 512, 3, 1, 2, 2, 1, False),    # the res5 head's 3x3 at full width (K = 4608)
+    (2, 30, 22, 256, 128, 1, 2, 0, 1, 1, False),    # layer2.0.conv1 geometry (stride_in_1x1)
 ]
 
 
+@pytest.mark.parametrize("implicit", [True, False], ids=["tma_im2col", "explicit_im2col"])
 @pytest.mark.parametrize("case", CONV_CASES)
-def test_conv_bn_act_forward_backward(case):
+def test_conv_bn_act_forward_backward(case, implicit, monkeypatch):
     from vlbert_b200 import functional as VF
+    monkeypatch.setattr(VF, "IMPLICIT_CONV", implicit)
     N, H, W, Cin, Cout, k, stride, pad, dil, relu_mode, has_res = case
     g = torch.Generator().manual_seed(hash(case) % 1000)
     x = bf(torch.randn(N, Cin, H, W, generator=g)).to(DEV)

@@ -62,6 +62,8 @@ def _declare(lib):
     decl("vlb_im2col_nhwc", [P, P] + [I] * 12 + [P])
     decl("vlb_col2im_nhwc", [P, P, P] + [I] * 12 + [P])
     decl("vlb_conv_gemm", [P, I, P, I, P, I, I, I, P, P, P, I, P])
+    decl("vlb_conv_fprop", [P, P, P, I, P, I, P, P, P, I, P])
+    decl("vlb_conv_wgrad", [P, P, P, I, P, I, I, P])
     decl("vlb_relu_bn_backward", [P, P, P, P, P, P, L, I, P])
     decl("vlb_maxpool3x3s2_nhwc", [P, P, I, I, I, I, P])
     decl("vlb_avgpool_forward", [P, P, I, I, I, P])
@@ -97,6 +99,11 @@ class GroupedProblem(ctypes.Structure):
     """VlbGroupedProblem"""
     _fields_ = [("M", c_int), ("N", c_int), ("A", c_void_p), ("lda", c_int), ("B", c_void_p), ("ldb", c_int),
                 ("out", c_void_p), ("ldo", c_int)]
+
+
+class ConvGeom(ctypes.Structure):
+    """VlbConvGeom"""
+    _fields_ = [(n, ctypes.c_int) for n in ("N", "H", "W", "C", "Ho", "Wo", "kh", "kw", "stride", "pad", "dil")]
 
 
 class CastDesc(ctypes.Structure):

@@ -221,6 +221,39 @@ int vlb_conv_gemm(const void* col, int ld_col, const void* w, int ld_w, void* y,
   e.act = relu_mode == 1 ? ACT_RELU : (relu_mode == 2 ? ACT_RELU_POST : ACT_NONE);
   COUNTED(1, gemm_bf16(GEMM_NT, P, Cout, K, col, ld_col, w, ld_w, e, 1, 0, ST));
 }
+static ConvGeom to_geom(const VlbConvGeom* g) {
+  ConvGeom c{g->N, g->H, g->W, g->C, g->Ho, g->Wo, g->kh, g->kw, g->stride, g->pad, g->dil, g->kh * g->kw * g->C};
+  return c;
+}
+static int check_geom(const VlbConvGeom* g) {
+  if (!g || g->N < 1 || g->C < 1 || g->kh < 1 || g->kw < 1 || g->stride < 1 || g->dil < 1 || g->pad < 0 ||
+      g->Ho != (g->H + 2 * g->pad - g->dil * (g->kh - 1) - 1) / g->stride + 1 ||
+      g->Wo != (g->W + 2 * g->pad - g->dil * (g->kw - 1) - 1) / g->stride + 1) {
+    set_last_error("conv: inconsistent geometry");
+    return VLB_ERR_INVALID;
+  }
+  return VLB_OK;
+}
+int vlb_conv_fprop(const void* x, const VlbConvGeom* g, const void* w, int ld_w, void* y, int Cout, const float* scale,
+                   const float* shift, const void* resid, int relu_mode, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  const ConvGeom cg = to_geom(g);
+  GemmEpilogue e;
+  e.out = y; e.ldo = Cout; e.out_kind = OUT_BF16;
+  e.colscale = scale; e.bias = shift;
+  if (resid) { e.resid = resid; e.ldr = Cout; e.resid_kind = RESID_BF16; }
+  e.act = relu_mode == 1 ? ACT_RELU : (relu_mode == 2 ? ACT_RELU_POST : ACT_NONE);
+  const long P = (long)g->N * g->Ho * g->Wo;
+  COUNTED(1, gemm_bf16(GEMM_NT, (int)P, Cout, cg.Kp, x, cg.C, w, ld_w, e, 1, 0, ST, &cg, 1));
+}
+int vlb_conv_wgrad(const void* x, const VlbConvGeom* g, const void* dy, int Cout, float* dw, int ld_dw, int split_k, void* stream) {
+  if (int rc = check_geom(g)) return rc;
+  const ConvGeom cg = to_geom(g);
+  GemmEpilogue e;
+  e.out = dw; e.ldo = ld_dw; e.out_kind = OUT_F32_ATOMIC;
+  const long P = (long)g->N * g->Ho * g->Wo;
+  COUNTED(1, gemm_bf16(GEMM_TN, Cout, cg.Kp, (int)P, dy, Cout, x, cg.C, e, split_k, 0, ST, &cg, 2));
+}
 int vlb_relu_bn_backward(const void* dy, const void* dy2, const void* y_mask, const float* scale, void* d_pre, void* d_conv,
                          int64_t rows, int C, void* stream) {
   COUNTED(1, relu_bn_backward(dy, dy2, y_mask, scale, d_pre, d_conv, rows, C, ST));

@@ -11,17 +11,11 @@
 // gather the taps is the next step), the elementwise ReLU/BN backward, 3x3/2 max-pool, the 14x14 average pool of the RoI
 // head, NCHW fp32 <-> NHWC bf16 layout changes, and an NHWC bf16 RoIAlign (lanes over channels, 128-bit accesses).
 #include "common.cuh"
+#include "gemm_sm100.cuh"
 
 namespace vlb {
 
 namespace {
-
-struct ConvGeom {
-  int N, H, W, C;      // input NHWC
-  int Ho, Wo;          // output spatial
-  int kh, kw, stride, pad, dil;
-  int Kp;              // padded row length of col (>= kh*kw*C, multiple of 8)
-};
 
 // col[(n,ho,wo), (r,s,c)] = x[n, ho*stride - pad + r*dil, wo*stride - pad + s*dil, c]   (0 outside) ; 8 channels per thread
 __global__ void im2col_v8_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, ConvGeom g) {

@@ -42,7 +42,24 @@ struct GemmParams {
   uint32_t a_lbo, a_sbo, a_kadv;
   uint32_t b_lbo, b_sbo, b_kadv;
   GemmEpilogue e;
+  // implicit convolution operand (TMA im2col mode): side 0 none; 1 = A of an NT GEMM (rows = output pixels, K = taps x channels);
+  // 2 = B of a TN GEMM (reduction rows = output pixels, N = taps x channels)
+  int cv_side;
+  int cv_C, cv_Ho, cv_Wo, cv_stride, cv_lower, cv_dil, cv_kw;
 };
+
+// linear output-pixel index -> base pixel (w, h, n) of the im2col traversal
+struct PixelCoord { int w, h, n; };
+__device__ __forceinline__ PixelCoord conv_base_pixel(const GemmParams& p, int pix) {
+  const int hw = p.cv_Ho * p.cv_Wo;
+  PixelCoord c;
+  c.n = pix / hw;
+  const int rem = pix - c.n * hw;
+  const int ho = rem / p.cv_Wo;
+  c.h = ho * p.cv_stride + p.cv_lower;
+  c.w = (rem - ho * p.cv_Wo) * p.cv_stride + p.cv_lower;
+  return c;
+}
 
 // CG2 = CTA-pair mode (tcgen05 cta_group::2): a cluster of two CTAs computes a 256 x BN tile; each CTA stages its own 128
 // rows of A and one HALF of the B tile, so the B operand crosses the L2->SM fabric once per pair instead of once per CTA.
@@ -306,7 +323,13 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
           auto load = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1) {
             if (CG2) tma_load_2d_cg2(dst, tm, fb, c0, c1); else tma_load_2d(dst, tm, fb, c0, c1);
           };
-          if (!A_MN) {
+          if (!A_MN && !GROUPED && p.cv_side == 1) {
+            // implicit convolution: 128 consecutive output pixels x 64 channels of filter tap (r, s), gathered by the TMA unit
+            const int tap = k0 / p.cv_C, c0 = k0 - tap * p.cv_C;
+            const int r = tap / p.cv_kw, sx = tap - r * p.cv_kw;
+            const PixelCoord px = conv_base_pixel(p, m0);
+            tma_load_im2col_4d(sa, pta, fb, c0, px.w, px.h, px.n, (uint16_t)(sx * p.cv_dil), (uint16_t)(r * p.cv_dil));
+          } else if (!A_MN) {
             load(sa, pta, k0, m0);  // box {64 k, 128 rows}
           } else {
 #pragma unroll
@@ -325,6 +348,20 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
             }
           } else if (!B_MN) {
             load(sb, ptb, k0, n0);  // box {64 k, B_ROWS rows}
+          } else if (!GROUPED && p.cv_side == 2) {
+            // implicit convolution (weight gradient): 64 output pixels (reduction rows) x 64 channels per 64-column chunk
+            const PixelCoord px = conv_base_pixel(p, k0);
+#pragma unroll
+            for (int c = 0; c < C::B_ROWS / 64; ++c) {
+              const int col = n0 + c * 64;
+              if (col < p.N) {
+                const int tap = col / p.cv_C, c0 = col - tap * p.cv_C;
+                const int r = tap / p.cv_kw, sx = tap - r * p.cv_kw;
+                tma_load_im2col_4d(sb + c * 8192, ptb, fb, c0, px.w, px.h, px.n, (uint16_t)(sx * p.cv_dil), (uint16_t)(r * p.cv_dil));
+              } else {
+                tma_load_im2col_4d(sb + c * 8192, ptb, fb, 0, 0, 0, 0x3fffff, 0, 0);   // past the last column: image index out of bounds -> zero fill, full tx count
+              }
+            }
           } else {
 #pragma unroll
             for (int c = 0; c < C::B_ROWS / 64; ++c) load(sb + c * 8192, ptb, n0 + c * 64, k0);
@@ -448,6 +485,23 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeIm2col get_encode_im2col_fn() {
+  static PFN_encodeIm2col fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<PFN_encodeIm2col>(p);
+    }
+  });
+  return fn;
+}
+
 struct TmapKey {
   const void* ptr;
   uint64_t rows, cols, ld;
@@ -566,6 +620,40 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t
   return VLB_OK;
 }
 
+// TMA im2col-mode map of an NHWC bf16 tensor: a load gathers `pixels` consecutive OUTPUT pixels (w fastest, then h, then n; the
+// traversal stride is the convolution stride) x 64 channels, displaced by the filter-tap offset given in the instruction;
+// taps that fall outside the image read zeros (the padding).  Bounding box as in the PTX ISA's im2col description:
+// lower corner = -pad, upper corner = pad - dil * (k - 1)  (relative to the last pixel).
+int make_tmap_im2col(CUtensorMap* out, const void* ptr, const ConvGeom& g, uint32_t pixels) {
+  PFN_encodeIm2col fn = get_encode_im2col_fn();
+  if (fn == nullptr) {
+    set_last_error("cuTensorMapEncodeIm2col entry point not available");
+    return VLB_ERR_CUDA;
+  }
+  VLB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+  VLB_REQUIRE(g.C % 64 == 0, "implicit convolution needs a multiple of 64 input channels (C=%d)", g.C);
+  cuuint64_t gdim[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
+  cuuint64_t gstride[3] = {(cuuint64_t)g.C * 2, (cuuint64_t)g.W * g.C * 2, (cuuint64_t)g.H * g.W * g.C * 2};
+  int lower[2] = {-g.pad, -g.pad};
+  int upper[2] = {g.pad - g.dil * (g.kw - 1), g.pad - g.dil * (g.kh - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1};
+  CUtensorMap m;
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstride, lower, upper, 64, pixels, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeIm2col failed with CUresult %d (N=%d H=%d W=%d C=%d k=%dx%d stride=%d pad=%d dil=%d)", (int)r,
+                   g.N, g.H, g.W, g.C, g.kh, g.kw, g.stride, g.pad, g.dil);
+    return VLB_ERR_CUDA;
+  }
+  // drivers up to 13.1 mis-encode im2col maps of tensors smaller than 128 KiB (same correction as CUTLASS's make_im2col_tma_copy_desc)
+  int drv = 0;
+  if (cudaDriverGetVersion(&drv) == cudaSuccess && drv <= 13010 && (size_t)g.N * g.H * g.W * g.C * 2 < 131072)
+    reinterpret_cast<uint64_t*>(&m)[1] &= ~(1ull << 21);
+  *out = m;
+  return VLB_OK;
+}
+
 void gemm_debug_override(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t mn_kadv) {
   g_dbg_mn_lbo = mn_lbo;
   g_dbg_mn_sbo = mn_sbo;
@@ -573,7 +661,7 @@ void gemm_debug_override(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t mn_kadv) {
 }
 
 int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
-              const GemmEpilogue& epi_in, int split_k, int force_bn, cudaStream_t stream) {
+              const GemmEpilogue& epi_in, int split_k, int force_bn, cudaStream_t stream, const ConvGeom* conv, int conv_side) {
   const GemmEpilogue& epi = epi_in;
   VLB_REQUIRE(mode >= GEMM_NT && mode <= GEMM_TN, "gemm: bad mode %d", mode);
   VLB_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
@@ -658,12 +746,26 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
   p.a_lbo = a_mn ? mn_lbo : 16u;  p.a_sbo = a_mn ? mn_sbo : 1024u;  p.a_kadv = a_mn ? mn_kadv : 32u;
   p.b_lbo = b_mn ? mn_lbo : 16u;  p.b_sbo = b_mn ? mn_sbo : 1024u;  p.b_kadv = b_mn ? mn_kadv : 32u;
 
+  p.cv_side = 0;
+  if (conv != nullptr && conv_side != 0) {
+    VLB_REQUIRE((conv_side == 1 && mode == GEMM_NT) || (conv_side == 2 && mode == GEMM_TN), "gemm: implicit-conv operand / mode mismatch");
+    VLB_REQUIRE(cm == 0, "gemm: implicit convolution runs in single-CTA mode");
+    const long pixels = (long)conv->N * conv->Ho * conv->Wo;
+    const int taps_k = conv->kh * conv->kw * conv->C;
+    VLB_REQUIRE(conv_side == 1 ? (M == pixels && K == taps_k) : (K == pixels && N == taps_k), "gemm: implicit-conv shape mismatch");
+    p.cv_side = conv_side;
+    p.cv_C = conv->C; p.cv_Ho = conv->Ho; p.cv_Wo = conv->Wo; p.cv_stride = conv->stride; p.cv_lower = -conv->pad;
+    p.cv_dil = conv->dil; p.cv_kw = conv->kw;
+  }
+
   CUtensorMap ta, tb;
   int rc;
-  if (!a_mn) rc = make_tmap_bf16_2d(&ta, A, M, K, lda, 64, BM);       // A [M, K]
+  if (p.cv_side == 1) rc = make_tmap_im2col(&ta, A, *conv, BM);        // A = im2col(x): 128 output pixels x 64 channels per load
+  else if (!a_mn) rc = make_tmap_bf16_2d(&ta, A, M, K, lda, 64, BM);       // A [M, K]
   else       rc = make_tmap_bf16_2d(&ta, A, K, M, lda, 64, 64);       // A stored [K, M]
   if (rc != VLB_OK) return rc;
-  if (!b_mn) rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, 64, cm != 0 ? bn / 2 : bn);  // B [N, K]; cluster modes fetch it in halves
+  if (p.cv_side == 2) rc = make_tmap_im2col(&tb, B, *conv, 64);        // B = im2col(x): 64 output pixels x 64 channels per load
+  else if (!b_mn) rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, 64, cm != 0 ? bn / 2 : bn);  // B [N, K]; cluster modes fetch it in halves
   else       rc = make_tmap_bf16_2d(&tb, B, K, N, ldb, 64, 64);       // B stored [K, N]
   if (rc != VLB_OK) return rc;
 

@@ -36,9 +36,21 @@ struct GemmEpilogue {
   const float* colscale = nullptr;  // optional [N] fp32: x = acc * colscale[col] before the bias (frozen BatchNorm scale)
 };
 
+// geometry of one convolution on an NHWC tensor (shared by the lowering kernels in conv.cu and the implicit-GEMM operand)
+struct ConvGeom {
+  int N, H, W, C;      // input NHWC
+  int Ho, Wo;          // output spatial
+  int kh, kw, stride, pad, dil;
+  int Kp;              // padded row length of an explicit col matrix (>= kh*kw*C, multiple of 8); unused by the implicit path
+};
+
 // All matrices are bf16 row-major with leading dimensions in elements (multiples of 8).
+// conv / conv_side: implicit convolution operand gathered by TMA im2col-mode loads from the NHWC tensor passed as that operand's
+// pointer (its leading dimension is ignored): conv_side 1 = A of an NT GEMM (M = N*Ho*Wo output pixels, K = kh*kw*C),
+// 2 = B of a TN GEMM (K = output pixels, N = kh*kw*C).  Needs C % 64 == 0.
 int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
-              const GemmEpilogue& epi, int split_k, int force_bn, cudaStream_t stream);
+              const GemmEpilogue& epi, int split_k, int force_bn, cudaStream_t stream, const ConvGeom* conv = nullptr,
+              int conv_side = 0);
 
 // Grouped weight-gradient launch: out_i[M_i, N_i] (+)= A_i[K, M_i]^T B_i[K, N_i] for up to 4 problems sharing K, in ONE
 // persistent grid (equal-cost tiles of all problems are interleaved -> full rounds).  accumulate: fp32 atomic "+="

@@ -5,6 +5,8 @@ hot path runs in libvlbert_b200.so.  All calls enqueue on torch's current CUDA s
 """
 import ctypes
 
+import os
+
 import torch
 
 from . import _lib
@@ -552,6 +554,21 @@ def _im2col(x, kh, kw, stride, pad, dil, Ho, Wo, Kp):
     return col
 
 
+# implicit GEMM (TMA im2col-mode operand) for every convolution whose input channels are a multiple of 64; the explicit
+# im2col lowering remains for the stem (C = 3) and for the data gradient of strided convolutions.  VLB_IMPLICIT_CONV=0 disables.
+IMPLICIT_CONV = os.environ.get("VLB_IMPLICIT_CONV", "1") != "0"
+
+
+def _geom(N, H, W, C, Ho, Wo, kh, kw, stride, pad, dil):
+    return _lib.ConvGeom(N, H, W, C, Ho, Wo, kh, kw, stride, pad, dil)
+
+
+def weight_to_dgrad(w16, Cout, kh, kw, C):
+    """bf16 [Cout, (r, s, c)] -> [C, (r', s', k)] with r' = kh-1-r, s' = kw-1-s: the filter of the convolution over dY that
+    yields dX for a stride-1 convolution."""
+    return w16[:, :kh * kw * C].view(Cout, kh, kw, C).flip(1, 2).permute(3, 1, 2, 0).reshape(C, kh * kw * Cout).contiguous()
+
+
 class ConvBnActFn(torch.autograd.Function):
     """y = act(conv(x, weight) * scale + shift (+ resid)) in NHWC bf16.
     relu_mode: 0 none, 1 ReLU, 2 ReLU after the residual add (Bottleneck output, resnet.py:110-116).
@@ -569,21 +586,28 @@ class ConvBnActFn(torch.autograd.Function):
         if w16 is None:
             w16 = weight_to_gemm(weight, Kp)
         direct = (kh == 1 and kw == 1 and stride == 1 and pad == 0)
-        col = x.view(N * H * W, C) if direct else _im2col(x, kh, kw, stride, pad, dil, Ho, Wo, Kp)
+        implicit = IMPLICIT_CONV and not direct and C % 64 == 0
         P = N * Ho * Wo
         y = torch.empty((N, Ho, Wo, Cout), dtype=BF16, device=x.device)
         r = None if resid is None else resid.contiguous()
-        _chk(_lib.lib().vlb_conv_gemm(_p(col), col.stride(0), _p(w16), w16.stride(0), _p(y), P, Cout, Kp, _p(scale), _p(shift),
-                                      _p(r), int(relu_mode), _stream()))
+        lib = _lib.lib()
+        if implicit:
+            g = _geom(N, H, W, C, Ho, Wo, kh, kw, stride, pad, dil)
+            _chk(lib.vlb_conv_fprop(_p(x), ctypes.byref(g), _p(w16), w16.stride(0), _p(y), Cout, _p(scale), _p(shift), _p(r),
+                                    int(relu_mode), _stream()))
+        else:
+            col = x.view(N * H * W, C) if direct else _im2col(x, kh, kw, stride, pad, dil, Ho, Wo, Kp)
+            _chk(lib.vlb_conv_gemm(_p(col), col.stride(0), _p(w16), w16.stride(0), _p(y), P, Cout, Kp, _p(scale), _p(shift),
+                                   _p(r), int(relu_mode), _stream()))
         ctx.save_for_backward(x, w16, y if relu_mode else None, scale)
-        ctx.geom = (N, H, W, C, Cout, kh, kw, stride, pad, dil, Ho, Wo, Kp, direct, relu_mode, resid is not None)
+        ctx.geom = (N, H, W, C, Cout, kh, kw, stride, pad, dil, Ho, Wo, Kp, direct, implicit, relu_mode, resid is not None)
         ctx.wshape = tuple(weight.shape)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w16, y, scale = ctx.saved_tensors
-        N, H, W, C, Cout, kh, kw, stride, pad, dil, Ho, Wo, Kp, direct, relu_mode, has_resid = ctx.geom
+        N, H, W, C, Cout, kh, kw, stride, pad, dil, Ho, Wo, Kp, direct, implicit, relu_mode, has_resid = ctx.geom
         lib = _lib.lib()
         st = _stream()
         dev = x.device
@@ -597,21 +621,33 @@ class ConvBnActFn(torch.autograd.Function):
         dconv2 = d_conv.view(P, Cout)
         dx = dw = None
         if need_w:
-            col = x.view(P, C) if direct else _im2col(x, kh, kw, stride, pad, dil, Ho, Wo, Kp)
             dwk = torch.zeros((Cout, Kp), dtype=F32, device=dev)
-            dwk._vlb_accumulate = True
             tiles = ((Cout + 127) // 128) * ((Kp + 255) // 256)
             split = max(1, min(16, 148 // max(1, tiles), (P + 63) // 64))
-            gemm(2, dconv2, col, dwk, split_k=split)
+            if implicit:
+                g = _geom(N, H, W, C, Ho, Wo, kh, kw, stride, pad, dil)
+                _chk(lib.vlb_conv_wgrad(_p(x), ctypes.byref(g), _p(dconv2), Cout, _p(dwk), Kp, split, st))
+            else:
+                col = x.view(P, C) if direct else _im2col(x, kh, kw, stride, pad, dil, Ho, Wo, Kp)
+                dwk._vlb_accumulate = True
+                gemm(2, dconv2, col, dwk, split_k=split)
             dw = dwk[:, :kh * kw * C].view(Cout, kh, kw, C).permute(0, 3, 1, 2).contiguous()
         if need_x:
-            dcol = torch.empty((P, Kp), dtype=BF16, device=dev)
-            gemm(1, dconv2, w16, dcol)
-            if direct:
-                dx = dcol.view(N, H, W, C)
-            else:
+            if implicit and stride == 1 and Cout % 64 == 0:
+                # dX = conv(dY, flipped filter): same implicit GEMM, no dcol / col2im
+                pad_t = dil * (kh - 1) - pad
+                g = _geom(N, Ho, Wo, Cout, H, W, kh, kw, 1, pad_t, dil)
+                wd = weight_to_dgrad(w16, Cout, kh, kw, C)
                 dx = torch.empty((N, H, W, C), dtype=BF16, device=dev)
-                _chk(lib.vlb_col2im_nhwc(_p(dcol), None, _p(dx), N, H, W, C, kh, kw, stride, pad, dil, Ho, Wo, Kp, st))
+                _chk(lib.vlb_conv_fprop(_p(d_conv), ctypes.byref(g), _p(wd), wd.stride(0), _p(dx), C, None, None, None, 0, st))
+            else:
+                dcol = torch.empty((P, Kp), dtype=BF16, device=dev)
+                gemm(1, dconv2, w16, dcol)
+                if direct:
+                    dx = dcol.view(N, H, W, C)
+                else:
+                    dx = torch.empty((N, H, W, C), dtype=BF16, device=dev)
+                    _chk(lib.vlb_col2im_nhwc(_p(dcol), None, _p(dx), N, H, W, C, kh, kw, stride, pad, dil, Ho, Wo, Kp, st))
         return dx, dw, None, None, d_pre, None, None, None, None, None
 
 
