@@ -41,22 +41,31 @@ __global__ void im2col_v8_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloa
   }
 }
 
-// generic (any C, e.g. the 3-channel stem): one element per thread, also zero-fills the K padding
+// generic (any C, e.g. the 3-channel stem): one thread per 8 consecutive columns of one row (one 16-byte store), scalar
+// reads of x (small and cache-resident: neighbouring rows re-read the same pixels); also zero-fills the K padding
 __global__ void im2col_scalar_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, ConvGeom g) {
-  const long total = (long)g.N * g.Ho * g.Wo * g.Kp;
+  const int k8n = g.Kp >> 3;
+  const long total = (long)g.N * g.Ho * g.Wo * k8n;
   const int K = g.kh * g.kw * g.C;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int k = (int)(i % g.Kp);
-    long p = i / g.Kp;
-    float v = 0.0f;
-    if (k < K) {
-      const int c = k % g.C, tap = k / g.C;
-      const int r = tap / g.kw, s = tap - r * g.kw;
-      const int wo = (int)(p % g.Wo), ho = (int)((p / g.Wo) % g.Ho), n = (int)(p / ((long)g.Wo * g.Ho));
-      const int h = ho * g.stride - g.pad + r * g.dil, w = wo * g.stride - g.pad + s * g.dil;
-      if (h >= 0 && h < g.H && w >= 0 && w < g.W) v = __bfloat162float(x[(((size_t)n * g.H + h) * g.W + w) * g.C + c]);
+    const int k8 = (int)(i % k8n);
+    const long p = i / k8n;
+    const int wo = (int)(p % g.Wo);
+    const long t = p / g.Wo;
+    const int ho = (int)(t % g.Ho), n = (int)(t / g.Ho);
+    const int h0 = ho * g.stride - g.pad, w0 = wo * g.stride - g.pad;
+    int k = k8 * 8;
+    int tap = k / g.C, c = k - tap * g.C;
+    int r = tap / g.kw, sx = tap - r * g.kw;
+    const __nv_bfloat16* xn = x + (size_t)n * g.H * g.W * g.C;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j, ++k) {
+      const int h = h0 + r * g.dil, w = w0 + sx * g.dil;
+      v[j] = (k < K && h >= 0 && h < g.H && w >= 0 && w < g.W) ? xn[((size_t)h * g.W + w) * g.C + c] : __float2bfloat16(0.0f);
+      if (++c == g.C) { c = 0; if (++sx == g.kw) { sx = 0; ++r; } }
     }
-    col[i] = __float2bfloat16(v);
+    *reinterpret_cast<uint4*>(col + p * g.Kp + k8 * 8) = *reinterpret_cast<const uint4*>(v);
   }
 }
 
@@ -319,7 +328,7 @@ int im2col_nhwc(const void* x, void* col, int N, int H, int W, int C, int kh, in
     const long total = (long)N * Ho * Wo * kh * kw * (C / 8);
     im2col_v8_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(col), g);
   } else {
-    const long total = (long)N * Ho * Wo * Kp;
+    const long total = (long)N * Ho * Wo * (Kp / 8);
     im2col_scalar_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(col), g);
   }
   VLB_CHECK_LAUNCH();

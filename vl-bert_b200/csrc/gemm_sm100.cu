@@ -24,14 +24,19 @@ constexpr int STAGE_F32_PER_WARP = 32 * 32;        // 4 KB transposition buffer 
 
 // Compile-time epilogue variants for the hot launches of the encoder layer (0 = generic, flags read at run time).
 enum : int { EPI_GENERIC = 0, EPI_BIAS_BF16, EPI_BIAS_RESID16_F32, EPI_BIAS_GELU_AUX_BF16, EPI_DGELU_BF16, EPI_RESID16_BF16,
-             EPI_ATOMIC_F32, EPI_NUM };
-template <int EPI> struct EpiTraits { static constexpr bool kStatic = false; static constexpr bool bias = false; static constexpr int act = 0, resid = 0, out = 0; };
-template <> struct EpiTraits<EPI_BIAS_BF16>          { static constexpr bool kStatic = true; static constexpr bool bias = true;  static constexpr int act = ACT_NONE, resid = RESID_NONE, out = OUT_BF16; };
-template <> struct EpiTraits<EPI_BIAS_RESID16_F32>   { static constexpr bool kStatic = true; static constexpr bool bias = true;  static constexpr int act = ACT_NONE, resid = RESID_BF16, out = OUT_F32; };
-template <> struct EpiTraits<EPI_BIAS_GELU_AUX_BF16> { static constexpr bool kStatic = true; static constexpr bool bias = true;  static constexpr int act = ACT_GELU, resid = RESID_NONE, out = OUT_BF16; };
-template <> struct EpiTraits<EPI_DGELU_BF16>         { static constexpr bool kStatic = true; static constexpr bool bias = false; static constexpr int act = ACT_DGELU_MUL, resid = RESID_NONE, out = OUT_BF16; };
-template <> struct EpiTraits<EPI_RESID16_BF16>       { static constexpr bool kStatic = true; static constexpr bool bias = false; static constexpr int act = ACT_NONE, resid = RESID_BF16, out = OUT_BF16; };
-template <> struct EpiTraits<EPI_ATOMIC_F32>         { static constexpr bool kStatic = true; static constexpr bool bias = false; static constexpr int act = ACT_NONE, resid = RESID_NONE, out = OUT_F32_ATOMIC; };
+             EPI_ATOMIC_F32, EPI_CONV_RELU_BF16, EPI_CONV_RESID_RELU_BF16, EPI_PLAIN_BF16, EPI_NUM };
+struct EpiTraitsBase { static constexpr bool kStatic = true; static constexpr bool bias = false, cscale = false; static constexpr int act = ACT_NONE, resid = RESID_NONE, out = OUT_BF16; };
+template <int EPI> struct EpiTraits : EpiTraitsBase { static constexpr bool kStatic = false; };
+template <> struct EpiTraits<EPI_BIAS_BF16>          : EpiTraitsBase { static constexpr bool bias = true; };
+template <> struct EpiTraits<EPI_BIAS_RESID16_F32>   : EpiTraitsBase { static constexpr bool bias = true; static constexpr int resid = RESID_BF16, out = OUT_F32; };
+template <> struct EpiTraits<EPI_BIAS_GELU_AUX_BF16> : EpiTraitsBase { static constexpr bool bias = true; static constexpr int act = ACT_GELU; };
+template <> struct EpiTraits<EPI_DGELU_BF16>         : EpiTraitsBase { static constexpr int act = ACT_DGELU_MUL; };
+template <> struct EpiTraits<EPI_RESID16_BF16>       : EpiTraitsBase { static constexpr int resid = RESID_BF16; };
+template <> struct EpiTraits<EPI_ATOMIC_F32>         : EpiTraitsBase { static constexpr int out = OUT_F32_ATOMIC; };
+// convolution + frozen BatchNorm: per-channel scale and shift, then ReLU / residual add + ReLU (Bottleneck, resnet.py:98-118)
+template <> struct EpiTraits<EPI_CONV_RELU_BF16>       : EpiTraitsBase { static constexpr bool bias = true, cscale = true; static constexpr int act = ACT_RELU; };
+template <> struct EpiTraits<EPI_CONV_RESID_RELU_BF16> : EpiTraitsBase { static constexpr bool bias = true, cscale = true; static constexpr int act = ACT_RELU_POST, resid = RESID_BF16; };
+template <> struct EpiTraits<EPI_PLAIN_BF16>           : EpiTraitsBase {};
 
 struct GemmParams {
   int M, N, K;
@@ -139,7 +144,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
   float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (has_bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
   float4 scale4 = make_float4(e.alpha, e.alpha, e.alpha, e.alpha);
-  if (!T::kStatic && e.colscale != nullptr && col_ok) {
+  if ((T::kStatic ? T::cscale : (e.colscale != nullptr)) && col_ok) {
     const float4 cs = __ldg(reinterpret_cast<const float4*>(e.colscale + col));
     scale4 = make_float4(cs.x * e.alpha, cs.y * e.alpha, cs.z * e.alpha, cs.w * e.alpha);
   }
@@ -210,7 +215,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
       } else if (resid_kind == RESID_F32) {
         x[0] += in32[i].x; x[1] += in32[i].y; x[2] += in32[i].z; x[3] += in32[i].w;
       }
-      if (!T::kStatic && act == ACT_RELU_POST) {
+      if (act == ACT_RELU_POST) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.0f);
       }
@@ -310,6 +315,40 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
         const int n0 = ic.n_blk * BN + (int)rank * (CG2 ? BN / 2 : 0);       // CG2: this CTA's half of the B tile
         const int kb_begin = ic.split * p.kb_per_split;
         const int kb_end = min(p.num_k_blocks, kb_begin + p.kb_per_split);
+        // implicit-convolution operand: all divisions happen once per item; the k loop only increments
+        PixelCoord cv_px{0, 0, 0};
+        int cv_c0 = 0, cv_r = 0, cv_s = 0, cv_wo = 0, cv_ho = 0;
+        int cvb_c0[C::B_ROWS / 64];
+        uint16_t cvb_ow[C::B_ROWS / 64], cvb_oh[C::B_ROWS / 64];
+        if (!GROUPED && p.cv_side == 1) {
+          cv_px = conv_base_pixel(p, m0);
+          const int k0 = kb_begin * BK;
+          const int tap = k0 / p.cv_C;
+          cv_c0 = k0 - tap * p.cv_C;
+          cv_r = tap / p.cv_kw;
+          cv_s = tap - cv_r * p.cv_kw;
+        } else if (!GROUPED && p.cv_side == 2) {
+          const int pix = kb_begin * BK;
+          const int hw = p.cv_Ho * p.cv_Wo;
+          cv_px.n = pix / hw;
+          const int rem = pix - cv_px.n * hw;
+          cv_ho = rem / p.cv_Wo;
+          cv_wo = rem - cv_ho * p.cv_Wo;
+          cv_px.w = cv_wo * p.cv_stride + p.cv_lower;
+          cv_px.h = cv_ho * p.cv_stride + p.cv_lower;
+#pragma unroll
+          for (int c = 0; c < C::B_ROWS / 64; ++c) {
+            const int col = n0 + c * 64;
+            cvb_c0[c] = -1; cvb_ow[c] = 0; cvb_oh[c] = 0;
+            if (col < p.N) {
+              const int tap = col / p.cv_C;
+              const int r = tap / p.cv_kw;
+              cvb_c0[c] = col - tap * p.cv_C;
+              cvb_ow[c] = (uint16_t)((tap - r * p.cv_kw) * p.cv_dil);
+              cvb_oh[c] = (uint16_t)(r * p.cv_dil);
+            }
+          }
+        }
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
           // pair mode: both CTAs signal the LEADER's full barrier (the leader's MMA thread consumes both halves)
@@ -325,10 +364,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
           };
           if (!A_MN && !GROUPED && p.cv_side == 1) {
             // implicit convolution: 128 consecutive output pixels x 64 channels of filter tap (r, s), gathered by the TMA unit
-            const int tap = k0 / p.cv_C, c0 = k0 - tap * p.cv_C;
-            const int r = tap / p.cv_kw, sx = tap - r * p.cv_kw;
-            const PixelCoord px = conv_base_pixel(p, m0);
-            tma_load_im2col_4d(sa, pta, fb, c0, px.w, px.h, px.n, (uint16_t)(sx * p.cv_dil), (uint16_t)(r * p.cv_dil));
+            tma_load_im2col_4d(sa, pta, fb, cv_c0, cv_px.w, cv_px.h, cv_px.n, (uint16_t)(cv_s * p.cv_dil), (uint16_t)(cv_r * p.cv_dil));
+            cv_c0 += BK;
+            if (cv_c0 == p.cv_C) { cv_c0 = 0; if (++cv_s == p.cv_kw) { cv_s = 0; ++cv_r; } }
           } else if (!A_MN) {
             load(sa, pta, k0, m0);  // box {64 k, 128 rows}
           } else {
@@ -350,17 +388,21 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
             load(sb, ptb, k0, n0);  // box {64 k, B_ROWS rows}
           } else if (!GROUPED && p.cv_side == 2) {
             // implicit convolution (weight gradient): 64 output pixels (reduction rows) x 64 channels per 64-column chunk
-            const PixelCoord px = conv_base_pixel(p, k0);
 #pragma unroll
             for (int c = 0; c < C::B_ROWS / 64; ++c) {
-              const int col = n0 + c * 64;
-              if (col < p.N) {
-                const int tap = col / p.cv_C, c0 = col - tap * p.cv_C;
-                const int r = tap / p.cv_kw, sx = tap - r * p.cv_kw;
-                tma_load_im2col_4d(sb + c * 8192, ptb, fb, c0, px.w, px.h, px.n, (uint16_t)(sx * p.cv_dil), (uint16_t)(r * p.cv_dil));
+              if (cvb_c0[c] >= 0) {
+                tma_load_im2col_4d(sb + c * 8192, ptb, fb, cvb_c0[c], cv_px.w, cv_px.h, cv_px.n, cvb_ow[c], cvb_oh[c]);
               } else {
                 tma_load_im2col_4d(sb + c * 8192, ptb, fb, 0, 0, 0, 0x3fffff, 0, 0);   // past the last column: image index out of bounds -> zero fill, full tx count
               }
+            }
+            // advance the base pixel by the 64 reduction rows of this k-block (w fastest, then h, then n)
+            {
+              int wo = cv_wo + BK;
+              while (wo >= p.cv_Wo) { wo -= p.cv_Wo; if (++cv_ho == p.cv_Ho) { cv_ho = 0; ++cv_px.n; } }
+              cv_wo = wo;
+              cv_px.w = wo * p.cv_stride + p.cv_lower;
+              cv_px.h = cv_ho * p.cv_stride + p.cv_lower;
             }
           } else {
 #pragma unroll
@@ -557,7 +599,12 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
 // which compile-time epilogue matches this runtime description (EPI_GENERIC if none)
 int classify_epilogue(int mode, const GemmEpilogue& e) {
   const bool bias = e.bias != nullptr;
-  if (e.colscale != nullptr) return EPI_GENERIC;  // per-column scale lives in the generic epilogue only
+  if (e.colsum == nullptr && e.aux == nullptr && e.alpha == 1.0f && mode == GEMM_NT && e.out_kind == OUT_BF16) {
+    if (e.colscale != nullptr && bias && e.act == ACT_RELU && e.resid_kind == RESID_NONE) return EPI_CONV_RELU_BF16;
+    if (e.colscale != nullptr && bias && e.act == ACT_RELU_POST && e.resid_kind == RESID_BF16) return EPI_CONV_RESID_RELU_BF16;
+    if (e.colscale == nullptr && !bias && e.act == ACT_NONE && e.resid_kind == RESID_NONE) return EPI_PLAIN_BF16;
+  }
+  if (e.colscale != nullptr) return EPI_GENERIC;  // other per-column-scale combinations: generic epilogue
   if (mode == GEMM_NT) {
     if (bias && e.act == ACT_NONE && e.resid_kind == RESID_NONE && e.out_kind == OUT_BF16) return EPI_BIAS_BF16;
     if (bias && e.act == ACT_NONE && e.resid_kind == RESID_BF16 && e.out_kind == OUT_F32) return EPI_BIAS_RESID16_F32;
@@ -775,6 +822,9 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
     if (epi_id == EPI_BIAS_BF16) return launch<BN_, false, false, EPI_BIAS_BF16, CG_>(ta, tb, p, stream);     \
     if (epi_id == EPI_BIAS_RESID16_F32) return launch<BN_, false, false, EPI_BIAS_RESID16_F32, CG_>(ta, tb, p, stream); \
     if (epi_id == EPI_BIAS_GELU_AUX_BF16) return launch<BN_, false, false, EPI_BIAS_GELU_AUX_BF16, CG_>(ta, tb, p, stream); \
+    if (CG_ == 0 && epi_id == EPI_CONV_RELU_BF16) return launch<BN_, false, false, EPI_CONV_RELU_BF16, 0>(ta, tb, p, stream); \
+    if (CG_ == 0 && epi_id == EPI_CONV_RESID_RELU_BF16) return launch<BN_, false, false, EPI_CONV_RESID_RELU_BF16, 0>(ta, tb, p, stream); \
+    if (CG_ == 0 && epi_id == EPI_PLAIN_BF16) return launch<BN_, false, false, EPI_PLAIN_BF16, 0>(ta, tb, p, stream); \
     return launch<BN_, false, false, EPI_GENERIC, CG_>(ta, tb, p, stream);                                    \
   }                                                                                                          \
   if (!a_mn && b_mn) {                                                                                       \
