@@ -37,6 +37,10 @@ int vlb_abi_version(void);
 const char* vlb_last_error_string(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t vlb_launch_count(void);
+/* Size the persistent grids (GEMM, grouped wgrad) for `sms` SMs instead of the whole device (0 = all).  Used when a
+ * concurrent NCCL collective owns some SMs: a persistent grid larger than the free SMs would run in two waves.
+ * Environment default: VLB_SM_LIMIT. */
+void vlb_set_sm_limit(int sms);
 
 /* Per-launch device timing for bench.py's roofline.  While enabled, GEMM / attention / LayerNorm launchers bracket
  * their kernel with CUDA events on the launch stream.  vlb_profile_collect() waits for the recorded events and

@@ -61,6 +61,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--torch", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="also time the step captured in a CUDA graph (vlbert_b200.GraphedStep)")
     a = ap.parse_args()
     import vlbert_b200
     from vlbert_b200 import _lib
@@ -97,7 +98,15 @@ def main():
         (post * gp).sum().backward()
 
     res = {"shape": {"images": B, "h": a.h, "w": a.w, "boxes": R}}
-    for name, fn in (("library", ours),) + ((("torch_cudnn_bf16", theirs),) if a.torch else ()):
+    runs = [("library", ours)]
+    if a.graph:
+        def loss_fn(mod, im, bx, bm, info):
+            return (mod(images=im, boxes=bx, box_mask=bm, im_info=info)["obj_reps"] * gw).sum()
+        gstep = vlbert_b200.GraphedStep(m, loss_fn, (images, boxes, box_mask, im_info))
+        runs.append(("library_cuda_graph", lambda: gstep()))
+    if a.torch:
+        runs.append(("torch_cudnn_bf16", theirs))
+    for name, fn in runs:
         for _ in range(a.warmup):
             fn()
         torch.cuda.synchronize()

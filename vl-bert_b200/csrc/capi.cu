@@ -29,6 +29,7 @@ int cuda_fail(cudaError_t e, const char* what) {
   return VLB_ERR_CUDA;
 }
 
+static std::atomic<int> g_sm_limit{-1};
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -37,7 +38,13 @@ int num_sms() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
-  return n;
+  int lim = g_sm_limit.load(std::memory_order_relaxed);
+  if (lim < 0) {  // first call: environment default
+    const char* v = getenv("VLB_SM_LIMIT");
+    lim = v ? atoi(v) : 0;
+    g_sm_limit.store(lim);
+  }
+  return (lim > 0 && lim < n) ? lim : n;
 }
 
 namespace {
@@ -83,6 +90,7 @@ using namespace vlb;
 extern "C" {
 
 int vlb_abi_version(void) { return 1; }
+void vlb_set_sm_limit(int sms) { g_sm_limit.store(sms > 0 ? sms : 0); }
 const char* vlb_last_error_string(void) { return g_err; }
 int64_t vlb_launch_count(void) { return g_launches.load(); }
 

@@ -575,8 +575,9 @@ class ConvBnActFn(torch.autograd.Function):
     scale/shift are the constants of a frozen eval-mode BatchNorm (no gradient)."""
 
     @staticmethod
-    def forward(ctx, x, weight, scale, shift, resid, stride, pad, dil, relu_mode, w16):
+    def forward(ctx, x, weight, scale, shift, resid, stride, pad, dil, relu_mode, w16, bag=None, role=None):
         _require_cuda(x, weight, scale)
+        ctx.bag, ctx.role = bag, role
         N, H, W, C = x.shape
         Cout, Cin, kh, kw = weight.shape
         assert Cin == C and x.dtype == BF16 and x.is_contiguous()
@@ -620,6 +621,15 @@ class ConvBnActFn(torch.autograd.Function):
         _chk(lib.vlb_relu_bn_backward(_p(dy), None, _p(y) if relu_mode else None, _p(scale), _p(d_pre), _p(d_conv), P, Cout, st))
         dconv2 = d_conv.view(P, Cout)
         dx = dw = None
+        # Bottleneck identity branch: instead of handing d_pre to autograd (which would add it to conv1's dX with a separate
+        # elementwise kernel), conv3 ("produce") parks it and conv1 ("consume") adds it in its data-gradient GEMM epilogue
+        extra = None
+        if ctx.role == "produce" and d_pre is not None:
+            ctx.bag["d_identity"] = d_pre
+            d_pre = None
+        elif ctx.role == "consume":
+            extra = ctx.bag.pop("d_identity", None)
+            assert direct
         if need_w:
             dwk = torch.zeros((Cout, Kp), dtype=F32, device=dev)
             tiles = ((Cout + 127) // 128) * ((Kp + 255) // 256)
@@ -642,17 +652,20 @@ class ConvBnActFn(torch.autograd.Function):
                 _chk(lib.vlb_conv_fprop(_p(d_conv), ctypes.byref(g), _p(wd), wd.stride(0), _p(dx), C, None, None, None, 0, st))
             else:
                 dcol = torch.empty((P, Kp), dtype=BF16, device=dev)
-                gemm(1, dconv2, w16, dcol)
+                gemm(1, dconv2, w16, dcol, resid=extra.view(P, Kp) if extra is not None else None)
+                extra = None
                 if direct:
                     dx = dcol.view(N, H, W, C)
                 else:
                     dx = torch.empty((N, H, W, C), dtype=BF16, device=dev)
                     _chk(lib.vlb_col2im_nhwc(_p(dcol), None, _p(dx), N, H, W, C, kh, kw, stride, pad, dil, Ho, Wo, Kp, st))
-        return dx, dw, None, None, d_pre, None, None, None, None, None
+        if extra is not None:   # x needs no gradient itself but the identity branch does: pass it through
+            dx = extra if dx is None else dx + extra
+        return dx, dw, None, None, d_pre, None, None, None, None, None, None, None
 
 
-def conv_bn_act(x, weight, scale, shift, resid=None, stride=1, pad=0, dil=1, relu_mode=1, w16=None):
-    return ConvBnActFn.apply(x, weight, scale, shift, resid, stride, pad, dil, relu_mode, w16)
+def conv_bn_act(x, weight, scale, shift, resid=None, stride=1, pad=0, dil=1, relu_mode=1, w16=None, bag=None, role=None):
+    return ConvBnActFn.apply(x, weight, scale, shift, resid, stride, pad, dil, relu_mode, w16, bag, role)
 
 
 def maxpool3x3s2(x):

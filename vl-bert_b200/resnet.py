@@ -30,10 +30,13 @@ class Bottleneck(nn.Module):
         self.stride = stride
 
     def forward(self, x):  # x: NHWC bf16
-        o = _cba(x, self.conv1, self.bn1, relu_mode=1)
+        # identity blocks: the residual-branch gradient is added inside conv1's data-gradient GEMM (see ConvBnActFn.backward)
+        fuse = self.downsample is None and self.conv1.stride[0] == 1 and x.requires_grad and torch.is_grad_enabled()
+        bag = {} if fuse else None
+        o = _cba(x, self.conv1, self.bn1, relu_mode=1, bag=bag, role="consume" if fuse else None)
         o = _cba(o, self.conv2, self.bn2, relu_mode=1)
         identity = x if self.downsample is None else _cba(x, self.downsample[0], self.downsample[1], relu_mode=0)
-        return _cba(o, self.conv3, self.bn3, resid=identity, relu_mode=2)
+        return _cba(o, self.conv3, self.bn3, resid=identity, relu_mode=2, bag=bag, role="produce" if fuse else None)
 
 
 def _bn_affine(bn):
@@ -51,7 +54,7 @@ def _bn_affine(bn):
     return cache[1], cache[2]
 
 
-def _cba(x, conv, bn, resid=None, relu_mode=1):
+def _cba(x, conv, bn, resid=None, relu_mode=1, bag=None, role=None):
     scale, shift = _bn_affine(bn)
     w16 = None
     if not conv.weight.requires_grad:  # frozen convolution: keep the bf16 GEMM operand
@@ -61,7 +64,7 @@ def _cba(x, conv, bn, resid=None, relu_mode=1):
             conv._vlb_w16 = cache = (key, VF.weight_to_gemm(conv.weight))
         w16 = cache[1]
     return VF.conv_bn_act(x, conv.weight, scale, shift, resid=resid, stride=conv.stride[0], pad=conv.padding[0],
-                          dil=conv.dilation[0], relu_mode=relu_mode, w16=w16)
+                          dil=conv.dilation[0], relu_mode=relu_mode, w16=w16, bag=bag, role=role)
 
 
 def make_layer(inplanes, planes, blocks, stride=1, dilation=1, stride_in_1x1=False):
