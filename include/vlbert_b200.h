@@ -41,6 +41,8 @@ int64_t vlb_launch_count(void);
  * concurrent NCCL collective owns some SMs: a persistent grid larger than the free SMs would run in two waves.
  * Environment default: VLB_SM_LIMIT. */
 void vlb_set_sm_limit(int sms);
+/* 1 if the experimental stream-K tail of the GEMM was compiled in (-DVLB_ENABLE_STREAMK=1; off by default: no gain measured). */
+int vlb_streamk_compiled(void);
 
 /* Per-launch device timing for bench.py's roofline.  While enabled, GEMM / attention / LayerNorm launchers bracket
  * their kernel with CUDA events on the launch stream.  vlb_profile_collect() waits for the recorded events and

@@ -143,6 +143,33 @@ def test_gemm_epilogues(VF):
     assert rel(acc, dy.t() @ a + 1.0) <= 2e-5
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("shape", [(6464, 768, 3072), (6464, 768, 2304), (700, 1024, 1600), (130, 512, 4096), (6464, 768, 1544)])
+def test_gemm_streamk_tail(VF, mode, shape):
+    """Long reductions whose tile count leaves a small last round: those tiles are split along K (stream-K), partial
+    accumulators meet in an fp32 scratch tile and the last unit applies the epilogue.  Repeated launches check that the
+    scratch / counters are left clean; the epilogue (bias + residual, bf16 out) runs in the fix-up pass."""
+    import vlbert_b200
+    if not vlbert_b200._lib.lib().vlb_streamk_compiled():
+        pytest.skip("stream-K tail not compiled in (experimental; build with -DVLB_ENABLE_STREAMK=1)")
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N + K)
+    a, b = bf(torch.randn(M, K, generator=g)), bf(torch.randn(N, K, generator=g) * 0.05)
+    bias = torch.randn(N, generator=g)
+    resid = bf(torch.randn(M, N, generator=g))
+    ref = a @ b.t()
+    A = a.to(DEV, BF16)
+    Bm = b.to(DEV, BF16) if mode == 0 else b.t().contiguous().to(DEV, BF16)
+    for bn in (0, 256, 128):
+        for _ in range(3):
+            out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32)
+            VF.gemm(mode, A, Bm, out, force_bn=bn)
+            assert rel(out, ref) <= 2e-5
+        o16 = torch.empty(M, N, device=DEV, dtype=BF16)
+        VF.gemm(mode, A, Bm, o16, bias=bias.to(DEV) if mode == 0 else None, resid=resid.to(DEV, BF16), force_bn=bn)
+        assert rel(o16.float(), ref + (bias if mode == 0 else 0) + resid) <= 3e-3
+
+
 # ------------------------------------------------------------------------------------------------ LayerNorm
 @pytest.mark.parametrize("M,H", [(6464, 768), (37, 128), (300, 1024), (5, 2048)])
 def test_layernorm_forward_backward(VF, M, H):

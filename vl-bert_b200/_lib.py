@@ -42,6 +42,7 @@ def _declare(lib):
 
     decl("vlb_gemm_grouped_tn", [P, P, I, I, I, I, P])
     decl("vlb_set_sm_limit", [I], None)
+    decl("vlb_streamk_compiled", [])
     decl("vlb_profile_enable", [I], None)
     decl("vlb_profile_collect", [P, P, P])
     decl("vlb_mhsa_forward", [P, P, P, P, I, I, I, I, P])

@@ -90,6 +90,7 @@ using namespace vlb;
 extern "C" {
 
 int vlb_abi_version(void) { return 1; }
+int vlb_streamk_compiled(void) { return gemm_streamk_compiled() ? 1 : 0; }
 void vlb_set_sm_limit(int sms) { g_sm_limit.store(sms > 0 ? sms : 0); }
 const char* vlb_last_error_string(void) { return g_err; }
 int64_t vlb_launch_count(void) { return g_launches.load(); }

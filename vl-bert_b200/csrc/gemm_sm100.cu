@@ -51,6 +51,13 @@ struct GemmParams {
   // 2 = B of a TN GEMM (reduction rows = output pixels, N = taps x channels)
   int cv_side;
   int cv_C, cv_Ho, cv_Wo, cv_stride, cv_lower, cv_dil, cv_kw;
+  // stream-K tail: the tiles of the last, partial round of the persistent grid are split along K into sk_chunks work units
+  // each; units add their partial accumulators into an fp32 scratch tile, the last unit to arrive applies the epilogue.
+  int sk_full_items;      // items [0, sk_full_items) are whole tiles; 0 chunks = feature off
+  int sk_chunks, sk_kb_per_chunk;
+  float* sk_scratch;      // [tail tiles][BM][BN] fp32, all zero between launches
+  int* sk_counters;       // [tail tiles], all zero between launches
+  int sk_debug;           // timing experiments only (VLB_SK_DEBUG): 1 = skip the partial reds, 2 = skip the fix-up pass
 };
 
 // linear output-pixel index -> base pixel (w, h, n) of the im2col traversal
@@ -82,8 +89,16 @@ struct GroupTable {
   int ldo[MAX_GROUP];
 };
 
+// Stream-K tail (experimental, compiled out by default): measured on B200 it does not pay for this workload -- the partial
+// reds + arrival fence + fix-up pass cost ~8-12 us per launch, more than the partial round they remove (profiles/r01_streamk_*.log).
+#ifndef VLB_ENABLE_STREAMK
+#define VLB_ENABLE_STREAMK 0
+#endif
+
 struct ItemCoord {
   int g, split, m_blk, n_blk;
+  int kb_begin, kb_end;   // k-block range of this work unit
+  int tail;               // >= 0: index of the stream-K tail tile this unit is a K-chunk of
 };
 template <bool GROUPED>
 __device__ __forceinline__ ItemCoord decode_item(int item, const GemmParams& p, const GroupTable& gt) {
@@ -98,11 +113,25 @@ __device__ __forceinline__ ItemCoord decode_item(int item, const GemmParams& p, 
     mb = gt.m_blocks[c.g];
     nb = gt.n_blocks[c.g];
   }
+  c.tail = -1;
+  if (VLB_ENABLE_STREAMK && !GROUPED && p.sk_chunks > 1 && item >= p.sk_full_items) {
+    const int u = item - p.sk_full_items;
+    c.tail = u / p.sk_chunks;
+    c.split = u - c.tail * p.sk_chunks;
+    const int tile = p.sk_full_items + c.tail;
+    c.m_blk = tile / nb;
+    c.n_blk = tile - c.m_blk * nb;
+    c.kb_begin = c.split * p.sk_kb_per_chunk;
+    c.kb_end = min(p.num_k_blocks, c.kb_begin + p.sk_kb_per_chunk);
+    return c;
+  }
   const int per_split = mb * nb;
   c.split = local / per_split;
   const int rem = local - c.split * per_split;
   c.m_blk = rem / nb;
   c.n_blk = rem - c.m_blk * nb;
+  c.kb_begin = c.split * p.kb_per_split;
+  c.kb_end = min(p.num_k_blocks, c.kb_begin + p.kb_per_split);
   return c;
 }
 
@@ -127,9 +156,12 @@ struct Cfg {
 //   every warp store touch 32 different cache lines, so the chunk is first transposed through a 4 KB XOR-swizzled
 //   shared-memory buffer: afterwards lane (r = lane/8, g = lane%8) owns 4 consecutive columns of rows r, r+4, ...,
 //   and all global loads (bias, residual, saved pre-activation) and stores are row-contiguous.
-template <int EPI>
+//   FROM_SCRATCH (stream-K fix-up): the accumulator chunk is not in registers but in an fp32 scratch tile in global memory
+//   (sk_src -> its first row / column, row stride sk_ld); it is read -- and reset to zero -- directly in the row-contiguous
+//   lane layout of phase 2, so those accesses are coalesced too.
+template <int EPI, bool FROM_SCRATCH = false>
 __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint32_t (&v)[32], float* stage, int lane,
-                                               int row_base, int col0, int M, int N) {
+                                               int row_base, int col0, int M, int N, float* sk_src = nullptr, int sk_ld = 0) {
   using T = EpiTraits<EPI>;
   const bool has_bias = T::kStatic ? T::bias : (e.bias != nullptr);
   const int act = T::kStatic ? T::act : e.act;
@@ -168,7 +200,18 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
     }
   }
   // ---- phase 1: transpose the accumulator chunk through shared memory ----
-  {
+  if (FROM_SCRATCH) {
+    float4 acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)   // all eight loads in flight before anything depends on them (one L2 round trip per chunk)
+      acc[i] = __ldcg(reinterpret_cast<const float4*>(sk_src + (size_t)(i * 4 + r0) * sk_ld + g * 4));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + r0;
+      __stcg(reinterpret_cast<float4*>(sk_src + (size_t)r * sk_ld + g * 4), make_float4(0.f, 0.f, 0.f, 0.f));   // scratch returns to zero
+      reinterpret_cast<float4*>(stage + r * 32)[g ^ (r & 7)] = acc[i];
+    }
+  } else {
     float4* dst = reinterpret_cast<float4*>(stage + lane * 32);
 #pragma unroll
     for (int gg = 0; gg < 8; ++gg)
@@ -271,6 +314,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
   uint64_t* tfull_bar = bars + 2 * C::STAGES;    // [2]
   uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  volatile uint32_t* sk_flag = tmem_slot + 2;   // stream-K: "this CTA delivered the last K-chunk of the tile"
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -313,8 +357,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
         const CUtensorMap* ptb = GROUPED ? &gt.tb[ic.g] : &tma_b;
         const int m0 = (ic.m_blk * (CL ? 2 : 1) + (int)rank) * BM;           // this CTA's 128 rows of the (256-row) super-tile
         const int n0 = ic.n_blk * BN + (int)rank * (CG2 ? BN / 2 : 0);       // CG2: this CTA's half of the B tile
-        const int kb_begin = ic.split * p.kb_per_split;
-        const int kb_end = min(p.num_k_blocks, kb_begin + p.kb_per_split);
+        const int kb_begin = ic.kb_begin, kb_end = ic.kb_end;
         // implicit-convolution operand: all divisions happen once per item; the k loop only increments
         PixelCoord cv_px{0, 0, 0};
         int cv_c0 = 0, cv_r = 0, cv_s = 0, cv_wo = 0, cv_ho = 0;
@@ -421,8 +464,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
       int it = 0;
       for (int item = worker; item < p.num_items; item += nworkers, ++it) {
         const ItemCoord ic = decode_item<GROUPED>(item, p, gt);
-        const int kb_begin = ic.split * p.kb_per_split;
-        const int kb_end = min(p.num_k_blocks, kb_begin + p.kb_per_split);
+        const int kb_begin = ic.kb_begin, kb_end = ic.kb_end;
         const int buf = it & 1;
         const uint32_t use = static_cast<uint32_t>(it >> 1);
         mbar_wait(smem_u32(&tempty_bar[buf]), (use & 1u) ^ 1u);
@@ -468,6 +510,41 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
       tc_fence_after();
       const int row_base = (m_blk * (CL ? 2 : 1) + (int)rank) * BM + q * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
+      if (VLB_ENABLE_STREAMK && !GROUPED && CM == 0 && ic.tail >= 0) {
+        // ---- stream-K work unit: add this K-chunk's partial tile into the scratch tile; the last chunk to arrive finishes it ----
+        float* sk_tile = p.sk_scratch + (size_t)ic.tail * (BM * BN);
+        GemmEpilogue es;
+        es.out = sk_tile; es.ldo = BN; es.out_kind = OUT_F32_ATOMIC;
+#pragma unroll 1
+        for (int c = half; c < BN / 32; c += 2) {
+          uint32_t v[32];
+          tmem_ld32(t_row + c * 32, v);
+          tmem_ld_wait();
+          if (!(p.sk_debug & 1)) epilogue_chunk<EPI_ATOMIC_F32>(es, v, stage, lane, q * 32, c * 32, BM, BN);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));   // the accumulator buffer is free again
+        __threadfence();                                           // this thread's reds are visible device-wide ...
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");   // ... for every epilogue thread of the CTA
+        if (warp == 2 && lane == 0) {
+          const int old = atomicAdd(p.sk_counters + ic.tail, 1);
+          const bool last = old == p.sk_chunks - 1;
+          if (last) p.sk_counters[ic.tail] = 0;                    // self-cleaning: ready for the next launch
+          *sk_flag = last ? 1u : 0u;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+        if (*sk_flag != 0u && !(p.sk_debug & 2)) {
+          __threadfence();
+#pragma unroll 1
+          for (int c = half; c < BN / 32; c += 2) {
+            uint32_t v[32];   // unused
+            epilogue_chunk<EPI, true>(eg, v, stage, lane, row_base, n_blk * BN + c * 32, Mg, Ng, sk_tile + (size_t)(q * 32) * BN + c * 32, BN);
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");   // sk_flag may be rewritten by the next unit
+        continue;
+      }
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
         uint32_t v[32];
@@ -701,11 +778,56 @@ int make_tmap_im2col(CUtensorMap* out, const void* ptr, const ConvGeom& g, uint3
   return VLB_OK;
 }
 
+bool gemm_streamk_compiled() { return VLB_ENABLE_STREAMK != 0; }
+
 void gemm_debug_override(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t mn_kadv) {
   g_dbg_mn_lbo = mn_lbo;
   g_dbg_mn_sbo = mn_sbo;
   g_dbg_mn_kadv = mn_kadv;
 }
+
+namespace {
+constexpr int SK_MAX_TAIL_TILES = 80;          // tail tiles are at most half a round (148 / 2)
+constexpr int SK_MAX_CHUNKS = 16;
+
+// how many K-chunks each tile of the last partial round is split into (0 / 1: leave the round as it is)
+int streamk_chunks(long tiles, int sms, int num_k_blocks) {
+  static const int on = [] { const char* v = getenv("VLB_STREAMK"); return v ? atoi(v) : 1; }();
+  if (!VLB_ENABLE_STREAMK || !on) return 0;
+  const int rem = (int)(tiles % sms);
+  static const int min_kb = [] { const char* v = getenv("VLB_SK_MIN_KB"); return v ? atoi(v) : 24; }();
+  // measured: partial reds + arrival + fix-up cost ~5 us per launch -- only a long reduction (K >= 1536) repays it
+  if (rem == 0 || rem * 2 > sms || rem > SK_MAX_TAIL_TILES || num_k_blocks < min_kb) return 0;
+  int chunks = sms / rem;
+  if (chunks > num_k_blocks / 2) chunks = num_k_blocks / 2;   // at least two k-blocks per unit
+  if (chunks > SK_MAX_CHUNKS) chunks = SK_MAX_CHUNKS;
+  static const int cap = [] { const char* v = getenv("VLB_SK_MAXCHUNKS"); return v ? atoi(v) : SK_MAX_CHUNKS; }();
+  if (chunks > cap) chunks = cap;
+  return chunks;
+}
+
+// fp32 scratch tiles + arrival counters of the stream-K tail: allocated once (never while a stream is capturing), zero on
+// entry of every launch and zeroed again by the unit that consumes them.  One GEMM stream per process.
+bool streamk_workspace(float** scratch, int** counters, cudaStream_t stream) {
+  static float* s_scratch = nullptr;
+  static int* s_counters = nullptr;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> g(mu);
+  if (s_scratch == nullptr) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return false;
+    const size_t bytes = (size_t)SK_MAX_TAIL_TILES * BM * 256 * sizeof(float);
+    if (cudaMalloc(&s_scratch, bytes) != cudaSuccess) { s_scratch = nullptr; return false; }
+    if (cudaMalloc(&s_counters, SK_MAX_TAIL_TILES * sizeof(int)) != cudaSuccess) { cudaFree(s_scratch); s_scratch = nullptr; return false; }
+    cudaMemset(s_scratch, 0, bytes);
+    cudaMemset(s_counters, 0, SK_MAX_TAIL_TILES * sizeof(int));
+    cudaDeviceSynchronize();
+  }
+  *scratch = s_scratch;
+  *counters = s_counters;
+  return true;
+}
+}  // namespace
 
 int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
               const GemmEpilogue& epi_in, int split_k, int force_bn, cudaStream_t stream, const ConvGeom* conv, int conv_side) {
@@ -743,12 +865,15 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
   } else if (force_bn == 128 || force_bn == 256 || force_bn == 64 || force_bn == 192) {
     bn = force_bn;
   } else {
-    // cost = rounds of the persistent grid x measured relative time of one tile
+    // cost = rounds of the persistent grid x measured relative time of one tile; with the stream-K tail the last partial
+    // round costs 1/chunks of a round plus the fix-up
     const int sk = split_k > 1 ? split_k : 1;
     auto cost1 = [&](int b) {
       const long items = (long)((M + BM - 1) / BM) * ((N + b - 1) / b) * sk;
-      const long rounds = (items + sms - 1) / sms;
       const double w = b == 64 ? 0.60 : (b == 128 ? 0.68 : (b == 192 ? 0.84 : 1.0));
+      const int chunks = (sk == 1 && mode != GEMM_TN) ? streamk_chunks(items, sms, (K + BK - 1) / BK) : 0;
+      if (chunks > 1) return ((double)(items / sms) + 1.0 / chunks + 0.2) * w;
+      const long rounds = (items + sms - 1) / sms;
       return rounds * w;
     };
     auto cost2 = [&](int b) {  // pair tiles: half the B traffic per CTA, same MMA time per round as the 128 x b tile
@@ -784,6 +909,20 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
   VLB_REQUIRE(sk == 1 || epi.out_kind == OUT_F32_ATOMIC, "gemm: split-K needs the atomic fp32 epilogue");
   p.num_items = p.num_m_blocks * p.num_n_blocks * sk;
   p.e = epi;
+  p.sk_full_items = p.num_items; p.sk_chunks = 0; p.sk_kb_per_chunk = 0; p.sk_scratch = nullptr; p.sk_counters = nullptr;
+  static const int sk_debug = [] { const char* v = getenv("VLB_SK_DEBUG"); return v ? atoi(v) : 0; }();
+  p.sk_debug = sk_debug;
+  if (cm == 0 && sk == 1 && mode != GEMM_TN) {
+    const int chunks = streamk_chunks(p.num_items, sms, p.num_k_blocks);
+    if (chunks > 1 && streamk_workspace(&p.sk_scratch, &p.sk_counters, stream)) {
+      const int tiles = p.num_items;
+      const int rem = tiles % sms;
+      p.sk_full_items = tiles - rem;
+      p.sk_kb_per_chunk = (p.num_k_blocks + chunks - 1) / chunks;
+      p.sk_chunks = (p.num_k_blocks + p.sk_kb_per_chunk - 1) / p.sk_kb_per_chunk;   // no empty chunks
+      p.num_items = p.sk_full_items + rem * p.sk_chunks;
+    }
+  }
   // K-major operand: rows x 128B, swizzle atoms of 8 rows -> SBO 1024B, 32B per UMMA_K step.
   // MN-major operand: boxes of 64(mn) x 64(k): k-groups of 8 rows at 1024B (SBO), next 64-wide mn
   // chunk at 8192B (LBO), 16 k-rows = 2048B per UMMA_K step.

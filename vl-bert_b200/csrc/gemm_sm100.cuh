@@ -36,6 +36,9 @@ struct GemmEpilogue {
   const float* colscale = nullptr;  // optional [N] fp32: x = acc * colscale[col] before the bias (frozen BatchNorm scale)
 };
 
+// whether the experimental stream-K tail was compiled in (-DVLB_ENABLE_STREAMK=1)
+bool gemm_streamk_compiled();
+
 // geometry of one convolution on an NHWC tensor (shared by the lowering kernels in conv.cu and the implicit-GEMM operand)
 struct ConvGeom {
   int N, H, W, C;      // input NHWC
