@@ -163,12 +163,40 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+_WATCHDOG = None
+
+
+def _arm_watchdog(seconds):
+    """A hang inside a CUDA/NCCL call holds the GIL, so the guard is a separate process: it polls this PID once a second, kills it
+    after `seconds`, and goes away by itself as soon as this process is gone (no stale PID is ever signalled)."""
+    global _WATCHDOG
+    import subprocess
+    script = "n=0; while kill -0 %d 2>/dev/null; do sleep 1; n=$((n+1)); if [ $n -ge %d ]; then kill -9 %d; exit 0; fi; done" % (
+        os.getpid(), int(seconds), os.getpid())
+    try:
+        _WATCHDOG = subprocess.Popen(["sh", "-c", script], stdin=subprocess.DEVNULL, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL,
+                                     start_new_session=True)
+    except Exception:  # noqa
+        _WATCHDOG = None
+
+
+def _disarm_watchdog():
+    global _WATCHDOG
+    if _WATCHDOG is not None:
+        try:
+            _WATCHDOG.kill()
+        except Exception:  # noqa
+            pass
+        _WATCHDOG = None
+
+
 def _bounded_teardown(dist):
     """End a multi-rank run without destroy_process_group(): tearing down a communicator whose collectives were captured in
     a CUDA graph hung once (and a hang there would eat the whole GPU lease).  Every rank has already passed the final
     barrier + device synchronize and rank 0 has printed its line, so the process simply exits."""
     sys.stdout.flush()
     sys.stderr.flush()
+    _disarm_watchdog()
     os._exit(0)
 
 
@@ -187,6 +215,7 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        _arm_watchdog(int(os.environ.get("VLB_BENCH_WATCHDOG_S", "900")))   # a multi-rank hang must not outlive the GPU lease
         dist.init_process_group("nccl", device_id=dev)
     import vlbert_b200
     lib = vlbert_b200._lib.lib()
