@@ -1,7 +1,7 @@
 #!/bin/bash
 # GPU bring-up driver for tools/gemm_probe.py: every section in its own process (a trapped kernel
 # poisons the CUDA context) and under its own timeout.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 {
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv

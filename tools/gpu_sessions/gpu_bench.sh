@@ -1,6 +1,6 @@
 #!/bin/bash
 # bench + ncu launch list (+ optional full capture of the GEMM kernels).  Usage: tools/gpu_bench.sh [full]
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 L=gpurun_out/gpu_bench.log
 : > $L

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Run the GPU parity tests section by section (separate processes: a trapped kernel poisons its CUDA context),
 # then smoke() and a short bench.  Logs land in gpurun_out/.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 L=gpurun_out/gpu_checks.log
 : > $L

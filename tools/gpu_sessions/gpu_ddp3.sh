@@ -1,6 +1,6 @@
 #!/bin/bash
 # N=2 data-parallel tuning: does the overlapped NCCL all-reduce steal SMs from the persistent GEMM grids?
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 L=gpurun_out/gpu_ddp3.log
 : > $L

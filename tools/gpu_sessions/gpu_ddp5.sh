@@ -1,6 +1,6 @@
 #!/bin/bash
 # N=4: CUDA-graph step with captured NCCL vs eager
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 L=gpurun_out/gpu_ddp5.log
 : > $L

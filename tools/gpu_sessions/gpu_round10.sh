@@ -1,14 +1,14 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
-L=gpurun_out/gpu_sk4.log
+L=gpurun_out/gpu_round10.log
 : > $L
 run() { echo "=== $*" >> $L; timeout "$1" "${@:2}" >> $L 2>&1; echo "--- exit $?" >> $L; }
-run 600 python -m pytest tests/test_gpu_kernels.py -q -x -k "streamk"
-for cfg in "VLB_STREAMK=0" "VLB_STREAMK=1"; do
-  echo "=== $cfg" >> $L
-  for shape in "0 6464 768 3072 0" "1 6464 768 3072 0" "1 6464 768 2304 0"; do
-    env $cfg timeout 120 python tools/gemm_one.py $shape 9 >> $L 2>&1
+run 900 python -m pytest tests/test_gpu_kernels.py -q -x -k "gemm"
+for sk in 0 1; do
+  echo "=== VLB_STREAMK=$sk" >> $L
+  for shape in "0 6464 768 3072" "0 6464 768 768" "0 6464 2304 768" "0 6464 3072 768" "1 6464 768 3072" "1 6464 768 2304" "1 6464 3072 768"; do
+    VLB_STREAMK=$sk timeout 120 python tools/gemm_one.py $shape 0 7 >> $L 2>&1
   done
 done
 echo "=== bench VLB_STREAMK=0" >> $L; VLB_STREAMK=0 timeout 400 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --skip-e2e >> $L 2>&1
@@ -16,7 +16,7 @@ echo "=== bench VLB_STREAMK=1" >> $L; VLB_STREAMK=1 timeout 400 python bench.py 
 grep -E "^===|^---|passed|failed|rror|mode " $L | head -60
 python - <<'PY'
 import json
-for line in open('gpurun_out/gpu_sk4.log'):
+for line in open('gpurun_out/gpu_round10.log'):
     if line.startswith('==='): hdr=line.strip()
     if line.startswith('{"metric"'):
         d=json.loads(line)
