@@ -231,6 +231,24 @@ int vlb_roi_align_nhwc_forward(const void* feat, const float* rois, void* out, i
 int vlb_roi_align_nhwc_backward(const void* grad_out, const float* rois, float* grad_feat, int K, int N, int C, int H,
                                 int W, int ph, int pw, float spatial_scale, int sampling_ratio, void* stream);
 
+/* ---- optimizer step after the path ---------------------------------------------
+ * Replaces AdamW.step (common/nlp/bert/optimization.py:129-187: Adam moments, bias-corrected step size, decoupled weight decay
+ * applied AFTER the update) and torch.nn.utils.clip_grad_norm_ of the trainer (common/trainer.py:139-147) for all parameter
+ * tensors at once.  `descs_device` is a DEVICE array of `count` descriptors (fp32 tensors); `hyper_device` a DEVICE array
+ * [count][4] f32 = (lr, lr * weight_decay, step_size, 0) per tensor for this step, 16-byte aligned.
+ * vlb_grad_sqnorm writes sum(g^2) over all tensors to sq[0]; vlb_adamw_step scales every gradient by
+ * min(1, max_norm / (sqrt(sq[0]) + 1e-6)) when sq != NULL and max_norm > 0 (gradients themselves are left untouched). */
+typedef struct VlbAdamWTensor {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t n;
+} VlbAdamWTensor;
+int vlb_grad_sqnorm(const VlbAdamWTensor* descs_device, int count, float* sq, void* stream);
+int vlb_adamw_step(const VlbAdamWTensor* descs_device, const float* hyper_device, int count, double beta1, double beta2,
+                   double eps, const float* sq, float max_norm, void* stream);
+
 /* ---- one BertLayer, forward and backward -------------------------------------------------------
  * Replaces BertLayer.forward (modeling.py:388-397) = BertAttention + BertIntermediate + BertOutput and
  * its autograd backward, as a fixed sequence of the kernels above on `stream`

@@ -13,6 +13,7 @@ Fixtures (kept small enough to commit):
   fastrcnn_e2e.npz       FastRCNN end to end (ResNet-101 C4 + RoIAlign + dilated res5 head, final_dim=64) on 2 images of
                          128x160: weights are re-generated from a seed (oracle/frontend_oracle.py:synth_frontend_state);
                          outputs, a slice of body4 and slices + norms of the conv-weight gradients are stored.
+  adamw.npz              4 steps of the reference AdamW (two param groups, warm-up lr, clip_grad_norm_ 1.0) on seeded tensors.
   roi_align_debug.npz    common/lib/roi_pooling/debug.py inputs + a 38x63 realistic case through the
                          reference's own CPU kernel (oracle/_ref, built by oracle/build_ref.py).
 """
@@ -252,6 +253,45 @@ def golden_fastrcnn_e2e():
           "|body4|", float(body4.abs().mean()))
 
 
+def adamw_case(seed=5):
+    """Shared with the tests: three parameter tensors in two groups (decay / no decay, different lr), 4 steps of seeded
+    gradients, a linear-warmup learning rate and global-norm clipping at 1.0."""
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(37, 19), (19,), (8, 3, 5)]
+    params = [torch.randn(s, generator=g) for s in shapes]
+    grads = [[torch.randn(s, generator=g) * (0.5 + k) for s in shapes] for k in range(4)]
+    groups = [dict(idx=[0, 2], lr=2e-3, weight_decay=0.01), dict(idx=[1], lr=1e-3, weight_decay=0.0)]
+    lr_scale = [0.25, 0.5, 0.75, 1.0]
+    return params, grads, groups, lr_scale
+
+
+def golden_adamw():
+    from common.nlp.bert.optimization import AdamW
+    import warnings
+    params, grads, groups, lr_scale = adamw_case()
+    ps = [torch.nn.Parameter(p.clone()) for p in params]
+    opt = AdamW([dict(params=[ps[i] for i in g["idx"]], lr=g["lr"], weight_decay=g["weight_decay"]) for g in groups],
+                lr=1e-3, betas=(0.9, 0.999), eps=1e-6)
+    base = [g["lr"] for g in groups]
+    out = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for k in range(4):
+            for grp, b in zip(opt.param_groups, base):
+                grp["lr"] = b * lr_scale[k]
+            for p, gr in zip(ps, grads[k]):
+                p.grad = gr.clone()
+            out["norm%d" % k] = np.float64(torch.nn.utils.clip_grad_norm_(ps, 1.0))     # common/trainer.py:139-147
+            opt.step()
+            for i, p in enumerate(ps):
+                out["p%d_step%d" % (i, k)] = p.detach().numpy().copy()
+    for i, p in enumerate(ps):
+        out["m%d" % i] = opt.state[p]["exp_avg"].numpy().copy()
+        out["v%d" % i] = opt.state[p]["exp_avg_sq"].numpy().copy()
+    np.savez_compressed(os.path.join(GOLD, "adamw.npz"), **out)
+    print("adamw: 4 steps, norms", [float(out["norm%d" % k]) for k in range(4)])
+
+
 def golden_roi_align():
     import build_ref
     ref = build_ref.load()
@@ -288,6 +328,7 @@ if __name__ == "__main__":
     golden_pretrain_heads()
     golden_fastrcnn()
     golden_fastrcnn_e2e()
+    golden_adamw()
     golden_roi_align()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)) // 1024, "KiB")

@@ -107,3 +107,14 @@ def frontend_shapes(num_layers=101, final_dim=64):
     shapes["obj_downsample.1.weight"] = (final_dim, 4096)
     shapes["obj_downsample.1.bias"] = (final_dim,)
     return shapes
+
+
+def adamw_case(seed=5):
+    """call-for-call identical to oracle/make_golden.py:adamw_case"""
+    g = torch.Generator().manual_seed(seed)
+    shapes = [(37, 19), (19,), (8, 3, 5)]
+    params = [torch.randn(s, generator=g) for s in shapes]
+    grads = [[torch.randn(s, generator=g) * (0.5 + k) for s in shapes] for k in range(4)]
+    groups = [dict(idx=[0, 2], lr=2e-3, weight_decay=0.01), dict(idx=[1], lr=1e-3, weight_decay=0.0)]
+    lr_scale = [0.25, 0.5, 0.75, 1.0]
+    return params, grads, groups, lr_scale

@@ -64,6 +64,8 @@ def _declare(lib):
     decl("vlb_im2col_nhwc", [P, P] + [I] * 12 + [P])
     decl("vlb_col2im_nhwc", [P, P, P] + [I] * 12 + [P])
     decl("vlb_conv_gemm", [P, I, P, I, P, I, I, I, P, P, P, I, P])
+    decl("vlb_grad_sqnorm", [P, I, P, P])
+    decl("vlb_adamw_step", [P, P, I, ctypes.c_double, ctypes.c_double, ctypes.c_double, P, ctypes.c_float, P])
     decl("vlb_conv_fprop", [P, P, P, I, P, I, P, P, P, I, P])
     decl("vlb_conv_wgrad", [P, P, P, I, P, I, I, P])
     decl("vlb_relu_bn_backward", [P, P, P, P, P, P, L, I, P])
@@ -106,6 +108,11 @@ class GroupedProblem(ctypes.Structure):
 class ConvGeom(ctypes.Structure):
     """VlbConvGeom"""
     _fields_ = [(n, ctypes.c_int) for n in ("N", "H", "W", "C", "Ho", "Wo", "kh", "kw", "stride", "pad", "dil")]
+
+
+class AdamWTensor(ctypes.Structure):
+    """VlbAdamWTensor"""
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p), ("n", c_int64)]
 
 
 class CastDesc(ctypes.Structure):

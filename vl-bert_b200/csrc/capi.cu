@@ -230,6 +230,13 @@ int vlb_conv_gemm(const void* col, int ld_col, const void* w, int ld_w, void* y,
   e.act = relu_mode == 1 ? ACT_RELU : (relu_mode == 2 ? ACT_RELU_POST : ACT_NONE);
   COUNTED(1, gemm_bf16(GEMM_NT, P, Cout, K, col, ld_col, w, ld_w, e, 1, 0, ST));
 }
+int vlb_grad_sqnorm(const VlbAdamWTensor* descs_device, int count, float* sq, void* stream) {
+  COUNTED(1, grad_sqnorm(descs_device, count, sq, ST));
+}
+int vlb_adamw_step(const VlbAdamWTensor* descs_device, const float* hyper_device, int count, double beta1, double beta2, double eps,
+                   const float* sq, float max_norm, void* stream) {
+  COUNTED(1, adamw_step(descs_device, hyper_device, count, beta1, beta2, eps, sq, max_norm, ST));
+}
 static ConvGeom to_geom(const VlbConvGeom* g) {
   ConvGeom c{g->N, g->H, g->W, g->C, g->Ho, g->Wo, g->kh, g->kw, g->stride, g->pad, g->dil, g->kh * g->kw * g->C};
   return c;

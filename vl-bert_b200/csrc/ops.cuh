@@ -66,4 +66,8 @@ int roi_align_nhwc_forward(const void* feat, const float* rois, void* out, int K
 int roi_align_nhwc_backward(const void* grad_out, const float* rois, float* grad_feat, int K, int N, int C, int H, int W, int ph, int pw,
                             float scale, int sampling_ratio, cudaStream_t stream);
 
+int grad_sqnorm(const VlbAdamWTensor* descs_device, int count, float* sq, cudaStream_t stream);
+int adamw_step(const VlbAdamWTensor* descs_device, const float* hyper_device, int count, double beta1, double beta2, double eps,
+               const float* sq, float max_norm, cudaStream_t stream);
+
 }  // namespace vlb

@@ -1,0 +1,115 @@
+// vlbert_b200 -- the optimizer step that follows the hot path: multi-tensor AdamW with decoupled weight
+// decay exactly as the reference's AdamW.step (common/nlp/bert/optimization.py:129-187) and the global-norm gradient clip of
+// the trainer (common/trainer.py:139-147, torch.nn.utils.clip_grad_norm_), in two launches for the whole model instead of
+// ~10 elementwise kernels per parameter tensor.  HBM-bound: 16 B read + 12 B written per parameter.
+#include "common.cuh"
+
+namespace vlb {
+
+namespace {
+
+// sum of squares of every gradient -> sq[0] (fp32 atomics of per-block partial sums; sq must be zero on entry)
+__global__ void grad_sqnorm_kernel(const VlbAdamWTensor* __restrict__ descs, float* __restrict__ sq) {
+  const VlbAdamWTensor d = descs[blockIdx.y];
+  const float* __restrict__ g = d.grad;
+  const size_t n = (size_t)d.n;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  float acc = 0.0f;
+  if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+    const size_t nv = n >> 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nv; i += stride) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(g) + i);
+      acc += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float a = g[(nv << 2) + threadIdx.x]; acc += a * a; }
+  } else {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += stride) { const float a = g[i]; acc += a * a; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float warp_sum[8];
+  if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += warp_sum[w];
+    if (t != 0.0f) atomicAdd(sq, t);
+  }
+}
+
+// hyper[t] = (lr, lr * weight_decay, step_size, unused) of tensor t for THIS step (step_size carries the bias correction)
+struct AdamConst { float beta1, beta2, omb1, omb2, eps; };   // omb = 1 - beta, rounded from the double-precision difference like torch does
+
+__device__ __forceinline__ float adamw_one(float& p, float g, float& m, float& v, const AdamConst& c, float step_size, float lr_wd) {
+  // optimization.py:160-169: m <- m*b1 + (1-b1) g ; v <- v*b2 + (1-b2) g*g ; denom = sqrt(v) + eps ; p <- p - step_size * m / denom
+  const float eps = c.eps;
+  m = __fadd_rn(__fmul_rn(m, c.beta1), __fmul_rn(c.omb1, g));
+  v = __fadd_rn(__fmul_rn(v, c.beta2), __fmul_rn(__fmul_rn(c.omb2, g), g));
+  const float denom = __fadd_rn(__fsqrt_rn(v), eps);
+  p = __fadd_rn(p, __fmul_rn(-step_size, __fdiv_rn(m, denom)));
+  // :180-181 decoupled decay AFTER the Adam update, on the updated parameter: p <- p - lr*wd*p
+  if (lr_wd > 0.0f) p = __fadd_rn(p, __fmul_rn(-lr_wd, p));
+  return p;
+}
+
+__global__ void adamw_kernel(const VlbAdamWTensor* __restrict__ descs, const float4* __restrict__ hyper, AdamConst c,
+                             const float* __restrict__ sq, float max_norm) {
+  const VlbAdamWTensor d = descs[blockIdx.y];
+  const float4 h = hyper[blockIdx.y];
+  // clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), applied only when < 1
+  float coef = 1.0f;
+  if (sq != nullptr && max_norm > 0.0f) {
+    const float c = max_norm / (sqrtf(*sq) + 1e-6f);
+    coef = c < 1.0f ? c : 1.0f;
+  }
+  const size_t n = (size_t)d.n;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  float* __restrict__ p = d.param;
+  const float* __restrict__ g = d.grad;
+  float* __restrict__ m = d.exp_avg;
+  float* __restrict__ v = d.exp_avg_sq;
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  const size_t nv = vec ? (n >> 2) : 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nv; i += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    adamw_one(pp.x, gg.x * coef, mm.x, vv.x, c, h.z, h.y);
+    adamw_one(pp.y, gg.y * coef, mm.y, vv.y, c, h.z, h.y);
+    adamw_one(pp.z, gg.z * coef, mm.z, vv.z, c, h.z, h.y);
+    adamw_one(pp.w, gg.w * coef, mm.w, vv.w, c, h.z, h.y);
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  for (size_t i = (nv << 2) + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    float pp = p[i], mm = m[i], vv = v[i];
+    adamw_one(pp, g[i] * coef, mm, vv, c, h.z, h.y);
+    p[i] = pp; m[i] = mm; v[i] = vv;
+  }
+}
+
+}  // namespace
+
+int grad_sqnorm(const VlbAdamWTensor* descs_device, int count, float* sq, cudaStream_t stream) {
+  VLB_REQUIRE(descs_device && sq && count > 0, "grad_sqnorm: bad arguments");
+  VLB_CHECK_CUDA(cudaMemsetAsync(sq, 0, sizeof(float), stream));
+  grad_sqnorm_kernel<<<dim3(16, count), 256, 0, stream>>>(descs_device, sq);
+  VLB_CHECK_LAUNCH();
+  return VLB_OK;
+}
+
+int adamw_step(const VlbAdamWTensor* descs_device, const float* hyper_device, int count, double beta1, double beta2, double eps,
+               const float* sq, float max_norm, cudaStream_t stream) {
+  VLB_REQUIRE(descs_device && hyper_device && count > 0, "adamw_step: bad arguments");
+  VLB_REQUIRE((reinterpret_cast<uintptr_t>(hyper_device) & 15) == 0, "adamw_step: hyper table must be 16-byte aligned");
+  VLB_REQUIRE(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps >= 0.0, "adamw_step: bad hyper-parameters");
+  const AdamConst c{(float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps};
+  adamw_kernel<<<dim3(16, count), 256, 0, stream>>>(descs_device, reinterpret_cast<const float4*>(hyper_device), c, sq, max_norm);
+  VLB_CHECK_LAUNCH();
+  return VLB_OK;
+}
+
+}  // namespace vlb
