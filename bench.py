@@ -190,6 +190,22 @@ def _disarm_watchdog():
         _WATCHDOG = None
 
 
+def _ncu_traffic():
+    """DRAM bytes per GEMM launch from the committed `ncu --set full` capture of one encoder layer's backward GEMMs
+    (dram__bytes_read.sum + dram__bytes_write.sum, mean over the captured launches); None if the capture is absent."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_full_gemm_v4_backward_layer.csv")
+    try:
+        import csv
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = sum(float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]] for r in rows[2:])
+        return {"bytes_per_launch": tot / max(1, len(rows) - 2), "launches": len(rows) - 2, "source": "profiles/" + os.path.basename(path)}
+    except Exception:  # noqa
+        return None
+
+
 def _bounded_teardown(dist):
     """End a multi-rank run without destroy_process_group(): tearing down a communicator whose collectives were captured in
     a CUDA graph hung once (and a hang there would eat the whole GPU lease).  Every rank has already passed the final
@@ -390,7 +406,8 @@ def main():
         "gpu_launches": int(launches), "cuda_graph": graphed is not None,
         "roofline": {"bound": "tensor", "kernel": "gemm_kernel<BN,A_MN,B_MN> (all tcgen05 GEMM launches of the step)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
-                     "peak_kind": pk_kind + " bf16_tflops_sustained", "traffic": None,
+                     "peak_kind": pk_kind + " bf16_tflops_sustained", "traffic": (_ncu_traffic() or {}).get("bytes_per_launch"),
+                     "traffic_source": (_ncu_traffic() or {}).get("source"),
                      "share_of_step": gemm_ms / prof_steps / ms if ms > 0 else None,
                      "measured": "CUDA events around every GEMM launch on the launch stream, %d eager steps of the same workload inside this run" % prof_steps},
         "kernel_profile": prof,
