@@ -116,3 +116,69 @@ def _unpatched_fastrcnn():
     import importlib
     import common.fast_rcnn as m
     return importlib.reload(m).FastRCNN
+
+
+def _fake_hf_checkpoint(kind, H=64, L=2, I=128, vocab=120, tmp_path=None):
+    """a state_dict with HuggingFace BERT (old TF-style gamma/beta names, cls.* heads) or RoBERTa (roberta.*, lm_head.*, one
+    token type) key names, random values"""
+    g = torch.Generator().manual_seed(7 if kind == "bert" else 8)
+    r = lambda *s: torch.randn(*s, generator=g)
+    pre = "bert." if kind == "bert" else "roberta."
+    ln_w, ln_b = ("gamma", "beta") if kind == "bert" else ("weight", "bias")
+    sd = {pre + "embeddings.word_embeddings.weight": r(vocab, H), pre + "embeddings.position_embeddings.weight": r(40, H),
+          pre + "embeddings.token_type_embeddings.weight": r(2 if kind == "bert" else 1, H),
+          pre + "embeddings.LayerNorm." + ln_w: r(H), pre + "embeddings.LayerNorm." + ln_b: r(H),
+          pre + "embeddings.position_ids": torch.arange(40)[None],                       # unexpected key
+          pre + "pooler.dense.weight": r(H, H), pre + "pooler.dense.bias": r(H)}
+    for l in range(L):
+        q = pre + "encoder.layer.%d." % l
+        for n, shp in (("attention.self.query", (H, H)), ("attention.self.key", (H, H)), ("attention.self.value", (H, H)),
+                       ("attention.output.dense", (H, H)), ("intermediate.dense", (I, H)), ("output.dense", (H, I))):
+            sd[q + n + ".weight"], sd[q + n + ".bias"] = r(*shp), r(shp[0])
+        for n in ("attention.output.LayerNorm", "output.LayerNorm"):
+            sd[q + n + "." + ln_w], sd[q + n + "." + ln_b] = r(H), r(H)
+    if kind == "bert":
+        sd.update({"cls.seq_relationship.weight": r(2, H), "cls.seq_relationship.bias": r(2),
+                   "cls.predictions.bias": r(vocab), "cls.predictions.transform.dense.weight": r(H, H),
+                   "cls.predictions.transform.dense.bias": r(H), "cls.predictions.transform.LayerNorm.gamma": r(H),
+                   "cls.predictions.transform.LayerNorm.beta": r(H), "cls.predictions.decoder.weight": r(vocab, H)})
+    else:
+        sd.update({"lm_head.bias": r(vocab), "lm_head.dense.weight": r(H, H), "lm_head.dense.bias": r(H),
+                   "lm_head.layer_norm.weight": r(H), "lm_head.layer_norm.bias": r(H), "lm_head.decoder.weight": r(vocab, H)})
+    sd["some.other.tensor"] = r(3)
+    return sd
+
+
+@pytest.mark.parametrize("kind", ["bert", "roberta"])
+@pytest.mark.parametrize("pretraining", [False, True])
+def test_language_checkpoint_loader_equals_the_reference(tmp_path, kind, pretraining, capsys):
+    """load_language_pretrained_model (common/visual_linguistic_bert.py:243-309 and :382-470): same tensors end up in the same
+    parameters, including the relationship / MLM heads of the pre-training class and the RoBERTa renames."""
+    ref_shim.install()
+    import vlbert_b200
+    import common.visual_linguistic_bert as ref_mod
+    import importlib
+    ref_mod = importlib.reload(ref_mod)            # undo a drop-in patch made by an earlier test
+    path = str(tmp_path / "lm.bin")
+    torch.save(_fake_hf_checkpoint(kind), path)
+    kw = dict(vocab_size=120, hidden_size=64, num_hidden_layers=2, num_attention_heads=1, intermediate_size=128,
+              max_position_embeddings=40, visual_size=64, visual_region_classes=7, pos_embedding_frozen=False)
+    if pretraining:
+        ref = ref_mod.VisualLinguisticBertForPretraining(ref_shim.vlbert_config(**kw), path)
+        ours = vlbert_b200.VisualLinguisticBertForPretraining(vo.default_config(**kw), path)
+    else:
+        ref = ref_mod.VisualLinguisticBert(ref_shim.vlbert_config(**kw), path)
+        ours = vlbert_b200.VisualLinguisticBert(vo.default_config(**kw), path)
+    capsys.readouterr()
+    a, b = ref.state_dict(), ours.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    heads = ("relationsip_head.", "mlm_head.") if kind == "bert" else ("mlm_head.",)     # RoBERTa ships no relationship head
+    loaded = [k for k in a if k.startswith(("encoder.", "embedding_LayerNorm.", "word_embeddings.", "position_embeddings.", "pooler.")
+                                           + heads)] + ["token_type_embeddings.weight"]
+    for k in loaded:
+        if k == "token_type_embeddings.weight":
+            rows = 2 if (kind == "bert" or pretraining) else 3    # rows the loader writes (the rest keep their random init)
+            assert torch.equal(a[k][:rows], b[k][:rows]), k
+        elif k.startswith("mlm_head.") and "decoder.weight" not in k or not k.startswith("mlm_head."):
+            assert torch.equal(a[k], b[k]), k
+    assert torch.equal(b["mlm_head.predictions.decoder.weight"], b["word_embeddings.weight"]) if pretraining else True

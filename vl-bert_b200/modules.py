@@ -238,45 +238,73 @@ class VisualLinguisticBert(BaseModel):
         return texts, objs, pooled_output
 
     def load_language_pretrained_model(self, language_pretrained_model_path):
-        """HF BERT checkpoint key remapping (common/visual_linguistic_bert.py:243-309)."""
+        """Initialise from a HuggingFace BERT / RoBERTa checkpoint (common/visual_linguistic_bert.py:243-309; the pre-training
+        subclass also takes the `cls.seq_relationship.*` / `cls.predictions.*` / `lm_head.*` heads, :382-470)."""
         sd = torch.load(language_pretrained_model_path, map_location="cpu")
-        enc, pool, emb_ln, unexpected = {}, {}, {}, []
-        for k, v in sd.items():
-            if k.startswith("bert."):
-                k = k[len("bert."):]
-            elif k.startswith("roberta."):
-                k = k[len("roberta."):]
+        own = {"encoder": self.encoder.state_dict(), "ln": self.embedding_LayerNorm.state_dict(),
+               "pooler": self.pooler.state_dict() if self.config.with_pooler else {}}
+        rel_head = getattr(self, "relationsip_head", None) if getattr(self, "with_rel_head", False) else None
+        mlm_head = getattr(self, "mlm_head", None) if getattr(self, "with_mlm_head", False) else None
+        picked = {"encoder": {}, "ln": {}, "pooler": {}, "rel": {}, "mlm": {}}
+        unexpected = []
+
+        def rename(k):  # TF-style parameter names of old checkpoints
+            return k.replace("gamma", "weight").replace("beta", "bias")
+
+        def put(table, k, v, raw, known):
+            if k in known:
+                picked[table][k] = v
             else:
-                unexpected.append(k)
-                continue
-            k = k.replace("gamma", "weight").replace("beta", "bias")
-            if k.startswith("encoder."):
-                enc[k[len("encoder."):]] = v
-            elif k.startswith("embeddings."):
-                k = k[len("embeddings."):]
-                if k.startswith("word_embeddings."):
-                    self.word_embeddings.weight.data = v.to(self.word_embeddings.weight.dtype)
-                elif k.startswith("position_embeddings."):
-                    self.position_embeddings.weight.data = v.to(self.position_embeddings.weight.dtype)
-                elif k.startswith("token_type_embeddings."):
-                    n = v.size(0)
-                    self.token_type_embeddings.weight.data[:n] = v.to(self.token_type_embeddings.weight.dtype)
-                    if n == 1:  # roberta: replicate for the second sentence type
-                        self.token_type_embeddings.weight.data[1] = v[0].clone().to(self.token_type_embeddings.weight.dtype)
-                elif k.startswith("LayerNorm."):
-                    emb_ln[k[len("LayerNorm."):]] = v
+                unexpected.append(raw)
+
+        for raw, v in sd.items():
+            if raw.startswith(("bert.", "roberta.")):
+                k = rename(raw.split(".", 1)[1])
+                if k.startswith("encoder."):
+                    put("encoder", k[len("encoder."):], v, raw, own["encoder"])
+                elif k.startswith("embeddings."):
+                    k = k[len("embeddings."):]
+                    if k == "word_embeddings.weight":
+                        self.word_embeddings.weight.data = v.to(self.word_embeddings.weight.data)
+                    elif k == "position_embeddings.weight":
+                        self.position_embeddings.weight.data = v.to(self.position_embeddings.weight.data)
+                    elif k == "token_type_embeddings.weight":
+                        w = self.token_type_embeddings.weight.data
+                        w[:v.size(0)] = v.to(w)
+                        if v.size(0) == 1:      # RoBERTa has one token type: replicate it (:280-287; the pre-training class
+                            w[1] = v[0].to(w)   # fills only row 1, :415-419)
+                            if rel_head is None and mlm_head is None and not isinstance(self, VisualLinguisticBertForPretraining):
+                                w[2] = v[0].to(w)
+                    elif k.startswith("LayerNorm."):
+                        put("ln", k[len("LayerNorm."):], v, raw, own["ln"])
+                    else:
+                        unexpected.append(raw)
+                elif self.config.with_pooler and k.startswith("pooler."):
+                    put("pooler", k[len("pooler."):], v, raw, own["pooler"])
+                # (anything else under bert./roberta. is silently ignored, like the reference)
+            elif rel_head is not None and raw.startswith("cls.seq_relationship."):
+                put("rel", rename(raw[len("cls.seq_relationship."):]), v, raw, rel_head.caption_image_relationship.state_dict())
+            elif mlm_head is not None and raw.startswith(("cls.predictions.", "lm_head.")):
+                if raw.startswith("lm_head."):  # RoBERTa naming of the LM head
+                    k = raw[len("lm_head."):]
+                    if "dense" in k or "layer_norm" in k:
+                        k = "transform." + k
+                    k = k.replace("layer_norm", "LayerNorm")
                 else:
-                    unexpected.append(k)
-            elif self.config.with_pooler and k.startswith("pooler."):
-                pool[k[len("pooler."):]] = v
+                    k = raw[len("cls.predictions."):]
+                put("mlm", rename(k), v, raw, mlm_head.predictions.state_dict())
             else:
-                unexpected.append(k)
+                unexpected.append(raw)
         if unexpected:
             print("Warnings: Unexpected keys: {}.".format(unexpected))
-        self.embedding_LayerNorm.load_state_dict(emb_ln)
-        self.encoder.load_state_dict(enc)
-        if self.config.with_pooler and pool:
-            self.pooler.load_state_dict(pool)
+        self.embedding_LayerNorm.load_state_dict(picked["ln"])
+        self.encoder.load_state_dict(picked["encoder"])
+        if self.config.with_pooler and picked["pooler"]:
+            self.pooler.load_state_dict(picked["pooler"])
+        if rel_head is not None and picked["rel"]:
+            rel_head.caption_image_relationship.load_state_dict(picked["rel"])
+        if mlm_head is not None:
+            mlm_head.predictions.load_state_dict(picked["mlm"])
 
 
 # ------------------------------------------------------------------------------------------------
