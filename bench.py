@@ -231,7 +231,7 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        _arm_watchdog(int(os.environ.get("VLB_BENCH_WATCHDOG_S", "900")))   # a multi-rank hang must not outlive the GPU lease
+        _arm_watchdog(int(os.environ.get("VLB_BENCH_WATCHDOG_S", "420")))   # a multi-rank hang must not outlive the GPU lease
         dist.init_process_group("nccl", device_id=dev)
     import vlbert_b200
     lib = vlbert_b200._lib.lib()
