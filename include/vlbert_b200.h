@@ -249,6 +249,17 @@ int vlb_grad_sqnorm(const VlbAdamWTensor* descs_device, int count, float* sq, vo
 int vlb_adamw_step(const VlbAdamWTensor* descs_device, const float* hyper_device, int count, double beta1, double beta2,
                    double eps, const float* sq, float max_norm, void* stream);
 
+/* ---- dropout contract -----------------------------------------------------------------------------
+ * Counter-based masks (Philox4x32-10): element i of a row-major tensor is kept iff word (i % 4) of
+ * philox(counter = (i/4 lo, i/4 hi, site, step), key = (seed lo, seed hi)) >= floor(p * 2^32); kept values are scaled by
+ * 1/(1-p).  `site` numbers the nn.Dropout call sites of the reference (modeling.py:283,316,334,379,
+ * common/visual_linguistic_bert.py:75, common/fast_rcnn.py:104), `step` the training step: forward and backward regenerate
+ * the same mask, nothing is stored, and oracle/philox.py reproduces it on the CPU.  The reference's own masks come from
+ * torch's global generator and cannot be reproduced by any implementation; this is the contract the fused kernels are
+ * specified against.  vlb_dropout_mask writes the keep flags (uint8), vlb_dropout applies them to a bf16 / f32 tensor. */
+int vlb_dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t seed, uint32_t site, uint32_t step, void* stream);
+int vlb_dropout(const void* x, void* y, int64_t n, int is_bf16, float p, uint64_t seed, uint32_t site, uint32_t step, void* stream);
+
 /* ---- one BertLayer, forward and backward -------------------------------------------------------
  * Replaces BertLayer.forward (modeling.py:388-397) = BertAttention + BertIntermediate + BertOutput and
  * its autograd backward, as a fixed sequence of the kernels above on `stream`

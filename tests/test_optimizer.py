@@ -95,3 +95,28 @@ def test_fused_adamw_against_reference_fixture(golden_dir):
         assert np.abs(opt.state[p]["exp_avg_sq"].cpu().numpy() - G["v%d" % i]).max() <= 4e-6 * np.abs(G["v%d" % i]).max()
     sd = opt.state_dict()
     assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"} and sd["state"][0]["step"] == 4
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: first hardware run is the driver's round-end "
+                                        "suite (XPASS = verified); the same source is executed on the host in tests/test_philox.py")
+def test_dropout_contract_on_the_device():
+    """vlb_dropout_mask / vlb_dropout against oracle/philox.py: bit-exact masks, kept values scaled by 1/(1-p)"""
+    import philox
+    import vlbert_b200
+    L = vlbert_b200._lib
+    st = torch.cuda.current_stream().cuda_stream
+    for (n, p, seed, site, step) in ((1003, 0.1, 1234567890123, 5, 17), (6464 * 768, 0.1, 42, 13, 3), (7, 0.5, 1, 0, 0)):
+        keep = torch.empty(n, dtype=torch.uint8, device="cuda")
+        L.check(L.lib().vlb_dropout_mask(keep.data_ptr(), n, p, seed, site, step, st))
+        ref = philox.keep_mask((n,), p, seed, site, step)
+        assert np.array_equal(keep.cpu().numpy().astype(bool), ref)
+        x = torch.randn(n, device="cuda")
+        y = torch.empty_like(x)
+        L.check(L.lib().vlb_dropout(x.data_ptr(), y.data_ptr(), n, 0, p, seed, site, step, st))
+        want = torch.where(torch.from_numpy(ref).cuda(), x * (1.0 / (1.0 - np.float32(p))), torch.zeros_like(x))
+        assert torch.allclose(y, want, rtol=1e-6, atol=0)
+        xb = x.to(torch.bfloat16)
+        yb = torch.empty_like(xb)
+        L.check(L.lib().vlb_dropout(xb.data_ptr(), yb.data_ptr(), n, 1, p, seed, site, step, st))
+        assert torch.equal(yb == 0, ~torch.from_numpy(ref).cuda() | (xb == 0))

@@ -64,6 +64,8 @@ def _declare(lib):
     decl("vlb_im2col_nhwc", [P, P] + [I] * 12 + [P])
     decl("vlb_col2im_nhwc", [P, P, P] + [I] * 12 + [P])
     decl("vlb_conv_gemm", [P, I, P, I, P, I, I, I, P, P, P, I, P])
+    decl("vlb_dropout_mask", [P, L, ctypes.c_float, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, P])
+    decl("vlb_dropout", [P, P, L, I, ctypes.c_float, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, P])
     decl("vlb_grad_sqnorm", [P, I, P, P])
     decl("vlb_adamw_step", [P, P, I, ctypes.c_double, ctypes.c_double, ctypes.c_double, P, ctypes.c_float, P])
     decl("vlb_conv_fprop", [P, P, P, I, P, I, P, P, P, I, P])

@@ -237,6 +237,12 @@ int vlb_adamw_step(const VlbAdamWTensor* descs_device, const float* hyper_device
                    const float* sq, float max_norm, void* stream) {
   COUNTED(1, adamw_step(descs_device, hyper_device, count, beta1, beta2, eps, sq, max_norm, ST));
 }
+int vlb_dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t seed, uint32_t site, uint32_t step, void* stream) {
+  COUNTED(1, dropout_mask(keep, n, p, seed, site, step, ST));
+}
+int vlb_dropout(const void* x, void* y, int64_t n, int is_bf16, float p, uint64_t seed, uint32_t site, uint32_t step, void* stream) {
+  COUNTED(1, dropout_apply(x, y, n, is_bf16, p, seed, site, step, ST));
+}
 static ConvGeom to_geom(const VlbConvGeom* g) {
   ConvGeom c{g->N, g->H, g->W, g->C, g->Ho, g->Wo, g->kh, g->kw, g->stride, g->pad, g->dil, g->kh * g->kw * g->C};
   return c;

@@ -70,4 +70,7 @@ int grad_sqnorm(const VlbAdamWTensor* descs_device, int count, float* sq, cudaSt
 int adamw_step(const VlbAdamWTensor* descs_device, const float* hyper_device, int count, double beta1, double beta2, double eps,
                const float* sq, float max_norm, cudaStream_t stream);
 
+int dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t seed, uint32_t site, uint32_t step, cudaStream_t stream);
+int dropout_apply(const void* x, void* y, int64_t n, int is_bf16, float p, uint64_t seed, uint32_t site, uint32_t step, cudaStream_t stream);
+
 }  // namespace vlb

@@ -113,3 +113,68 @@ int adamw_step(const VlbAdamWTensor* descs_device, const float* hyper_device, in
 }
 
 }  // namespace vlb
+
+// ---- dropout contract on the device (csrc/philox.cuh): the mask itself, and a stand-alone bf16/f32 dropout -------------
+#include "philox.cuh"
+
+namespace vlb {
+namespace {
+
+__global__ void dropout_mask_kernel(uint8_t* __restrict__ keep, size_t n, uint32_t thresh, uint64_t seed, uint32_t site, uint32_t step) {
+  const size_t groups = (n + 3) >> 2;
+  for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x) {
+    const Philox4 r = dropout_words(g, seed, site, step);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (g * 4 + j < n) keep[g * 4 + j] = w[j] >= thresh ? 1 : 0;
+  }
+}
+
+template <typename T>
+__global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, size_t n, uint32_t thresh, float scale, uint64_t seed,
+                               uint32_t site, uint32_t step) {
+  const size_t groups = (n + 3) >> 2;
+  for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x) {
+    const Philox4 r = dropout_words(g, seed, site, step);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const size_t i = g * 4 + j;
+      if (i < n) y[i] = w[j] >= thresh ? (T)((float)x[i] * scale) : (T)0.0f;
+    }
+  }
+}
+
+int dropout_grid(size_t n) {
+  const size_t groups = (n + 3) >> 2;
+  size_t g = (groups + 255) / 256;
+  const size_t cap = (size_t)num_sms() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+int dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t seed, uint32_t site, uint32_t step, cudaStream_t stream) {
+  VLB_REQUIRE(keep && n >= 0 && p >= 0.0f && p < 1.0f, "dropout_mask: bad arguments");
+  if (n == 0) return VLB_OK;
+  dropout_mask_kernel<<<dropout_grid((size_t)n), 256, 0, stream>>>(keep, (size_t)n, dropout_threshold(p), seed, site, step);
+  VLB_CHECK_LAUNCH();
+  return VLB_OK;
+}
+
+int dropout_apply(const void* x, void* y, int64_t n, int is_bf16, float p, uint64_t seed, uint32_t site, uint32_t step, cudaStream_t stream) {
+  VLB_REQUIRE(x && y && n >= 0 && p >= 0.0f && p < 1.0f, "dropout: bad arguments");
+  if (n == 0) return VLB_OK;
+  const float scale = 1.0f / (1.0f - p);
+  if (is_bf16)
+    dropout_kernel<__nv_bfloat16><<<dropout_grid((size_t)n), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y),
+                                                                             (size_t)n, dropout_threshold(p), scale, seed, site, step);
+  else
+    dropout_kernel<float><<<dropout_grid((size_t)n), 256, 0, stream>>>(static_cast<const float*>(x), static_cast<float*>(y), (size_t)n,
+                                                                     dropout_threshold(p), scale, seed, site, step);
+  VLB_CHECK_LAUNCH();
+  return VLB_OK;
+}
+
+}  // namespace vlb
