@@ -83,6 +83,8 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.rows, self.stop_flag, self.index = [], False, index
         self.max_mhz = None
+        self.active = False      # samples are kept only while a timed region is running (the thread itself starts earlier: NVML init takes ~0.1 s)
+        self.ready = threading.Event()
 
     def run(self):
         try:
@@ -91,21 +93,30 @@ class ClockSampler(threading.Thread):
             h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
             names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            self.ready.set()
             while not self.stop_flag:
+                if not self.active:
+                    time.sleep(0.002)
+                    continue
                 mhz = int(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
                 try:
                     mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
                 except Exception:
                     mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-                self.rows.append((mhz, [n for b, n in names.items() if mask & b]))
-                time.sleep(0.01)
+                if self.active:
+                    self.rows.append((mhz, [n for b, n in names.items() if mask & b]))
+                time.sleep(0.005)
             return
         except Exception:
             pass
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        self.ready.set()
         while not self.stop_flag:
+            if not self.active:
+                time.sleep(0.002)
+                continue
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
@@ -297,25 +308,29 @@ def main():
     vlbert_b200._lib.check(lib.vlb_profile_collect(pms, pwork, pcnt))
 
     # ---------------- device-resident arm ----------------
-    for _ in range(max(3, args.warmup)):
-        step(dev_inputs)
-    barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    for _ in range(max(3, args.warmup)):
+        step(dev_inputs)
+    if sampler:
+        sampler.ready.wait(5.0)
+    barrier()
     n0 = vlbert_b200._lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if sampler:
+        sampler.active = True
     e0.record()
     for _ in range(args.steps):
         step(dev_inputs)
     e1.record()
     barrier()
+    if sampler:
+        sampler.active = False
     launches_eager = 0
     if graphed is None:
         launches_eager = (vlbert_b200._lib.launch_count() - n0) // max(1, args.steps)
-    if sampler:
-        sampler.stop_flag = True
     ms = e0.elapsed_time(e1) / args.steps
     t = torch.tensor([ms], device=dev)
     if dist is not None:
@@ -365,13 +380,19 @@ def main():
             barrier()
             t0 = torch.cuda.Event(enable_timing=True)
             t1 = torch.cuda.Event(enable_timing=True)
+            if sampler:
+                sampler.active = True       # the end-to-end repeats are timed regions too: more clock samples
             t0.record()
             wall0 = time.perf_counter()
             last_loss = e2e_loop(args.steps)
             t1.record()
             barrier()
+            if sampler:
+                sampler.active = False
             e2e_runs.append(max(t0.elapsed_time(t1), (time.perf_counter() - wall0) * 1e3) / args.steps)
         e2e_ms = min(e2e_runs)
+    if sampler:
+        sampler.stop_flag = True
     t = torch.tensor([e2e_ms], device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
