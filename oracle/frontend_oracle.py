@@ -106,7 +106,7 @@ class _RoIAlign(torch.autograd.Function):
 
 
 def fast_rcnn_end2end(sd, images, boxes, box_mask, im_info, layers=(3, 4, 23), stride_in_1x1=True, c5_dilated=True,
-                      mvrc_ops=None, mask_visual_embed=None, storage=None):
+                      mvrc_ops=None, mask_visual_embed=None, storage=None, segms=None):
     """common/fast_rcnn.py:128-193 (no classes / segms, dropout p = 0).  Returns obj_reps [B,R,D], obj_reps_raw [B,R,2048]."""
     q = _q(storage)
     B, R = box_mask.shape
@@ -115,6 +115,8 @@ def fast_rcnn_end2end(sd, images, boxes, box_mask, im_info, layers=(3, 4, 23), s
     rois = torch.cat((idx[:, 0, None].to(boxes.dtype), boxes[idx[:, 0], idx[:, 1]][:, :4]), 1)
     pooled = q(_RoIAlign.apply(feat, rois, 14, 14, 1.0 / 16, 1))
     x = res_layer(sd, "roi_head_feature_extractor", pooled, 3, 1 if c5_dilated else 2, 2 if c5_dilated else 1, stride_in_1x1, storage)
+    if segms is not None:                      # common/fast_rcnn.py:151-156 (VCR instance masks)
+        x = q(x * segms[idx[:, 0], None, idx[:, 1]].to(x.dtype))
     post = F.avg_pool2d(x, 14 if c5_dilated else 7, stride=1).flatten(1)
     feats = post
     if mvrc_ops is not None and mask_visual_embed is not None:

@@ -93,3 +93,24 @@ def test_cnn_regularisation_head(monkeypatch):
         assert torch.allclose(o["cnn_regularization_loss"], ce[None])
     assert torch.allclose(outs[0]["obj_logits"], outs[1]["obj_logits"], atol=1e-4, rtol=1e-4)
     assert torch.allclose(outs[0]["obj_reps"], outs[1]["obj_reps"], atol=1e-4, rtol=1e-4)
+
+
+def test_instance_mask_weighted_pooling(model):
+    """VCR passes per-box 14x14 instance masks (`segms`): the res5 map is multiplied by the mask before the mean pool
+    (common/fast_rcnn.py:151-156, vcr/modules/resnet_vlbert_for_vcr.py:244-261)"""
+    m, sd = model
+    images, boxes, box_mask, im_info, gw = synth_frontend_inputs(11, B=2, R=3, H=96, W=128)
+    box_mask[1, 2] = False
+    g = torch.Generator().manual_seed(4)
+    segms = (torch.rand(2, 3, 14, 14, generator=g) > 0.4).float()
+    segms[0, 0] = 1.0                                                  # the whole-image box of VCR
+    ref_obj, ref_raw = fo.fast_rcnn_end2end(sd, images, boxes, box_mask, im_info, segms=segms)
+    plain_obj, _ = fo.fast_rcnn_end2end(sd, images, boxes, box_mask, im_info)
+    assert not torch.allclose(ref_obj, plain_obj)
+    for compact in (True, False):
+        m.compact_rois = compact
+        out = m(images=images, boxes=boxes, box_mask=box_mask, im_info=im_info, segms=segms)
+        _close(out["obj_reps"].detach().numpy(), ref_obj.detach().numpy(), name="obj_reps")
+        _close(out["obj_reps_raw"].detach().numpy(), ref_raw.detach().numpy(), name="raw")
+    with pytest.raises(ValueError):
+        m(images=images, boxes=boxes, box_mask=box_mask, im_info=im_info, segms=segms[:, :, :7, :7])

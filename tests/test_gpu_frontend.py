@@ -293,3 +293,21 @@ def test_cnn_reg_loss_outputs():
     K = int(box_mask.sum())
     assert out["obj_logits"].shape == (K, 81) and out["obj_labels"].shape == (K,) and out["cnn_regularization_loss"].shape == (1,)
     assert torch.isfinite(out["cnn_regularization_loss"]).all()
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: first hardware run is the driver's round-end suite "
+                                        "(XPASS = verified); the same module code is checked on the CPU in tests/test_frontend_host_logic.py")
+def test_fastrcnn_with_instance_masks_against_the_oracle():
+    """`segms` (VCR): mask-weighted mean pool of the res5 map, common/fast_rcnn.py:151-156"""
+    m, sd = _load_e2e()
+    images, boxes, box_mask, im_info, gw = synth_frontend_inputs(11, B=2, R=3, H=96, W=128)
+    box_mask[1, 2] = False
+    segms = (torch.rand(2, 3, 14, 14, generator=torch.Generator().manual_seed(4)) > 0.4).float()
+    ref_obj, ref_raw = fo.fast_rcnn_end2end(sd, images, boxes, box_mask, im_info, segms=segms)
+    for compact in (True, False):
+        m.compact_rois = compact
+        out = m(images=images.to(DEV), boxes=boxes.to(DEV), box_mask=box_mask.to(DEV), im_info=im_info.to(DEV), segms=segms.to(DEV))
+        assert rel(out["obj_reps_raw"], ref_raw) <= 3e-2 and rel(out["obj_reps"], ref_obj) <= 3e-2
+        m.zero_grad()
+        (out["obj_reps"] * gw.to(DEV)).sum().backward()
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters() if p.requires_grad)

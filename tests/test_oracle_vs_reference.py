@@ -182,3 +182,31 @@ def test_language_checkpoint_loader_equals_the_reference(tmp_path, kind, pretrai
         elif k.startswith("mlm_head.") and "decoder.weight" not in k or not k.startswith("mlm_head."):
             assert torch.equal(a[k], b[k]), k
     assert torch.equal(b["mlm_head.predictions.decoder.weight"], b["word_embeddings.weight"]) if pretraining else True
+
+
+def test_frontend_oracle_with_instance_masks_equals_the_reference(monkeypatch):
+    """FastRCNN end to end with `segms` (the VCR path): oracle/frontend_oracle.py against the live reference module."""
+    ref_shim.install()
+    import warnings
+    import torch.utils.model_zoo as model_zoo
+    import frontend_oracle as fo
+    from synth import frontend_config, synth_frontend_inputs
+    monkeypatch.setattr(model_zoo, "load_url", lambda *a, **k: {})
+    ref_cls = _unpatched_fastrcnn()
+    from easydict import EasyDict
+    cfg = EasyDict({"NETWORK": dict(vars(frontend_config(50).NETWORK))})
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = ref_cls(cfg, True, 32, False)
+    sd = fo.synth_frontend_state({k: v.shape for k, v in ref.state_dict().items()}, 21)
+    ref.load_state_dict(sd, strict=True)
+    ref.eval()
+    images, boxes, box_mask, im_info, _ = synth_frontend_inputs(12, B=2, R=3, H=80, W=112)
+    box_mask[0, 2] = False
+    segms = (torch.rand(2, 3, 14, 14, generator=torch.Generator().manual_seed(2)) > 0.5).float()
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        want = ref(images=images, boxes=boxes, box_mask=box_mask, im_info=im_info, segms=segms)
+        got_obj, got_raw = fo.fast_rcnn_end2end(sd, images, boxes, box_mask, im_info, layers=fo.LAYERS[50], segms=segms)
+    assert (got_obj - want["obj_reps"]).abs().max() <= 1e-4 * want["obj_reps"].abs().max()
+    assert (got_raw - want["obj_reps_raw"]).abs().max() <= 1e-4 * want["obj_reps_raw"].abs().max()

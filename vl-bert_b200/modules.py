@@ -530,9 +530,8 @@ class FastRCNN(nn.Module):
                     m.eval()
 
     def _region_features(self, images, boxes, box_mask, segms):
-        """images -> per-slot res5 features f32 [B, R, 2048] (zeros in invalid slots); common/fast_rcnn.py:143-158"""
-        if segms is not None:
-            raise NotImplementedError("vlbert_b200: segms (mask-weighted pooling) is not implemented")
+        """images -> per-slot res5 features f32 [B, R, 2048] (zeros in invalid slots); common/fast_rcnn.py:143-158.
+        `segms` [B, R, 14, 14] (VCR instance masks): the res5 map is multiplied by the box's mask before the mean pool (:151-156)."""
         B, R = box_mask.shape
         feat = self.backbone(images)["body4"]
         b4 = boxes[:, :, :4].float()
@@ -548,6 +547,11 @@ class FastRCNN(nn.Module):
         x = self.roi_head_feature_extractor(pooled)
         if x.shape[1] != (7 if not self.c5_dilated else 14):
             raise NotImplementedError("vlbert_b200: AvgPool2d window must cover the whole res5 map")
+        if segms is not None:
+            m = segms[inds[:, 0], inds[:, 1]] if inds is not None else segms.reshape(B * R, *segms.shape[2:])
+            if tuple(m.shape[1:]) != tuple(x.shape[1:3]):
+                raise ValueError("vlbert_b200: segms of size %s do not match the res5 map %s" % (tuple(m.shape[1:]), tuple(x.shape[1:3])))
+            x = x * m.to(x.dtype).unsqueeze(-1)                                      # NHWC: mask broadcast over channels
         post = VF.AvgPoolFn.apply(x)                                              # [K, 2048] f32
         if inds is None:
             return post.view(B, R, -1), post, None
@@ -563,9 +567,7 @@ class FastRCNN(nn.Module):
         lin = self.obj_downsample[1]
         extra = {}
         if self.image_feat_precomputed:
-            if segms is not None:
-                raise NotImplementedError("vlbert_b200: segms input is not implemented on the precomputed path")
-            feats = boxes[:, :, 4:]
+            feats = boxes[:, :, 4:]                      # (segms are unused on the precomputed path, as in the reference)
         else:
             feats, post, inds = self._region_features(images, boxes, box_mask, segms)
             if self.enable_cnn_reg_loss:
