@@ -29,6 +29,21 @@ def _stub(name, **attrs):
     return m
 
 
+def cpu_roi_functions():
+    """CPU stand-ins for the reference's native C_ROIPooling.roi_align_forward/backward (torchvision's op of the same
+    maskrcnn-benchmark lineage; bit-identical to the reference CPU kernel for aligned=False)."""
+    import torch
+    import torchvision.ops as tvo
+
+    def roi_align_forward(input, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio):
+        return tvo.roi_align(input, rois, (pooled_h, pooled_w), spatial_scale, sampling_ratio, aligned=False)
+
+    def roi_align_backward(grad, rois, spatial_scale, ph, pw, bs, ch, h, w, sampling_ratio):
+        return torch.ops.torchvision._roi_align_backward(grad, rois, spatial_scale, ph, pw, bs, ch, h, w,
+                                                         sampling_ratio, False)
+    return roi_align_forward, roi_align_backward
+
+
 def install():
     """Make `import common.visual_linguistic_bert` etc. work.  Idempotent."""
     if not available():
@@ -78,15 +93,7 @@ def install():
 
     # the native extension: forward/backward via torchvision's maskrcnn-benchmark-lineage op
     # (bit-identical to the reference CPU kernel for aligned=False).
-    import torch
-    import torchvision.ops as tvo
-
-    def roi_align_forward(input, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio):
-        return tvo.roi_align(input, rois, (pooled_h, pooled_w), spatial_scale, sampling_ratio, aligned=False)
-
-    def roi_align_backward(grad, rois, spatial_scale, ph, pw, bs, ch, h, w, sampling_ratio):
-        return torch.ops.torchvision._roi_align_backward(grad, rois, spatial_scale, ph, pw, bs, ch, h, w,
-                                                         sampling_ratio, False)
+    roi_align_forward, roi_align_backward = cpu_roi_functions()
 
     import importlib
     import importlib.machinery

@@ -193,6 +193,10 @@ def test_frontend_oracle_with_instance_masks_equals_the_reference(monkeypatch):
     from synth import frontend_config, synth_frontend_inputs
     monkeypatch.setattr(model_zoo, "load_url", lambda *a, **k: {})
     ref_cls = _unpatched_fastrcnn()
+    import common.lib.roi_pooling.roi_align as ref_roi      # an earlier test may have installed the (CUDA-only) drop-in extension
+    f, b = ref_shim.cpu_roi_functions()
+    monkeypatch.setattr(ref_roi.C_ROIPooling, "roi_align_forward", f, raising=False)
+    monkeypatch.setattr(ref_roi.C_ROIPooling, "roi_align_backward", b, raising=False)
     from easydict import EasyDict
     cfg = EasyDict({"NETWORK": dict(vars(frontend_config(50).NETWORK))})
     with warnings.catch_warnings():
