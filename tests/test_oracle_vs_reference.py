@@ -1,5 +1,7 @@
 """CPU, build container only: the oracle against the LIVE unmodified reference (skipped where
 /root/reference is absent, e.g. on the GPU box -- there the committed fixtures pin it)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -214,3 +216,85 @@ def test_frontend_oracle_with_instance_masks_equals_the_reference(monkeypatch):
         got_obj, got_raw = fo.fast_rcnn_end2end(sd, images, boxes, box_mask, im_info, layers=fo.LAYERS[50], segms=segms)
     assert (got_obj - want["obj_reps"]).abs().max() <= 1e-4 * want["obj_reps"].abs().max()
     assert (got_raw - want["obj_reps_raw"]).abs().max() <= 1e-4 * want["obj_reps_raw"].abs().max()
+
+
+def test_reference_pretraining_task_module_runs_unchanged_on_the_dropin(tmp_path, monkeypatch, capsys):
+    """The boundary itself: pretrain/modules/resnet_vlbert_for_pretraining.py built from the reference's own
+    cfgs/pretrain/base_prec_4x16G_fp32.yaml (2 layers), once untouched and once after vlbert_b200.dropin.install() -- same
+    state_dict keys, and on the same weights and inputs the same logits, losses and parameter gradients.  The kernels are
+    replaced by fp32 torch stand-ins (tests/cpu_shim.py), so this checks everything the Python layer of the drop-in decides."""
+    import importlib
+    import warnings
+    ref_shim.install()
+    import cpu_shim
+    import vlbert_b200
+    vocab_dir = tmp_path / "bert-base-uncased"
+    vocab_dir.mkdir()
+    (vocab_dir / "vocab.txt").write_text("\n".join(["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + ["tok%d" % i for i in range(30517)]) + "\n")
+    from pretrain.function.config import config, update_config
+    update_config(os.path.join(ref_shim.REFERENCE_ROOT, "cfgs", "pretrain", "base_prec_4x16G_fp32.yaml"))
+    config.NETWORK.VLBERT.num_hidden_layers = 2
+    config.NETWORK.VLBERT.hidden_dropout_prob = 0.0
+    config.NETWORK.VLBERT.attention_probs_dropout_prob = 0.0
+    config.NETWORK.BERT_MODEL_NAME = str(vocab_dir)
+    config.NETWORK.BERT_PRETRAINED = ""
+    import common.fast_rcnn
+    import common.visual_linguistic_bert
+    import pretrain.modules.resnet_vlbert_for_pretraining as tm
+
+    def fresh():
+        importlib.reload(common.fast_rcnn)
+        importlib.reload(common.visual_linguistic_bert)
+        return importlib.reload(tm)
+
+    g = torch.Generator().manual_seed(3)
+    B, R, T, C = 2, 4, 8, config.NETWORK.VLBERT.visual_region_classes
+    x1, y1 = torch.rand(B, R, generator=g) * 300, torch.rand(B, R, generator=g) * 200
+    boxes = torch.cat((torch.stack((x1, y1, x1 + 20 + torch.rand(B, R, generator=g) * 250, y1 + 20 + torch.rand(B, R, generator=g) * 150), -1),
+                       torch.randn(B, R, 2048, generator=g)), -1)
+    boxes[1, 3] = -2.0                                                       # pretrain/data/collate_batch.py:39
+    im_info = torch.tensor([[600., 400., 1., 1., 0.], [600., 400., 1., 1., 1.]])
+    text = torch.randint(1000, 30522, (B, T), generator=g)
+    text[1, 6:] = 0
+    rel_label = torch.ones(B, dtype=torch.long)
+    mlm_labels = torch.full((B, T), -1, dtype=torch.long)
+    mlm_labels[0, 2], mlm_labels[1, 4] = 1234, 4321
+    mvrc_ops = torch.tensor([[0, 1, 0, 0], [1, 0, 0, 0]])
+    mvrc_labels = torch.zeros(B, R, C)
+    mvrc_labels[mvrc_ops == 1] = torch.softmax(torch.randn(2, C, generator=g), -1)
+
+    def run(model):
+        model.zero_grad()
+        out, loss = model(None, boxes.clone(), im_info, text, rel_label, mlm_labels, mvrc_ops, mvrc_labels.clone())
+        loss.backward()
+        return out, loss, {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+
+    try:
+        torch.manual_seed(0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = fresh().ResNetVLBERTForPretraining(config)
+            ref.eval()          # (the reference's train() override returns None)
+            sd = {k: v.clone() for k, v in ref.state_dict().items()}
+            o1, l1, g1 = run(ref)                 # the untouched reference first: install() rebinds the names its super() calls use
+            assert vlbert_b200.dropin.install()
+            cpu_shim.install(monkeypatch)
+            cpu_shim.install_encoder(monkeypatch)
+            ours = importlib.reload(tm).ResNetVLBERTForPretraining(config)
+            ours.eval()
+            assert isinstance(ours.vlbert, vlbert_b200.VisualLinguisticBertForPretraining)
+            assert isinstance(ours.image_feature_extractor, vlbert_b200.FastRCNN)
+            assert list(ours.state_dict().keys()) == list(sd.keys())
+            ours.load_state_dict(sd, strict=True)
+            o2, l2, g2 = run(ours)
+        capsys.readouterr()
+        assert abs(float(l1.detach()) - float(l2.detach())) <= 1e-5 * abs(float(l1.detach())), (float(l1.detach()), float(l2.detach()))
+        for k in ("relationship_logits", "mlm_logits", "mvrc_logits", "relationship_loss", "mlm_loss", "mvrc_loss"):
+            assert (o1[k] is None) == (o2[k] is None), k
+            if o1[k] is not None:
+                assert (o1[k] - o2[k]).abs().max() <= 2e-4 * o1[k].abs().max().clamp_min(1e-6), k
+        assert set(g1.keys()) == set(g2.keys())
+        for k in g1:
+            assert (g1[k] - g2[k]).abs().max() <= 5e-4 * g1[k].abs().max().clamp_min(1e-9), k
+    finally:
+        fresh()
