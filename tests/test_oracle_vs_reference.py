@@ -1,6 +1,7 @@
 """CPU, build container only: the oracle against the LIVE unmodified reference (skipped where
 /root/reference is absent, e.g. on the GPU box -- there the committed fixtures pin it)."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -120,17 +121,17 @@ def _unpatched_fastrcnn():
     return importlib.reload(m).FastRCNN
 
 
-def _fake_hf_checkpoint(kind, H=64, L=2, I=128, vocab=120, tmp_path=None):
+def _fake_hf_checkpoint(kind, H=64, L=2, I=128, vocab=120, max_pos=40):
     """a state_dict with HuggingFace BERT (old TF-style gamma/beta names, cls.* heads) or RoBERTa (roberta.*, lm_head.*, one
     token type) key names, random values"""
     g = torch.Generator().manual_seed(7 if kind == "bert" else 8)
     r = lambda *s: torch.randn(*s, generator=g)
     pre = "bert." if kind == "bert" else "roberta."
     ln_w, ln_b = ("gamma", "beta") if kind == "bert" else ("weight", "bias")
-    sd = {pre + "embeddings.word_embeddings.weight": r(vocab, H), pre + "embeddings.position_embeddings.weight": r(40, H),
+    sd = {pre + "embeddings.word_embeddings.weight": r(vocab, H), pre + "embeddings.position_embeddings.weight": r(max_pos, H),
           pre + "embeddings.token_type_embeddings.weight": r(2 if kind == "bert" else 1, H),
           pre + "embeddings.LayerNorm." + ln_w: r(H), pre + "embeddings.LayerNorm." + ln_b: r(H),
-          pre + "embeddings.position_ids": torch.arange(40)[None],                       # unexpected key
+          pre + "embeddings.position_ids": torch.arange(max_pos)[None],                       # unexpected key
           pre + "pooler.dense.weight": r(H, H), pre + "pooler.dense.bias": r(H)}
     for l in range(L):
         q = pre + "encoder.layer.%d." % l
@@ -298,3 +299,183 @@ def test_reference_pretraining_task_module_runs_unchanged_on_the_dropin(tmp_path
             assert (g1[k] - g2[k]).abs().max() <= 5e-4 * g1[k].abs().max().clamp_min(1e-9), k
     finally:
         fresh()
+
+
+def _task_module_parity(monkeypatch, capsys, task, yaml_name, cls_name, tweak, build_inputs, call, vocab_dir, tol_out=2e-4, tol_grad=5e-4, zoo=None, after_build=None):
+    """Build `<task>.modules.<cls_name>` from the reference's own yaml twice -- untouched, then with vlbert_b200.dropin installed
+    and the kernels replaced by the fp32 stand-ins of tests/cpu_shim.py -- load the same weights, run the same inputs, and compare
+    every tensor output, the loss and every parameter gradient."""
+    import importlib
+    import warnings
+    import cpu_shim
+    import vlbert_b200
+    import torch.utils.model_zoo as model_zoo
+    monkeypatch.setattr(model_zoo, "load_url", lambda *a, **k: (zoo if zoo is not None else {}))   # no network: the "model zoo"
+    cfgmod = importlib.import_module(task + ".function.config")
+    config = cfgmod.config
+    cfgmod.update_config(os.path.join(ref_shim.REFERENCE_ROOT, "cfgs", task, yaml_name))
+    config.NETWORK.VLBERT.hidden_dropout_prob = 0.0
+    config.NETWORK.VLBERT.attention_probs_dropout_prob = 0.0
+    config.NETWORK.BERT_MODEL_NAME = str(vocab_dir)
+    config.NETWORK.BERT_PRETRAINED = ""
+    tweak(config)
+    import common.fast_rcnn
+    import common.visual_linguistic_bert
+    import common.lib.roi_pooling.roi_align as ref_roi
+    f, b = ref_shim.cpu_roi_functions()
+    monkeypatch.setattr(ref_roi.C_ROIPooling, "roi_align_forward", f, raising=False)
+    monkeypatch.setattr(ref_roi.C_ROIPooling, "roi_align_backward", b, raising=False)
+    tm = importlib.import_module(task + ".modules")
+
+    def fresh():
+        importlib.reload(common.fast_rcnn)
+        importlib.reload(common.visual_linguistic_bert)
+        for name in sorted(k for k in sys.modules if k.startswith(task + ".modules.")):
+            importlib.reload(sys.modules[name])
+        return importlib.reload(tm)
+
+    inputs = build_inputs(config)
+
+    def run(model):
+        model.zero_grad()
+        out, loss = call(model, [t.clone() if torch.is_tensor(t) else t for t in inputs])
+        loss.backward()
+        return out, loss.detach(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+
+    try:
+        torch.manual_seed(0)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = getattr(fresh(), cls_name)(config)
+            ref.eval()
+            sd = {k: v.clone() for k, v in ref.state_dict().items()}
+            o1, l1, g1 = run(ref)                 # the untouched reference first: install() rebinds the names its super() calls use
+            assert vlbert_b200.dropin.install()
+            cpu_shim.install(monkeypatch)
+            cpu_shim.install_encoder(monkeypatch)
+            for name in sorted(k for k in sys.modules if k.startswith(task + ".modules.")):
+                importlib.reload(sys.modules[name])
+            ours = getattr(importlib.reload(tm), cls_name)(config)
+            ours.eval()
+            assert isinstance(ours.image_feature_extractor, vlbert_b200.FastRCNN)
+            assert list(ours.state_dict().keys()) == list(sd.keys())
+            if after_build is not None:
+                after_build(sd, ours)
+            ours.load_state_dict(sd, strict=True)
+            o2, l2, g2 = run(ours)
+        capsys.readouterr()
+        assert abs(float(l1) - float(l2)) <= 1e-5 * max(1e-6, abs(float(l1))), (float(l1), float(l2))
+        for k in o1:
+            if torch.is_tensor(o1[k]) and o1[k].is_floating_point():
+                assert (o1[k] - o2[k]).abs().max() <= tol_out * o1[k].abs().max().clamp_min(1e-6), k
+        assert set(g1.keys()) == set(g2.keys())
+        for k in g1:
+            assert (g1[k] - g2[k]).abs().max() <= tol_grad * g1[k].abs().max().clamp_min(1e-9), k
+        return ours
+    finally:
+        fresh()
+
+
+def _vocab_dir(tmp_path, n, with_checkpoint=None):
+    d = tmp_path / "bert-base-uncased"
+    d.mkdir()
+    (d / "vocab.txt").write_text("\n".join(["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + ["tok%d" % i for i in range(n - 5)]) + "\n")
+    if with_checkpoint is not None:
+        torch.save(with_checkpoint, str(d / "pytorch_model.bin"))
+    return d
+
+
+def test_reference_vqa_task_module_runs_unchanged_on_the_dropin(tmp_path, monkeypatch, capsys):
+    """vqa/modules/resnet_vlbert_for_vqa.py from cfgs/vqa/base_4x16G_fp32.yaml (BASELINE config 3's module; 2 layers, vocabulary cut to
+    1000): `mlm` classifier initialised from a BERT checkpoint through the module's own loader, uint8 text masks from
+    prepare_text_from_qa, precomputed region features."""
+    ref_shim.install()
+    vocab = 1000
+    d = _vocab_dir(tmp_path, vocab, _fake_hf_checkpoint("bert", H=768, L=2, I=3072, vocab=vocab, max_pos=512))
+
+    def tweak(config):
+        config.NETWORK.VLBERT.num_hidden_layers = 2
+        config.NETWORK.VLBERT.vocab_size = vocab
+        config.NETWORK.CLASSIFIER_DROPOUT = 0.0
+        config.DATASET.ANSWER_VOCAB_SIZE = 37
+
+    def build_inputs(config):
+        g = torch.Generator().manual_seed(5)
+        B, R, T = 3, 5, 7
+        x1, y1 = torch.rand(B, R, generator=g) * 300, torch.rand(B, R, generator=g) * 200
+        boxes = torch.cat((torch.stack((x1, y1, x1 + 20 + torch.rand(B, R, generator=g) * 250, y1 + 20 + torch.rand(B, R, generator=g) * 150), -1),
+                           torch.randn(B, R, 2048, generator=g)), -1)
+        boxes[1, 3:] = -2.0
+        boxes[2, 4:] = -2.0
+        im_info = torch.tensor([[600., 400., 1., 1.]] * B)
+        question = torch.randint(5, vocab, (B, T), generator=g)
+        question[0, 5:] = 0
+        question[2, 3:] = 0
+        label = torch.rand(B, 37, generator=g)
+        return [None, boxes, im_info, question, label]
+
+    _task_module_parity(monkeypatch, capsys, "vqa", "base_4x16G_fp32.yaml", "ResNetVLBERT", tweak, build_inputs,
+                        lambda m, ins: m.train_forward(*ins), d)
+
+
+def test_reference_vcr_task_module_runs_unchanged_on_the_dropin(tmp_path, monkeypatch, capsys):
+    """vcr/modules/resnet_vlbert_for_vcr.py from cfgs/vcr/base_q2a_4x16G_fp32.yaml (BASELINE config 4's module at base width; 2 layers):
+    images through the END-TO-END FastRCNN (ResNet-101 C4 + RoIAlign + dilated res5) with instance masks (`segms`) and object classes,
+    TimeDistributed VL-BERT over the four answer choices, text/object outputs returned separately, the CNN regularisation head on
+    the object outputs.  Exercises the drop-in's end-to-end front end under its real caller."""
+    ref_shim.install()
+    import torch.utils.model_zoo as model_zoo
+    from common.backbone.resnet.resnet import Bottleneck, ResNet
+    vocab = 600
+    d = _vocab_dir(tmp_path, vocab)
+    torch.manual_seed(1)
+    zoo = ResNet(Bottleneck, [3, 4, 23, 3], num_classes=None, expose_stages=[5]).state_dict()      # what the model zoo would return
+    for k, v in zoo.items():                                                                      # non-trivial frozen statistics
+        if k.endswith("running_var"):
+            v.uniform_(0.5, 1.5)
+        elif k.endswith("running_mean"):
+            v.normal_(0, 0.1)
+        elif ".bn" in k and k.endswith("weight") or "downsample.1.weight" in k:
+            v.uniform_(0.3, 0.6)
+
+    torch.save(zoo, str(tmp_path / "resnet101-0000.model"))                                       # NETWORK.IMAGE_PRETRAINED checkpoint
+
+    def tweak(config):
+        config.NETWORK.VLBERT.num_hidden_layers = 2
+        config.NETWORK.VLBERT.vocab_size = vocab
+        config.NETWORK.CLASSIFIER_DROPOUT = 0.0
+        config.NETWORK.IMAGE_PRETRAINED = str(tmp_path / "resnet101")
+        config.NETWORK.IMAGE_PRETRAINED_EPOCH = 0
+        assert config.NETWORK.IMAGE_FEAT_PRECOMPUTED is False and config.NETWORK.ENABLE_CNN_REG_LOSS and config.NETWORK.CNN_LOSS_TOP
+
+    def after_build(ref_sd, ours):
+        # both sides initialise the backbone and the res5 head (layer4.*) from the same IMAGE_PRETRAINED file (common/fast_rcnn.py:41-63,111-120)
+        mine = ours.state_dict()
+        for k in ref_sd:
+            if k.startswith(("image_feature_extractor.backbone.", "image_feature_extractor.roi_head_feature_extractor.", "image_feature_extractor.head.")):
+                assert torch.equal(mine[k], ref_sd[k]), k
+
+    def build_inputs(config):
+        g = torch.Generator().manual_seed(9)
+        B, R, NC, Lq, La, H, W = 2, 3, 4, 5, 4, 64, 96
+        image = torch.randn(B, 3, H, W, generator=g)
+        x1, y1 = torch.rand(B, R, generator=g) * 40, torch.rand(B, R, generator=g) * 25
+        boxes = torch.stack((x1, y1, x1 + 16 + torch.rand(B, R, generator=g) * 38, y1 + 16 + torch.rand(B, R, generator=g) * 20,
+                             torch.randint(1, 81, (B, R), generator=g).float()), -1)
+        boxes[:, 0, :4] = torch.tensor([0.0, 0.0, W - 1.0, H - 1.0])          # the whole image as the first box (ADD_IMAGE_AS_A_BOX)
+        boxes[:, 0, 4] = 0
+        boxes[1, 2] = -1.0                                                     # padded box
+        masks = (torch.rand(B, R, 14, 14, generator=g) > 0.35).float()
+        masks[:, 0] = 1.0
+        question = torch.stack((torch.randint(5, vocab, (B, Lq), generator=g), torch.randint(-1, 2, (B, Lq), generator=g)), -1)
+        question[1, 3:] = 0
+        answers = torch.stack((torch.randint(5, vocab, (B, NC, La), generator=g), torch.randint(-1, 2, (B, NC, La), generator=g)), -1)
+        answers[0, 1, 2:] = 0
+        answers[1, 3, 3:] = 0
+        answer_label = torch.tensor([2, 0])
+        im_info = torch.tensor([[float(W), float(H), 1.0, 1.0]] * B)
+        return [image, boxes, masks, question, None, answers, None, answer_label, im_info]
+
+    torch.set_num_threads(8)
+    _task_module_parity(monkeypatch, capsys, "vcr", "base_q2a_4x16G_fp32.yaml", "ResNetVLBERT", tweak, build_inputs,
+                        lambda m, ins: m.train_forward(*ins), d, zoo=zoo, after_build=after_build)
