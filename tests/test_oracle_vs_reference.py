@@ -479,3 +479,43 @@ def test_reference_vcr_task_module_runs_unchanged_on_the_dropin(tmp_path, monkey
     torch.set_num_threads(8)
     _task_module_parity(monkeypatch, capsys, "vcr", "base_q2a_4x16G_fp32.yaml", "ResNetVLBERT", tweak, build_inputs,
                         lambda m, ins: m.train_forward(*ins), d, zoo=zoo, after_build=after_build)
+
+
+def test_reference_refcoco_task_module_runs_unchanged_on_the_dropin(tmp_path, monkeypatch, capsys):
+    """refcoco/modules/resnet_vlbert_for_refcoco.py from cfgs/refcoco/base_detected_regions_4x16G.yaml (2 layers): end-to-end FastRCNN
+    without masks, `with_pooler: false`, per-region classifier on the object outputs."""
+    ref_shim.install()
+    from common.backbone.resnet.resnet import Bottleneck, ResNet
+    vocab = 500
+    d = _vocab_dir(tmp_path, vocab)
+    torch.manual_seed(2)
+    zoo = ResNet(Bottleneck, [3, 4, 23, 3], num_classes=None, expose_stages=[5]).state_dict()
+    for k, v in zoo.items():
+        if k.endswith("running_var"):
+            v.uniform_(0.5, 1.5)
+        elif ".bn" in k and k.endswith("weight") or "downsample.1.weight" in k:
+            v.uniform_(0.3, 0.6)
+    torch.save(zoo, str(tmp_path / "resnet101-0000.model"))
+
+    def tweak(config):
+        config.NETWORK.VLBERT.num_hidden_layers = 2
+        config.NETWORK.VLBERT.vocab_size = vocab
+        config.NETWORK.IMAGE_PRETRAINED = str(tmp_path / "resnet101")
+        config.NETWORK.IMAGE_PRETRAINED_EPOCH = 0
+
+    def build_inputs(config):
+        g = torch.Generator().manual_seed(13)
+        B, R, T, H, W = 2, 4, 6, 64, 80
+        image = torch.randn(B, 3, H, W, generator=g)
+        x1, y1 = torch.rand(B, R, generator=g) * 30, torch.rand(B, R, generator=g) * 25
+        boxes = torch.stack((x1, y1, x1 + 16 + torch.rand(B, R, generator=g) * 30, y1 + 16 + torch.rand(B, R, generator=g) * 20), -1)
+        boxes[0, 3] = -2.0
+        im_info = torch.tensor([[float(W), float(H), 1.0, 1.0]] * B)
+        expression = torch.randint(5, vocab, (B, T), generator=g)
+        expression[1, 4:] = 0
+        label = (torch.rand(B, R, generator=g) > 0.5).float()
+        return [image, boxes, im_info, expression, label]
+
+    torch.set_num_threads(8)
+    _task_module_parity(monkeypatch, capsys, "refcoco", "base_detected_regions_4x16G.yaml", "ResNetVLBERT", tweak, build_inputs,
+                        lambda m, ins: m.train_forward(*ins), d, zoo=zoo)
