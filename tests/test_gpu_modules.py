@@ -223,3 +223,30 @@ def test_encoder_linearity_of_backward_at_full_config2_size():
     for k in res[0]:
         if res[0][k].abs().max() > 0:
             assert rel(res[1][k], 2 * res[0][k]) <= 2e-3, k  # power-of-two scaling commutes with bf16 rounding
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: first hardware run is the driver's round-end suite "
+                                        "(XPASS = verified); the module logic for this case is checked on the CPU in "
+                                        "tests/test_oracle_vs_reference.py::test_reference_multitask_pretraining_module_runs_unchanged_on_the_dropin")
+def test_text_only_samples_in_the_batch():
+    """The reference's multitask pre-training module appends text-only samples to the batch: their box_mask is all False, so the
+    packed sequence is [text ; END] with no region token (pretrain/modules/resnet_vlbert_for_pretraining_multitask.py:163-180)."""
+    import vlbert_b200
+    cfg = vo.default_config(num_hidden_layers=2)
+    ora = vo.VisualLinguisticBertOracle(cfg)
+    sd = seeded_state_dict(ora, 14)
+    ora.load_state_dict(sd)
+    model = vlbert_b200.VisualLinguisticBert(cfg).to(DEV)
+    model.load_state_dict(sd, strict=True)
+    ids, types, tvis, tmask, ovl, omask = synth_vlbert_inputs(B=4, T=10, R=4, H=768, vocab=30522, seed=24, ragged=True)
+    omask[1] = False                    # text-only samples
+    omask[3] = False
+    ovl[1] = 0
+    ovl[3] = 0
+    inputs = (ids, types, tvis, tmask, ovl, omask)
+    _compare(_run(model, inputs, 34, DEV), _run(ora, inputs, 34, "cpu"))
+    with torch.no_grad():
+        tx, ob, _ = model(*[t.to(DEV) for t in inputs], output_all_encoded_layers=False, output_text_and_object_separately=True)
+        tx_o, ob_o, _ = ora(*inputs, output_all_encoded_layers=False, output_text_and_object_separately=True)
+    assert rel(tx, tx_o) <= TOL_OUT and rel(ob, ob_o) <= TOL_OUT
+    assert bool((ob[1] == 0).all()) and bool((ob[3] == 0).all())

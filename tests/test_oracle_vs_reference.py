@@ -232,7 +232,9 @@ def test_reference_pretraining_task_module_runs_unchanged_on_the_dropin(tmp_path
     vocab_dir = tmp_path / "bert-base-uncased"
     vocab_dir.mkdir()
     (vocab_dir / "vocab.txt").write_text("\n".join(["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + ["tok%d" % i for i in range(30517)]) + "\n")
-    from pretrain.function.config import config, update_config
+    import pretrain.function.config as cfgmod
+    cfgmod = importlib.reload(cfgmod)               # update_config() is not idempotent on the module-level singleton
+    config, update_config = cfgmod.config, cfgmod.update_config
     update_config(os.path.join(ref_shim.REFERENCE_ROOT, "cfgs", "pretrain", "base_prec_4x16G_fp32.yaml"))
     config.NETWORK.VLBERT.num_hidden_layers = 2
     config.NETWORK.VLBERT.hidden_dropout_prob = 0.0
@@ -311,7 +313,7 @@ def _task_module_parity(monkeypatch, capsys, task, yaml_name, cls_name, tweak, b
     import vlbert_b200
     import torch.utils.model_zoo as model_zoo
     monkeypatch.setattr(model_zoo, "load_url", lambda *a, **k: (zoo if zoo is not None else {}))   # no network: the "model zoo"
-    cfgmod = importlib.import_module(task + ".function.config")
+    cfgmod = importlib.reload(importlib.import_module(task + ".function.config"))   # update_config() is not idempotent on the singleton
     config = cfgmod.config
     cfgmod.update_config(os.path.join(ref_shim.REFERENCE_ROOT, "cfgs", task, yaml_name))
     config.NETWORK.VLBERT.hidden_dropout_prob = 0.0
@@ -519,3 +521,62 @@ def test_reference_refcoco_task_module_runs_unchanged_on_the_dropin(tmp_path, mo
     torch.set_num_threads(8)
     _task_module_parity(monkeypatch, capsys, "refcoco", "base_detected_regions_4x16G.yaml", "ResNetVLBERT", tweak, build_inputs,
                         lambda m, ins: m.train_forward(*ins), d, zoo=zoo)
+
+
+@pytest.mark.parametrize("yaml_name", ["base_e2e_16x16G_fp16.yaml", "base_prec_4x16G_fp32.yaml"])
+def test_reference_multitask_pretraining_module_runs_unchanged_on_the_dropin(tmp_path, monkeypatch, capsys, yaml_name):
+    """pretrain/modules/resnet_vlbert_for_pretraining_multitask.py -- the MODULE both pre-training yamls name, i.e. the real caller of
+    BASELINE config 2 (precomputed features) and config 5 (end to end).  It appends text-only samples (no boxes at all: box_mask
+    all False) to the batch, masks region features with `mask_visual_embed` on the end-to-end path, and uses all three heads."""
+    ref_shim.install()
+    from common.backbone.resnet.resnet import Bottleneck, ResNet
+    e2e = "e2e" in yaml_name
+    vocab = 700
+    d = _vocab_dir(tmp_path, vocab)
+    zoo = None
+    if e2e:
+        torch.manual_seed(4)
+        zoo = ResNet(Bottleneck, [3, 4, 23, 3], num_classes=None, expose_stages=[5]).state_dict()
+        for k, v in zoo.items():
+            if k.endswith("running_var"):
+                v.uniform_(0.5, 1.5)
+            elif ".bn" in k and k.endswith("weight") or "downsample.1.weight" in k:
+                v.uniform_(0.3, 0.6)
+        torch.save(zoo, str(tmp_path / "resnet101-0000.model"))
+
+    def tweak(config):
+        config.NETWORK.VLBERT.num_hidden_layers = 2
+        config.NETWORK.VLBERT.vocab_size = vocab
+        config.NETWORK.VLBERT.visual_region_classes = 23
+        if e2e:
+            config.NETWORK.IMAGE_PRETRAINED = str(tmp_path / "resnet101")
+            config.NETWORK.IMAGE_PRETRAINED_EPOCH = 0
+
+    def build_inputs(config):
+        g = torch.Generator().manual_seed(17)
+        B, R, T, C, H, W = 2, 4, 7, 23, 64, 96
+        x1, y1 = torch.rand(B, R, generator=g) * 40, torch.rand(B, R, generator=g) * 25
+        box4 = torch.stack((x1, y1, x1 + 16 + torch.rand(B, R, generator=g) * 38, y1 + 16 + torch.rand(B, R, generator=g) * 20), -1)
+        if e2e:
+            image, boxes = torch.randn(B, 3, H, W, generator=g), box4
+        else:
+            image, boxes = None, torch.cat((box4, torch.randn(B, R, 2048, generator=g)), -1)
+        boxes[1, 3] = -2.0
+        im_info = torch.tensor([[float(W), float(H), 1.0, 1.0, 0.0], [float(W), float(H), 1.0, 1.0, 1.0]])
+        text = torch.randint(5, vocab, (B, T), generator=g)
+        text[1, 5:] = 0
+        rel = torch.ones(B, dtype=torch.long)
+        mlm = torch.full((B, T), -1, dtype=torch.long)
+        mlm[0, 2], mlm[1, 3] = 77, 88
+        mvrc_ops = torch.tensor([[0, 1, 0, 0], [1, 0, 0, 0]])
+        mvrc_labels = torch.zeros(B, R, C)
+        mvrc_labels[mvrc_ops == 1] = torch.softmax(torch.randn(2, C, generator=g), -1)
+        aux_text = torch.randint(5, vocab, (3, 9), generator=g)            # three text-only samples, longer than the captions
+        aux_text[0, 6:] = 0
+        aux_mlm = torch.full((3, 9), -1, dtype=torch.long)
+        aux_mlm[0, 1], aux_mlm[2, 8] = 99, 111
+        return [image, boxes, im_info, text, rel, mlm, mvrc_ops, mvrc_labels, aux_text, aux_mlm]
+
+    torch.set_num_threads(8)
+    _task_module_parity(monkeypatch, capsys, "pretrain", yaml_name, "ResNetVLBERTForPretrainingMultitask", tweak, build_inputs,
+                        lambda m, ins: m(*ins), d, zoo=zoo)
