@@ -53,6 +53,19 @@ int vlb_streamk_compiled(void);
 void vlb_profile_enable(int on);
 int vlb_profile_collect(double* ms, double* work, int64_t* launches);
 
+/* ---- dropout configuration of a fused call site ---------------------------------------------------
+ * The reference applies nn.Dropout at six kinds of call sites of the path (modeling.py:283 embedding -- in VL-BERT
+ * common/visual_linguistic_bert.py:75,239 --, :310 attention probabilities, :331 / :376 the two dense outputs of a layer,
+ * common/fast_rcnn.py:106 obj_downsample input).  The fused kernels regenerate the keep-mask from a counter-based stream
+ * (Philox4x32-10, see "dropout contract" below) instead of storing it: `rng` points to DEVICE memory holding
+ * {uint64 seed, uint64 step}, read by the kernel when it RUNS (a CUDA-graph replay therefore sees the current step);
+ * `site` numbers the call site.  p == 0 or a NULL VlbDropout* means no dropout (eval mode). */
+typedef struct VlbDropout {
+  float p;             /* drop probability, 0 <= p < 1 */
+  uint32_t site;       /* call-site id (counter word 2) */
+  const uint64_t* rng; /* device: {seed, step} */
+} VlbDropout;
+
 /* ---- GEMM (tcgen05) --------------------------------------------------------------------------
  * Replaces the torch.nn.Linear / F.linear calls of the encoder layer and their autograd backward
  * (modeling.py:291-293, :330, :362, :375; common/fast_rcnn.py:105-109 obj_downsample).
@@ -69,6 +82,12 @@ int vlb_gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const v
                   void* out, int ldo, int out_kind, const float* bias, const void* resid, int ldr,
                   int resid_kind, int act, void* aux, int ld_aux, float alpha, int split_k,
                   int force_bn, void* stream);
+/* Same, with dropout applied to the [M,N] value after bias + activation and BEFORE the residual add
+ * (BertSelfOutput / BertOutput: LayerNorm(dropout(dense(x)) + input), modeling.py:330-333,375-378). */
+int vlb_gemm_bf16_dropout(int mode, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
+                          void* out, int ldo, int out_kind, const float* bias, const void* resid, int ldr,
+                          int resid_kind, int act, void* aux, int ld_aux, float alpha, int split_k,
+                          int force_bn, const VlbDropout* drop, void* stream);
 
 /* Grouped weight-gradient GEMM: out_i[M_i,N_i] (+)= A_i[K,M_i]^T B_i[K,N_i], i < count <= 4, same K, ONE launch
  * (the four wgrad GEMMs of a BertLayer backward).  accumulate != 0: fp32 atomic "+=" (required for split_k > 1);
@@ -100,6 +119,14 @@ int vlb_mhsa_forward(const void* qkv, const float* add_mask, void* ctx, float* l
 int vlb_mhsa_backward(const void* qkv, const float* add_mask, const void* ctx, const float* lse,
                       const void* dctx, void* dqkv, float* scratch_f32, int B, int S, int H, int heads,
                       void* stream);
+/* With dropout on the attention probabilities (modeling.py:310): ctx = dropout(softmax(..)) v.  The mask is indexed as a
+ * [B*heads*S, S] matrix (row = (b, head, query), column = key) under the 2-D contract below; lse is of the UNdropped
+ * probabilities.  The backward must be given the same VlbDropout (and the same *rng contents) as the forward. */
+int vlb_mhsa_forward_dropout(const void* qkv, const float* add_mask, void* ctx, float* lse, int B, int S, int H,
+                             int heads, const VlbDropout* drop, void* stream);
+int vlb_mhsa_backward_dropout(const void* qkv, const float* add_mask, const void* ctx, const float* lse,
+                              const void* dctx, void* dqkv, float* scratch_f32, int B, int S, int H, int heads,
+                              const VlbDropout* drop, void* stream);
 
 /* ---- LayerNorm (TF style, eps inside the sqrt) -----------------------------------------------
  * Replaces BertLayerNorm.forward (modeling.py:231-235) and its autograd backward.
@@ -114,6 +141,21 @@ int vlb_layernorm_backward(const void* dy_bf16, const float* dy_f32, const float
                            const float* mean, const float* rstd, const float* gamma, void* dx_bf16,
                            float* dx_f32, int ld_dx, float* dgamma, float* dbeta, float* dcolsum, int M,
                            int H, void* stream);
+/* LayerNorm followed by dropout on its output (the embedding: dropout(LayerNorm(e)), visual_linguistic_bert.py:237-239);
+ * mask indexed over the [M, H] output. */
+int vlb_layernorm_forward_dropout(const float* x, int ldx, const float* gamma, const float* beta, void* y_bf16,
+                                  float* y_f32, float* mean, float* rstd, int M, int H, float eps,
+                                  const VlbDropout* out_drop, void* stream);
+/* Backward with the dropout sites either side of a LayerNorm:
+ *   in_drop  : dy is first multiplied by the keep-mask / (1-p) of `in_drop`   (LayerNorm output was dropped: embedding)
+ *   out_drop : a second bf16 output dx_bf16_drop = dx * keep-mask / (1-p) is written and dcolsum sums THAT tensor
+ *              (LayerNorm input was dropout(dense(.)) + residual: the dense branch sees the masked gradient, the
+ *              residual branch the plain dx).  Either may be NULL. */
+int vlb_layernorm_backward_dropout(const void* dy_bf16, const float* dy_f32, const float* x, int ldx,
+                                   const float* mean, const float* rstd, const float* gamma, void* dx_bf16,
+                                   float* dx_f32, int ld_dx, float* dgamma, float* dbeta, float* dcolsum, int M,
+                                   int H, const VlbDropout* in_drop, void* dx_bf16_drop, const VlbDropout* out_drop,
+                                   void* stream);
 /* out[n] += sum_m x[m, n]   (x bf16 [M, N], ld in elements) -- bias gradients */
 int vlb_colsum_bf16(const void* x, int ld, float* out, int M, int N, void* stream);
 int vlb_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
@@ -133,7 +175,9 @@ int vlb_multi_cast(const VlbCastDesc* descs_device, int count, int blocks_per_te
  * gathers, and the output un-packing (:146-159).
  * vlb_pack_index: masks are uint8 [B,T] / [B,R]; S = caller's max_length (>= max_b(text_end+object_end)+1).
  *   kind/src/pos_id/type_id int32 [B,S]; add_mask f32 [B,S]; obj_row int32 [B,R]; lens int32 [B,2];
- *   err int32[1] is OR-ed with 1 (S too small), 2 (position id out of range), 4 (token id out of range).
+ *   err int32[1] is OR-ed with 1 (S too small), 2 (position id out of range), 4 (token id out of range), 8 (token type
+ *   id outside 0..2); offending ids are remapped to row 0 so the kernels never read out of bounds -- the CALLER must check
+ *   err (the reference raises an IndexError in these cases).
  *   pos_offset = position_padding_idx + 1.
  * vlb_pack_forward: e f32 [B*S, H] = vl + position_emb + token_type_emb (pre-LayerNorm sum).
  *   text_vis_ln f32 [B*T,H] / obj_vis_ln f32 [B*R,H] are the already LayerNorm-ed visual streams;
@@ -186,6 +230,11 @@ int vlb_roi_align_backward(const float* grad_out, const float* rois, float* grad
 int vlb_region_operand(const float* boxes, int ld_box, const uint8_t* box_mask, const float* im_info,
                        int ld_info, const int64_t* mvrc_ops, const float* mask_visual_embed, void* A,
                        int32_t* gather_idx, int B, int R, int feat_dim, void* stream);
+/* Same with the Dropout(0.1) that heads obj_downsample (common/fast_rcnn.py:104-109) applied to A (mask indexed over the
+ * [B*R, 2048 + feat_dim] slot layout; rows of invalid boxes stay zero). */
+int vlb_region_operand_dropout(const float* boxes, int ld_box, const uint8_t* box_mask, const float* im_info,
+                               int ld_info, const int64_t* mvrc_ops, const float* mask_visual_embed, void* A,
+                               int32_t* gather_idx, int B, int R, int feat_dim, const VlbDropout* drop, void* stream);
 
 /* ---- convolution front end (ResNet-101 C4 + res5 RoI head), NHWC bf16 ------------------------------
  * Replaces the nn.Conv2d / BatchNorm2d(eval, frozen) / ReLU / residual stack of Bottleneck.forward
@@ -258,12 +307,23 @@ int vlb_adamw_step(const VlbAdamWTensor* descs_device, const float* hyper_device
  * torch's global generator and cannot be reproduced by any implementation; this is the contract the fused kernels are
  * specified against.  vlb_dropout_mask writes the keep flags (uint8), vlb_dropout applies them to a bf16 / f32 tensor. */
 int vlb_dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t seed, uint32_t site, uint32_t step, void* stream);
+/* 2-D form used by every fused site: element (r, c) of a [rows, cols] tensor belongs to Philox group
+ * r * ceil(cols / 4) + c / 4, word c % 4 -- identical to the linear contract when cols % 4 == 0; rows of the attention
+ * probabilities (cols = S keys) are padded to a multiple of four so that a row never shares a Philox call. */
+int vlb_dropout_mask_2d(uint8_t* keep, int64_t rows, int cols, float p, uint64_t seed, uint32_t site, uint32_t step,
+                        void* stream);
+/* y[r, c] = x[r, c] * keep(r, col_offset + c) / (1-p) for a [rows, cols] window (leading dimensions ldx / ldy, elements) of a tensor
+ * whose mask is indexed over [rows, total_cols]; (seed, step) are read from drop->rng on the device.  cols, col_offset and
+ * total_cols must be multiples of 4.  Stand-alone form of what the fused sites do (used for the gradient wrt the region
+ * features behind obj_downsample's dropout and by the tests). */
+int vlb_dropout_2d(const void* x, int ldx, void* y, int ldy, int64_t rows, int cols, int col_offset, int total_cols,
+                   int is_bf16, const VlbDropout* drop, void* stream);
 int vlb_dropout(const void* x, void* y, int64_t n, int is_bf16, float p, uint64_t seed, uint32_t site, uint32_t step, void* stream);
 
 /* ---- one BertLayer, forward and backward -------------------------------------------------------
  * Replaces BertLayer.forward (modeling.py:388-397) = BertAttention + BertIntermediate + BertOutput and
  * its autograd backward, as a fixed sequence of the kernels above on `stream`
- * (dropout probabilities are 0 on this path).  M = B*S rows.
+ * M = B*S rows.  ABI version 2: the trailing VlbLayerDropout* (same contents in forward and backward).
  */
 typedef struct VlbLayerWeights {
   const void* w_qkv;   /* bf16 [3H, H]  rows: query | key | value weights (modeling.py:277-279) */
@@ -302,16 +362,25 @@ typedef struct VlbLayerGrads { /* f32, ACCUMULATED (+=); caller zero-fills or pa
   float* dw_1; float* db_1; float* dw_2; float* db_2; float* dln2_g; float* dln2_b;
 } VlbLayerGrads;
 
+/* Dropout of one BertLayer: attention probabilities (p_attn, modeling.py:310) and the two dense outputs (p_hidden,
+ * :331 and :376).  NULL or both p == 0: the layer runs without dropout. */
+typedef struct VlbLayerDropout {
+  float p_attn;
+  float p_hidden;
+  uint32_t site_attn, site_self_out, site_out;   /* 1+3l, 2+3l, 3+3l for layer l */
+  const uint64_t* rng;                           /* device: {seed, step} */
+} VlbLayerDropout;
+
 int vlb_bert_layer_forward(const VlbLayerWeights* w, const void* x_bf16, const float* add_mask,
                            const VlbLayerActs* acts, int B, int S, int H, int heads, int I, float eps,
-                           void* stream);
+                           const VlbLayerDropout* drop, void* stream);
 /* bytes of scratch vlb_bert_layer_backward needs */
 int64_t vlb_bert_layer_backward_workspace(int M, int H, int I);
 /* dy = dy_bf16 (+ dy_f32), either may be NULL; dx_bf16 [M, H] receives the gradient wrt x. */
 int vlb_bert_layer_backward(const VlbLayerWeights* w, const VlbLayerActs* acts, const void* x_bf16,
                             const float* add_mask, const void* dy_bf16, const float* dy_f32, void* dx_bf16,
                             const VlbLayerGrads* grads, void* workspace, int64_t workspace_bytes, int B, int S,
-                            int H, int heads, int I, void* stream);
+                            int H, int heads, int I, const VlbLayerDropout* drop, void* stream);
 
 #ifdef __cplusplus
 }

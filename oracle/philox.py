@@ -10,8 +10,14 @@ mask in forward and backward.  Contract (one Philox call covers four consecutive
     counter = (group & 0xffffffff, group >> 32, site, step)       group = linear_element_index // 4
     keep[4*group + j] = philox(counter, key)[j] >= floor(float32(p) * 2^32)     (j = 0..3)
 
-`site` numbers the dropout call sites of one step: 0 = embedding, then per layer l: 1+3l = attention probabilities
-(element index over [B, heads, S, S]), 2+3l = self-output dense, 3+3l = output dense; 1+3L = obj_downsample input.
+2-D form (what every fused site uses): element (r, c) of a row-major [rows, cols] tensor belongs to
+    group = r * ceil(cols / 4) + c // 4,  word = c % 4
+which IS the linear contract whenever cols % 4 == 0 (all hidden-size tensors); the attention probabilities
+(rows = (b, head, query), cols = S keys) pad every row to a multiple of four so that a row never shares a Philox call.
+
+`site` numbers the dropout call sites of one step: 0 = embedding output [B*S, H], then per layer l: 1+3l = attention
+probabilities [B*heads*S, S], 2+3l = self-output dense [B*S, H], 3+3l = output dense [B*S, H]; FastRCNN's obj_downsample
+input [B*R, 4096] uses site 1000 with the FastRCNN module's own (seed, step).
 `step` is the training step counter, so the masks differ every step and the backward regenerates them from (seed, step).
 """
 import numpy as np
@@ -55,3 +61,18 @@ def dropout(x, p, seed, site, step):
         return x, np.ones(x.shape, bool)
     keep = keep_mask(x.shape, p, seed, site, step)
     return (x * keep / np.float32(1.0 - p)).astype(x.dtype), keep
+
+
+def keep_mask_2d(rows, cols, p, seed, site, step):
+    """boolean keep-mask [rows, cols] under the 2-D contract (rows padded to a multiple of four columns)"""
+    gpr = (cols + 3) // 4
+    full = keep_mask((rows * gpr * 4,), p, seed, site, step).reshape(rows, gpr * 4)
+    return full[:, :cols]
+
+
+def dropout_2d(x2d, p, seed, site, step):
+    """x2d: numpy [rows, cols] -> x * keep / (1 - p) under the 2-D contract"""
+    if p <= 0.0:
+        return x2d
+    keep = keep_mask_2d(x2d.shape[0], x2d.shape[1], p, seed, site, step)
+    return (x2d * keep * (np.float32(1.0) / np.float32(1.0 - np.float32(p)))).astype(x2d.dtype)

@@ -55,8 +55,31 @@ def layer_norm_tf(x, weight, bias, eps=1e-12):
     return weight * ((x - mu) / torch.sqrt(var + eps)) + bias
 
 
-def self_attention(x, add_mask, wq, bq, wk, bk, wv, bv, num_heads):
-    """modeling.py:290-315 (dropout p=0).  x [B,S,H]; add_mask [B,1,1,S] additive (0 / -10000)."""
+class DropSpec(object):
+    """Dropout of one forward pass of the oracle.
+    mode "philox": the library's counter-based contract (oracle/philox.py) -- masks reproducible bit for bit, used by the
+    parity tests; mode "torch": torch.nn.functional.dropout on the global generator, i.e. what the reference itself executes
+    (modeling.py:283,310,331,376) -- used only to TIME the reference's CPU path with its dropout work included."""
+
+    def __init__(self, p_hidden, p_attn, seed=0, step=0, mode="philox"):
+        self.p_hidden, self.p_attn, self.seed, self.step, self.mode = float(p_hidden), float(p_attn), int(seed), int(step), mode
+
+    def apply(self, x, p, site):
+        """x: [..., cols]; the mask is indexed over x viewed as [rows, cols]"""
+        if p <= 0.0:
+            return x
+        if self.mode == "torch":
+            return F.dropout(x, p, training=True)
+        import philox
+        cols = x.shape[-1]
+        rows = x.numel() // cols
+        keep = torch.from_numpy(philox.keep_mask_2d(rows, cols, p, self.seed, site, self.step)).view(x.shape)
+        scale = float(1.0 / (1.0 - float(torch.tensor(p, dtype=torch.float32))))
+        return x * (keep.to(x.dtype) * scale)
+
+
+def self_attention(x, add_mask, wq, bq, wk, bk, wv, bv, num_heads, drop=None, site=0):
+    """modeling.py:290-315.  x [B,S,H]; add_mask [B,1,1,S] additive (0 / -10000); drop: DropSpec or None (p = 0)."""
     B, S, H = x.shape
     d = H // num_heads
 
@@ -66,20 +89,29 @@ def self_attention(x, add_mask, wq, bq, wk, bk, wv, bv, num_heads):
     q, k, v = split(F.linear(x, wq, bq)), split(F.linear(x, wk, bk)), split(F.linear(x, wv, bv))
     scores = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(d) + add_mask
     probs = torch.softmax(scores, dim=-1)
+    if drop is not None:
+        probs = drop.apply(probs, drop.p_attn, site)            # modeling.py:310
     ctx = torch.matmul(probs, v).permute(0, 2, 1, 3).contiguous().view(B, S, H)
     return ctx
 
 
-def bert_layer(x, add_mask, p, num_heads, eps=1e-12):
-    """modeling.py:388-397.  `p` maps the reference's per-layer state_dict suffixes to tensors."""
+def bert_layer(x, add_mask, p, num_heads, eps=1e-12, drop=None, layer=0):
+    """modeling.py:388-397.  `p` maps the reference's per-layer state_dict suffixes to tensors.
+    drop: DropSpec or None; sites 1+3l (attention probabilities), 2+3l (:331), 3+3l (:376)."""
     ctx = self_attention(x, add_mask,
                          p["attention.self.query.weight"], p["attention.self.query.bias"],
                          p["attention.self.key.weight"], p["attention.self.key.bias"],
-                         p["attention.self.value.weight"], p["attention.self.value.bias"], num_heads)
-    a = F.linear(ctx, p["attention.output.dense.weight"], p["attention.output.dense.bias"]) + x
+                         p["attention.self.value.weight"], p["attention.self.value.bias"], num_heads, drop, 1 + 3 * layer)
+    d = F.linear(ctx, p["attention.output.dense.weight"], p["attention.output.dense.bias"])
+    if drop is not None:
+        d = drop.apply(d, drop.p_hidden, 2 + 3 * layer)
+    a = d + x
     h = layer_norm_tf(a, p["attention.output.LayerNorm.weight"], p["attention.output.LayerNorm.bias"], eps)
     u = gelu_erf(F.linear(h, p["intermediate.dense.weight"], p["intermediate.dense.bias"]))
-    y = F.linear(u, p["output.dense.weight"], p["output.dense.bias"]) + h
+    d = F.linear(u, p["output.dense.weight"], p["output.dense.bias"])
+    if drop is not None:
+        d = drop.apply(d, drop.p_hidden, 3 + 3 * layer)
+    y = d + h
     return layer_norm_tf(y, p["output.LayerNorm.weight"], p["output.LayerNorm.bias"], eps)
 
 
@@ -198,7 +230,21 @@ class VisualLinguisticBertOracle(nn.Module):
         if config.with_pooler:
             self.pooler = _Pooler(H)
         self.position_padding_idx = config.position_padding_idx
+        #: dropout of the next forward passes: None = off (also when in eval mode or the config's probabilities are 0);
+        #: ("philox", seed, step) = the library's contract with that state; ("torch",) = torch's generator (timing only)
+        self.dropout_state = None
         self.reset_parameters()
+
+    def _drop_spec(self):
+        cfg = self.config
+        if self.dropout_state is None or not self.training:
+            return None
+        if cfg.hidden_dropout_prob == 0 and cfg.attention_probs_dropout_prob == 0:
+            return None
+        if self.dropout_state[0] == "torch":
+            return DropSpec(cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob, mode="torch")
+        _, seed, step = self.dropout_state
+        return DropSpec(cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob, seed, step)
 
     def reset_parameters(self):
         std = self.config.initializer_range
@@ -215,8 +261,10 @@ class VisualLinguisticBertOracle(nn.Module):
 
     # -- embedding (visual_linguistic_bert.py:173-241) ---------------------------------------------
     def embedding(self, text_input_ids, text_token_type_ids, text_visual_embeddings, text_mask,
-                  object_vl_embeddings, object_mask):
+                  object_vl_embeddings, object_mask, drop="auto"):
         cfg = self.config
+        if drop == "auto":
+            drop = self._drop_spec()
         VS = cfg.visual_size
         tv = text_visual_embeddings
         ov = object_vl_embeddings[:, :, :VS]
@@ -240,6 +288,8 @@ class VisualLinguisticBertOracle(nn.Module):
         position_ids = pos_id + self.position_padding_idx + 1
         emb = vl + self.position_embeddings(position_ids) + self.token_type_embeddings(type_ids)
         emb = self.embedding_LayerNorm(emb)
+        if drop is not None:
+            emb = drop.apply(emb, drop.p_hidden, 0)              # embedding_dropout, visual_linguistic_bert.py:239
         mask = (kind != 3).to(text_mask.dtype)
         return emb, mask, is_t, is_o
 
@@ -252,13 +302,14 @@ class VisualLinguisticBertOracle(nn.Module):
                 object_vl_embeddings, object_mask, output_all_encoded_layers=True,
                 output_text_and_object_separately=False, output_attention_probs=False):
         assert not output_attention_probs
+        drop = self._drop_spec()
         emb, mask, is_t, is_o = self.embedding(text_input_ids, text_token_type_ids, text_visual_embeddings,
-                                               text_mask, object_vl_embeddings, object_mask)
+                                               text_mask, object_vl_embeddings, object_mask, drop)
         add_mask = (1.0 - mask.to(emb.dtype)).unsqueeze(1).unsqueeze(2) * -10000.0
         layers = []
         h = emb
         for i in range(self.config.num_hidden_layers):
-            h = bert_layer(h, add_mask, self._layer_params(i), self.config.num_attention_heads)
+            h = bert_layer(h, add_mask, self._layer_params(i), self.config.num_attention_heads, drop=drop, layer=i)
             layers.append(h)
         pooled = torch.tanh(self.pooler.dense(h[:, 0])) if self.config.with_pooler else None
         encoded = layers if output_all_encoded_layers else layers[-1]
@@ -289,9 +340,11 @@ def coordinate_embeddings(boxes6, dim=256):
     return torch.cat((arg.sin(), arg.cos()), dim=-1)
 
 
-def fast_rcnn_precomputed(boxes, box_mask, im_info, weight, bias, mvrc_ops=None, mask_visual_embed=None):
-    """common/fast_rcnn.py:136-193 with IMAGE_FEAT_PRECOMPUTED, no classes/segms, dropout p=0.
-    boxes [B,R,4+2048]; weight [final_dim,4096]; returns (obj_reps [B,R,final_dim], obj_reps_raw [B,R,2048])."""
+def fast_rcnn_precomputed(boxes, box_mask, im_info, weight, bias, mvrc_ops=None, mask_visual_embed=None, drop=None):
+    """common/fast_rcnn.py:136-193 with IMAGE_FEAT_PRECOMPUTED, no classes/segms.
+    boxes [B,R,4+2048]; weight [final_dim,4096]; returns (obj_reps [B,R,final_dim], obj_reps_raw [B,R,2048]).
+    drop = (p, seed, step) applies obj_downsample's Dropout (:104-109) under the library's contract: the mask is indexed
+    over the [B*R, 4096] SLOT layout (row b*R + r of the box the operand row was built from), site 1000."""
     B, R = box_mask.shape
     idx = box_mask.nonzero()
     assert idx.shape[0] > 0
@@ -302,6 +355,11 @@ def fast_rcnn_precomputed(boxes, box_mask, im_info, weight, bias, mvrc_ops=None,
         feats[(mvrc_ops == 1)[idx[:, 0], idx[:, 1]]] = mask_visual_embed
     ce = coordinate_embeddings(torch.cat((coords, im_info[idx[:, 0], :2]), 1), 256)
     x = torch.cat((ce.reshape(ce.shape[0], -1), feats), -1)
+    if drop is not None and drop[0] > 0:
+        import philox
+        p_, seed_, step_ = drop
+        keep = torch.from_numpy(philox.keep_mask_2d(B * R, x.shape[1], p_, seed_, 1000, step_))[idx[:, 0] * R + idx[:, 1]]
+        x = x * (keep.to(x.dtype) * float(1.0 / (1.0 - float(torch.tensor(p_, dtype=torch.float32)))))
     final = torch.relu(F.linear(x, weight, bias))
     # pad_sequence (common/utils/pad_sequence.py): the k-th valid box of sample b lands in slot k
     slot = torch.cumsum(box_mask.long(), 1) - 1

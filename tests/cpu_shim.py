@@ -59,7 +59,8 @@ class _AvgPool(object):
 
 class _Region(object):
     @staticmethod
-    def apply(boxes, weight, bias, box_mask, im_info):
+    def apply(boxes, weight, bias, box_mask, im_info, drop=None):
+        assert drop is None, "the CPU stand-ins have no dropout: run the module in eval mode or with p = 0"
         return vo.fast_rcnn_precomputed(boxes, box_mask, im_info, weight, bias)
 
 
@@ -79,6 +80,9 @@ def install(monkeypatch):
 # GatherRowsFn / EncoderWeights (fp32 torch ops on the oracle's primitives)
 # ------------------------------------------------------------------------------------------------------------------
 class PackIndexShim(object):
+    def check(self):
+        pass
+
     def __init__(self, text_mask, object_mask, text_token_type_ids, S, pos_offset):
         kind, src, pos_id, te, oe, S_true = vo.pack_indices(text_mask.bool(), object_mask.bool())
         B, T = text_mask.shape
@@ -103,7 +107,8 @@ class PackIndexShim(object):
 
 class _EmbeddingShim(object):
     @staticmethod
-    def apply(text_visual, object_vl, word, end, pos, typ, ln_w, ln_b, vt_w, vt_b, vo_w, vo_b, ids, pidx, eps):
+    def apply(text_visual, object_vl, word, end, pos, typ, ln_w, ln_b, vt_w, vt_b, vo_w, vo_b, ids, pidx, eps, drop=None):
+        assert drop is None, "the CPU stand-ins have no dropout: run the module in eval mode or with p = 0"
         H = word.shape[1]
         B, S = pidx.kind.shape
         text_vl = word[ids] + vo.layer_norm_tf(text_visual.float(), vt_w, vt_b, eps)
@@ -145,6 +150,12 @@ class _GatherRowsShim(object):
         return torch.where(ok.unsqueeze(-1), src2d[idx.clamp(min=0)], out)
 
 
+class _LinearShim(object):
+    @staticmethod
+    def apply(x, weight, bias):
+        return F.linear(x, weight, bias)
+
+
 class _EncoderWeightsShim(object):
     def __init__(self, L, H, I, device):
         self.w_qkv = torch.zeros(1, device=device)
@@ -157,3 +168,4 @@ def install_encoder(monkeypatch):
     monkeypatch.setattr(VF, "EncoderFn", _EncoderShim)
     monkeypatch.setattr(VF, "GatherRowsFn", _GatherRowsShim)
     monkeypatch.setattr(VF, "EncoderWeights", _EncoderWeightsShim)
+    monkeypatch.setattr(VF, "LinearFn", _LinearShim)

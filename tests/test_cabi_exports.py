@@ -43,7 +43,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_no_compute_needed_calls(lib):
     lib.vlb_abi_version.restype = ctypes.c_int
-    assert lib.vlb_abi_version() == 1
+    assert lib.vlb_abi_version() == 2
     lib.vlb_last_error_string.restype = ctypes.c_char_p
     assert isinstance(lib.vlb_last_error_string(), bytes)
     lib.vlb_bert_layer_backward_workspace.restype = ctypes.c_int64

@@ -1,0 +1,323 @@
+"""GPU parity of the fused dropout sites (through the C ABI) against the oracle applying the SAME counter-based masks
+(oracle/philox.py).  The reference's own masks come from torch's global generator and cannot be matched by anyone; what is
+pinned here is the contract: which elements are dropped (bit-exact: checked through exact zeros / exact residual values),
+the 1/(1-p) scaling, and that the backward re-uses the forward's mask (gradients match the oracle's autograd).
+
+Tolerances: identical to the p = 0 tests of the same kernels (tests/test_gpu_kernels.py, tests/test_gpu_modules.py); mask
+positions bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import philox
+import vlbert_oracle as vo
+from synth import seeded_state_dict, synth_vlbert_inputs, vlbert_loss
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+BF16 = torch.bfloat16
+SEED, STEP = 0x1234ABCD5678, 41
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def bf(x):
+    return x.to(BF16).float()
+
+
+@pytest.fixture(scope="module")
+def VF():
+    import vlbert_b200
+    return vlbert_b200.functional
+
+
+def rng_state(seed=SEED, step=STEP):
+    return torch.tensor([seed, step], dtype=torch.int64, device=DEV)
+
+
+def keep_t(rows, cols, p, site, seed=SEED, step=STEP):
+    return torch.from_numpy(philox.keep_mask_2d(rows, cols, p, seed, site, step))
+
+
+# ------------------------------------------------------------------------------------------------ the mask itself
+@pytest.mark.parametrize("rows,cols", [(37, 101), (64, 768), (5, 13), (3, 4096), (12 * 7, 165)])
+def test_mask_2d_bit_exact(rows, cols):
+    import vlbert_b200
+    lib = vlbert_b200._lib.lib()
+    keep = torch.empty((rows, cols), dtype=torch.uint8, device=DEV)
+    vlbert_b200._lib.check(lib.vlb_dropout_mask_2d(keep.data_ptr(), rows, cols, 0.1, SEED, 7, STEP, torch.cuda.current_stream().cuda_stream))
+    assert np.array_equal(keep.cpu().numpy().astype(bool), philox.keep_mask_2d(rows, cols, 0.1, SEED, 7, STEP))
+
+
+def test_dropout_2d_window_reads_the_device_state(VF):
+    x = torch.randn(50, 64, device=DEV)
+    st = rng_state()
+    d = VF.DropSite(0.25, 9, st)
+    y = VF.dropout_2d(x, d, col_offset=32, total_cols=128)
+    keep = keep_t(50, 128, 0.25, 9)[:, 32:96].to(DEV)
+    assert torch.equal(y == 0, ~keep | (x == 0))
+    assert rel(y, x * keep / 0.75) <= 1e-6
+    st[1] += 1   # same DropSite object, new step on the device: a different mask
+    y2 = VF.dropout_2d(x, d, col_offset=32, total_cols=128)
+    keep2 = keep_t(50, 128, 0.25, 9, step=STEP + 1)[:, 32:96].to(DEV)
+    assert torch.equal(y2 == 0, ~keep2 | (x == 0)) and not torch.equal(keep, keep2)
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm sites
+@pytest.mark.parametrize("M,H", [(6464, 768), (37, 128), (300, 1024)])
+def test_layernorm_output_dropout_and_its_backward(VF, M, H):
+    g = torch.Generator().manual_seed(M + H)
+    x = torch.randn(M, H, generator=g) * 2 + 0.3
+    gamma, beta = 1 + 0.1 * torch.randn(H, generator=g), 0.5 + 0.1 * torch.randn(H, generator=g)
+    dy = bf(torch.randn(M, H, generator=g))
+    p = 0.1
+    keep = keep_t(M, H, p, 0)
+    xt, gt, bt = x.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y = vo.layer_norm_tf(xt, gt, bt) * keep / (1 - p)
+    (y * dy).sum().backward()
+    d = VF.DropSite(p, 0, rng_state())
+    y16, y32, mean, rstd = VF.layernorm_forward(x.to(DEV), gamma.to(DEV), beta.to(DEV), want_f32=True, drop=d)
+    assert torch.equal((y32 == 0).cpu(), ~keep)          # dropped positions: bit-exact (LN output + 0.5 bias is never 0)
+    assert torch.equal((y16 == 0).cpu(), ~keep)
+    assert rel(y32, y.detach()) <= 1e-5
+    dg, db = torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)
+    _, dx32 = VF.layernorm_backward(dy.to(DEV, BF16), None, x.to(DEV), mean, rstd, gamma.to(DEV), dg, db, None, want_bf16=False,
+                                    want_f32=True, in_drop=d)
+    assert rel(dx32, xt.grad) <= 1e-4
+    assert rel(dg, gt.grad) <= 1e-4 and rel(db, bt.grad) <= 1e-4
+
+
+def test_layernorm_backward_second_output_for_the_dense_branch(VF):
+    """x = dropout(dense) + residual -> LN: backward writes dx (residual branch) and dx o mask / (1-p) (dense branch);
+    the bias gradient (dcolsum) sums the masked tensor."""
+    M, H, p = 777, 768, 0.1
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(M, H, generator=g)
+    gamma = 1 + 0.1 * torch.randn(H, generator=g)
+    dy = bf(torch.randn(M, H, generator=g))
+    _, _, mean, rstd = VF.layernorm_forward(x.to(DEV), gamma.to(DEV), torch.zeros(H, device=DEV))
+    dg, db, dc = (torch.zeros(H, device=DEV) for _ in range(3))
+    dg0, db0, dc0 = (torch.zeros(H, device=DEV) for _ in range(3))
+    plain16, plain32 = VF.layernorm_backward(dy.to(DEV, BF16), None, x.to(DEV), mean, rstd, gamma.to(DEV), dg0, db0, dc0, want_f32=True)
+    d = VF.DropSite(p, 8, rng_state())
+    dx16, dx32, dxm = VF.layernorm_backward(dy.to(DEV, BF16), None, x.to(DEV), mean, rstd, gamma.to(DEV), dg, db, dc, want_f32=True,
+                                            out_drop=d)
+    keep = keep_t(M, H, p, 8).to(DEV)
+    assert torch.equal(dx16, plain16) and torch.equal(dx32, plain32)          # the residual branch is untouched
+    assert torch.equal(dxm == 0, ~keep | (plain32 == 0))
+    assert rel(dxm.float(), plain32 * keep / (1 - p)) <= 3e-3
+    assert rel(dc, (plain32 * keep / (1 - p)).sum(0)) <= 2e-3
+    assert torch.equal(dg, dg0) and torch.equal(db, db0)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM epilogue site
+@pytest.mark.parametrize("M,N,K", [(6464, 768, 768), (300, 768, 3072), (26, 1024, 256)])
+@pytest.mark.parametrize("bn", [0, 128, 256])
+def test_gemm_bias_dropout_residual_epilogue(VF, M, N, K, bn):
+    g = torch.Generator().manual_seed(M + N + K)
+    a, w = bf(torch.randn(M, K, generator=g)), bf(torch.randn(N, K, generator=g) * 0.05)
+    bias = torch.randn(N, generator=g)
+    resid = bf(torch.randn(M, N, generator=g))
+    p = 0.1
+    keep = keep_t(M, N, p, 5)
+    ref = (a @ w.t() + bias) * keep / (1 - p) + resid
+    out = torch.full((M, N), float("nan"), device=DEV)
+    VF.gemm(0, a.to(DEV, BF16), w.to(DEV, BF16), out, bias=bias.to(DEV), resid=resid.to(DEV, BF16), force_bn=bn,
+            drop=VF.DropSite(p, 5, rng_state()))
+    assert torch.equal((out.cpu() == resid), ~keep)      # dropped elements are EXACTLY the residual
+    assert rel(out, ref) <= 2e-5
+    # generic (non compile-time) epilogue path: bf16 output
+    o16 = torch.empty((M, N), device=DEV, dtype=BF16)
+    VF.gemm(0, a.to(DEV, BF16), w.to(DEV, BF16), o16, bias=bias.to(DEV), resid=resid.to(DEV, BF16), force_bn=bn,
+            drop=VF.DropSite(p, 5, rng_state()))
+    assert rel(o16.float(), ref) <= 3e-3
+
+
+# ------------------------------------------------------------------------------------------------ attention site
+def _attn_oracle(qkv, add_mask, B, S, H, heads, keep, p):
+    q, k, v = qkv.view(B, S, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) / 8.0 + add_mask.view(B, 1, 1, S)
+    pr = torch.softmax(s, -1) * keep.view(B, heads, S, S) / (1 - p)
+    return (pr @ v).permute(0, 2, 1, 3).reshape(B * S, H)
+
+
+@pytest.mark.parametrize("B,S,heads", [(64, 101, 12), (3, 13, 2), (5, 128, 4), (4, 121, 12), (3, 165, 16), (2, 256, 4)])
+@pytest.mark.parametrize("p", [0.1, 0.5])
+def test_mhsa_probability_dropout(VF, B, S, heads, p):
+    H = heads * 64
+    g = torch.Generator().manual_seed(B * 1000 + S)
+    qkv = bf(torch.randn(B * S, 3 * H, generator=g))
+    lens = torch.randint(1, S + 1, (B,), generator=g)
+    lens[0] = S
+    add_mask = torch.where(torch.arange(S)[None] < lens[:, None], 0.0, -10000.0)
+    dctx = bf(torch.randn(B * S, H, generator=g))
+    keep = keep_t(B * heads * S, S, p, 4)
+    qt = qkv.clone().requires_grad_(True)
+    ref = _attn_oracle(qt, add_mask, B, S, H, heads, keep, p)
+    (ref * dctx).sum().backward()
+    d = VF.DropSite(p, 4, rng_state())
+    ctx, lse = VF.mhsa_forward(qkv.to(DEV, BF16), add_mask.to(DEV), B, S, H, heads, drop=d)
+    assert rel(ctx.float(), ref.detach()) <= 4e-3
+    # log-sum-exp is that of the full softmax (dropout acts after the normalisation)
+    ctx0, lse0 = VF.mhsa_forward(qkv.to(DEV, BF16), add_mask.to(DEV), B, S, H, heads)
+    assert torch.equal(lse, lse0)
+    dqkv = VF.mhsa_backward(qkv.to(DEV, BF16), add_mask.to(DEV), ctx, lse, dctx.to(DEV, BF16), B, S, H, heads, drop=d)
+    assert rel(dqkv.float(), qt.grad) <= 8e-3
+
+
+def test_mhsa_single_key_row_is_dropped_exactly(VF):
+    """S = 1: the only probability is 1; with p = 0.5 a row's context is either 2 v or exactly 0 -- the mask position test."""
+    B, S, heads, p = 64, 1, 2, 0.5
+    H = heads * 64
+    g = torch.Generator().manual_seed(9)
+    qkv = bf(torch.randn(B * S, 3 * H, generator=g))
+    keep = keep_t(B * heads * S, S, p, 4).view(B, heads)
+    ctx, _ = VF.mhsa_forward(qkv.to(DEV, BF16), None, B, S, H, heads, drop=VF.DropSite(p, 4, rng_state()))
+    c = ctx.float().cpu().view(B, heads, 64)
+    v = qkv[:, 2 * H:].view(B, heads, 64)
+    assert torch.equal(c.abs().sum(-1) == 0, ~keep)
+    assert rel(c, v * keep.unsqueeze(-1) * 2) <= 4e-3
+
+
+# ------------------------------------------------------------------------------------------------ modules
+def _run(model, inputs, seed, dev):
+    ids, types, tvis, tmask, ovl, omask = [t.to(dev) for t in inputs]
+    tvis = tvis.clone().requires_grad_(True)
+    ovl = ovl.clone().requires_grad_(True)
+    layers, pooled = model(ids, types, tvis, tmask, ovl, omask, output_all_encoded_layers=True)
+    loss = vlbert_loss(layers, pooled, seed)
+    model.zero_grad()
+    loss.backward()
+    grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    return layers, pooled, grads, tvis.grad, ovl.grad
+
+
+@pytest.mark.parametrize("shape", [dict(L=2, B=2, T=8, R=4), dict(L=1, B=8, T=64, R=36), dict(L=2, B=4, T=20, R=100)])
+def test_training_mode_module_against_oracle_with_the_same_masks(shape):
+    """hidden_dropout_prob = attention_probs_dropout_prob = 0.1 (every reference cfg), train mode: outputs and every
+    parameter gradient against the oracle that applies the identical Philox masks; same bounds as the p = 0 module tests."""
+    import vlbert_b200
+    from test_gpu_modules import TOL_GRAD, TOL_OUT, grad_ok
+    cfg = vo.default_config(num_hidden_layers=shape["L"], hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1)
+    ora = vo.VisualLinguisticBertOracle(cfg)
+    sd = seeded_state_dict(ora, 12)
+    ora.load_state_dict(sd)
+    model = vlbert_b200.VisualLinguisticBert(cfg).to(DEV)
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    model.set_dropout_seed(987654321, step=5)
+    inputs = synth_vlbert_inputs(B=shape["B"], T=shape["T"], R=shape["R"], H=768, vocab=30522, seed=22, ragged=True)
+    ours = _run(model, inputs, 32, DEV)
+    seed, step = model.dropout_state()
+    assert (seed, step) == (987654321, 6)                 # the forward advanced the step counter on the device
+    ora.train()
+    ora.dropout_state = ("philox", seed, step)
+    ref = _run(ora, inputs, 32, "cpu")
+    for a, b in zip(ours[0], ref[0]):
+        assert rel(a, b) <= TOL_OUT
+    assert rel(ours[1], ref[1]) <= TOL_OUT
+    assert rel(ours[3], ref[3]) <= TOL_GRAD and rel(ours[4], ref[4]) <= TOL_GRAD
+    for k in ref[2]:
+        assert grad_ok(k, ours[2][k], ref[2][k], ref[2], TOL_GRAD), (k, rel(ours[2][k], ref[2][k]))
+    # a p = 0 oracle is far away: the masks matter (guards against a silently disabled dropout)
+    ora.dropout_state = None
+    plain = _run(ora, inputs, 32, "cpu")
+    assert rel(ours[0][-1], plain[0][-1]) > 0.1
+    # the embedding site: dropped positions are exactly zero
+    model.set_dropout_seed(987654321, step=5)
+    emb, mask, _, _ = model.embedding(*[t.to(DEV) for t in inputs])
+    B, S, H = emb.shape
+    keep = torch.from_numpy(philox.keep_mask_2d(B * S, H, 0.1, 987654321, 0, 6)).view(B, S, H)
+    assert torch.equal((emb == 0).cpu(), ~keep)
+
+
+def test_eval_mode_and_step_counter():
+    import vlbert_b200
+    cfg = vlbert_b200.default_config(num_hidden_layers=1)
+    assert cfg.hidden_dropout_prob == 0.1 and cfg.attention_probs_dropout_prob == 0.1   # the reference's defaults
+    torch.manual_seed(0)
+    model = vlbert_b200.VisualLinguisticBert(cfg).to(DEV)
+    inputs = [t.to(DEV) for t in synth_vlbert_inputs(B=3, T=10, R=5, H=768, vocab=30522, seed=1)]
+    model.eval()
+    with torch.no_grad():
+        a, _ = model(*inputs, output_all_encoded_layers=False)
+        b, _ = model(*inputs, output_all_encoded_layers=False)
+    assert torch.equal(a, b) and model.dropout_state()[1] == 0     # eval: no dropout, no step
+    model.train()
+    with torch.no_grad():
+        c, _ = model(*inputs, output_all_encoded_layers=False)
+        d, _ = model(*inputs, output_all_encoded_layers=False)
+    assert model.dropout_state()[1] == 2 and not torch.equal(c, d) and not torch.equal(a, c)
+    model.set_dropout_seed(model.dropout_state()[0], step=0)
+    with torch.no_grad():
+        e, _ = model(*inputs, output_all_encoded_layers=False)
+    assert torch.equal(c, e)                                        # same (seed, step) -> same masks
+
+
+def test_graph_replay_advances_the_masks():
+    """The step counter lives on the device and is incremented inside the captured graph: every replay draws new masks, and
+    the backward inside the same replay re-uses the forward's."""
+    import vlbert_b200
+    cfg = vlbert_b200.default_config(num_hidden_layers=2)
+    torch.manual_seed(0)
+    model = vlbert_b200.VisualLinguisticBert(cfg).to(DEV)
+    model.max_length_hint = 16
+    inputs = [t.to(DEV) for t in synth_vlbert_inputs(B=4, T=10, R=5, H=768, vocab=30522, seed=1, ragged=False)]
+
+    def loss_fn(m, *ins):
+        out, _ = m(*ins, output_all_encoded_layers=False)
+        return (out.float() ** 2).mean()
+
+    gs = vlbert_b200.GraphedStep(model, loss_fn, inputs, warmup=2)
+    s0 = model.dropout_state()[1]
+    l1 = float(gs(*inputs))
+    g1 = model.encoder.layer[0].output.dense.weight.grad.clone()
+    l2 = float(gs(*inputs))
+    assert model.dropout_state()[1] == s0 + 2 and l1 != l2
+    # replay n equals an eager step at the same (seed, step)
+    seed, step = model.dropout_state()
+    model.set_dropout_seed(seed, step - 2)
+    model.zero_grad(set_to_none=True)
+    le = loss_fn(model, *inputs)
+    le.backward()
+    assert abs(float(le) - l1) <= 1e-6 * abs(l1)
+    assert rel(model.encoder.layer[0].output.dense.weight.grad, g1) <= 1e-6
+    model.check_errors()
+
+
+def test_fastrcnn_obj_downsample_dropout_against_oracle(golden_dir):
+    import os
+    from types import SimpleNamespace as NS
+
+    import vlbert_b200
+    G = np.load(os.path.join(golden_dir, "fastrcnn_prec.npz"))
+    cfg = NS(NETWORK=NS(IMAGE_FEAT_PRECOMPUTED=True, IMAGE_SEMANTIC=False))
+    m = vlbert_b200.FastRCNN(cfg, average_pool=True, final_dim=32).to(DEV).train()
+    W, b = torch.from_numpy(G["weight"]), torch.from_numpy(G["bias"])
+    m.obj_downsample[1].weight.data.copy_(W)
+    m.obj_downsample[1].bias.data.copy_(b)
+    m.set_dropout_seed(4242, step=10)
+    boxes = torch.from_numpy(G["boxes"])
+    box_mask, im_info = torch.from_numpy(G["box_mask"]), torch.from_numpy(G["im_info"])
+    bx = boxes.clone().to(DEV).requires_grad_(True)
+    out = m(images=None, boxes=bx, box_mask=box_mask.to(DEV), im_info=im_info.to(DEV))
+    assert m.dropout_state() == (4242, 11)
+    bo = boxes.clone().requires_grad_(True)
+    Wt, bt = W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref, raw = vo.fast_rcnn_precomputed(bo, box_mask, im_info, Wt, bt, drop=(0.1, 4242, 11))
+    assert np.array_equal(out["obj_reps_raw"].detach().cpu().numpy(), raw.detach().numpy())
+    assert rel(out["obj_reps"], ref.detach()) <= 1e-2
+    go = torch.from_numpy(G["grad_out"])
+    (out["obj_reps"] * go.to(DEV)).sum().backward()
+    (ref * go).sum().backward()
+    assert rel(m.obj_downsample[1].weight.grad, Wt.grad) <= 1.5e-2
+    assert rel(m.obj_downsample[1].bias.grad, bt.grad) <= 1.5e-2
+    assert rel(bx.grad[:, :, 4:], bo.grad[:, :, 4:]) <= 1.5e-2
+    # eval mode: bit-identical to the p = 0 fixture path
+    m.eval()
+    with torch.no_grad():
+        o2 = m(images=None, boxes=boxes.to(DEV), box_mask=box_mask.to(DEV), im_info=im_info.to(DEV))
+    assert rel(o2["obj_reps"], torch.from_numpy(G["obj_reps"])) <= 1e-2

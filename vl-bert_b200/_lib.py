@@ -78,9 +78,19 @@ def _declare(lib):
     decl("vlb_nhwc_bf16_to_nchw_f32", [P, P, I, I, I, I, P])
     decl("vlb_roi_align_nhwc_forward", [P, P, P, I, I, I, I, I, I, F, I, P])
     decl("vlb_roi_align_nhwc_backward", [P, P, P, I, I, I, I, I, I, I, F, I, P])
-    decl("vlb_bert_layer_forward", [P, P, P, P, I, I, I, I, I, F, P])
+    decl("vlb_bert_layer_forward", [P, P, P, P, I, I, I, I, I, F, P, P])
     decl("vlb_bert_layer_backward_workspace", [I, I, I], L)
-    decl("vlb_bert_layer_backward", [P, P, P, P, P, P, P, P, P, L, I, I, I, I, I, P])
+    decl("vlb_bert_layer_backward", [P, P, P, P, P, P, P, P, P, L, I, I, I, I, I, P, P])
+    # dropout-aware forms (ABI version 2): trailing VlbDropout* before the stream
+    decl("vlb_gemm_bf16_dropout", [c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p,
+                                   c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_float, c_int, c_int, P, P])
+    decl("vlb_mhsa_forward_dropout", [P, P, P, P, I, I, I, I, P, P])
+    decl("vlb_mhsa_backward_dropout", [P, P, P, P, P, P, P, I, I, I, I, P, P])
+    decl("vlb_layernorm_forward_dropout", [P, I, P, P, P, P, P, P, I, I, F, P, P])
+    decl("vlb_layernorm_backward_dropout", [P, P, P, I, P, P, P, P, P, I, P, P, P, I, I, P, P, P, P])
+    decl("vlb_region_operand_dropout", [P, I, P, P, I, P, P, P, P, I, I, I, P, P])
+    decl("vlb_dropout_mask_2d", [P, L, I, ctypes.c_float, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, P])
+    decl("vlb_dropout_2d", [P, I, P, I, L, I, I, I, I, P, P])
 
 
 class LayerWeights(ctypes.Structure):
@@ -99,6 +109,17 @@ class LayerGrads(ctypes.Structure):
     """VlbLayerGrads"""
     _fields_ = [(n, c_void_p) for n in ("dw_qkv", "db_qkv", "dw_o", "db_o", "dln1_g", "dln1_b", "dw_1", "db_1", "dw_2",
                                         "db_2", "dln2_g", "dln2_b")]
+
+
+class Dropout(ctypes.Structure):
+    """VlbDropout"""
+    _fields_ = [("p", c_float), ("site", c_uint32), ("rng", c_void_p)]
+
+
+class LayerDropout(ctypes.Structure):
+    """VlbLayerDropout"""
+    _fields_ = [("p_attn", c_float), ("p_hidden", c_float), ("site_attn", c_uint32), ("site_self_out", c_uint32),
+                ("site_out", c_uint32), ("rng", c_void_p)]
 
 
 class GroupedProblem(ctypes.Structure):

@@ -77,11 +77,11 @@ bool pdl_enabled() {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 void gemm_debug_override(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t mn_kadv);
 int bert_layer_forward(const VlbLayerWeights& w, const void* x, const float* add_mask, const VlbLayerActs& a, int B, int S, int H,
-                       int heads, int I, float eps, cudaStream_t st);
+                       int heads, int I, float eps, const VlbLayerDropout* drop, cudaStream_t st);
 int64_t bert_layer_backward_workspace(int M, int H, int I);
 int bert_layer_backward(const VlbLayerWeights& w, const VlbLayerActs& a, const void* x, const float* add_mask, const void* dy16,
                         const float* dy32, void* dx, const VlbLayerGrads& g, void* workspace, int64_t ws_bytes, int B, int S,
-                        int H, int heads, int I, cudaStream_t st);
+                        int H, int heads, int I, const VlbLayerDropout* drop, cudaStream_t st);
 
 }  // namespace vlb
 
@@ -89,7 +89,7 @@ using namespace vlb;
 
 extern "C" {
 
-int vlb_abi_version(void) { return 1; }
+int vlb_abi_version(void) { return 2; }
 int vlb_streamk_compiled(void) { return gemm_streamk_compiled() ? 1 : 0; }
 void vlb_set_sm_limit(int sms) { g_sm_limit.store(sms > 0 ? sms : 0); }
 const char* vlb_last_error_string(void) { return g_err; }
@@ -103,6 +103,21 @@ int vlb_gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const v
   e.bias = bias;
   e.resid = resid; e.ldr = ldr; e.resid_kind = resid_kind;
   e.act = act; e.aux = aux; e.ld_aux = ld_aux; e.alpha = alpha;
+  int rc = gemm_bf16(mode, M, N, K, A, lda, B, ldb, e, split_k, force_bn, static_cast<cudaStream_t>(stream));
+  if (rc == VLB_OK) count_launch(1);
+  return rc;
+}
+
+int vlb_gemm_bf16_dropout(int mode, int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* out,
+                          int ldo, int out_kind, const float* bias, const void* resid, int ldr, int resid_kind, int act,
+                          void* aux, int ld_aux, float alpha, int split_k, int force_bn, const VlbDropout* drop, void* stream) {
+  if (!drop_valid(drop)) { set_last_error("vlb_gemm_bf16_dropout: bad dropout configuration"); return VLB_ERR_INVALID; }
+  GemmEpilogue e;
+  e.out = out; e.ldo = ldo; e.out_kind = out_kind;
+  e.bias = bias;
+  e.resid = resid; e.ldr = ldr; e.resid_kind = resid_kind;
+  e.act = act; e.aux = aux; e.ld_aux = ld_aux; e.alpha = alpha;
+  e.drop = make_drop(drop);
   int rc = gemm_bf16(mode, M, N, K, A, lda, B, ldb, e, split_k, force_bn, static_cast<cudaStream_t>(stream));
   if (rc == VLB_OK) count_launch(1);
   return rc;
@@ -150,6 +165,25 @@ int vlb_mhsa_forward(const void* qkv, const float* add_mask, void* ctx, float* l
 int vlb_mhsa_backward(const void* qkv, const float* add_mask, const void* ctx, const float* lse, const void* dctx, void* dqkv,
                       float* scratch_f32, int B, int S, int H, int heads, void* stream) {
   COUNTED(1, mhsa_backward(qkv, add_mask, ctx, lse, dctx, dqkv, scratch_f32, B, S, H, heads, ST));
+}
+int vlb_mhsa_forward_dropout(const void* qkv, const float* add_mask, void* ctx, float* lse, int B, int S, int H, int heads,
+                             const VlbDropout* drop, void* stream) {
+  COUNTED(1, mhsa_forward(qkv, add_mask, ctx, lse, B, S, H, heads, ST, drop));
+}
+int vlb_mhsa_backward_dropout(const void* qkv, const float* add_mask, const void* ctx, const float* lse, const void* dctx,
+                              void* dqkv, float* scratch_f32, int B, int S, int H, int heads, const VlbDropout* drop, void* stream) {
+  COUNTED(1, mhsa_backward(qkv, add_mask, ctx, lse, dctx, dqkv, scratch_f32, B, S, H, heads, ST, drop));
+}
+int vlb_layernorm_forward_dropout(const float* x, int ldx, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
+                                  float* mean, float* rstd, int M, int H, float eps, const VlbDropout* out_drop, void* stream) {
+  COUNTED(1, layernorm_forward(x, ldx, gamma, beta, y_bf16, y_f32, mean, rstd, M, H, eps, ST, out_drop));
+}
+int vlb_layernorm_backward_dropout(const void* dy_bf16, const float* dy_f32, const float* x, int ldx, const float* mean,
+                                   const float* rstd, const float* gamma, void* dx_bf16, float* dx_f32, int ld_dx, float* dgamma,
+                                   float* dbeta, float* dcolsum, int M, int H, const VlbDropout* in_drop, void* dx_bf16_drop,
+                                   const VlbDropout* out_drop, void* stream) {
+  COUNTED(1, layernorm_backward(dy_bf16, dy_f32, x, ldx, mean, rstd, gamma, dx_bf16, dx_f32, ld_dx, dgamma, dbeta, dcolsum, M, H, ST,
+                                in_drop, dx_bf16_drop, out_drop));
 }
 int vlb_layernorm_forward(const float* x, int ldx, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
                           float* mean, float* rstd, int M, int H, float eps, void* stream) {
@@ -213,6 +247,12 @@ int vlb_region_operand(const float* boxes, int ld_box, const uint8_t* box_mask, 
   COUNTED(2, region_operand(boxes, ld_box, box_mask, im_info, ld_info, mvrc_ops, mask_visual_embed, A, gather_idx, B, R,
                             feat_dim, ST));
 }
+int vlb_region_operand_dropout(const float* boxes, int ld_box, const uint8_t* box_mask, const float* im_info, int ld_info,
+                               const int64_t* mvrc_ops, const float* mask_visual_embed, void* A, int32_t* gather_idx, int B, int R,
+                               int feat_dim, const VlbDropout* drop, void* stream) {
+  COUNTED(2, region_operand(boxes, ld_box, box_mask, im_info, ld_info, mvrc_ops, mask_visual_embed, A, gather_idx, B, R,
+                            feat_dim, ST, drop));
+}
 int vlb_im2col_nhwc(const void* x, void* col, int N, int H, int W, int C, int kh, int kw, int stride, int pad, int dil, int Ho,
                     int Wo, int Kp, void* stream) {
   COUNTED(1, im2col_nhwc(x, col, N, H, W, C, kh, kw, stride, pad, dil, Ho, Wo, Kp, ST));
@@ -239,6 +279,13 @@ int vlb_adamw_step(const VlbAdamWTensor* descs_device, const float* hyper_device
 }
 int vlb_dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t seed, uint32_t site, uint32_t step, void* stream) {
   COUNTED(1, dropout_mask(keep, n, p, seed, site, step, ST));
+}
+int vlb_dropout_mask_2d(uint8_t* keep, int64_t rows, int cols, float p, uint64_t seed, uint32_t site, uint32_t step, void* stream) {
+  COUNTED(1, dropout_mask_2d(keep, rows, cols, p, seed, site, step, ST));
+}
+int vlb_dropout_2d(const void* x, int ldx, void* y, int ldy, int64_t rows, int cols, int col_offset, int total_cols, int is_bf16,
+                   const VlbDropout* drop, void* stream) {
+  COUNTED(1, dropout_2d(x, ldx, y, ldy, rows, cols, col_offset, total_cols, is_bf16, drop, ST));
 }
 int vlb_dropout(const void* x, void* y, int64_t n, int is_bf16, float p, uint64_t seed, uint32_t site, uint32_t step, void* stream) {
   COUNTED(1, dropout_apply(x, y, n, is_bf16, p, seed, site, step, ST));
@@ -300,20 +347,21 @@ int vlb_roi_align_nhwc_backward(const void* grad_out, const float* rois, float* 
   COUNTED(1, roi_align_nhwc_backward(grad_out, rois, grad_feat, K, N, C, H, W, ph, pw, spatial_scale, sampling_ratio, ST));
 }
 int vlb_bert_layer_forward(const VlbLayerWeights* w, const void* x_bf16, const float* add_mask, const VlbLayerActs* acts, int B,
-                           int S, int H, int heads, int I, float eps, void* stream) {
+                           int S, int H, int heads, int I, float eps, const VlbLayerDropout* drop, void* stream) {
   if (!w || !acts || !x_bf16) { set_last_error("vlb_bert_layer_forward: null pointer"); return VLB_ERR_INVALID; }
-  return bert_layer_forward(*w, x_bf16, add_mask, *acts, B, S, H, heads, I, eps, ST);
+  return bert_layer_forward(*w, x_bf16, add_mask, *acts, B, S, H, heads, I, eps, drop, ST);
 }
 int64_t vlb_bert_layer_backward_workspace(int M, int H, int I) { return bert_layer_backward_workspace(M, H, I); }
 int vlb_bert_layer_backward(const VlbLayerWeights* w, const VlbLayerActs* acts, const void* x_bf16, const float* add_mask,
                             const void* dy_bf16, const float* dy_f32, void* dx_bf16, const VlbLayerGrads* grads, void* workspace,
-                            int64_t workspace_bytes, int B, int S, int H, int heads, int I, void* stream) {
+                            int64_t workspace_bytes, int B, int S, int H, int heads, int I, const VlbLayerDropout* drop,
+                            void* stream) {
   if (!w || !acts || !x_bf16 || !grads || !workspace || !dx_bf16 || (!dy_bf16 && !dy_f32)) {
     set_last_error("vlb_bert_layer_backward: null pointer");
     return VLB_ERR_INVALID;
   }
   return bert_layer_backward(*w, *acts, x_bf16, add_mask, dy_bf16, dy_f32, dx_bf16, *grads, workspace, workspace_bytes, B, S, H,
-                             heads, I, ST);
+                             heads, I, drop, ST);
 }
 
 }  // extern "C"

@@ -92,7 +92,9 @@ pack_fwd_kernel(const int32_t* __restrict__ kind, const int32_t* __restrict__ sr
   int pid = pos_id[row];
   if (pid < 0 || pid >= max_pos) { if (lane == 0) atomicOr(err, 2); pid = 0; }
   const float* pe = pos_emb + (size_t)pid * H;
-  const float* te = type_emb + (size_t)type_id[row] * H;
+  int ty = type_id[row];
+  if (ty < 0 || ty > 2) { if (lane == 0) atomicOr(err, 8); ty = 0; }   // token types: 0/1 text segments, 2 regions and [END]
+  const float* te = type_emb + (size_t)ty * H;
   const float* a0 = nullptr;
   const float* a1 = nullptr;
   if (k == 0) {

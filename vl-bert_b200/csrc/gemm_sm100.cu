@@ -24,11 +24,13 @@ constexpr int STAGE_F32_PER_WARP = 32 * 32;        // 4 KB transposition buffer 
 
 // Compile-time epilogue variants for the hot launches of the encoder layer (0 = generic, flags read at run time).
 enum : int { EPI_GENERIC = 0, EPI_BIAS_BF16, EPI_BIAS_RESID16_F32, EPI_BIAS_GELU_AUX_BF16, EPI_DGELU_BF16, EPI_RESID16_BF16,
-             EPI_ATOMIC_F32, EPI_CONV_RELU_BF16, EPI_CONV_RESID_RELU_BF16, EPI_PLAIN_BF16, EPI_NUM };
-struct EpiTraitsBase { static constexpr bool kStatic = true; static constexpr bool bias = false, cscale = false; static constexpr int act = ACT_NONE, resid = RESID_NONE, out = OUT_BF16; };
+             EPI_ATOMIC_F32, EPI_CONV_RELU_BF16, EPI_CONV_RESID_RELU_BF16, EPI_PLAIN_BF16, EPI_BIAS_DROP_RESID16_F32, EPI_NUM };
+struct EpiTraitsBase { static constexpr bool kStatic = true; static constexpr bool bias = false, cscale = false, drop = false; static constexpr int act = ACT_NONE, resid = RESID_NONE, out = OUT_BF16; };
 template <int EPI> struct EpiTraits : EpiTraitsBase { static constexpr bool kStatic = false; };
 template <> struct EpiTraits<EPI_BIAS_BF16>          : EpiTraitsBase { static constexpr bool bias = true; };
 template <> struct EpiTraits<EPI_BIAS_RESID16_F32>   : EpiTraitsBase { static constexpr bool bias = true; static constexpr int resid = RESID_BF16, out = OUT_F32; };
+// dense + bias -> dropout -> + residual (BertSelfOutput / BertOutput in training mode, modeling.py:330-333,375-378)
+template <> struct EpiTraits<EPI_BIAS_DROP_RESID16_F32> : EpiTraitsBase { static constexpr bool bias = true, drop = true; static constexpr int resid = RESID_BF16, out = OUT_F32; };
 template <> struct EpiTraits<EPI_BIAS_GELU_AUX_BF16> : EpiTraitsBase { static constexpr bool bias = true; static constexpr int act = ACT_GELU; };
 template <> struct EpiTraits<EPI_DGELU_BF16>         : EpiTraitsBase { static constexpr int act = ACT_DGELU_MUL; };
 template <> struct EpiTraits<EPI_RESID16_BF16>       : EpiTraitsBase { static constexpr int resid = RESID_BF16; };
@@ -161,13 +163,15 @@ struct Cfg {
 //   lane layout of phase 2, so those accesses are coalesced too.
 template <int EPI, bool FROM_SCRATCH = false>
 __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint32_t (&v)[32], float* stage, int lane,
-                                               int row_base, int col0, int M, int N, float* sk_src = nullptr, int sk_ld = 0) {
+                                               int row_base, int col0, int M, int N, float* sk_src = nullptr, int sk_ld = 0,
+                                               DropState dstate = DropState{0ull, 0u}) {
   using T = EpiTraits<EPI>;
   const bool has_bias = T::kStatic ? T::bias : (e.bias != nullptr);
   const int act = T::kStatic ? T::act : e.act;
   const int resid_kind = T::kStatic ? T::resid : e.resid_kind;
   const int out_kind = T::kStatic ? T::out : e.out_kind;
   const bool need_aux_in = (act == ACT_DGELU_MUL || act == ACT_DRELU_MUL);
+  const bool has_drop = T::kStatic ? T::drop : (e.drop.thresh != 0u);
   const int g = lane & 7;
   const int col = col0 + g * 4;
   const bool col_ok = col < N;
@@ -253,6 +257,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
 #pragma unroll
         for (int j = 0; j < 4; ++j) x[j] = (act == ACT_DGELU_MUL) ? x[j] * zz[j] : (zz[j] > 0.0f ? x[j] : 0.0f);
       }
+      if (has_drop) drop4(x, ((uint64_t)row * (uint64_t)N + (uint64_t)col) >> 2, e.drop, dstate);   // N % 8 == 0: one Philox group per lane
       if (resid_kind == RESID_BF16) {
         x[0] += bf16lo(in16[i].x); x[1] += bf16hi(in16[i].x); x[2] += bf16lo(in16[i].y); x[3] += bf16hi(in16[i].y);
       } else if (resid_kind == RESID_F32) {
@@ -497,6 +502,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;  // which of the two warps sharing that quarter
     float* stage = epi_stage + (warp - 2) * STAGE_F32_PER_WARP;
+    const DropState dstate = drop_state(p.e.drop);
     int it = 0;
     for (int item = worker; item < p.num_items; item += nworkers, ++it) {
       const ItemCoord ic = decode_item<GROUPED>(item, p, gt);
@@ -551,7 +557,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
         tmem_ld32(t_row + c * 32, v);
         tmem_ld_wait();
         const int col0 = n_blk * BN + c * 32;
-        if (row_base < Mg && col0 < Ng) epilogue_chunk<EPI>(eg, v, stage, lane, row_base, col0, Mg, Ng);
+        if (row_base < Mg && col0 < Ng) epilogue_chunk<EPI>(eg, v, stage, lane, row_base, col0, Mg, Ng, nullptr, 0, dstate);
       }
       tc_fence_before();
       __syncwarp();
@@ -682,6 +688,12 @@ int classify_epilogue(int mode, const GemmEpilogue& e) {
     if (e.colscale == nullptr && !bias && e.act == ACT_NONE && e.resid_kind == RESID_NONE) return EPI_PLAIN_BF16;
   }
   if (e.colscale != nullptr) return EPI_GENERIC;  // other per-column-scale combinations: generic epilogue
+  if (e.drop.thresh != 0u) {
+    if (mode == GEMM_NT && bias && e.act == ACT_NONE && e.resid_kind == RESID_BF16 && e.out_kind == OUT_F32 && e.colsum == nullptr &&
+        e.alpha == 1.0f)
+      return EPI_BIAS_DROP_RESID16_F32;
+    return EPI_GENERIC;
+  }
   if (mode == GEMM_NT) {
     if (bias && e.act == ACT_NONE && e.resid_kind == RESID_NONE && e.out_kind == OUT_BF16) return EPI_BIAS_BF16;
     if (bias && e.act == ACT_NONE && e.resid_kind == RESID_BF16 && e.out_kind == OUT_F32) return EPI_BIAS_RESID16_F32;
@@ -960,6 +972,7 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
   if (!a_mn && !b_mn) {                                                                                      \
     if (epi_id == EPI_BIAS_BF16) return launch<BN_, false, false, EPI_BIAS_BF16, CG_>(ta, tb, p, stream);     \
     if (epi_id == EPI_BIAS_RESID16_F32) return launch<BN_, false, false, EPI_BIAS_RESID16_F32, CG_>(ta, tb, p, stream); \
+    if (CG_ == 0 && epi_id == EPI_BIAS_DROP_RESID16_F32) return launch<BN_, false, false, EPI_BIAS_DROP_RESID16_F32, 0>(ta, tb, p, stream); \
     if (epi_id == EPI_BIAS_GELU_AUX_BF16) return launch<BN_, false, false, EPI_BIAS_GELU_AUX_BF16, CG_>(ta, tb, p, stream); \
     if (CG_ == 0 && epi_id == EPI_CONV_RELU_BF16) return launch<BN_, false, false, EPI_CONV_RELU_BF16, 0>(ta, tb, p, stream); \
     if (CG_ == 0 && epi_id == EPI_CONV_RESID_RELU_BF16) return launch<BN_, false, false, EPI_CONV_RESID_RELU_BF16, 0>(ta, tb, p, stream); \

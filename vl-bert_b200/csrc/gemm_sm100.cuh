@@ -1,6 +1,7 @@
 // Host-side interface of the tcgen05 GEMM (see gemm_sm100.cu).
 #pragma once
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace vlb {
 
@@ -34,6 +35,7 @@ struct GemmEpilogue {
   float alpha = 1.0f;            // scale applied to the accumulator before everything else
   float* colsum = nullptr;       // optional [N] fp32: += column sums of the stored values (bias gradient of the producer)
   const float* colscale = nullptr;  // optional [N] fp32: x = acc * colscale[col] before the bias (frozen BatchNorm scale)
+  DropCfg drop = DropCfg{0u, 1.0f, 0u, nullptr};  // dropout on the [M,N] value after bias/activation, before the residual add
 };
 
 // whether the experimental stream-K tail was compiled in (-DVLB_ENABLE_STREAMK=1)

@@ -16,6 +16,7 @@
 // (K-major for dQ, MN-major for dK / dV).
 #include "common.cuh"
 #include "gemm_sm100.cuh"
+#include "philox.cuh"
 
 namespace vlb {
 
@@ -36,7 +37,21 @@ struct MhsaParams {
   __nv_bfloat16* dqkv;        // [B*S, 3H]
   float* dqkv_f32;            // [B*S, 3H] fp32 accumulation buffer, only for S > 128 (several (q-tile, k-tile) blocks)
   int ktiles;                 // number of 128-key tiles (blockIdx.z = q_tile * ktiles + k_tile)
+  DropCfg drop;               // dropout on the probabilities (modeling.py:310); mask rows = (b, head, query), columns = keys
 };
+
+// keep-mask x 1/(1-p) applied to 32 consecutive probabilities (keys c0 .. c0+31, c0 % 4 == 0) of mask row `mrow`
+__device__ __forceinline__ void drop_row32(float (&x)[32], uint64_t mrow, int groups_per_row, int c0, int S, const DropCfg& d,
+                                           const DropState& st) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    if (c0 + g * 4 < S) {   // groups past the sequence hold only masked-out keys (probability exactly 0)
+      float v[4] = {x[g * 4], x[g * 4 + 1], x[g * 4 + 2], x[g * 4 + 3]};
+      drop4(v, mrow * (uint64_t)groups_per_row + (uint64_t)((c0 >> 2) + g), d, st);
+      x[g * 4] = v[0]; x[g * 4 + 1] = v[1]; x[g * 4 + 2] = v[2]; x[g * 4 + 3] = v[3];
+    }
+  }
+}
 
 // Shared memory maps (bytes from the 1024-aligned dynamic shared memory base).  Regions are re-used once their first
 // consumer is done so that more CTAs fit an SM (the kernels are latency-bound chains, occupancy is what hides them):
@@ -162,6 +177,9 @@ mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   // pass 2: p = exp(x - m), row sum, stage P (bf16) for the second product.  P overwrites the Q|K tiles (the S MMAs
   // that read them completed before bars[1] fired).
   float l = 0.0f;
+  const DropState dstate = drop_state(p.drop);
+  const uint64_t mrow = ((uint64_t)b * p.heads + h) * (uint64_t)p.S + (uint64_t)(q0 + t);
+  const int mgroups = (p.S + 3) >> 2;
 #pragma unroll 1
   for (int c = 0; c < NKEYS / 32; ++c) {
     uint32_t v[32];
@@ -173,6 +191,8 @@ mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       x[j] = __expf(fmaf(__uint_as_float(v[j]), p.scale, smask[c * 32 + j]) - m);
       l += x[j];
     }
+    // dropout acts on the normalised probabilities; the row sum (and the saved log-sum-exp) stay those of the full softmax
+    if (p.drop.thresh != 0u && q0 + t < p.S) drop_row32(x, mrow, mgroups, c * 32, p.S, p.drop, dstate);
     store_tile_row32(smem, t, c * 32, x);  // P tile starts at offset 0 (aliases Q | K)
   }
   fence_proxy_async_smem();
@@ -349,6 +369,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) mhsa_bwd_kernel(const __grid_c
   mbar_wait(smem_u32(&bars[1]), 0);
   tc_fence_after();
   const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  const DropState dstate = drop_state(p.drop);
+  const uint64_t mrow = ((uint64_t)b * p.heads + h) * (uint64_t)p.S + (uint64_t)(q0 + t);
+  const int mgroups = (p.S + 3) >> 2;
 #pragma unroll 1
   for (int cc = 0; cc < NK / 64; ++cc) {
     const int c = half * (NK / 64) + cc;  // this thread's 32-column chunks: [half*64, half*64 + 64)
@@ -357,14 +380,30 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) mhsa_bwd_kernel(const __grid_c
     tmem_ld32(t_row + c * 32, vs);
     tmem_ld32(t_row + 128 + c * 32, vd);
     tmem_ld_wait();
+    if (p.drop.thresh != 0u && valid) {
+      // ctx = (P o M / (1-p)) V:  dV = (P o M')^T dO ;  dP = (dO V^T) o M' ;  dS = P o (dP - D) with D = rowsum(dO o O)
+      float keep[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      // query rows beyond this sample's sequence must contribute nothing to dK / dV; keys beyond it are masked out
-      const int col = k0 + c * 32 + j;
-      const float mk = col < p.S ? (gmask ? __ldg(gmask + col) : 0.0f) : -INFINITY;
-      const float pj = valid ? __expf(fmaf(__uint_as_float(vs[j]), p.scale, mk) - lse) : 0.0f;
-      pr[j] = pj;
-      ds[j] = pj * (__uint_as_float(vd[j]) - Dsum) * p.scale;
+      for (int j = 0; j < 32; ++j) keep[j] = 1.0f;
+      drop_row32(keep, mrow, mgroups, k0 + c * 32, p.S, p.drop, dstate);   // keep[j] = 0 or 1/(1-p)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = k0 + c * 32 + j;
+        const float mk = col < p.S ? (gmask ? __ldg(gmask + col) : 0.0f) : -INFINITY;
+        const float pj = __expf(fmaf(__uint_as_float(vs[j]), p.scale, mk) - lse);
+        pr[j] = pj * keep[j];
+        ds[j] = pj * (__uint_as_float(vd[j]) * keep[j] - Dsum) * p.scale;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        // query rows beyond this sample's sequence must contribute nothing to dK / dV; keys beyond it are masked out
+        const int col = k0 + c * 32 + j;
+        const float mk = col < p.S ? (gmask ? __ldg(gmask + col) : 0.0f) : -INFINITY;
+        const float pj = valid ? __expf(fmaf(__uint_as_float(vs[j]), p.scale, mk) - lse) : 0.0f;
+        pr[j] = pj;
+        ds[j] = pj * (__uint_as_float(vd[j]) - Dsum) * p.scale;
+      }
     }
     store_tile_row32(smem + BWD_SM_P, t, c * 32, pr);   // P overwrites V (+ spare): dP = dO V^T completed before bars[1]
     store_tile_row32(smem + SM_DS, t, c * 32, ds);
@@ -428,8 +467,9 @@ static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tkv, const MhsaP
 }
 
 int mhsa_forward(const void* qkv, const float* add_mask, void* ctx, float* lse, int B, int S, int H, int heads,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, const VlbDropout* drop) {
   VLB_REQUIRE(qkv && ctx, "mhsa_forward: null pointer");
+  VLB_REQUIRE(drop_valid(drop), "mhsa_forward: bad dropout configuration");
   VLB_REQUIRE(H == heads * D_HEAD, "mhsa: head size must be 64 (H=%d heads=%d)", H, heads);
   VLB_REQUIRE(S >= 1 && S <= 256, "mhsa: sequence length %d not supported (1..256)", S);
   MhsaParams p{};
@@ -438,6 +478,7 @@ int mhsa_forward(const void* qkv, const float* add_mask, void* ctx, float* lse, 
   p.add_mask = add_mask;
   p.ctx = static_cast<__nv_bfloat16*>(ctx);
   p.lse = lse;
+  p.drop = make_drop(drop);
   const int nkt = S <= 128 ? 1 : 2;
   CUtensorMap tq, tkv;
   int rc = make_tmap_bf16_2d(&tq, qkv, (uint64_t)B * S, 3 * H, 3 * H, 64, 128);
@@ -452,8 +493,9 @@ int mhsa_forward(const void* qkv, const float* add_mask, void* ctx, float* lse, 
 int cast_f32_to_bf16(const float* in, void* out, size_t n, cudaStream_t stream);
 
 int mhsa_backward(const void* qkv, const float* add_mask, const void* ctx, const float* lse, const void* dctx, void* dqkv,
-                  float* scratch_f32, int B, int S, int H, int heads, cudaStream_t stream) {
+                  float* scratch_f32, int B, int S, int H, int heads, cudaStream_t stream, const VlbDropout* drop) {
   VLB_REQUIRE(qkv && ctx && lse && dctx && dqkv, "mhsa_backward: null pointer");
+  VLB_REQUIRE(drop_valid(drop), "mhsa_backward: bad dropout configuration");
   VLB_REQUIRE(H == heads * D_HEAD, "mhsa: head size must be 64 (H=%d heads=%d)", H, heads);
   VLB_REQUIRE(S >= 1 && S <= 256, "mhsa: sequence length %d not supported (1..256)", S);
   const int tiles = (S + TQ - 1) / TQ;
@@ -468,6 +510,7 @@ int mhsa_backward(const void* qkv, const float* add_mask, const void* ctx, const
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
   p.dqkv_f32 = tiles == 1 ? nullptr : scratch_f32;
   p.ktiles = tiles;
+  p.drop = make_drop(drop);
   CUtensorMap tm, tmd;
   int rc = make_tmap_bf16_2d(&tm, qkv, (uint64_t)B * S, 3 * H, 3 * H, 64, 128);
   if (rc != VLB_OK) return rc;

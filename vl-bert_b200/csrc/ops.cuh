@@ -9,16 +9,17 @@ void count_launch(int n);
 
 // mhsa_sm100.cu
 int mhsa_forward(const void* qkv, const float* add_mask, void* ctx, float* lse, int B, int S, int H, int heads,
-                 cudaStream_t stream);
+                 cudaStream_t stream, const VlbDropout* drop = nullptr);
 int mhsa_backward(const void* qkv, const float* add_mask, const void* ctx, const float* lse, const void* dctx, void* dqkv,
-                  float* scratch_f32, int B, int S, int H, int heads, cudaStream_t stream);
+                  float* scratch_f32, int B, int S, int H, int heads, cudaStream_t stream, const VlbDropout* drop = nullptr);
 
 // rowops.cu
 int layernorm_forward(const float* x, int ldx, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean,
-                      float* rstd, int M, int H, float eps, cudaStream_t stream);
+                      float* rstd, int M, int H, float eps, cudaStream_t stream, const VlbDropout* out_drop = nullptr);
 int layernorm_backward(const void* dy_bf16, const float* dy_f32, const float* x, int ldx, const float* mean, const float* rstd,
                        const float* gamma, void* dx_bf16, float* dx_f32, int ld_dx, float* dgamma, float* dbeta, float* dcolsum,
-                       int M, int H, cudaStream_t stream);
+                       int M, int H, cudaStream_t stream, const VlbDropout* in_drop = nullptr, void* dx_bf16_drop = nullptr,
+                       const VlbDropout* out_drop = nullptr);
 int colsum_bf16(const void* x, int ld, float* out, int M, int N, cudaStream_t stream);
 int cast_f32_to_bf16(const float* in, void* out, size_t n, cudaStream_t stream);
 int cast_bf16_to_f32(const void* in, float* out, size_t n, cudaStream_t stream);
@@ -47,7 +48,7 @@ int roi_align_backward(const float* grad_out, const float* rois, float* grad_in,
                        int pw, float spatial_scale, int sampling_ratio, cudaStream_t stream);
 int region_operand(const float* boxes, int ld_box, const uint8_t* box_mask, const float* im_info, int ld_info,
                    const int64_t* mvrc_ops, const float* mask_visual_embed, void* A, int32_t* gather_idx, int B, int R,
-                   int feat_dim, cudaStream_t stream);
+                   int feat_dim, cudaStream_t stream, const VlbDropout* drop = nullptr);
 
 // conv.cu
 int im2col_nhwc(const void* x, void* col, int N, int H, int W, int C, int kh, int kw, int stride, int pad, int dil, int Ho, int Wo,
@@ -71,6 +72,9 @@ int adamw_step(const VlbAdamWTensor* descs_device, const float* hyper_device, in
                const float* sq, float max_norm, cudaStream_t stream);
 
 int dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t seed, uint32_t site, uint32_t step, cudaStream_t stream);
+int dropout_mask_2d(uint8_t* keep, int64_t rows, int cols, float p, uint64_t seed, uint32_t site, uint32_t step, cudaStream_t stream);
+int dropout_2d(const void* x, int ldx, void* y, int ldy, int64_t rows, int cols, int col_offset, int total_cols, int is_bf16,
+               const VlbDropout* drop, cudaStream_t stream);
 int dropout_apply(const void* x, void* y, int64_t n, int is_bf16, float p, uint64_t seed, uint32_t site, uint32_t step, cudaStream_t stream);
 
 }  // namespace vlb

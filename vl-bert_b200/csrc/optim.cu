@@ -146,6 +146,41 @@ __global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, size_
   }
 }
 
+__global__ void dropout_mask_2d_kernel(uint8_t* __restrict__ keep, size_t rows, int cols, uint32_t thresh, uint64_t seed, uint32_t site,
+                                       uint32_t step) {
+  const size_t gpr = (size_t)((cols + 3) >> 2);
+  const size_t groups = rows * gpr;
+  for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = g / gpr;
+    const int c0 = (int)(g - r * gpr) * 4;
+    const Philox4 w4 = dropout_words(g, seed, site, step);
+    const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (c0 + j < cols) keep[r * (size_t)cols + c0 + j] = w[j] >= thresh ? 1 : 0;
+  }
+}
+
+// y[r, c] = x[r, c] * keep(r, col_offset + c) / (1 - p), keep indexed over a [rows, total_cols] tensor (2-D contract);
+// (seed, step) come from device memory.  cols, col_offset, total_cols multiples of 4.
+template <typename T>
+__global__ void dropout_2d_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, size_t rows, int cols, int col_offset,
+                                  int total_cols, const DropCfg drop) {
+  const DropState st = drop_state(drop);
+  const size_t gpr = (size_t)(cols >> 2), tg = (size_t)(total_cols >> 2);
+  const size_t groups = rows * gpr;
+  for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = g / gpr;
+    const int c = (int)(g - r * gpr) * 4;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = (float)x[r * (size_t)ldx + c + j];
+    if (drop.thresh != 0u) drop4(v, r * tg + (size_t)((col_offset + c) >> 2), drop, st);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[r * (size_t)ldy + c + j] = (T)v[j];
+  }
+}
+
 int dropout_grid(size_t n) {
   const size_t groups = (n + 3) >> 2;
   size_t g = (groups + 255) / 256;
@@ -159,6 +194,33 @@ int dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t seed, uint32_t site
   VLB_REQUIRE(keep && n >= 0 && p >= 0.0f && p < 1.0f, "dropout_mask: bad arguments");
   if (n == 0) return VLB_OK;
   dropout_mask_kernel<<<dropout_grid((size_t)n), 256, 0, stream>>>(keep, (size_t)n, dropout_threshold(p), seed, site, step);
+  VLB_CHECK_LAUNCH();
+  return VLB_OK;
+}
+
+int dropout_mask_2d(uint8_t* keep, int64_t rows, int cols, float p, uint64_t seed, uint32_t site, uint32_t step, cudaStream_t stream) {
+  VLB_REQUIRE(keep && rows >= 0 && cols > 0 && p >= 0.0f && p < 1.0f, "dropout_mask_2d: bad arguments");
+  if (rows == 0) return VLB_OK;
+  const size_t n = (size_t)rows * (size_t)(((cols + 3) >> 2) << 2);
+  dropout_mask_2d_kernel<<<dropout_grid(n), 256, 0, stream>>>(keep, (size_t)rows, cols, dropout_threshold(p), seed, site, step);
+  VLB_CHECK_LAUNCH();
+  return VLB_OK;
+}
+
+int dropout_2d(const void* x, int ldx, void* y, int ldy, int64_t rows, int cols, int col_offset, int total_cols, int is_bf16,
+               const VlbDropout* drop, cudaStream_t stream) {
+  VLB_REQUIRE(x && y && rows >= 0 && cols > 0 && cols % 4 == 0 && col_offset % 4 == 0 && total_cols % 4 == 0 &&
+              col_offset + cols <= total_cols && ldx >= cols && ldy >= cols, "dropout_2d: bad arguments");
+  VLB_REQUIRE(drop_valid(drop), "dropout_2d: bad dropout configuration");
+  if (rows == 0) return VLB_OK;
+  const DropCfg d = make_drop(drop);
+  const int grid = dropout_grid((size_t)rows * cols);
+  if (is_bf16)
+    dropout_2d_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(y), ldy,
+                                                               (size_t)rows, cols, col_offset, total_cols, d);
+  else
+    dropout_2d_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), ldx, static_cast<float*>(y), ldy, (size_t)rows, cols,
+                                                       col_offset, total_cols, d);
   VLB_CHECK_LAUNCH();
   return VLB_OK;
 }

@@ -38,3 +38,47 @@ __host__ __device__ __forceinline__ Philox4 dropout_words(uint64_t group, uint64
 }
 
 }  // namespace vlb
+
+// ---- dropout configuration handed to the kernels -----------------------------------------------------------------
+// `rng` is a DEVICE pointer to {seed, step}: the kernels read it at run time, so a CUDA-graph replay sees the current
+// training step without re-capturing.  thresh == 0 means "no dropout at this site".
+// 2-D contract (every fused site): element (r, c) of a row-major [rows, cols] tensor belongs to
+//   group = r * ceil(cols / 4) + c / 4, word = c % 4
+// which is the linear contract above whenever cols % 4 == 0 (all hidden-size tensors); attention probabilities
+// (rows = (b, head, query), cols = S keys) pad each row to a multiple of four so a row never shares a Philox call.
+#include "../../include/vlbert_b200.h"
+namespace vlb {
+struct DropCfg {
+  uint32_t thresh;
+  float scale;
+  uint32_t site;
+  const uint64_t* rng;
+};
+inline DropCfg make_drop(const VlbDropout* d) {
+  DropCfg c{0u, 1.0f, 0u, nullptr};
+  if (d != nullptr && d->p > 0.0f && d->rng != nullptr) {
+    c.thresh = dropout_threshold(d->p);
+    c.scale = 1.0f / (1.0f - d->p);
+    c.site = d->site;
+    c.rng = d->rng;
+  }
+  return c;
+}
+inline bool drop_valid(const VlbDropout* d) { return d == nullptr || (d->p >= 0.0f && d->p < 1.0f && (d->p == 0.0f || d->rng != nullptr)); }
+#if defined(__CUDACC__)
+struct DropState { uint64_t seed; uint32_t step; };
+__device__ __forceinline__ DropState drop_state(const DropCfg& d) {
+  DropState s{0ull, 0u};
+  if (d.thresh != 0u) { s.seed = __ldg(d.rng); s.step = (uint32_t)__ldg(d.rng + 1); }
+  return s;
+}
+// apply the mask of one Philox group to four consecutive values
+__device__ __forceinline__ void drop4(float (&x)[4], uint64_t group, const DropCfg& d, const DropState& s) {
+  const Philox4 r = dropout_words(group, s.seed, d.site, s.step);
+  x[0] = r.x >= d.thresh ? x[0] * d.scale : 0.0f;
+  x[1] = r.y >= d.thresh ? x[1] * d.scale : 0.0f;
+  x[2] = r.z >= d.thresh ? x[2] * d.scale : 0.0f;
+  x[3] = r.w >= d.thresh ? x[3] * d.scale : 0.0f;
+}
+#endif
+}  // namespace vlb

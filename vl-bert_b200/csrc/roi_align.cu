@@ -12,6 +12,7 @@
 //  * coordinate embedding + feature concat (common/utils/bbox.py:33-65, common/fast_rcnn.py:170-174): builds the
 //    bf16 A operand [B*R, 4096] of the obj_downsample GEMM for the precomputed-feature path.
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace vlb {
 
@@ -162,7 +163,8 @@ __global__ void roi_align_bwd_kernel(const float* __restrict__ grad_out, const f
 __global__ void __launch_bounds__(256)
 region_operand_kernel(const float* __restrict__ boxes, int ld_box, const uint8_t* __restrict__ box_mask,
                       const float* __restrict__ im_info, int ld_info, const int64_t* __restrict__ mvrc_ops,
-                      const float* __restrict__ mask_visual_embed, __nv_bfloat16* __restrict__ A, int R, int feat_dim) {
+                      const float* __restrict__ mask_visual_embed, __nv_bfloat16* __restrict__ A, int R, int feat_dim,
+                      const DropCfg drop) {
   const int slot = blockIdx.x;
   const int b = slot / R;
   __nv_bfloat16* arow = A + (size_t)slot * (2048 + feat_dim);
@@ -179,23 +181,37 @@ region_operand_kernel(const float* __restrict__ boxes, int ld_box, const uint8_t
   pos[1] = (y1 + y2) / 2.0f / Hd * 100.0f;
   pos[2] = (x2 - x1) / Wd * 100.0f;
   pos[3] = (y2 - y1) / Hd * 100.0f;
-  // 4 x 256 frequencies; thread -> (coordinate, frequency)
-  for (int e = threadIdx.x; e < 1024; e += 256) {
-    const int c = e >> 8, i = e & 255;
-    const float dim = powf(1000.0f, (float)i / 256.0f);
-    const float arg = pos[c] / dim;
-    float sv, cv;
-    sincosf(arg, &sv, &cv);
-    arow[c * 512 + i] = __float2bfloat16(sv);
-    arow[c * 512 + 256 + i] = __float2bfloat16(cv);
+  // Dropout(0.1) at the head of obj_downsample (common/fast_rcnn.py:104-109): mask over the [B*R, ncol] slot layout
+  const DropState dstate = drop_state(drop);
+  const uint64_t row_group0 = ((uint64_t)slot * (uint64_t)ncol) >> 2;   // ncol % 8 == 0
+  // 4 coordinates x (sin | cos) x 256 frequencies (common/utils/bbox.py:33-65)
+  for (int e = threadIdx.x; e < 512; e += 256) {   // e -> (coordinate c, sin/cos half, group of four frequencies q)
+    const int c = e >> 7, hc = (e >> 6) & 1, q = e & 63;
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = q * 4 + k;
+      const float dim = powf(1000.0f, (float)i / 256.0f);
+      float sv, cv;
+      sincosf(pos[c] / dim, &sv, &cv);
+      v[k] = hc ? cv : sv;
+    }
+    const int col = c * 512 + hc * 256 + q * 4;
+    if (drop.thresh != 0u) drop4(v, row_group0 + (uint64_t)(col >> 2), drop, dstate);
+    uint2 pk;
+    pk.x = pack_bf16x2(v[0], v[1]);
+    pk.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(arow + col) = pk;
   }
   const float* f = bx + 4;
   if (mvrc_ops != nullptr && mask_visual_embed != nullptr && mvrc_ops[slot] == 1) f = mask_visual_embed;
   for (int c = threadIdx.x * 4; c < feat_dim; c += 256 * 4) {
-    const float4 v = *reinterpret_cast<const float4*>(f + c);
+    const float4 vv = *reinterpret_cast<const float4*>(f + c);
+    float v[4] = {vv.x, vv.y, vv.z, vv.w};
+    if (drop.thresh != 0u) drop4(v, row_group0 + (uint64_t)((2048 + c) >> 2), drop, dstate);
     uint2 pk;
-    pk.x = pack_bf16x2(v.x, v.y);
-    pk.y = pack_bf16x2(v.z, v.w);
+    pk.x = pack_bf16x2(v[0], v[1]);
+    pk.y = pack_bf16x2(v[2], v[3]);
     *reinterpret_cast<uint2*>(arow + 2048 + c) = pk;
   }
 }
@@ -252,11 +268,12 @@ int roi_align_backward(const float* grad_out, const float* rois, float* grad_in,
 
 int region_operand(const float* boxes, int ld_box, const uint8_t* box_mask, const float* im_info, int ld_info,
                    const int64_t* mvrc_ops, const float* mask_visual_embed, void* A, int32_t* gather_idx, int B, int R,
-                   int feat_dim, cudaStream_t stream) {
+                   int feat_dim, cudaStream_t stream, const VlbDropout* drop) {
   VLB_REQUIRE(boxes && box_mask && im_info && A && gather_idx, "region_operand: null pointer");
+  VLB_REQUIRE(drop_valid(drop), "region_operand: bad dropout configuration");
   VLB_REQUIRE(feat_dim % 8 == 0 && ld_box % 4 == 0 && ld_box >= 4 + feat_dim, "region_operand: bad feature layout");
   region_operand_kernel<<<B * R, 256, 0, stream>>>(boxes, ld_box, box_mask, im_info, ld_info, mvrc_ops, mask_visual_embed,
-                                                   static_cast<__nv_bfloat16*>(A), R, feat_dim);
+                                                   static_cast<__nv_bfloat16*>(A), R, feat_dim, make_drop(drop));
   VLB_CHECK_LAUNCH();
   box_slot_index_kernel<<<B, 32, 0, stream>>>(box_mask, gather_idx, R);
   VLB_CHECK_LAUNCH();

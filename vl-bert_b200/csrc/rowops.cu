@@ -5,6 +5,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace vlb {
 
@@ -40,7 +41,7 @@ template <int ITERS>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      __nv_bfloat16* __restrict__ y, float* __restrict__ y32, float* __restrict__ mean,
-                     float* __restrict__ rstd, int M, int H, int ldx, float eps) {
+                     float* __restrict__ rstd, int M, int H, int ldx, float eps, const DropCfg drop) {
   const int lane = threadIdx.x & 31;
   const int nvec = H >> 3;
   const int wstride = gridDim.x * LN_WARPS;
@@ -48,6 +49,7 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   pdl_trigger();
   pdl_wait();
   if (row >= M) return;
+  const DropState dstate = drop_state(drop);
   RowRaw<ITERS> cur, nxt;
   load_row_f32<ITERS>(cur, x + (size_t)row * ldx, lane, nvec);
   for (; row < M; row += wstride) {
@@ -93,6 +95,13 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = gg[j] * ((v[i][j] - mu) * rs) + bb[j];
+        if (drop.thresh != 0u) {   // dropout on the LayerNorm output (embedding, visual_linguistic_bert.py:239)
+          const uint64_t g0i = ((uint64_t)row * (uint64_t)H + (uint64_t)vi * 8) >> 2;
+          float lo[4] = {o[0], o[1], o[2], o[3]}, hi[4] = {o[4], o[5], o[6], o[7]};
+          drop4(lo, g0i, drop, dstate);
+          drop4(hi, g0i + 1, drop, dstate);
+          o[0] = lo[0]; o[1] = lo[1]; o[2] = lo[2]; o[3] = lo[3]; o[4] = hi[0]; o[5] = hi[1]; o[6] = hi[2]; o[7] = hi[3];
+        }
         uint4 pk;
         pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
         pk.z = pack_bf16x2(o[4], o[5]); pk.w = pack_bf16x2(o[6], o[7]);
@@ -149,13 +158,14 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
                      const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx16, float* __restrict__ dx32,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcolsum, int M, int H,
-                     int ldx, int ld_dx) {
+                     int ldx, int ld_dx, const DropCfg in_drop, __nv_bfloat16* __restrict__ dx16_drop, const DropCfg out_drop) {
   __shared__ float red[3][LN_WARPS][32 * 8 + 8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = H >> 3;
   const int wstride = gridDim.x * LN_WARPS;
   pdl_trigger();
   pdl_wait();
+  const DropState in_state = drop_state(in_drop), out_state = drop_state(out_drop);
   float gam[ITERS][8];
   float acc_g[ITERS][8], acc_b[ITERS][8], acc_c[ITERS][8];
 #pragma unroll
@@ -195,6 +205,13 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
           d[0] += cur.da[i].x; d[1] += cur.da[i].y; d[2] += cur.da[i].z; d[3] += cur.da[i].w;
           d[4] += cur.db[i].x; d[5] += cur.db[i].y; d[6] += cur.db[i].z; d[7] += cur.db[i].w;
         }
+        if (in_drop.thresh != 0u) {   // the LayerNorm output was dropped in forward: its gradient passes through the same mask
+          const uint64_t g0i = ((uint64_t)row * (uint64_t)H + (uint64_t)vi * 8) >> 2;
+          float lo[4] = {d[0], d[1], d[2], d[3]}, hi[4] = {d[4], d[5], d[6], d[7]};
+          drop4(lo, g0i, in_drop, in_state);
+          drop4(hi, g0i + 1, in_drop, in_state);
+          d[0] = lo[0]; d[1] = lo[1]; d[2] = lo[2]; d[3] = lo[3]; d[4] = hi[0]; d[5] = hi[1]; d[6] = hi[2]; d[7] = hi[3];
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           dy[i][j] = d[j];
@@ -220,9 +237,23 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
           o[j] = rs * (dy[i][j] * gam[i][j] - m1 - xh[i][j] * m2);
           acc_g[i][j] += dy[i][j] * xh[i][j];
           acc_b[i][j] += dy[i][j];
-          acc_c[i][j] += o[j];
         }
         const size_t off = (size_t)row * H + vi * 8;
+        if (out_drop.thresh != 0u) {
+          // x = dropout(dense(.)) + residual: the dense branch (next GEMM operand, bias gradient) sees dx o mask / (1-p)
+          float lo[4] = {o[0], o[1], o[2], o[3]}, hi[4] = {o[4], o[5], o[6], o[7]};
+          drop4(lo, off >> 2, out_drop, out_state);
+          drop4(hi, (off >> 2) + 1, out_drop, out_state);
+          uint4 pk;
+          pk.x = pack_bf16x2(lo[0], lo[1]); pk.y = pack_bf16x2(lo[2], lo[3]);
+          pk.z = pack_bf16x2(hi[0], hi[1]); pk.w = pack_bf16x2(hi[2], hi[3]);
+          if (dx16_drop) *reinterpret_cast<uint4*>(dx16_drop + off) = pk;
+          acc_c[i][0] += lo[0]; acc_c[i][1] += lo[1]; acc_c[i][2] += lo[2]; acc_c[i][3] += lo[3];
+          acc_c[i][4] += hi[0]; acc_c[i][5] += hi[1]; acc_c[i][6] += hi[2]; acc_c[i][7] += hi[3];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc_c[i][j] += o[j];
+        }
         if (dx16) {
           uint4 pk;
           pk.x = pack_bf16x2(o[0], o[1]); pk.y = pack_bf16x2(o[2], o[3]);
@@ -370,7 +401,9 @@ int multi_cast(const VlbCastDesc* descs_device, int count, int blocks_per_tensor
   }
 
 int layernorm_forward(const float* x, int ldx, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean,
-                      float* rstd, int M, int H, float eps, cudaStream_t stream) {
+                      float* rstd, int M, int H, float eps, cudaStream_t stream, const VlbDropout* out_drop) {
+  VLB_REQUIRE(drop_valid(out_drop), "layernorm_forward: bad dropout configuration");
+  const DropCfg dcfg = make_drop(out_drop);
   VLB_REQUIRE(x && gamma && beta && (y_bf16 || y_f32), "layernorm_forward: null pointer");
   VLB_REQUIRE(ldx % 4 == 0 && ldx >= H, "layernorm_forward: bad ldx %d", ldx);
   VLB_REQUIRE(H % 8 == 0 && H >= 8 && H <= 2048, "layernorm: H=%d must be a multiple of 8 in [8, 2048]", H);
@@ -381,14 +414,17 @@ int layernorm_forward(const float* x, int ldx, const float* gamma, const float* 
   ProfScope prof(PROF_LN_FWD, (double)M * H * (4.0 + (y_bf16 ? 2.0 : 0.0) + (y_f32 ? 4.0 : 0.0)), stream);
   cudaError_t lerr = cudaSuccess;
   VLB_LN_DISPATCH(iters, (lerr = launch_pdl(layernorm_fwd_kernel<IT>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, x, gamma, beta,
-                                            static_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, M, H, ldx, eps)));
+                                            static_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, M, H, ldx, eps, dcfg)));
   VLB_CHECK_CUDA(lerr);
   return VLB_OK;
 }
 
 int layernorm_backward(const void* dy_bf16, const float* dy_f32, const float* x, int ldx, const float* mean, const float* rstd,
                        const float* gamma, void* dx_bf16, float* dx_f32, int ld_dx, float* dgamma, float* dbeta, float* dcolsum,
-                       int M, int H, cudaStream_t stream) {
+                       int M, int H, cudaStream_t stream, const VlbDropout* in_drop, void* dx_bf16_drop, const VlbDropout* out_drop) {
+  VLB_REQUIRE(drop_valid(in_drop) && drop_valid(out_drop), "layernorm_backward: bad dropout configuration");
+  const DropCfg din = make_drop(in_drop), dout = make_drop(out_drop);
+  VLB_REQUIRE(dout.thresh == 0u || dx_bf16_drop != nullptr || dcolsum != nullptr, "layernorm_backward: out_drop without a consumer");
   VLB_REQUIRE(ldx % 4 == 0 && ldx >= H && (dx_f32 == nullptr || (ld_dx % 4 == 0 && ld_dx >= H)), "layernorm_backward: bad ld");
   VLB_REQUIRE((dy_bf16 || dy_f32) && x && mean && rstd && gamma, "layernorm_backward: null pointer");
   VLB_REQUIRE(H % 8 == 0 && H >= 8 && H <= 2048, "layernorm: H=%d must be a multiple of 8 in [8, 2048]", H);
@@ -398,11 +434,13 @@ int layernorm_backward(const void* dy_bf16, const float* dy_f32, const float* x,
   static const int per_sm = [] { const char* v = getenv("VLB_LN_BWD_BLOCKS_PER_SM"); return v ? atoi(v) : 2; }();
   const int cap = num_sms() * per_sm;
   if (grid > cap) grid = cap;
-  ProfScope prof(PROF_LN_BWD, (double)M * H * (4.0 + (dy_bf16 ? 2.0 : 0.0) + (dy_f32 ? 4.0 : 0.0) + (dx_bf16 ? 2.0 : 0.0) + (dx_f32 ? 4.0 : 0.0)), stream);
+  ProfScope prof(PROF_LN_BWD, (double)M * H * (4.0 + (dy_bf16 ? 2.0 : 0.0) + (dy_f32 ? 4.0 : 0.0) + (dx_bf16 ? 2.0 : 0.0) + (dx_f32 ? 4.0 : 0.0) +
+                                               (dx_bf16_drop ? 2.0 : 0.0)), stream);
 #define VLB_LN_BWD(H16, H32)                                                                                    \
   VLB_LN_DISPATCH(iters, (lerr = launch_pdl(layernorm_bwd_kernel<IT, H16, H32>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, \
                              static_cast<const __nv_bfloat16*>(dy_bf16), dy_f32, x, mean, rstd, gamma,             \
-                             static_cast<__nv_bfloat16*>(dx_bf16), dx_f32, dgamma, dbeta, dcolsum, M, H, ldx, ld_dx)))
+                             static_cast<__nv_bfloat16*>(dx_bf16), dx_f32, dgamma, dbeta, dcolsum, M, H, ldx, ld_dx, din,   \
+                             static_cast<__nv_bfloat16*>(dx_bf16_drop), dout)))
   cudaError_t lerr = cudaSuccess;
   if (dy_bf16 && dy_f32) { VLB_LN_BWD(true, true) }
   else if (dy_bf16) { VLB_LN_BWD(true, false) }

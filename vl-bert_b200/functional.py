@@ -34,6 +34,18 @@ def _require_cuda(*ts):
             raise RuntimeError("vlbert_b200 has no CPU path: expected CUDA tensors (got %s)" % t.device)
 
 
+def _require_param(t, name, device):
+    """Parameters reach the C ABI as raw pointers: the kernels assume contiguous fp32 on the input's device.  A model converted
+    with .half() / .bfloat16() / apex amp O2 must be rejected here instead of being reinterpreted (the reference's FP16 cfgs
+    rely on amp; this library keeps fp32 master weights and computes its GEMMs in bf16 itself)."""
+    if t is None:
+        return
+    if t.dtype != F32 or not t.is_contiguous() or t.device != device:
+        raise RuntimeError("vlbert_b200: parameter %s must be a contiguous float32 tensor on %s (got %s, %s, contiguous=%s); "
+                           "half / bfloat16 / amp-O2 converted models are not supported" %
+                           (name, device, t.dtype, t.device, t.is_contiguous()))
+
+
 def _align(n, a=256):
     return (n + a - 1) // a * a
 
@@ -64,11 +76,48 @@ class _Carver(object):
         return self.buf[off: off + n * esz].view(dtype).view(*shape)
 
 
+class DropSite(object):
+    """One dropout call site (VlbDropout): probability, site id and the DEVICE rng state tensor (int64 [2] = seed, step).
+    The kernels read (seed, step) when they run, so the same object serves the forward, its backward and CUDA-graph replays."""
+
+    __slots__ = ("p", "site", "rng", "_struct")
+
+    def __init__(self, p, site, rng):
+        if not (0.0 <= p < 1.0):
+            raise ValueError("dropout probability has to be in [0, 1), got %r" % (p,))
+        if not (rng.is_cuda and rng.dtype == torch.int64 and rng.numel() >= 2 and rng.is_contiguous()):
+            raise RuntimeError("vlbert_b200: the dropout rng state must be a contiguous CUDA int64 tensor (seed, step)")
+        self.p, self.site, self.rng = float(p), int(site), rng
+        d = _lib.Dropout()
+        d.p, d.site, d.rng = self.p, self.site, rng.data_ptr()
+        self._struct = d
+
+    def ref(self):
+        return ctypes.byref(self._struct)
+
+
+def _dref(drop):
+    return None if drop is None or drop.p == 0.0 else drop.ref()
+
+
+def dropout_2d(x, drop, col_offset=0, total_cols=None):
+    """y = x * keep / (1-p) for a 2-D window x [rows, cols] of a tensor whose mask is indexed over [rows, total_cols]."""
+    _require_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1
+    y = torch.empty_like(x, memory_format=torch.contiguous_format)
+    total = x.shape[1] if total_cols is None else total_cols
+    _chk(_lib.lib().vlb_dropout_2d(_p(x), x.stride(0), _p(y), y.stride(0), x.shape[0], x.shape[1], col_offset, total,
+                                   int(x.dtype == BF16), _dref(drop), _stream()))
+    return y
+
+
 # ------------------------------------------------------------------------------------------------
 # primitive wrappers (used by tests and by the composites below)
 # ------------------------------------------------------------------------------------------------
-def gemm(mode, A, B, out, bias=None, resid=None, act=0, aux=None, alpha=1.0, split_k=1, force_bn=0, M=None, N=None, K=None):
-    """See vlb_gemm_bf16.  A/B bf16 2-D (row-major, last dim contiguous); out bf16 or f32 2-D."""
+def gemm(mode, A, B, out, bias=None, resid=None, act=0, aux=None, alpha=1.0, split_k=1, force_bn=0, M=None, N=None, K=None,
+         drop=None):
+    """See vlb_gemm_bf16.  A/B bf16 2-D (row-major, last dim contiguous); out bf16 or f32 2-D.
+    drop: DropSite applied after bias/activation and before the residual add (vlb_gemm_bf16_dropout)."""
     _require_cuda(A, B, out)
     if mode == 0:
         m, k = A.shape; n = B.shape[0]
@@ -79,13 +128,19 @@ def gemm(mode, A, B, out, bias=None, resid=None, act=0, aux=None, alpha=1.0, spl
     M, N, K = M or m, N or n, K or k
     out_kind = 0 if out.dtype == BF16 else (2 if split_k > 1 or getattr(out, "_vlb_accumulate", False) else 1)
     resid_kind = 0 if resid is None else (1 if resid.dtype == BF16 else 2)
+    if drop is not None:
+        _chk(_lib.lib().vlb_gemm_bf16_dropout(mode, M, N, K, _p(A), A.stride(0), _p(B), B.stride(0), _p(out), out.stride(0),
+                                              out_kind, _p(bias), _p(resid), resid.stride(0) if resid is not None else 0,
+                                              resid_kind, act, _p(aux), aux.stride(0) if aux is not None else 0, float(alpha),
+                                              split_k, force_bn, _dref(drop), _stream()))
+        return out
     _chk(_lib.lib().vlb_gemm_bf16(mode, M, N, K, _p(A), A.stride(0), _p(B), B.stride(0), _p(out), out.stride(0), out_kind,
                                   _p(bias), _p(resid), resid.stride(0) if resid is not None else 0, resid_kind, act,
                                   _p(aux), aux.stride(0) if aux is not None else 0, float(alpha), split_k, force_bn, _stream()))
     return out
 
 
-def layernorm_forward(x, gamma, beta, eps=1e-12, want_bf16=True, want_f32=False, ldx=None, H=None):
+def layernorm_forward(x, gamma, beta, eps=1e-12, want_bf16=True, want_f32=False, ldx=None, H=None, drop=None):
     M = x.numel() // x.shape[-1] if ldx is None else x.shape[0]
     H = H or x.shape[-1]
     ldx = ldx or H
@@ -94,13 +149,14 @@ def layernorm_forward(x, gamma, beta, eps=1e-12, want_bf16=True, want_f32=False,
     y32 = torch.empty((M, H), dtype=F32, device=dev) if want_f32 else None
     mean = torch.empty((M,), dtype=F32, device=dev)
     rstd = torch.empty((M,), dtype=F32, device=dev)
-    _chk(_lib.lib().vlb_layernorm_forward(_p(x), ldx, _p(gamma), _p(beta), _p(y16), _p(y32), _p(mean), _p(rstd), M, H,
-                                          float(eps), _stream()))
+    _chk(_lib.lib().vlb_layernorm_forward_dropout(_p(x), ldx, _p(gamma), _p(beta), _p(y16), _p(y32), _p(mean), _p(rstd), M, H,
+                                                  float(eps), _dref(drop), _stream()))
     return y16, y32, mean, rstd
 
 
 def layernorm_backward(dy16, dy32, x, mean, rstd, gamma, dgamma, dbeta, dcolsum=None, want_bf16=True, want_f32=False,
-                       ldx=None, H=None, dx32=None, ld_dx=None):
+                       ldx=None, H=None, dx32=None, ld_dx=None, in_drop=None, out_drop=None):
+    """out_drop: additionally returns dx * keep / (1-p) (bf16) as a third value and makes dcolsum sum that tensor."""
     H = H or x.shape[-1]
     M = mean.numel()
     ldx = ldx or H
@@ -109,23 +165,27 @@ def layernorm_backward(dy16, dy32, x, mean, rstd, gamma, dgamma, dbeta, dcolsum=
     if want_f32 and dx32 is None:
         dx32 = torch.empty((M, H), dtype=F32, device=dev)
         ld_dx = H
-    _chk(_lib.lib().vlb_layernorm_backward(_p(dy16), _p(dy32), _p(x), ldx, _p(mean), _p(rstd), _p(gamma), _p(dx16), _p(dx32),
-                                           ld_dx or 0, _p(dgamma), _p(dbeta), _p(dcolsum), M, H, _stream()))
+    dx16_drop = torch.empty((M, H), dtype=BF16, device=dev) if out_drop is not None else None
+    _chk(_lib.lib().vlb_layernorm_backward_dropout(_p(dy16), _p(dy32), _p(x), ldx, _p(mean), _p(rstd), _p(gamma), _p(dx16),
+                                                   _p(dx32), ld_dx or 0, _p(dgamma), _p(dbeta), _p(dcolsum), M, H, _dref(in_drop),
+                                                   _p(dx16_drop), _dref(out_drop), _stream()))
+    if out_drop is not None:
+        return dx16, dx32, dx16_drop
     return dx16, dx32
 
 
-def mhsa_forward(qkv, add_mask, B, S, H, heads):
+def mhsa_forward(qkv, add_mask, B, S, H, heads, drop=None):
     ctx = torch.empty((B * S, H), dtype=BF16, device=qkv.device)
     lse = torch.empty((B, heads, S), dtype=F32, device=qkv.device)
-    _chk(_lib.lib().vlb_mhsa_forward(_p(qkv), _p(add_mask), _p(ctx), _p(lse), B, S, H, heads, _stream()))
+    _chk(_lib.lib().vlb_mhsa_forward_dropout(_p(qkv), _p(add_mask), _p(ctx), _p(lse), B, S, H, heads, _dref(drop), _stream()))
     return ctx, lse
 
 
-def mhsa_backward(qkv, add_mask, ctx, lse, dctx, B, S, H, heads):
+def mhsa_backward(qkv, add_mask, ctx, lse, dctx, B, S, H, heads, drop=None):
     dqkv = torch.empty((B * S, 3 * H), dtype=BF16, device=qkv.device)
     scratch = torch.empty((B * S, 3 * H), dtype=F32, device=qkv.device) if S > 128 else None
-    _chk(_lib.lib().vlb_mhsa_backward(_p(qkv), _p(add_mask), _p(ctx), _p(lse), _p(dctx), _p(dqkv), _p(scratch), B, S, H, heads,
-                                      _stream()))
+    _chk(_lib.lib().vlb_mhsa_backward_dropout(_p(qkv), _p(add_mask), _p(ctx), _p(lse), _p(dctx), _p(dqkv), _p(scratch), B, S, H,
+                                              heads, _dref(drop), _stream()))
     return dqkv
 
 
@@ -226,6 +286,26 @@ def _acts_struct(car, l, y_f32):
     return a
 
 
+def _layer_drop_structs(drop, L):
+    """drop: None (eval / p = 0) or an object with p_attn, p_hidden, rng (int64 CUDA tensor: seed, step).  Returns one
+    ctypes reference (or None) per layer; sites follow the contract: 1+3l attention, 2+3l self-output, 3+3l output."""
+    if drop is None or (drop.p_attn == 0.0 and drop.p_hidden == 0.0):
+        return [None] * L
+    rng = drop.rng
+    if not (rng.is_cuda and rng.dtype == torch.int64 and rng.numel() >= 2 and rng.is_contiguous()):
+        raise RuntimeError("vlbert_b200: the dropout rng state must be a contiguous CUDA int64 tensor (seed, step)")
+    out = []
+    for l in range(L):
+        d = _lib.LayerDropout()
+        d.p_attn, d.p_hidden = float(drop.p_attn), float(drop.p_hidden)
+        d.site_attn, d.site_self_out, d.site_out = 1 + 3 * l, 2 + 3 * l, 3 + 3 * l
+        d.rng = rng.data_ptr()
+        out.append(d)
+    refs = [ctypes.byref(d) for d in out]
+    refs.append(out)   # keep the structs alive as long as the reference list is
+    return refs
+
+
 class EncoderFn(torch.autograd.Function):
     """L BertLayers (BertEncoder.forward, modeling.py:406-421) on vlb_bert_layer_forward/backward.
 
@@ -239,26 +319,37 @@ class EncoderFn(torch.autograd.Function):
         L, heads, I = meta.L, meta.heads, meta.I
         lib = _lib.lib()
         st = _stream()
+        if emb.dtype != BF16:
+            raise RuntimeError("vlbert_b200: EncoderFn expects the bf16 embedding produced by EmbeddingFn (got %s)" % emb.dtype)
+        if getattr(meta.weights, "_checked", None) != tuple(p.data_ptr() for p in params):
+            for i, p in enumerate(params):
+                _require_param(p, "encoder.layer.%d.%s" % (i // 16, EncoderWeights.PER_LAYER[i % 16]), emb.device)
+            meta.weights._checked = tuple(p.data_ptr() for p in params)
+        emb = emb.contiguous()          # kept alive in ctx: the layer-0 kernels and the backward read this very buffer
+        add_mask = add_mask.contiguous()
         meta.weights.refresh(params)
         specs = []
         for l in range(L):
             specs += _act_specs(l, B, S, H, heads, I, False)
         car = _Carver(specs, emb.device)
         outs = []
-        x_ptr = emb.contiguous().data_ptr()
+        x_ptr = emb.data_ptr()
+        drops = _layer_drop_structs(getattr(meta, "drop", None), L)
         for l in range(L):
             want = meta.all_layers or l == L - 1
             y32 = torch.empty((B, S, H), dtype=F32, device=emb.device) if want else None
             w = meta.weights.layer_struct(l, params)
             a = _acts_struct(car, l, y32)
             _chk(lib.vlb_bert_layer_forward(ctypes.byref(w), x_ptr, _p(add_mask), ctypes.byref(a), B, S, H, heads, I,
-                                            float(meta.eps), st))
+                                            float(meta.eps), drops[l], st))
             x_ptr = car.ptr("y%d" % l)
             if want:
                 outs.append(y32)
         ctx.meta = meta
         ctx.car = car
         ctx.dims = (B, S, H)
+        ctx.drops = drops
+        ctx.drop_rng = None if getattr(meta, "drop", None) is None else meta.drop.rng   # keeps the state tensor alive
         ctx.emb = emb
         ctx.add_mask = add_mask
         ctx.params = params
@@ -308,7 +399,7 @@ class EncoderFn(torch.autograd.Function):
             out_dx = dx[l & 1]
             _chk(lib.vlb_bert_layer_backward(ctypes.byref(w), ctypes.byref(a), x_ptr, _p(ctx.add_mask), _p(dy16),
                                              _p(dy32), out_dx.data_ptr(), ctypes.byref(g), ws.data_ptr(), ws_bytes, B, S, H,
-                                             heads, I, st))
+                                             heads, I, ctx.drops[l], st))
             dy16 = out_dx
             if meta.reducer is not None:
                 meta.reducer.launch(f)
@@ -350,14 +441,33 @@ class PackIndex(object):
                                        pos_offset, _p(self.kind), _p(self.src), _p(self.pos_id), _p(self.type_id),
                                        _p(self.add_mask), _p(self.obj_row), _p(self.lens), _p(self.err), _stream()))
 
+    ERRORS = ((1, "max_length_hint is smaller than the longest packed sequence (text + regions + [END]): it must be a true upper bound"),
+              (2, "position id out of range of position_embeddings"),
+              (4, "token id out of range of word_embeddings"),
+              (8, "token type id outside 0..2"))
+
+    def check(self):
+        """Raise IndexError if any kernel of the embedding flagged bad indices (one device->host sync).  The reference raises
+        from the indexing op itself; here the flag is set asynchronously and the offending ids were remapped to row 0."""
+        code = int(self.err.item())
+        if code:
+            raise IndexError("vlbert_b200 embedding: " + "; ".join(m for bit, m in self.ERRORS if code & bit))
+
 
 class EmbeddingFn(torch.autograd.Function):
     """forward(text_visual f32 [B,T,H], object_vl f32 [B,R,2H], word, end, pos, type, ln_w, ln_b, vt_w, vt_b, vo_w, vo_b,
     ids int64 [B,T], pidx: PackIndex, eps) -> emb bf16 [B,S,H]"""
 
     @staticmethod
-    def forward(ctx, text_visual, object_vl, word, end, pos, typ, ln_w, ln_b, vt_w, vt_b, vo_w, vo_b, ids, pidx, eps):
+    def forward(ctx, text_visual, object_vl, word, end, pos, typ, ln_w, ln_b, vt_w, vt_b, vo_w, vo_b, ids, pidx, eps, drop=None):
         _require_cuda(text_visual, object_vl, word)
+        for nm, t in (("word_embeddings.weight", word), ("end_embedding.weight", end), ("position_embeddings.weight", pos),
+                      ("token_type_embeddings.weight", typ), ("embedding_LayerNorm.weight", ln_w), ("embedding_LayerNorm.bias", ln_b),
+                      ("visual_ln_text.weight", vt_w), ("visual_ln_text.bias", vt_b), ("visual_ln_object.weight", vo_w),
+                      ("visual_ln_object.bias", vo_b)):
+            _require_param(t, nm, text_visual.device)
+        if typ.shape[0] < 3:
+            raise RuntimeError("vlbert_b200: token_type_embeddings needs at least 3 rows (types 0/1 text, 2 regions and [END])")
         B, T, R, S = pidx.B, pidx.T, pidx.R, pidx.S
         H = word.shape[1]
         lib = _lib.lib()
@@ -373,7 +483,8 @@ class EmbeddingFn(torch.autograd.Function):
         _chk(lib.vlb_pack_forward(_p(pidx.kind), _p(pidx.src), _p(pidx.pos_id), _p(pidx.type_id), _p(ids), _p(word), _p(end),
                                   _p(pos), _p(typ), _p(tv_ln), _p(ov_ln), _p(ov), 2 * H, H, _p(e), B, T, R, S, H,
                                   word.shape[0], pos.shape[0], _p(pidx.err), st))
-        emb, _, e_mean, e_rstd = layernorm_forward(e, ln_w, ln_b, eps)
+        emb, _, e_mean, e_rstd = layernorm_forward(e, ln_w, ln_b, eps, drop=drop)   # dropout(LayerNorm(.)), :237-239
+        ctx.drop = drop
         ctx.save_for_backward(tv, ov, word, end, pos, typ, ln_w, vt_w, vo_w, ids, e, e_mean, e_rstd, tv_mean, tv_rstd,
                               ov_mean, ov_rstd)
         ctx.pidx = pidx
@@ -393,7 +504,8 @@ class EmbeddingFn(torch.autograd.Function):
         d_ln_w, d_ln_b, d_vt_w, d_vt_b, d_vo_w, d_vo_b = z(H), z(H), z(H), z(H), z(H), z(H)
         d16 = d_emb.contiguous().view(B * S, H)
         dy16, dy32 = (d16, None) if d16.dtype == BF16 else (None, d16.float())
-        _, de = layernorm_backward(dy16, dy32, e, e_mean, e_rstd, ln_w, d_ln_w, d_ln_b, want_bf16=False, want_f32=True)
+        _, de = layernorm_backward(dy16, dy32, e, e_mean, e_rstd, ln_w, d_ln_w, d_ln_b, want_bf16=False, want_f32=True,
+                                   in_drop=ctx.drop)
         d_word, d_end, d_pos, d_typ = z(*word.shape), z(*end.shape), z(*pos.shape), z(*typ.shape)
         d_text_vl, d_obj_vl = z(B * T, H), z(B * R, H)
         _chk(lib.vlb_pack_backward(_p(pidx.kind), _p(pidx.src), _p(pidx.pos_id), _p(pidx.type_id), _p(ids), _p(de), _p(d_word),
@@ -406,7 +518,55 @@ class EmbeddingFn(torch.autograd.Function):
                            want_f32=True, ldx=2 * H, H=H, dx32=d_ov, ld_dx=2 * H)
         d_ov[:, H:] = d_obj_vl
         return (d_tv.view(B, T, H), d_ov.view(B, R, 2 * H), d_word, d_end, d_pos, d_typ, d_ln_w, d_ln_b, d_vt_w, d_vt_b,
-                d_vo_w, d_vo_b, None, None, None)
+                d_vo_w, d_vo_b, None, None, None, None)
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b on the tcgen05 GEMM for a small dense layer outside the encoder stack (BertPooler.dense,
+    modeling.py:430-434): x f32/bf16 [N, K], W f32 [O, K], b f32 [O] -> y f32 [N, O].  bf16 operands, fp32 accumulation."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _require_cuda(x, weight, bias)
+        _require_param(weight, "dense.weight", x.device)
+        _require_param(bias, "dense.bias", x.device)
+        N, K = x.shape
+        O = weight.shape[0]
+        st = _stream()
+        lib = _lib.lib()
+        x16 = x.contiguous().to(BF16)
+        w16 = torch.empty(weight.shape, dtype=BF16, device=x.device)
+        _chk(lib.vlb_cast_f32_to_bf16(_p(weight), _p(w16), weight.numel(), st))
+        y = torch.empty((N, O), dtype=F32, device=x.device)
+        gemm(0, x16, w16, y, bias=bias)
+        ctx.save_for_backward(x16, w16)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x16, w16 = ctx.saved_tensors
+        N, K = x16.shape
+        O = w16.shape[0]
+        dev = x16.device
+        # the reduction dimension of the weight gradient (N rows) is padded to a multiple of 8 (TMA leading dimension)
+        Np = (N + 7) // 8 * 8
+        dy16 = torch.zeros((Np, O), dtype=BF16, device=dev)
+        dy16[:N] = dy
+        xp = x16
+        if Np != N:
+            xp = torch.zeros((Np, K), dtype=BF16, device=dev)
+            xp[:N] = x16
+        d_b = torch.zeros((O,), dtype=F32, device=dev)
+        _chk(_lib.lib().vlb_colsum_bf16(_p(dy16), O, _p(d_b), N, O, _stream()))
+        d_w = torch.zeros((O, K), dtype=F32, device=dev)
+        d_w._vlb_accumulate = True
+        gemm(2, dy16, xp, d_w)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx16 = torch.empty((Np, K), dtype=BF16, device=dev)
+            gemm(1, dy16, w16, dx16)
+            dx = dx16[:N].float()
+        return dx, d_w, d_b
 
 
 class GatherRowsFn(torch.autograd.Function):
@@ -435,8 +595,10 @@ class RegionFn(torch.autograd.Function):
       -> obj_reps f32 [B,R,D], obj_reps_raw f32 [B,R,F]   (both re-padded: k-th valid box in slot k)"""
 
     @staticmethod
-    def forward(ctx, boxes, weight, bias, box_mask, im_info):
+    def forward(ctx, boxes, weight, bias, box_mask, im_info, drop=None):
         _require_cuda(boxes, weight, bias, box_mask, im_info)
+        _require_param(weight, "obj_downsample.1.weight", boxes.device)
+        _require_param(bias, "obj_downsample.1.bias", boxes.device)
         B, R, C = boxes.shape
         Fd = C - 4
         D = weight.shape[0]
@@ -448,11 +610,14 @@ class RegionFn(torch.autograd.Function):
         mask_u8 = box_mask.to(torch.uint8).contiguous()
         A = torch.empty((B * R, 2048 + Fd), dtype=BF16, device=dev)
         gidx = torch.empty((B * R,), dtype=torch.int32, device=dev)
-        _chk(lib.vlb_region_operand(_p(bx), C, _p(mask_u8), _p(info), info.shape[1], None, None, _p(A), _p(gidx), B, R, Fd, st))
+        # (the Dropout(0.1) heading obj_downsample, common/fast_rcnn.py:104-109, is applied while A is written)
+        _chk(lib.vlb_region_operand_dropout(_p(bx), C, _p(mask_u8), _p(info), info.shape[1], None, None, _p(A), _p(gidx), B, R, Fd,
+                                            _dref(drop), st))
+        ctx.drop = drop
         w16 = torch.empty(weight.shape, dtype=BF16, device=dev)
         _chk(lib.vlb_cast_f32_to_bf16(_p(weight.contiguous()), _p(w16), weight.numel(), st))
         Y = torch.empty((B * R, D), dtype=BF16, device=dev)
-        gemm(0, A, w16, Y, bias=bias.contiguous().float(), act=2)
+        gemm(0, A, w16, Y, bias=bias, act=2)
         obj = gather_rows(Y, gidx, B * R, F32).view(B, R, D)
         raw = torch.empty((B * R, Fd), dtype=F32, device=dev)
         _chk(lib.vlb_gather_rows(bx.data_ptr() + 16, 0, C, _p(gidx), _p(raw), 0, Fd, B * R, Fd, st))
@@ -481,12 +646,14 @@ class RegionFn(torch.autograd.Function):
         gemm(2, dY, A, d_w, split_k=max(1, min(16, (B * R) // 256)))
         # gradient wrt the feature half of boxes (the coordinate half is not propagated: the reference's boxes are data)
         if not ctx.needs_input_grad[0]:
-            return None, d_w, d_bias, None, None
+            return None, d_w, d_bias, None, None, None
         d_boxes = torch.zeros((B * R, C), dtype=F32, device=dev)
         d_feat = torch.empty((B * R, Fd), dtype=BF16, device=dev)
         gemm(1, dY, w16[:, 2048:], d_feat, M=B * R, N=Fd, K=D)
+        if ctx.drop is not None and ctx.drop.p > 0:      # the features entered the GEMM through the dropout mask
+            d_feat = dropout_2d(d_feat, ctx.drop, col_offset=2048, total_cols=2048 + Fd)
         d_boxes[:, 4:] = d_feat.float()
-        return d_boxes.view(B, R, C), d_w, d_bias, None, None
+        return d_boxes.view(B, R, C), d_w, d_bias, None, None, None
 
 
 class RoIAlignFn(torch.autograd.Function):

@@ -21,10 +21,10 @@ NUM_SPECIAL_WORDS = 1000
 
 
 def default_config(**over):
-    """NETWORK.VLBERT defaults for VL-BERT-base (reference: pretrain/function/config.py:87-115, cfgs/pretrain/base_*.yaml)
-    with the dropout probabilities at 0 (the fused path has no dropout yet)."""
+    """NETWORK.VLBERT defaults for VL-BERT-base (reference: pretrain/function/config.py:87-115, cfgs/pretrain/base_*.yaml):
+    hidden_dropout_prob = attention_probs_dropout_prob = 0.1 like every shipped cfg."""
     cfg = dict(vocab_size=30522, hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072,
-               hidden_act="gelu", hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, max_position_embeddings=512,
+               hidden_act="gelu", hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, max_position_embeddings=512,
                type_vocab_size=3, initializer_range=0.02, visual_size=768, visual_scale_text_init=1.0,
                visual_scale_object_init=1.0, visual_ln=True, word_embedding_frozen=False, with_pooler=True,
                position_padding_idx=-1, obj_pos_id_relative=True)
@@ -97,12 +97,14 @@ class BertEncoder(nn.Module):
 
 
 class BertPooler(nn.Module):
+    """modeling.py:424-436: tanh(dense(first token)) -- the dense layer runs on the library's tcgen05 GEMM (VF.LinearFn)."""
+
     def __init__(self, config):
         super().__init__()
         self.dense = nn.Linear(config.hidden_size, config.hidden_size)
 
     def forward(self, hidden_states):
-        return torch.tanh(self.dense(hidden_states[:, 0]))
+        return torch.tanh(VF.LinearFn.apply(hidden_states[:, 0], self.dense.weight, self.dense.bias))
 
 
 class BaseModel(nn.Module):
@@ -135,9 +137,9 @@ class VisualLinguisticBert(BaseModel):
             raise ValueError("vlbert_b200: visual_ln=False (scalar visual scale) is not implemented")
         if not config.obj_pos_id_relative:
             raise AssertionError("Don't use position id 510/511 for objects and [END]!!!")  # visual_linguistic_bert.py:229
-        if config.hidden_dropout_prob != 0 or config.attention_probs_dropout_prob != 0:
-            import warnings
-            warnings.warn("vlbert_b200: dropout is not implemented on the fused path; running with p = 0")
+        for nm in ("hidden_dropout_prob", "attention_probs_dropout_prob"):
+            if not (0.0 <= getattr(config, nm) < 1.0):
+                raise ValueError("dropout probability has to be between 0 and 1, but got {}".format(getattr(config, nm)))
         self.word_embeddings = nn.Embedding(config.vocab_size, H)
         self.end_embedding = nn.Embedding(1, H)
         self.position_embeddings = nn.Embedding(config.max_position_embeddings, H)
@@ -163,6 +165,37 @@ class VisualLinguisticBert(BaseModel):
         # (the reference's `max_length = (...).max() + 1`, visual_linguistic_bert.py:202, syncs every forward).
         self.max_length_hint = None
         self._weights = None
+        self._last_pidx = None
+        # Dropout (modeling.py:283,310,331,376 / visual_linguistic_bert.py:75,239) is fused into the kernels as counter-based
+        # masks: (seed, step) live in this DEVICE buffer, non-persistent so the state_dict keys stay the reference's.  The
+        # default seed derives from torch.initial_seed() without consuming torch's generator (the reference's masks follow
+        # torch.manual_seed(RNG_SEED) too, and every rank of a DDP job uses the same stream there as well).
+        seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + 0x1234567) & 0x7FFFFFFFFFFFFFFF
+        self.register_buffer("_rng_state", torch.tensor([seed, 0], dtype=torch.int64), persistent=False)
+
+    def set_dropout_seed(self, seed, step=0):
+        """(Re)seed the dropout stream: the masks of training step n are a pure function of (seed, step0 + n, site, element)."""
+        self._rng_state.copy_(torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF, int(step)], dtype=torch.int64))
+
+    def dropout_state(self):
+        """(seed, step) of the most recent training forward (one device->host sync; tests and checkpointing)."""
+        v = self._rng_state.tolist()
+        return int(v[0]), int(v[1])
+
+    def _dropout_rng(self):
+        """Advance the step counter on the device and return a snapshot tensor for this forward (its backward re-reads the
+        same snapshot, so interleaved forwards / gradient accumulation keep their own masks).  None when dropout is off."""
+        cfg = self.config
+        if not self.training or (cfg.hidden_dropout_prob == 0 and cfg.attention_probs_dropout_prob == 0):
+            return None
+        self._rng_state[1] += 1
+        return self._rng_state.clone()
+
+    def check_errors(self):
+        """Deferred index check of the most recent forward (the graph-friendly path never syncs by itself): raises IndexError
+        if `max_length_hint` was too small or token / position / type ids were out of range.  One device->host sync."""
+        if self._last_pidx is not None:
+            self._last_pidx.check()
 
     # -- helpers -----------------------------------------------------------------------------------
     def _encoder_meta(self, all_layers, device):
@@ -171,7 +204,7 @@ class VisualLinguisticBert(BaseModel):
             self._weights = VF.EncoderWeights(cfg.num_hidden_layers, cfg.hidden_size, cfg.intermediate_size, device)
         return types.SimpleNamespace(L=cfg.num_hidden_layers, H=cfg.hidden_size, heads=cfg.num_attention_heads,
                                      I=cfg.intermediate_size, eps=1e-12, all_layers=all_layers, weights=self._weights,
-                                     reducer=getattr(self, "_grad_reducer", None))
+                                     reducer=getattr(self, "_grad_reducer", None), drop=None)
 
     def _packed_length(self, text_mask, object_mask):
         T, R = text_mask.shape[1], object_mask.shape[1]
@@ -185,12 +218,12 @@ class VisualLinguisticBert(BaseModel):
     def embedding(self, text_input_ids, text_token_type_ids, text_visual_embeddings, text_mask, object_vl_embeddings,
                   object_mask):
         emb, pidx = self._embedding_impl(text_input_ids, text_token_type_ids, text_visual_embeddings, text_mask,
-                                         object_vl_embeddings, object_mask)
+                                         object_vl_embeddings, object_mask, self._dropout_rng())
         kind = pidx.kind
         return emb.float(), (kind != 3).to(text_mask.dtype), kind == 0, kind == 1
 
     def _embedding_impl(self, text_input_ids, text_token_type_ids, text_visual_embeddings, text_mask, object_vl_embeddings,
-                        object_mask):
+                        object_mask, rng=None):
         cfg = self.config
         VS = cfg.visual_size
         if self.visual_1x1_text is not None:
@@ -199,11 +232,17 @@ class VisualLinguisticBert(BaseModel):
                                               object_vl_embeddings[:, :, VS:]), -1)
         S = self._packed_length(text_mask, object_mask)
         pidx = VF.PackIndex(text_mask, object_mask, text_token_type_ids, S, self.position_padding_idx + 1)
+        drop = None
+        if rng is not None and cfg.hidden_dropout_prob > 0:
+            drop = VF.DropSite(cfg.hidden_dropout_prob, 0, rng)            # site 0: embedding_dropout (:75, :239)
         emb = VF.EmbeddingFn.apply(text_visual_embeddings, object_vl_embeddings, self.word_embeddings.weight,
                                    self.end_embedding.weight, self.position_embeddings.weight,
                                    self.token_type_embeddings.weight, self.embedding_LayerNorm.weight,
                                    self.embedding_LayerNorm.bias, self.visual_ln_text.weight, self.visual_ln_text.bias,
-                                   self.visual_ln_object.weight, self.visual_ln_object.bias, text_input_ids, pidx, 1e-12)
+                                   self.visual_ln_object.weight, self.visual_ln_object.bias, text_input_ids, pidx, 1e-12, drop)
+        self._last_pidx = pidx
+        if self.max_length_hint is None:
+            pidx.check()      # this path already synchronised for the packed length; surface bad ids like the reference does
         return emb, pidx
 
     def forward(self, text_input_ids, text_token_type_ids, text_visual_embeddings, text_mask, object_vl_embeddings,
@@ -212,9 +251,13 @@ class VisualLinguisticBert(BaseModel):
         if output_attention_probs:
             raise NotImplementedError("vlbert_b200: the fused attention never materialises probabilities "
                                       "(output_attention_probs is a visualisation-only path of the reference)")
+        rng = self._dropout_rng()
         emb, pidx = self._embedding_impl(text_input_ids, text_token_type_ids, text_visual_embeddings, text_mask,
-                                         object_vl_embeddings, object_mask)
+                                         object_vl_embeddings, object_mask, rng)
         meta = self._encoder_meta(bool(output_all_encoded_layers), emb.device)
+        if rng is not None:
+            meta.drop = types.SimpleNamespace(p_attn=float(self.config.attention_probs_dropout_prob),
+                                              p_hidden=float(self.config.hidden_dropout_prob), rng=rng)
         params = []
         for layer in self.encoder.layer:
             params += layer.flat_params()
@@ -484,10 +527,20 @@ class FastRCNN(nn.Module):
             self.backbone = ResNetC4(_RESNET_LAYERS[self.num_layers], stride_in_1x1=self.stride_in_1x1)
             if self.pretrained_model_path is not None:
                 import os
-                if os.path.exists(self.pretrained_model_path):
-                    sd = torch.load(self.pretrained_model_path, map_location="cpu")
-                    own = self.backbone.state_dict()
-                    self.backbone.load_state_dict({k: sd.get(k, v) for k, v in own.items()})
+                if not os.path.exists(self.pretrained_model_path):
+                    # the reference fails inside torch.load on a missing checkpoint (common/backbone/resnet/resnet.py:279-283);
+                    # a silently random-initialised backbone with frozen stages must not happen
+                    raise FileNotFoundError("vlbert_b200.FastRCNN: IMAGE_PRETRAINED checkpoint %s not found" % self.pretrained_model_path)
+                sd = torch.load(self.pretrained_model_path, map_location="cpu")
+                own = self.backbone.state_dict()
+                missing = [k for k in own if k not in sd]
+                if missing:
+                    print("Warnings: Missing keys: {}.".format(missing))
+                self.backbone.load_state_dict({k: sd.get(k, v) for k, v in own.items()})
+            else:
+                import warnings
+                warnings.warn("vlbert_b200.FastRCNN: IMAGE_PRETRAINED is empty -- the backbone keeps its random (Kaiming) "
+                              "initialisation (the reference would download the model-zoo weights; there is no network here)")
             self.mask_upsample = None
             self.roi_head_feature_extractor, _ = make_layer(self.backbone.inplanes, 512, 3,
                                                             stride=2 if not self.c5_dilated else 1,
@@ -516,6 +569,20 @@ class FastRCNN(nn.Module):
             torch.nn.Linear(2 * 2048, final_dim),
             torch.nn.ReLU(inplace=True),
         )
+        # obj_downsample[0] (Dropout(0.1), common/fast_rcnn.py:104-109) is fused into the kernel that writes the GEMM operand:
+        # counter-based masks from this device-resident (seed, step) state (non-persistent: not a state_dict key)
+        seed = (torch.initial_seed() * 0xD1B54A32D192ED03 + 0x7654321) & 0x7FFFFFFFFFFFFFFF
+        self.register_buffer("_rng_state", torch.tensor([seed, 0], dtype=torch.int64), persistent=False)
+
+    #: dropout call-site id of obj_downsample (the encoder uses 0 .. 3L)
+    DROP_SITE = 1000
+
+    def set_dropout_seed(self, seed, step=0):
+        self._rng_state.copy_(torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF, int(step)], dtype=torch.int64))
+
+    def dropout_state(self):
+        v = self._rng_state.tolist()
+        return int(v[0]), int(v[1])
 
     def init_weight(self):
         """common/fast_rcnn.py:111-120: the res5 head starts from the checkpoint's layer4.* (no model-zoo download here)."""
@@ -560,10 +627,10 @@ class FastRCNN(nn.Module):
         return full, post, inds
 
     def forward(self, images, boxes, box_mask, im_info, classes=None, segms=None, mvrc_ops=None, mask_visual_embed=None):
-        if self.training and self.obj_downsample[0].p > 0 and not getattr(self, "_warned", False):
-            import warnings
-            warnings.warn("vlbert_b200: obj_downsample dropout is not implemented on the fused path; running with p = 0")
-            self._warned = True
+        drop = None
+        if self.training and self.obj_downsample[0].p > 0:
+            self._rng_state[1] += 1
+            drop = VF.DropSite(self.obj_downsample[0].p, self.DROP_SITE, self._rng_state.clone())
         lin = self.obj_downsample[1]
         extra = {}
         if self.image_feat_precomputed:
@@ -582,7 +649,7 @@ class FastRCNN(nn.Module):
             feats = feats.clone()
             feats[mvrc_ops == 1] = mask_visual_embed
         packed = torch.cat((boxes[:, :, :4].to(feats.dtype), feats), -1)
-        obj_reps, raw = VF.RegionFn.apply(packed, lin.weight, lin.bias, box_mask, im_info)
+        obj_reps, raw = VF.RegionFn.apply(packed, lin.weight, lin.bias, box_mask, im_info, drop)
         out = {"obj_reps_raw": raw, "obj_reps": obj_reps}
         out.update(extra)
         return out
