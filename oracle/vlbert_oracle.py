@@ -41,6 +41,57 @@ def default_config(**over):
 
 
 # ------------------------------------------------------------------------------------------------
+# bf16 comparator: the same graph with every GEMM evaluated the way a bf16 tensor-core path (or the reference under
+# torch.autocast(bfloat16)) evaluates it -- operands rounded to bf16, fp32 accumulation, result rounded to bf16, in forward
+# AND backward -- and everything else (softmax, LayerNorm, GELU, residual adds) left in fp32.  It is the yardstick for
+# the floating-point tolerance: err(CUDA path, fp32 oracle) is asserted against err(this, fp32 oracle).  Real autocast is
+# strictly worse (it also runs the Python LayerNorm's mean/pow in bf16), so this is the stricter comparator.
+# ------------------------------------------------------------------------------------------------
+_GEMM_BF16 = False
+
+
+class bf16_gemms(object):
+    """context manager: `with vo.bf16_gemms(): ...` evaluates the oracle with bf16-rounded GEMMs"""
+
+    def __enter__(self):
+        global _GEMM_BF16
+        self.prev = _GEMM_BF16
+        _GEMM_BF16 = True
+
+    def __exit__(self, *a):
+        global _GEMM_BF16
+        _GEMM_BF16 = self.prev
+
+
+class _RoundBF16(torch.autograd.Function):
+    """value and gradient both pass through a bf16 rounding (what a bf16 tensor crossing a GEMM boundary does)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+def _rb(x):
+    return _RoundBF16.apply(x) if _GEMM_BF16 else x
+
+
+def linear(x, w, b):
+    if not _GEMM_BF16:
+        return F.linear(x, w, b)
+    return _rb(F.linear(_rb(x), _rb(w), b))
+
+
+def matmul(a, b):
+    if not _GEMM_BF16:
+        return torch.matmul(a, b)
+    return _rb(torch.matmul(_rb(a), _rb(b)))
+
+
+# ------------------------------------------------------------------------------------------------
 # primitives
 # ------------------------------------------------------------------------------------------------
 def gelu_erf(x):
@@ -73,7 +124,7 @@ class DropSpec(object):
         import philox
         cols = x.shape[-1]
         rows = x.numel() // cols
-        keep = torch.from_numpy(philox.keep_mask_2d(rows, cols, p, self.seed, site, self.step)).view(x.shape)
+        keep = torch.from_numpy(philox.keep_mask_2d(rows, cols, p, self.seed, site, self.step)).view(x.shape).to(x.device)
         scale = float(1.0 / (1.0 - float(torch.tensor(p, dtype=torch.float32))))
         return x * (keep.to(x.dtype) * scale)
 
@@ -86,12 +137,12 @@ def self_attention(x, add_mask, wq, bq, wk, bk, wv, bv, num_heads, drop=None, si
     def split(t):
         return t.view(B, S, num_heads, d).permute(0, 2, 1, 3)
 
-    q, k, v = split(F.linear(x, wq, bq)), split(F.linear(x, wk, bk)), split(F.linear(x, wv, bv))
-    scores = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(d) + add_mask
+    q, k, v = split(linear(x, wq, bq)), split(linear(x, wk, bk)), split(linear(x, wv, bv))
+    scores = matmul(q, k.transpose(-1, -2)) / math.sqrt(d) + add_mask
     probs = torch.softmax(scores, dim=-1)
     if drop is not None:
         probs = drop.apply(probs, drop.p_attn, site)            # modeling.py:310
-    ctx = torch.matmul(probs, v).permute(0, 2, 1, 3).contiguous().view(B, S, H)
+    ctx = matmul(probs, v).permute(0, 2, 1, 3).contiguous().view(B, S, H)
     return ctx
 
 
@@ -102,13 +153,13 @@ def bert_layer(x, add_mask, p, num_heads, eps=1e-12, drop=None, layer=0):
                          p["attention.self.query.weight"], p["attention.self.query.bias"],
                          p["attention.self.key.weight"], p["attention.self.key.bias"],
                          p["attention.self.value.weight"], p["attention.self.value.bias"], num_heads, drop, 1 + 3 * layer)
-    d = F.linear(ctx, p["attention.output.dense.weight"], p["attention.output.dense.bias"])
+    d = linear(ctx, p["attention.output.dense.weight"], p["attention.output.dense.bias"])
     if drop is not None:
         d = drop.apply(d, drop.p_hidden, 2 + 3 * layer)
     a = d + x
     h = layer_norm_tf(a, p["attention.output.LayerNorm.weight"], p["attention.output.LayerNorm.bias"], eps)
-    u = gelu_erf(F.linear(h, p["intermediate.dense.weight"], p["intermediate.dense.bias"]))
-    d = F.linear(u, p["output.dense.weight"], p["output.dense.bias"])
+    u = gelu_erf(linear(h, p["intermediate.dense.weight"], p["intermediate.dense.bias"]))
+    d = linear(u, p["output.dense.weight"], p["output.dense.bias"])
     if drop is not None:
         d = drop.apply(d, drop.p_hidden, 3 + 3 * layer)
     y = d + h
@@ -125,16 +176,17 @@ def pack_indices(text_mask, object_mask):
     The k-th True of text_mask[b] lands at packed position k, exactly what the reference's
     boolean-mask assignment `vl[grid_pos < text_end] = text_vl[text_mask]` does."""
     B = text_mask.shape[0]
+    dev = text_mask.device
     text_end = text_mask.sum(1)
     object_end = text_end + object_mask.sum(1)
     S = int(object_end.max().item()) + 1
-    pos = torch.arange(S, dtype=torch.long).unsqueeze(0).expand(B, S)
+    pos = torch.arange(S, dtype=torch.long, device=dev).unsqueeze(0).expand(B, S)
     te, oe = text_end.unsqueeze(1), object_end.unsqueeze(1)
-    kind = torch.full((B, S), 3, dtype=torch.long)
+    kind = torch.full((B, S), 3, dtype=torch.long, device=dev)
     kind[pos < te] = 0
     kind[(pos >= te) & (pos < oe)] = 1
     kind[pos == oe] = 2
-    src = torch.zeros((B, S), dtype=torch.long)
+    src = torch.zeros((B, S), dtype=torch.long, device=dev)
     for b in range(B):
         t_idx = torch.nonzero(text_mask[b], as_tuple=False).flatten()
         o_idx = torch.nonzero(object_mask[b], as_tuple=False).flatten()
@@ -276,13 +328,13 @@ class VisualLinguisticBertOracle(nn.Module):
 
         kind, src, pos_id, text_end, object_end, S = pack_indices(text_mask, object_mask)
         B, H = text_vl.shape[0], text_vl.shape[-1]
-        bidx = torch.arange(B).unsqueeze(1).expand(B, S)
+        bidx = torch.arange(B, device=text_vl.device).unsqueeze(1).expand(B, S)
         vl = text_vl.new_zeros((B, S, H))
         is_t, is_o, is_e = kind == 0, kind == 1, kind == 2
         vl[is_t] = text_vl[bidx[is_t], src[is_t]]
         vl[is_o] = obj_vl[bidx[is_o], src[is_o]]
         vl[is_e] = self.end_embedding.weight[0]
-        type_ids = torch.zeros((B, S), dtype=torch.long)
+        type_ids = torch.zeros((B, S), dtype=torch.long, device=text_vl.device)
         type_ids[is_t] = text_token_type_ids[bidx[is_t], src[is_t]]
         type_ids[is_o | is_e] = 2
         position_ids = pos_id + self.position_padding_idx + 1
@@ -311,7 +363,7 @@ class VisualLinguisticBertOracle(nn.Module):
         for i in range(self.config.num_hidden_layers):
             h = bert_layer(h, add_mask, self._layer_params(i), self.config.num_attention_heads, drop=drop, layer=i)
             layers.append(h)
-        pooled = torch.tanh(self.pooler.dense(h[:, 0])) if self.config.with_pooler else None
+        pooled = torch.tanh(linear(h[:, 0], self.pooler.dense.weight, self.pooler.dense.bias)) if self.config.with_pooler else None
         encoded = layers if output_all_encoded_layers else layers[-1]
         if not output_text_and_object_separately:
             return encoded, pooled

@@ -110,7 +110,7 @@ def test_layernorm_backward_second_output_for_the_dense_branch(VF):
     assert torch.equal(dxm == 0, ~keep | (plain32 == 0))
     assert rel(dxm.float(), plain32 * keep / (1 - p)) <= 3e-3
     assert rel(dc, (plain32 * keep / (1 - p)).sum(0)) <= 2e-3
-    assert torch.equal(dg, dg0) and torch.equal(db, db0)
+    assert rel(dg, dg0) <= 1e-5 and rel(db, db0) <= 1e-5      # (fp32 atomics: equal up to summation order)
 
 
 # ------------------------------------------------------------------------------------------------ GEMM epilogue site

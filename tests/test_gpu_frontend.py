@@ -295,8 +295,6 @@ def test_cnn_reg_loss_outputs():
     assert torch.isfinite(out["cnn_regularization_loss"]).all()
 
 
-@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: first hardware run is the driver's round-end suite "
-                                        "(XPASS = verified); the same module code is checked on the CPU in tests/test_frontend_host_logic.py")
 def test_fastrcnn_with_instance_masks_against_the_oracle():
     """`segms` (VCR): mask-weighted mean pool of the res5 map, common/fast_rcnn.py:151-156"""
     m, sd = _load_e2e()

@@ -64,8 +64,6 @@ def test_fused_adamw_host_side():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: its first hardware run is the driver's "
-                                        "round-end suite (XPASS = verified); the CPU oracle is pinned to the reference above")
 def test_fused_adamw_against_reference_fixture(golden_dir):
     """kernels vlb_grad_sqnorm + vlb_adamw_step through FusedAdamW: parameters after each of 4 steps, moments and the clip norm
     against the reference's run.  fp32 with the reference's operation order (no FMA contraction): 4e-6 of max."""
@@ -98,8 +96,6 @@ def test_fused_adamw_against_reference_fixture(golden_dir):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: first hardware run is the driver's round-end "
-                                        "suite (XPASS = verified); the same source is executed on the host in tests/test_philox.py")
 def test_dropout_contract_on_the_device():
     """vlb_dropout_mask / vlb_dropout against oracle/philox.py: bit-exact masks, kept values scaled by 1/(1-p)"""
     import philox
