@@ -144,6 +144,39 @@ def test_gemm_epilogues(VF):
 
 
 @pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("shape", [(6464, 768, 768), (6464, 768, 3072), (6464, 2304, 768), (6464, 3072, 768), (7744, 768, 768), (10560, 1024, 1024),
+                                   (19072, 3080, 136)])
+@pytest.mark.parametrize("bn", [0, 128, 192, 256])
+def test_gemm_tail_split_units(VF, mode, shape, bn):
+    """The encoder's own GEMM shapes at config 2 / 3 / 4 token counts: the tile count leaves a partial last round of the
+    persistent grid, whose tiles are cut along N into 64-column units (GemmParams::tail_split).  Every epilogue family that
+    reads a second operand tile (bias + residual -> fp32, GELU'-multiply with column sums, residual -> bf16) runs through the
+    narrow units and through the L2 prefetch of that operand."""
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N + K + mode)
+    a, b = bf(torch.randn(M, K, generator=g)), bf(torch.randn(N, K, generator=g) * 0.05)
+    bias = torch.randn(N, generator=g)
+    resid = bf(torch.randn(M, N, generator=g))
+    ref = a @ b.t()
+    A = a.to(DEV, BF16)
+    Bm = b.to(DEV, BF16) if mode == 0 else b.t().contiguous().to(DEV, BF16)
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32)
+    VF.gemm(mode, A, Bm, out, bias=bias.to(DEV) if mode == 0 else None, resid=resid.to(DEV, BF16), force_bn=bn)
+    assert rel(out, ref + (bias if mode == 0 else 0) + resid) <= 2e-5
+    o16 = torch.full((M, N), float("nan"), device=DEV, dtype=BF16)
+    if mode == 0:
+        VF.gemm(0, A, Bm, o16, bias=bias.to(DEV), force_bn=bn)
+        assert rel(o16.float(), ref + bias) <= 3e-3
+    else:
+        gp = bf(torch.rand(M, N, generator=g) * 1.2 - 0.1)
+        VF.gemm(1, A, Bm, o16, act=3, aux=gp.to(DEV, BF16), force_bn=bn)
+        assert rel(o16.float(), ref * gp) <= 3e-3
+        VF.gemm(1, A, Bm, o16, resid=resid.to(DEV, BF16), force_bn=bn)
+        assert rel(o16.float(), ref + resid) <= 3e-3
+    assert bool(torch.isfinite(o16.float()).all())
+
+
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("shape", [(6464, 768, 3072), (6464, 768, 2304), (700, 1024, 1600), (130, 512, 4096), (6464, 768, 1544)])
 def test_gemm_streamk_tail(VF, mode, shape):
     """Long reductions whose tile count leaves a small last round: those tiles are split along K (stream-K), partial

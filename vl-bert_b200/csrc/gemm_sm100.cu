@@ -60,6 +60,12 @@ struct GemmParams {
   float* sk_scratch;      // [tail tiles][BM][BN] fp32, all zero between launches
   int* sk_counters;       // [tail tiles], all zero between launches
   int sk_debug;           // timing experiments only (VLB_SK_DEBUG): 1 = skip the partial reds, 2 = skip the fix-up pass
+  // Tail split: the tiles of the last, partial round of the persistent grid are cut along N into `tail_split` units of
+  // BN / tail_split (= 64) columns each, so that the partial round is spread over every CTA instead of leaving most SMs idle
+  // for a whole tile time.  Items [0, tail_first) are whole tiles; item tail_first + u is unit u % tail_split of tile
+  // tail_first + u / tail_split.  0 = off.
+  int tail_first, tail_split;
+  int epi_prefetch;       // 1: epilogue warps L2-prefetch the tile's residual / aux input while its mainloop runs
 };
 
 // linear output-pixel index -> base pixel (w, h, n) of the im2col traversal
@@ -101,11 +107,27 @@ struct ItemCoord {
   int g, split, m_blk, n_blk;
   int kb_begin, kb_end;   // k-block range of this work unit
   int tail;               // >= 0: index of the stream-K tail tile this unit is a K-chunk of
+  int n0, bn;             // first column and width of this work unit (bn < BN for the N-split units of the last round)
 };
-template <bool GROUPED>
+template <bool GROUPED, int BN>
 __device__ __forceinline__ ItemCoord decode_item(int item, const GemmParams& p, const GroupTable& gt) {
   ItemCoord c;
   c.g = 0;
+  c.bn = BN;
+  if (!GROUPED && p.tail_split > 1 && item >= p.tail_first) {
+    const int u = item - p.tail_first;
+    const int tile = p.tail_first + u / p.tail_split;
+    const int sub = u - (u / p.tail_split) * p.tail_split;
+    c.tail = -1;
+    c.split = 0;
+    c.m_blk = tile / p.num_n_blocks;
+    c.n_blk = tile - c.m_blk * p.num_n_blocks;
+    c.kb_begin = 0;
+    c.kb_end = p.num_k_blocks;
+    c.bn = BN / p.tail_split;
+    c.n0 = c.n_blk * BN + sub * c.bn;
+    return c;
+  }
   int local = item, mb = p.num_m_blocks, nb = p.num_n_blocks;
   if (GROUPED) {
 #pragma unroll
@@ -125,6 +147,7 @@ __device__ __forceinline__ ItemCoord decode_item(int item, const GemmParams& p, 
     c.n_blk = tile - c.m_blk * nb;
     c.kb_begin = c.split * p.sk_kb_per_chunk;
     c.kb_end = min(p.num_k_blocks, c.kb_begin + p.sk_kb_per_chunk);
+    c.n0 = c.n_blk * BN;
     return c;
   }
   const int per_split = mb * nb;
@@ -134,6 +157,7 @@ __device__ __forceinline__ ItemCoord decode_item(int item, const GemmParams& p, 
   c.n_blk = rem - c.m_blk * nb;
   c.kb_begin = c.split * p.kb_per_split;
   c.kb_end = min(p.num_k_blocks, c.kb_begin + p.kb_per_split);
+  c.n0 = c.n_blk * BN;
   return c;
 }
 
@@ -301,7 +325,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int CM, bool GROUPED>
 __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtensorMap& tma_b, const GemmParams& p,
-                                          const GroupTable& gt) {
+                                          const GroupTable& gt, const CUtensorMap& tma_b_tail) {
   using C = Cfg<BN, CM>;
   constexpr bool CG2 = CM == 1;   // pair MMA
   constexpr bool MC2 = CM == 2;   // independent MMAs, B tile multicast
@@ -357,11 +381,13 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
       int stage = 0;
       uint32_t phase = 0;
       for (int item = worker; item < p.num_items; item += nworkers) {
-        const ItemCoord ic = decode_item<GROUPED>(item, p, gt);
+        const ItemCoord ic = decode_item<GROUPED, BN>(item, p, gt);
         const CUtensorMap* pta = GROUPED ? &gt.ta[ic.g] : &tma_a;
         const CUtensorMap* ptb = GROUPED ? &gt.tb[ic.g] : &tma_b;
         const int m0 = (ic.m_blk * (CL ? 2 : 1) + (int)rank) * BM;           // this CTA's 128 rows of the (256-row) super-tile
-        const int n0 = ic.n_blk * BN + (int)rank * (CG2 ? BN / 2 : 0);       // CG2: this CTA's half of the B tile
+        const int n0 = ic.n0 + (int)rank * (CG2 ? BN / 2 : 0);               // CG2: this CTA's half of the B tile
+        const bool narrow = !CL && ic.bn != BN;                              // N-split unit of the last round (64 columns)
+        const uint32_t stage_tx = narrow ? (uint32_t)(C::A_BYTES + ic.bn * BK * 2) : (uint32_t)C::STAGE_BYTES;
         const int kb_begin = ic.kb_begin, kb_end = ic.kb_end;
         // implicit-convolution operand: all divisions happen once per item; the k loop only increments
         PixelCoord cv_px{0, 0, 0};
@@ -403,7 +429,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
           const uint32_t fb = CG2 ? mapa_cluster(smem_u32(&full_bar[stage]), 0) : smem_u32(&full_bar[stage]);
           // (default .release.cta semantics as in CUTLASS: a cluster-scope release here costs ~1000 cycles per k-block)
           if (CG2 && !leader) mbar_arrive_expect_tx_cluster(fb, C::STAGE_BYTES);
-          else mbar_arrive_expect_tx(smem_u32(&full_bar[stage]), C::STAGE_BYTES);
+          else mbar_arrive_expect_tx(smem_u32(&full_bar[stage]), stage_tx);
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t sb = sa + C::A_BYTES;
           const int k0 = kb * BK;
@@ -433,7 +459,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
               }
             }
           } else if (!B_MN) {
-            load(sb, ptb, k0, n0);  // box {64 k, B_ROWS rows}
+            if (narrow) tma_load_2d(sb, &tma_b_tail, fb, k0, n0);   // box {64 k, 64 rows}
+            else load(sb, ptb, k0, n0);  // box {64 k, B_ROWS rows}
           } else if (!GROUPED && p.cv_side == 2) {
             // implicit convolution (weight gradient): 64 output pixels (reduction rows) x 64 channels per 64-column chunk
 #pragma unroll
@@ -454,7 +481,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
             }
           } else {
 #pragma unroll
-            for (int c = 0; c < C::B_ROWS / 64; ++c) load(sb + c * 8192, ptb, n0 + c * 64, k0);
+            for (int c = 0; c < C::B_ROWS / 64; ++c)
+              if (!narrow || c * 64 < ic.bn) load(sb + c * 8192, ptb, n0 + c * 64, k0);
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -463,13 +491,14 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0 && leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(CG2 ? 2 * BM : BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc_full = make_idesc_bf16(CG2 ? 2 * BM : BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int item = worker; item < p.num_items; item += nworkers, ++it) {
-        const ItemCoord ic = decode_item<GROUPED>(item, p, gt);
+        const ItemCoord ic = decode_item<GROUPED, BN>(item, p, gt);
         const int kb_begin = ic.kb_begin, kb_end = ic.kb_end;
+        const uint32_t idesc = ic.bn == BN ? idesc_full : make_idesc_bf16(BM, ic.bn, A_MN ? 1 : 0, B_MN ? 1 : 0);
         const int buf = it & 1;
         const uint32_t use = static_cast<uint32_t>(it >> 1);
         mbar_wait(smem_u32(&tempty_bar[buf]), (use & 1u) ^ 1u);
@@ -505,13 +534,35 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
     const DropState dstate = drop_state(p.e.drop);
     int it = 0;
     for (int item = worker; item < p.num_items; item += nworkers, ++it) {
-      const ItemCoord ic = decode_item<GROUPED>(item, p, gt);
+      const ItemCoord ic = decode_item<GROUPED, BN>(item, p, gt);
       const int m_blk = ic.m_blk, n_blk = ic.n_blk;
       GemmEpilogue eg = p.e;
       int Mg = p.M, Ng = p.N;
       if (GROUPED) { eg.out = gt.out[ic.g]; eg.ldo = gt.ldo[ic.g]; Mg = gt.M[ic.g]; Ng = gt.N[ic.g]; }
       const int buf = it & 1;
       const uint32_t use = static_cast<uint32_t>(it >> 1);
+      if (p.epi_prefetch) {
+        // The residual / saved-activation tile this epilogue will read is fetched into L2 while the tile's MMAs run: the
+        // per-chunk loads below then cost an L2 hit instead of a DRAM round trip per chunk (the epilogue was latency-bound).
+        using T = EpiTraits<EPI>;
+        const int act = T::kStatic ? T::act : eg.act;
+        const int rk = T::kStatic ? T::resid : eg.resid_kind;
+        const bool aux_in = (act == ACT_DGELU_MUL || act == ACT_DRELU_MUL);
+        if (aux_in || rk != RESID_NONE) {
+          const char* src = reinterpret_cast<const char*>(aux_in ? eg.aux : eg.resid);
+          const int esz = (!aux_in && rk == RESID_F32) ? 4 : 2;
+          const size_t ld_bytes = (size_t)(aux_in ? eg.ld_aux : eg.ldr) * esz;
+          const int row0 = (m_blk * (CL ? 2 : 1) + (int)rank) * BM;
+          const int width = min(ic.bn, Ng - ic.n0) * esz;           // bytes per row of this unit
+          const int lpr = (width + 127) >> 7;                        // 128-byte lines per row
+          const int et = (int)threadIdx.x - 64;                      // epilogue thread index 0 .. 255
+          for (int l = et; l < BM * lpr; l += EPI_WARPS * 32) {
+            const int r = l / lpr, sgm = l - r * lpr;
+            if (row0 + r < Mg)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)(row0 + r) * ld_bytes + (size_t)ic.n0 * esz + (size_t)sgm * 128));
+          }
+        }
+      }
       mbar_wait(smem_u32(&tfull_bar[buf]), use & 1u);
       tc_fence_after();
       const int row_base = (m_blk * (CL ? 2 : 1) + (int)rank) * BM + q * 32;
@@ -552,11 +603,11 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
         continue;
       }
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
+      for (int c = half; c < ic.bn / 32; c += 2) {
         uint32_t v[32];
         tmem_ld32(t_row + c * 32, v);
         tmem_ld_wait();
-        const int col0 = n_blk * BN + c * 32;
+        const int col0 = ic.n0 + c * 32;
         if (row_base < Mg && col0 < Ng) epilogue_chunk<EPI>(eg, v, stage, lane, row_base, col0, Mg, Ng, nullptr, 0, dstate);
       }
       tc_fence_before();
@@ -578,14 +629,15 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int CM>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
-  gemm_body<BN, A_MN, B_MN, EPI, CM, false>(tma_a, tma_b, p, *reinterpret_cast<const GroupTable*>(&tma_a));  // table unused
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+            const __grid_constant__ CUtensorMap tma_b_tail, const GemmParams p) {
+  gemm_body<BN, A_MN, B_MN, EPI, CM, false>(tma_a, tma_b, p, *reinterpret_cast<const GroupTable*>(&tma_a), tma_b_tail);  // table unused
 }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_grouped_tn_kernel(const __grid_constant__ GroupTable gt, const GemmParams p) {
-  gemm_body<BN, true, true, EPI, 0, true>(gt.ta[0], gt.tb[0], p, gt);
+  gemm_body<BN, true, true, EPI, 0, true>(gt.ta[0], gt.tb[0], p, gt, gt.tb[0]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -646,7 +698,7 @@ struct TmapKeyHash {
 };
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int CM>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbt, const GemmParams& p, cudaStream_t stream) {
   using C = Cfg<BN, CM>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -656,7 +708,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
   }
   if (CM == 0) {
     const int grid = p.num_items < num_sms() ? p.num_items : num_sms();
-    VLB_CHECK_CUDA(launch_pdl(gemm_kernel<BN, A_MN, B_MN, EPI, CM>, dim3(grid), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, ta, tb, p));
+    VLB_CHECK_CUDA(launch_pdl(gemm_kernel<BN, A_MN, B_MN, EPI, CM>, dim3(grid), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, ta, tb, tbt, p));
     return VLB_OK;
   }
   const int pairs = num_sms() / 2;
@@ -675,7 +727,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  VLB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, A_MN, B_MN, EPI, CM>, ta, tb, p));
+  VLB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, A_MN, B_MN, EPI, CM>, ta, tb, tbt, p));
   return VLB_OK;
 }
 
@@ -799,6 +851,19 @@ void gemm_debug_override(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t mn_kadv) {
 }
 
 namespace {
+// N-split of the last partial round (see GemmParams::tail_split): relative cost of one 128 x 64 unit against a 128 x 256 tile
+// (a quarter of the MMA work, but the same A tile per k-block: the unit is operand-feed bound, not MMA bound).
+constexpr double kTailUnitCost = 0.45;
+int tail_split_for(long tiles, int sms, int bn, int split_k, int mode, bool conv) {
+  static const int on = [] { const char* v = getenv("VLB_TAIL_SPLIT"); return v ? atoi(v) : 1; }();
+  if (!on || conv || split_k > 1 || mode == GEMM_TN || bn < 128) return 0;
+  const long rem = tiles % sms;
+  if (rem == 0 || tiles < sms) return 0;          // a single (partial) round gains nothing
+  const int split = bn / 64;
+  if (rem * split > sms) return 0;                // the units must fit one extra (short) round
+  return split;
+}
+
 constexpr int SK_MAX_TAIL_TILES = 80;          // tail tiles are at most half a round (148 / 2)
 constexpr int SK_MAX_CHUNKS = 16;
 
@@ -886,6 +951,7 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
       const int chunks = (sk == 1 && mode != GEMM_TN) ? streamk_chunks(items, sms, (K + BK - 1) / BK) : 0;
       if (chunks > 1) return ((double)(items / sms) + 1.0 / chunks + 0.2) * w;
       const long rounds = (items + sms - 1) / sms;
+      if (tail_split_for(items, sms, b, sk, mode, conv != nullptr && conv_side != 0) > 1) return (double)(items / sms) * w + kTailUnitCost;
       return rounds * w;
     };
     auto cost2 = [&](int b) {  // pair tiles: half the B traffic per CTA, same MMA time per round as the 128 x b tile
@@ -944,6 +1010,20 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
   p.a_lbo = a_mn ? mn_lbo : 16u;  p.a_sbo = a_mn ? mn_sbo : 1024u;  p.a_kadv = a_mn ? mn_kadv : 32u;
   p.b_lbo = b_mn ? mn_lbo : 16u;  p.b_sbo = b_mn ? mn_sbo : 1024u;  p.b_kadv = b_mn ? mn_kadv : 32u;
 
+  // N-split units for the last partial round
+  p.tail_first = p.num_items; p.tail_split = 0;
+  if (cm == 0 && p.sk_chunks == 0) {
+    const int ts = tail_split_for(p.num_items, sms, bn, sk, mode, conv != nullptr && conv_side != 0);
+    if (ts > 1) {
+      const int rem = p.num_items % sms;
+      p.tail_first = p.num_items - rem;
+      p.tail_split = ts;
+      p.num_items = p.tail_first + rem * ts;
+    }
+  }
+  static const int env_prefetch = [] { const char* v = getenv("VLB_EPI_PREFETCH"); return v ? atoi(v) : 1; }();
+  p.epi_prefetch = env_prefetch;
+
   p.cv_side = 0;
   if (conv != nullptr && conv_side != 0) {
     VLB_REQUIRE((conv_side == 1 && mode == GEMM_NT) || (conv_side == 2 && mode == GEMM_TN), "gemm: implicit-conv operand / mode mismatch");
@@ -966,26 +1046,31 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
   else if (!b_mn) rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, 64, cm != 0 ? bn / 2 : bn);  // B [N, K]; cluster modes fetch it in halves
   else       rc = make_tmap_bf16_2d(&tb, B, K, N, ldb, 64, 64);       // B stored [K, N]
   if (rc != VLB_OK) return rc;
+  CUtensorMap tbt = tb;                                                 // 64-row box of a K-major B for the N-split units
+  if (p.tail_split > 1 && !b_mn) {
+    rc = make_tmap_bf16_2d(&tbt, B, N, K, ldb, 64, 64);
+    if (rc != VLB_OK) return rc;
+  }
 
   ProfScope prof(mode == GEMM_NT ? PROF_GEMM_NT : (mode == GEMM_NN ? PROF_GEMM_NN : PROF_GEMM_TN), 2.0 * M * N * K, stream);
 #define VLB_GEMM_DISPATCH(BN_, CG_)                                                                          \
   if (!a_mn && !b_mn) {                                                                                      \
-    if (epi_id == EPI_BIAS_BF16) return launch<BN_, false, false, EPI_BIAS_BF16, CG_>(ta, tb, p, stream);     \
-    if (epi_id == EPI_BIAS_RESID16_F32) return launch<BN_, false, false, EPI_BIAS_RESID16_F32, CG_>(ta, tb, p, stream); \
-    if (CG_ == 0 && epi_id == EPI_BIAS_DROP_RESID16_F32) return launch<BN_, false, false, EPI_BIAS_DROP_RESID16_F32, 0>(ta, tb, p, stream); \
-    if (epi_id == EPI_BIAS_GELU_AUX_BF16) return launch<BN_, false, false, EPI_BIAS_GELU_AUX_BF16, CG_>(ta, tb, p, stream); \
-    if (CG_ == 0 && epi_id == EPI_CONV_RELU_BF16) return launch<BN_, false, false, EPI_CONV_RELU_BF16, 0>(ta, tb, p, stream); \
-    if (CG_ == 0 && epi_id == EPI_CONV_RESID_RELU_BF16) return launch<BN_, false, false, EPI_CONV_RESID_RELU_BF16, 0>(ta, tb, p, stream); \
-    if (CG_ == 0 && epi_id == EPI_PLAIN_BF16) return launch<BN_, false, false, EPI_PLAIN_BF16, 0>(ta, tb, p, stream); \
-    return launch<BN_, false, false, EPI_GENERIC, CG_>(ta, tb, p, stream);                                    \
+    if (epi_id == EPI_BIAS_BF16) return launch<BN_, false, false, EPI_BIAS_BF16, CG_>(ta, tb, tbt, p, stream);     \
+    if (epi_id == EPI_BIAS_RESID16_F32) return launch<BN_, false, false, EPI_BIAS_RESID16_F32, CG_>(ta, tb, tbt, p, stream); \
+    if (CG_ == 0 && epi_id == EPI_BIAS_DROP_RESID16_F32) return launch<BN_, false, false, EPI_BIAS_DROP_RESID16_F32, 0>(ta, tb, tbt, p, stream); \
+    if (epi_id == EPI_BIAS_GELU_AUX_BF16) return launch<BN_, false, false, EPI_BIAS_GELU_AUX_BF16, CG_>(ta, tb, tbt, p, stream); \
+    if (CG_ == 0 && epi_id == EPI_CONV_RELU_BF16) return launch<BN_, false, false, EPI_CONV_RELU_BF16, 0>(ta, tb, tbt, p, stream); \
+    if (CG_ == 0 && epi_id == EPI_CONV_RESID_RELU_BF16) return launch<BN_, false, false, EPI_CONV_RESID_RELU_BF16, 0>(ta, tb, tbt, p, stream); \
+    if (CG_ == 0 && epi_id == EPI_PLAIN_BF16) return launch<BN_, false, false, EPI_PLAIN_BF16, 0>(ta, tb, tbt, p, stream); \
+    return launch<BN_, false, false, EPI_GENERIC, CG_>(ta, tb, tbt, p, stream);                                    \
   }                                                                                                          \
   if (!a_mn && b_mn) {                                                                                       \
-    if (epi_id == EPI_DGELU_BF16) return launch<BN_, false, true, EPI_DGELU_BF16, CG_>(ta, tb, p, stream);    \
-    if (epi_id == EPI_RESID16_BF16) return launch<BN_, false, true, EPI_RESID16_BF16, CG_>(ta, tb, p, stream); \
-    return launch<BN_, false, true, EPI_GENERIC, CG_>(ta, tb, p, stream);                                     \
+    if (epi_id == EPI_DGELU_BF16) return launch<BN_, false, true, EPI_DGELU_BF16, CG_>(ta, tb, tbt, p, stream);    \
+    if (epi_id == EPI_RESID16_BF16) return launch<BN_, false, true, EPI_RESID16_BF16, CG_>(ta, tb, tbt, p, stream); \
+    return launch<BN_, false, true, EPI_GENERIC, CG_>(ta, tb, tbt, p, stream);                                     \
   }                                                                                                          \
-  if (epi_id == EPI_ATOMIC_F32) return launch<BN_, true, true, EPI_ATOMIC_F32, CG_>(ta, tb, p, stream);       \
-  return launch<BN_, true, true, EPI_GENERIC, CG_>(ta, tb, p, stream);
+  if (epi_id == EPI_ATOMIC_F32) return launch<BN_, true, true, EPI_ATOMIC_F32, CG_>(ta, tb, tbt, p, stream);       \
+  return launch<BN_, true, true, EPI_GENERIC, CG_>(ta, tb, tbt, p, stream);
   const int epi_id = classify_epilogue(mode, epi_in);
   if (cm == 1) {
     if (bn == 256) { VLB_GEMM_DISPATCH(256, 1) }
@@ -1033,6 +1118,9 @@ int gemm_grouped_tn(int count, const GroupedProblem* probs, int K, int split_k, 
   VLB_REQUIRE(sk == 1 || accumulate, "gemm_grouped_tn: split-K needs accumulate");
   p.e = GemmEpilogue();
   p.e.out_kind = accumulate ? OUT_F32_ATOMIC : OUT_F32;
+  p.tail_first = 0; p.tail_split = 0; p.epi_prefetch = 0;
+  p.sk_full_items = 0; p.sk_chunks = 0; p.sk_kb_per_chunk = 0; p.sk_scratch = nullptr; p.sk_counters = nullptr; p.sk_debug = 0;
+  p.cv_side = 0;
   p.a_lbo = p.b_lbo = g_dbg_mn_lbo ? g_dbg_mn_lbo : 8192u;
   p.a_sbo = p.b_sbo = g_dbg_mn_sbo ? g_dbg_mn_sbo : 1024u;
   p.a_kadv = p.b_kadv = g_dbg_mn_kadv ? g_dbg_mn_kadv : 2048u;

@@ -40,17 +40,22 @@ struct MhsaParams {
   DropCfg drop;               // dropout on the probabilities (modeling.py:310); mask rows = (b, head, query), columns = keys
 };
 
-// keep-mask x 1/(1-p) applied to 32 consecutive probabilities (keys c0 .. c0+31, c0 % 4 == 0) of mask row `mrow`
-__device__ __forceinline__ void drop_row32(float (&x)[32], uint64_t mrow, int groups_per_row, int c0, int S, const DropCfg& d,
-                                           const DropState& st) {
+// keep flags (bit j = key c0 + j is kept) of 32 consecutive probabilities (c0 % 4 == 0) of mask row `mrow`.  The flags depend
+// only on (seed, step, site, position), so the kernels evaluate them BEFORE waiting for the TMA loads / score MMAs: the ten
+// Philox rounds per four keys overlap that latency instead of extending the softmax phase.
+__device__ __forceinline__ uint32_t keep_bits32(uint64_t mrow, int groups_per_row, int c0, int S, const DropCfg& d, const DropState& st) {
+  uint32_t bits = 0u;
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
     if (c0 + g * 4 < S) {   // groups past the sequence hold only masked-out keys (probability exactly 0)
-      float v[4] = {x[g * 4], x[g * 4 + 1], x[g * 4 + 2], x[g * 4 + 3]};
-      drop4(v, mrow * (uint64_t)groups_per_row + (uint64_t)((c0 >> 2) + g), d, st);
-      x[g * 4] = v[0]; x[g * 4 + 1] = v[1]; x[g * 4 + 2] = v[2]; x[g * 4 + 3] = v[3];
+      const Philox4 r = dropout_words(mrow * (uint64_t)groups_per_row + (uint64_t)((c0 >> 2) + g), st.seed, d.site, st.step);
+      bits |= (r.x >= d.thresh ? 1u : 0u) << (4 * g);
+      bits |= (r.y >= d.thresh ? 2u : 0u) << (4 * g);
+      bits |= (r.z >= d.thresh ? 4u : 0u) << (4 * g);
+      bits |= (r.w >= d.thresh ? 8u : 0u) << (4 * g);
     }
   }
+  return bits;
 }
 
 // Shared memory maps (bytes from the 1024-aligned dynamic shared memory base).  Regions are re-used once their first
@@ -161,6 +166,16 @@ mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     umma_commit(smem_u32(&bars[1]));
   }
 
+  // dropout keep flags of this thread's probability row (independent of the data: evaluated while the loads / MMAs fly)
+  uint32_t keep[NKEYS / 32];
+  const bool dropping = p.drop.thresh != 0u && q0 + t < p.S;
+  if (dropping) {
+    const DropState dstate = drop_state(p.drop);
+    const uint64_t mrow = ((uint64_t)b * p.heads + h) * (uint64_t)p.S + (uint64_t)(q0 + t);
+    const int mgroups = (p.S + 3) >> 2;
+#pragma unroll
+    for (int c = 0; c < NKEYS / 32; ++c) keep[c] = keep_bits32(mrow, mgroups, c * 32, p.S, p.drop, dstate);
+  }
   mbar_wait(smem_u32(&bars[1]), 0);
   tc_fence_after();
   const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
@@ -177,10 +192,7 @@ mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   // pass 2: p = exp(x - m), row sum, stage P (bf16) for the second product.  P overwrites the Q|K tiles (the S MMAs
   // that read them completed before bars[1] fired).
   float l = 0.0f;
-  const DropState dstate = drop_state(p.drop);
-  const uint64_t mrow = ((uint64_t)b * p.heads + h) * (uint64_t)p.S + (uint64_t)(q0 + t);
-  const int mgroups = (p.S + 3) >> 2;
-#pragma unroll 1
+#pragma unroll
   for (int c = 0; c < NKEYS / 32; ++c) {
     uint32_t v[32];
     float x[32];
@@ -192,7 +204,11 @@ mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       l += x[j];
     }
     // dropout acts on the normalised probabilities; the row sum (and the saved log-sum-exp) stay those of the full softmax
-    if (p.drop.thresh != 0u && q0 + t < p.S) drop_row32(x, mrow, mgroups, c * 32, p.S, p.drop, dstate);
+    if (dropping) {
+      const uint32_t kb = keep[c];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = ((kb >> j) & 1u) ? x[j] * p.drop.scale : 0.0f;
+    }
     store_tile_row32(smem, t, c * 32, x);  // P tile starts at offset 0 (aliases Q | K)
   }
   fence_proxy_async_smem();
@@ -366,13 +382,20 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) mhsa_bwd_kernel(const __grid_c
     lse = p.lse[((size_t)b * p.heads + h) * p.S + q0 + t];
   }
 
+  // dropout keep flags of this thread's 64 probabilities: evaluated before the wait, they overlap the loads / MMAs
+  uint32_t keepb[NK / 64];
+  const bool dropping = p.drop.thresh != 0u && valid;
+  if (dropping) {
+    const DropState dstate = drop_state(p.drop);
+    const uint64_t mrow = ((uint64_t)b * p.heads + h) * (uint64_t)p.S + (uint64_t)(q0 + t);
+    const int mgroups = (p.S + 3) >> 2;
+#pragma unroll
+    for (int cc = 0; cc < NK / 64; ++cc) keepb[cc] = keep_bits32(mrow, mgroups, k0 + (half * (NK / 64) + cc) * 32, p.S, p.drop, dstate);
+  }
   mbar_wait(smem_u32(&bars[1]), 0);
   tc_fence_after();
   const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-  const DropState dstate = drop_state(p.drop);
-  const uint64_t mrow = ((uint64_t)b * p.heads + h) * (uint64_t)p.S + (uint64_t)(q0 + t);
-  const int mgroups = (p.S + 3) >> 2;
-#pragma unroll 1
+#pragma unroll
   for (int cc = 0; cc < NK / 64; ++cc) {
     const int c = half * (NK / 64) + cc;  // this thread's 32-column chunks: [half*64, half*64 + 64)
     uint32_t vs[32], vd[32];
@@ -380,19 +403,17 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) mhsa_bwd_kernel(const __grid_c
     tmem_ld32(t_row + c * 32, vs);
     tmem_ld32(t_row + 128 + c * 32, vd);
     tmem_ld_wait();
-    if (p.drop.thresh != 0u && valid) {
+    if (dropping) {
       // ctx = (P o M / (1-p)) V:  dV = (P o M')^T dO ;  dP = (dO V^T) o M' ;  dS = P o (dP - D) with D = rowsum(dO o O)
-      float keep[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) keep[j] = 1.0f;
-      drop_row32(keep, mrow, mgroups, k0 + c * 32, p.S, p.drop, dstate);   // keep[j] = 0 or 1/(1-p)
+      const uint32_t kb = keepb[cc];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int col = k0 + c * 32 + j;
         const float mk = col < p.S ? (gmask ? __ldg(gmask + col) : 0.0f) : -INFINITY;
         const float pj = __expf(fmaf(__uint_as_float(vs[j]), p.scale, mk) - lse);
-        pr[j] = pj * keep[j];
-        ds[j] = pj * (__uint_as_float(vd[j]) * keep[j] - Dsum) * p.scale;
+        const float kj = ((kb >> j) & 1u) ? p.drop.scale : 0.0f;
+        pr[j] = pj * kj;
+        ds[j] = pj * (__uint_as_float(vd[j]) * kj - Dsum) * p.scale;
       }
     } else {
 #pragma unroll
