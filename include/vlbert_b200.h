@@ -64,6 +64,11 @@ typedef struct VlbDropout {
   float p;             /* drop probability, 0 <= p < 1 */
   uint32_t site;       /* call-site id (counter word 2) */
   const uint64_t* rng; /* device: {seed, step} */
+  /* Optional (REQUIRED by the attention, GEMM-epilogue and LayerNorm-backward `out_drop` consumers): the keep flags of this
+   * site as a device bit array written by vlb_dropout_bits from the same (p, site, rng): bit (c % 32) of word
+   * r * ceil(cols / 32) + c / 32 = element (r, c) is kept.  Same mask as the inline evaluation; generated once, read by the
+   * forward and the backward kernels (ten Philox rounds per four elements made the attention kernels instruction-bound). */
+  const uint32_t* keep_bits;
 } VlbDropout;
 
 /* ---- GEMM (tcgen05) --------------------------------------------------------------------------
@@ -98,6 +103,14 @@ typedef struct VlbGroupedProblem {
   const void* B; int ldb;
   float* out; int ldo;
 } VlbGroupedProblem;
+/* "dense + dropout + residual" of BertSelfOutput / BertOutput (modeling.py:329-333, :374-378) with the residual stream in fp32:
+ *   out f32 [M,N] = dropout(A[M,K] W[N,K]^T + bias) + R,   R = resid->x_f32 (mean == NULL) or LayerNorm(resid->x_f32) recomputed
+ * from its row statistics (see VlbResidual below).  drop may be NULL; otherwise drop->keep_bits is required. */
+struct VlbResidual;
+int vlb_gemm_bias_residual_f32(int M, int N, int K, const void* A, int lda, const void* W, int ldw, float* out, int ldo,
+                               const float* bias, const struct VlbResidual* resid, const VlbDropout* drop, int force_bn,
+                               void* stream);
+
 int vlb_gemm_grouped_tn(int count, const VlbGroupedProblem* problems, int K, int split_k, int accumulate, int bn,
                         void* stream);
 
@@ -312,6 +325,10 @@ int vlb_dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t seed, uint32_t 
  * probabilities (cols = S keys) are padded to a multiple of four so that a row never shares a Philox call. */
 int vlb_dropout_mask_2d(uint8_t* keep, int64_t rows, int cols, float p, uint64_t seed, uint32_t site, uint32_t step,
                         void* stream);
+/* The same flags as a bit array for VlbDropout.keep_bits: bits uint32 [rows, ceil(cols / 32)], (seed, step) read from
+ * drop->rng on the device.  vlb_dropout_bits_words(rows, cols) = number of uint32 words. */
+int64_t vlb_dropout_bits_words(int64_t rows, int cols);
+int vlb_dropout_bits(uint32_t* bits, int64_t rows, int cols, const VlbDropout* drop, void* stream);
 /* y[r, c] = x[r, c] * keep(r, col_offset + c) / (1-p) for a [rows, cols] window (leading dimensions ldx / ldy, elements) of a tensor
  * whose mask is indexed over [rows, total_cols]; (seed, step) are read from drop->rng on the device.  cols, col_offset and
  * total_cols must be multiples of 4.  Stand-alone form of what the fused sites do (used for the gradient wrt the region
@@ -355,7 +372,25 @@ typedef struct VlbLayerActs { /* saved activations of one layer, caller-allocate
   float* ln2_rstd;
   void* y;         /* bf16 [M, H]  layer output */
   float* y_f32;    /* optional f32 copy of the layer output (NULL to skip) */
+  /* dropout keep flags of the layer's three sites (VlbDropout.keep_bits layout), WRITTEN by the forward and read by the
+   * backward; required where the corresponding probability is > 0, else NULL: */
+  uint32_t* keep_attn;      /* [B*heads*S, ceil(S/32)] words */
+  uint32_t* keep_self_out;  /* [M, ceil(H/32)] */
+  uint32_t* keep_out;       /* [M, ceil(H/32)] */
 } VlbLayerActs;
+
+/* fp32 residual stream: the layer input x (bf16, the GEMM operand) described a second time for the residual add.
+ * mean == NULL: x_f32 is x itself in fp32 [M, H] (the embedding output).  Otherwise x is the output of a LayerNorm that is
+ * not stored in fp32: x_f32 is that LayerNorm's fp32 INPUT [M, H], mean / rstd [M] its row statistics and gamma / beta [H]
+ * its parameters (for layer l > 0: acts(l-1).y0, ln2_mean, ln2_rstd, weights(l-1).ln2_g, ln2_b) -- the epilogue recomputes
+ * the fp32 LayerNorm output instead of reading a stored copy. */
+typedef struct VlbResidual {
+  const float* x_f32;
+  const float* mean;
+  const float* rstd;
+  const float* gamma;
+  const float* beta;
+} VlbResidual;
 
 typedef struct VlbLayerGrads { /* f32, ACCUMULATED (+=); caller zero-fills or passes existing .grad */
   float* dw_qkv; float* db_qkv; float* dw_o; float* db_o; float* dln1_g; float* dln1_b;
@@ -371,14 +406,17 @@ typedef struct VlbLayerDropout {
   const uint64_t* rng;                           /* device: {seed, step} */
 } VlbLayerDropout;
 
-int vlb_bert_layer_forward(const VlbLayerWeights* w, const void* x_bf16, const float* add_mask,
+/* x_resid: NULL = the residual add uses x_bf16 (all-bf16 residual stream); else the fp32 residual stream (see VlbResidual). */
+int vlb_bert_layer_forward(const VlbLayerWeights* w, const void* x_bf16, const VlbResidual* x_resid, const float* add_mask,
                            const VlbLayerActs* acts, int B, int S, int H, int heads, int I, float eps,
                            const VlbLayerDropout* drop, void* stream);
 /* bytes of scratch vlb_bert_layer_backward needs */
 int64_t vlb_bert_layer_backward_workspace(int M, int H, int I);
-/* dy = dy_bf16 (+ dy_f32), either may be NULL; dx_bf16 [M, H] receives the gradient wrt x. */
+/* dy = dy_bf16 (+ dy_f32), either may be NULL.  dx_f32 == NULL: dx_bf16 [M, H] receives the whole gradient wrt x.
+ * dx_f32 != NULL (fp32 residual stream): the gradient wrt x is dx_bf16 (the GEMM part) + dx_f32 (the residual part, fp32
+ * [M, H]); hand both to the layer below as its dy_bf16 / dy_f32. */
 int vlb_bert_layer_backward(const VlbLayerWeights* w, const VlbLayerActs* acts, const void* x_bf16,
-                            const float* add_mask, const void* dy_bf16, const float* dy_f32, void* dx_bf16,
+                            const float* add_mask, const void* dy_bf16, const float* dy_f32, void* dx_bf16, float* dx_f32,
                             const VlbLayerGrads* grads, void* workspace, int64_t workspace_bytes, int B, int S,
                             int H, int heads, int I, const VlbLayerDropout* drop, void* stream);
 

@@ -119,7 +119,8 @@ class _EmbeddingShim(object):
         e = torch.where((pidx.kind == 1).unsqueeze(-1), obj_vl[bidx, pidx.src.clamp(max=obj_vl.shape[1] - 1)], e)
         e = torch.where((pidx.kind == 2).unsqueeze(-1), end[0].expand(B, S, H), e)
         e = e + pos[pidx.pos_id] + typ[pidx.type_id]
-        return vo.layer_norm_tf(e, ln_w, ln_b, eps)
+        out = vo.layer_norm_tf(e, ln_w, ln_b, eps)
+        return out, out          # (bf16 GEMM operand, fp32 residual operand): one and the same tensor in the fp32 stand-in
 
 
 _PER_LAYER = ("attention.self.query.weight", "attention.self.query.bias", "attention.self.key.weight", "attention.self.key.bias",
@@ -130,7 +131,7 @@ _PER_LAYER = ("attention.self.query.weight", "attention.self.query.bias", "atten
 
 class _EncoderShim(object):
     @staticmethod
-    def apply(emb, add_mask, meta, *params):
+    def apply(emb, emb32, add_mask, meta, *params):
         assert len(params) == 16 * meta.L
         outs, h = [], emb
         am = add_mask.view(add_mask.shape[0], 1, 1, add_mask.shape[1])

@@ -56,6 +56,20 @@ def _worker(rank, world, port, ret):
         w2 = w.detach().clone().requires_grad_(True)
         (x @ w2).pow(2).mean().backward()
         ok = ok and torch.allclose(g, w2.grad, atol=1e-6)
+        # bf16 wire format with the depth-2 pipeline (the NCCL default): five buffers launched back to back, each result is
+        # cast back over the fp32 gradients two launches later / at drain; values chosen exactly representable in bf16
+        red16 = vlbert_b200.ddp.LayerGradReducer(wire_dtype=torch.bfloat16, pipeline_depth=2)
+        bufs = [torch.full((4096,), float(rank + 1) * (l + 1)) for l in range(5)]
+        for l in range(5):
+            red16.launch(bufs[l])
+            assert len(red16.pending) <= 2
+        red16.drain()
+        ok = ok and all(torch.allclose(bufs[l], torch.full((4096,), mean * (l + 1))) for l in range(5))
+        ok = ok and len(red16._staging) == 5 and all(b.dtype == torch.bfloat16 for b in red16._staging.values())
+        bufs[0].fill_(float(rank + 1))
+        red16.launch(bufs[0])           # same buffer again: the staging buffer is re-used (static addresses under CUDA graphs)
+        red16.drain()
+        ok = ok and len(red16._staging) == 5 and torch.allclose(bufs[0], torch.full((4096,), mean))
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

@@ -93,7 +93,11 @@ def _check(cfg, B, T, R, seed):
               e_ours["layer%02d" % (cfg.num_hidden_layers - 1)], e_cmp["layer%02d" % (cfg.num_hidden_layers - 1)],
               sorted(r[2] for r in grads)[len(grads) // 2], sorted(r[3] for r in grads)[len(grads) // 2],
               max(r[2] for r in grads), max(r[3] for r in grads), rows[0][0], rows[0][1]))
-    bad = [(k, "%.3e" % a, "%.3e" % b, "%.2f" % r) for r, k, a, b in rows if a > C_RATIO * b + 1e-7]
+    # attention.self.key.bias: the exact gradient is 0 (softmax shift invariance), so both sides measure pure rounding noise
+    # of a 6000-row column sum against the sibling query.bias scale; it is bounded absolutely (1e-2 of that scale) instead of
+    # by the ratio of two noise terms
+    bad = [(k, "%.3e" % a, "%.3e" % b, "%.2f" % r) for r, k, a, b in rows
+           if (a > 1e-2 if k.endswith("attention.self.key.bias") else a > C_RATIO * b + 1e-7)]
     assert not bad, bad
 
 

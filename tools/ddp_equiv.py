@@ -12,7 +12,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-cfg = vlbert_b200.default_config(num_hidden_layers=2)
+cfg = vlbert_b200.default_config(num_hidden_layers=2, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)  # (masks depend on the batch shape: compare without)
 torch.manual_seed(0)
 model = vlbert_b200.VisualLinguisticBert(cfg).to(dev)
 per = 4
@@ -39,7 +39,14 @@ for k in g_full:
     a, b = g_ddp[k].double(), g_full[k].double()
     if b.norm() > 0 and not k.endswith("key.bias"):
         worst = max(worst, ((a - b).norm() / b.norm()).item())
+wire = os.environ.get("VLB_DDP_WIRE", "bf16")
 if rank == 0:
-    print("ddp gradient equivalence (world %d): worst rel-L2 %.3e" % (world, worst))
-    assert worst < 5e-3, worst  # bf16 rounding differs between per-shard and full-batch wgrad accumulation order only
+    print("ddp gradient equivalence (world %d, wire %s): worst rel-L2 %.3e" % (world, wire, worst))
+    # fp32 wire: only the bf16 rounding of per-shard vs full-batch wgrad accumulation differs; bf16 wire adds one rounding
+    # of every gradient element (2^-9 relative, 1.1e-3 RMS) before the sum
+    assert worst < (5e-3 if wire == "fp32" else 8e-3), worst
+torch.cuda.synchronize()
+dist.barrier()
 dist.destroy_process_group()
+if rank == 0:
+    print("teardown ok")

@@ -36,7 +36,7 @@ def main():
         return (torch.randn(*shape, device=dev, generator=g) * scale).to(dtype)
 
     rng = torch.tensor([1234, 1], dtype=torch.int64, device=dev)
-    drop = VF.DropSite(a.drop, 2, rng) if a.drop > 0 else None
+    drop = VF.DropSite(a.drop, 2, rng).with_bits(M, H) if a.drop > 0 else None
     sets = []
     for _ in range(a.sets):
         s = dict(x=rnd(M, H), wqkv=rnd(3 * H, H, scale=0.03), bqkv=rnd(3 * H, dtype=f32), qkv=torch.empty(M, 3 * H, device=dev, dtype=bf),
@@ -46,7 +46,8 @@ def main():
                  y0=torch.empty(M, H, device=dev, dtype=f32), dy0=rnd(M, H), dz=torch.empty(M, I, device=dev, dtype=bf),
                  db1=torch.zeros(I, device=dev), dh=torch.empty(M, H, device=dev, dtype=bf), da=rnd(M, H),
                  dctx=torch.empty(M, H, device=dev, dtype=bf), dqkv=rnd(M, 3 * H), dx=torch.empty(M, H, device=dev, dtype=bf),
-                 gp=rnd(M, I))
+                 gp=rnd(M, I), r32=rnd(M, H, dtype=f32), mean=rnd(M, dtype=f32, scale=0.1), rstd=rnd(M, dtype=f32).abs() + 0.5,
+                 gam=rnd(H, dtype=f32), bet=rnd(H, dtype=f32))
         sets.append(s)
     lib = vlbert_b200._lib.lib()
 
@@ -55,34 +56,45 @@ def main():
 
     launches = [
         ("fwd qkv     NT N=3H K=H  bias->bf16", 2.0 * M * 3 * H * H, lambda s: VF.gemm(0, s["x"], s["wqkv"], s["qkv"], bias=s["bqkv"])),
-        ("fwd attnout NT N=H  K=H  bias+drop+resid->f32", 2.0 * M * H * H, lambda s: VF.gemm(0, s["ctx"], s["wo"], s["a32"], bias=s["bo"], resid=s["x"], drop=drop)),
+        ("fwd attnout NT N=H  K=H  bias+drop+LN-resid(f32)->f32", 2.0 * M * H * H,
+         lambda s: VF.gemm_bias_residual_f32(s["ctx"], s["wo"], s["bo"], s["r32"], ln=(s["mean"], s["rstd"], s["gam"], s["bet"]), drop=drop)),
         ("fwd ffn-up  NT N=I  K=H  bias+gelu+aux", 2.0 * M * I * H, lambda s: VF.gemm(0, s["h"], s["w1"], s["u"], bias=s["b1"], act=1, aux=s["z"])),
-        ("fwd ffn-dn  NT N=H  K=I  bias+drop+resid->f32", 2.0 * M * H * I, lambda s: VF.gemm(0, s["u"], s["w2"], s["y0"], bias=s["b2"], resid=s["h"], drop=drop)),
+        ("fwd ffn-dn  NT N=H  K=I  bias+drop+LN-resid(f32)->f32", 2.0 * M * H * I,
+         lambda s: VF.gemm_bias_residual_f32(s["u"], s["w2"], s["b2"], s["r32"], ln=(s["mean"], s["rstd"], s["gam"], s["bet"]), drop=drop)),
         ("bwd dz      NN N=I  K=H  x gelu'", 2.0 * M * I * H, colsum_gemm),
-        ("bwd dh      NN N=H  K=I  +resid->bf16", 2.0 * M * H * I, lambda s: VF.gemm(1, s["dz"], s["w1"], s["dh"], resid=s["dy0"])),
+        ("bwd dh      NN N=H  K=I  plain->bf16", 2.0 * M * H * I, lambda s: VF.gemm(1, s["dz"], s["w1"], s["dh"])),
         ("bwd dctx    NN N=H  K=H  plain", 2.0 * M * H * H, lambda s: VF.gemm(1, s["da"], s["wo"], s["dctx"])),
-        ("bwd dx      NN N=H  K=3H +resid->bf16", 2.0 * M * H * 3 * H, lambda s: VF.gemm(1, s["dqkv"], s["wqkv"], s["dx"], resid=s["da"])),
+        ("bwd dx      NN N=H  K=3H plain->bf16", 2.0 * M * H * 3 * H, lambda s: VF.gemm(1, s["dqkv"], s["wqkv"], s["dx"])),
     ]
     res = {"config": a.config, "M": M, "H": H, "I": I, "env": {k: v for k, v in os.environ.items() if k.startswith("VLB_")}, "gemms": {}}
     tot_us, tot_fl = 0.0, 0.0
+    side = torch.cuda.Stream()
     for name, flops, fn in launches:
-        for s in sets:
-            fn(s)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for r in range(a.reps):
-            fn(sets[r % a.sets])
-        e1.record()
-        torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) * 1e3 / a.reps
+        # `reps` launches captured in one CUDA graph (no host launch gaps: what the step graph sees), replayed 3 times
+        with torch.cuda.stream(side):
+            for s in sets:
+                fn(s)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                for r in range(a.reps):
+                    fn(sets[r % a.sets])
+            graph.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(side)
+            for _ in range(3):
+                graph.replay()
+            e1.record(side)
+            torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / (3 * a.reps)
         res["gemms"][name] = {"us": round(us, 2), "tflops": round(flops / us / 1e6, 1)}
         tot_us += us
         tot_fl += flops
         print("%-50s %8.2f us  %7.1f TFLOP/s" % (name, us, flops / us / 1e6))
     res["sum_us"] = round(tot_us, 2)
     res["tflops"] = round(tot_fl / tot_us / 1e6, 1)
-    print("sum %.1f us  %.1f TFLOP/s  (back-to-back launches of one kind; includes the launch gaps)" % (tot_us, tot_fl / tot_us / 1e6))
+    print("sum %.1f us  %.1f TFLOP/s  (graph-replayed back-to-back launches of one kind)" % (tot_us, tot_fl / tot_us / 1e6))
     print(json.dumps(res))
 
 

@@ -78,9 +78,12 @@ def _declare(lib):
     decl("vlb_nhwc_bf16_to_nchw_f32", [P, P, I, I, I, I, P])
     decl("vlb_roi_align_nhwc_forward", [P, P, P, I, I, I, I, I, I, F, I, P])
     decl("vlb_roi_align_nhwc_backward", [P, P, P, I, I, I, I, I, I, I, F, I, P])
-    decl("vlb_bert_layer_forward", [P, P, P, P, I, I, I, I, I, F, P, P])
+    decl("vlb_bert_layer_forward", [P, P, P, P, P, I, I, I, I, I, F, P, P])
     decl("vlb_bert_layer_backward_workspace", [I, I, I], L)
-    decl("vlb_bert_layer_backward", [P, P, P, P, P, P, P, P, P, L, I, I, I, I, I, P, P])
+    decl("vlb_bert_layer_backward", [P, P, P, P, P, P, P, P, P, P, L, I, I, I, I, I, P, P])
+    decl("vlb_gemm_bias_residual_f32", [I, I, I, P, I, P, I, P, I, P, P, P, I, P])
+    decl("vlb_dropout_bits_words", [L, I], L)
+    decl("vlb_dropout_bits", [P, L, I, P, P])
     # dropout-aware forms (ABI version 2): trailing VlbDropout* before the stream
     decl("vlb_gemm_bf16_dropout", [c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p,
                                    c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_float, c_int, c_int, P, P])
@@ -102,7 +105,7 @@ class LayerWeights(ctypes.Structure):
 class LayerActs(ctypes.Structure):
     """VlbLayerActs"""
     _fields_ = [(n, c_void_p) for n in ("qkv", "ctx", "lse", "a", "ln1_mean", "ln1_rstd", "h", "z", "u", "y0", "ln2_mean",
-                                        "ln2_rstd", "y", "y_f32")]
+                                        "ln2_rstd", "y", "y_f32", "keep_attn", "keep_self_out", "keep_out")]
 
 
 class LayerGrads(ctypes.Structure):
@@ -113,7 +116,12 @@ class LayerGrads(ctypes.Structure):
 
 class Dropout(ctypes.Structure):
     """VlbDropout"""
-    _fields_ = [("p", c_float), ("site", c_uint32), ("rng", c_void_p)]
+    _fields_ = [("p", c_float), ("site", c_uint32), ("rng", c_void_p), ("keep_bits", c_void_p)]
+
+
+class Residual(ctypes.Structure):
+    """VlbResidual"""
+    _fields_ = [(n, c_void_p) for n in ("x_f32", "mean", "rstd", "gamma", "beta")]
 
 
 class LayerDropout(ctypes.Structure):

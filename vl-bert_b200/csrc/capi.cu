@@ -76,11 +76,11 @@ bool pdl_enabled() {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 void gemm_debug_override(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t mn_kadv);
-int bert_layer_forward(const VlbLayerWeights& w, const void* x, const float* add_mask, const VlbLayerActs& a, int B, int S, int H,
-                       int heads, int I, float eps, const VlbLayerDropout* drop, cudaStream_t st);
+int bert_layer_forward(const VlbLayerWeights& w, const void* x, const VlbResidual* x_resid, const float* add_mask, const VlbLayerActs& a,
+                       int B, int S, int H, int heads, int I, float eps, const VlbLayerDropout* drop, cudaStream_t st);
 int64_t bert_layer_backward_workspace(int M, int H, int I);
 int bert_layer_backward(const VlbLayerWeights& w, const VlbLayerActs& a, const void* x, const float* add_mask, const void* dy16,
-                        const float* dy32, void* dx, const VlbLayerGrads& g, void* workspace, int64_t ws_bytes, int B, int S,
+                        const float* dy32, void* dx, float* dx_f32, const VlbLayerGrads& g, void* workspace, int64_t ws_bytes, int B, int S,
                         int H, int heads, int I, const VlbLayerDropout* drop, cudaStream_t st);
 
 }  // namespace vlb
@@ -119,6 +119,19 @@ int vlb_gemm_bf16_dropout(int mode, int M, int N, int K, const void* A, int lda,
   e.act = act; e.aux = aux; e.ld_aux = ld_aux; e.alpha = alpha;
   e.drop = make_drop(drop);
   int rc = gemm_bf16(mode, M, N, K, A, lda, B, ldb, e, split_k, force_bn, static_cast<cudaStream_t>(stream));
+  if (rc == VLB_OK) count_launch(1);
+  return rc;
+}
+
+int vlb_gemm_bias_residual_f32(int M, int N, int K, const void* A, int lda, const void* W, int ldw, float* out, int ldo, const float* bias,
+                               const VlbResidual* resid, const VlbDropout* drop, int force_bn, void* stream) {
+  if (!resid || !resid->x_f32 || !drop_valid(drop)) { set_last_error("vlb_gemm_bias_residual_f32: bad residual / dropout arguments"); return VLB_ERR_INVALID; }
+  GemmEpilogue e;
+  e.out = out; e.ldo = ldo; e.out_kind = OUT_F32; e.bias = bias;
+  e.resid = resid->x_f32; e.ldr = N; e.resid_kind = RESID_LN_F32;
+  e.ln_mean = resid->mean; e.ln_rstd = resid->rstd; e.ln_gamma = resid->gamma; e.ln_beta = resid->beta;
+  e.drop = make_drop(drop);
+  int rc = gemm_bf16(GEMM_NT, M, N, K, A, lda, W, ldw, e, 1, force_bn, static_cast<cudaStream_t>(stream));
   if (rc == VLB_OK) count_launch(1);
   return rc;
 }
@@ -283,6 +296,10 @@ int vlb_dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t seed, uint32_t 
 int vlb_dropout_mask_2d(uint8_t* keep, int64_t rows, int cols, float p, uint64_t seed, uint32_t site, uint32_t step, void* stream) {
   COUNTED(1, dropout_mask_2d(keep, rows, cols, p, seed, site, step, ST));
 }
+int64_t vlb_dropout_bits_words(int64_t rows, int cols) { return dropout_bits_words(rows, cols); }
+int vlb_dropout_bits(uint32_t* bits, int64_t rows, int cols, const VlbDropout* drop, void* stream) {
+  COUNTED(1, dropout_bits(bits, rows, cols, drop, ST));
+}
 int vlb_dropout_2d(const void* x, int ldx, void* y, int ldy, int64_t rows, int cols, int col_offset, int total_cols, int is_bf16,
                    const VlbDropout* drop, void* stream) {
   COUNTED(1, dropout_2d(x, ldx, y, ldy, rows, cols, col_offset, total_cols, is_bf16, drop, ST));
@@ -346,21 +363,22 @@ int vlb_roi_align_nhwc_backward(const void* grad_out, const float* rois, float* 
                                 int pw, float spatial_scale, int sampling_ratio, void* stream) {
   COUNTED(1, roi_align_nhwc_backward(grad_out, rois, grad_feat, K, N, C, H, W, ph, pw, spatial_scale, sampling_ratio, ST));
 }
-int vlb_bert_layer_forward(const VlbLayerWeights* w, const void* x_bf16, const float* add_mask, const VlbLayerActs* acts, int B,
-                           int S, int H, int heads, int I, float eps, const VlbLayerDropout* drop, void* stream) {
+int vlb_bert_layer_forward(const VlbLayerWeights* w, const void* x_bf16, const VlbResidual* x_resid, const float* add_mask,
+                           const VlbLayerActs* acts, int B, int S, int H, int heads, int I, float eps, const VlbLayerDropout* drop,
+                           void* stream) {
   if (!w || !acts || !x_bf16) { set_last_error("vlb_bert_layer_forward: null pointer"); return VLB_ERR_INVALID; }
-  return bert_layer_forward(*w, x_bf16, add_mask, *acts, B, S, H, heads, I, eps, drop, ST);
+  return bert_layer_forward(*w, x_bf16, x_resid, add_mask, *acts, B, S, H, heads, I, eps, drop, ST);
 }
 int64_t vlb_bert_layer_backward_workspace(int M, int H, int I) { return bert_layer_backward_workspace(M, H, I); }
 int vlb_bert_layer_backward(const VlbLayerWeights* w, const VlbLayerActs* acts, const void* x_bf16, const float* add_mask,
-                            const void* dy_bf16, const float* dy_f32, void* dx_bf16, const VlbLayerGrads* grads, void* workspace,
+                            const void* dy_bf16, const float* dy_f32, void* dx_bf16, float* dx_f32, const VlbLayerGrads* grads, void* workspace,
                             int64_t workspace_bytes, int B, int S, int H, int heads, int I, const VlbLayerDropout* drop,
                             void* stream) {
   if (!w || !acts || !x_bf16 || !grads || !workspace || !dx_bf16 || (!dy_bf16 && !dy_f32)) {
     set_last_error("vlb_bert_layer_backward: null pointer");
     return VLB_ERR_INVALID;
   }
-  return bert_layer_backward(*w, *acts, x_bf16, add_mask, dy_bf16, dy_f32, dx_bf16, *grads, workspace, workspace_bytes, B, S, H,
+  return bert_layer_backward(*w, *acts, x_bf16, add_mask, dy_bf16, dy_f32, dx_bf16, dx_f32, *grads, workspace, workspace_bytes, B, S, H,
                              heads, I, drop, ST);
 }
 

@@ -24,13 +24,17 @@ constexpr int STAGE_F32_PER_WARP = 32 * 32;        // 4 KB transposition buffer 
 
 // Compile-time epilogue variants for the hot launches of the encoder layer (0 = generic, flags read at run time).
 enum : int { EPI_GENERIC = 0, EPI_BIAS_BF16, EPI_BIAS_RESID16_F32, EPI_BIAS_GELU_AUX_BF16, EPI_DGELU_BF16, EPI_RESID16_BF16,
-             EPI_ATOMIC_F32, EPI_CONV_RELU_BF16, EPI_CONV_RESID_RELU_BF16, EPI_PLAIN_BF16, EPI_BIAS_DROP_RESID16_F32, EPI_NUM };
+             EPI_ATOMIC_F32, EPI_CONV_RELU_BF16, EPI_CONV_RESID_RELU_BF16, EPI_PLAIN_BF16, EPI_BIAS_DROP_RESID16_F32, EPI_BIAS_RESIDLN_F32,
+             EPI_BIAS_DROP_RESIDLN_F32, EPI_NUM };
 struct EpiTraitsBase { static constexpr bool kStatic = true; static constexpr bool bias = false, cscale = false, drop = false; static constexpr int act = ACT_NONE, resid = RESID_NONE, out = OUT_BF16; };
 template <int EPI> struct EpiTraits : EpiTraitsBase { static constexpr bool kStatic = false; };
 template <> struct EpiTraits<EPI_BIAS_BF16>          : EpiTraitsBase { static constexpr bool bias = true; };
 template <> struct EpiTraits<EPI_BIAS_RESID16_F32>   : EpiTraitsBase { static constexpr bool bias = true; static constexpr int resid = RESID_BF16, out = OUT_F32; };
 // dense + bias -> dropout -> + residual (BertSelfOutput / BertOutput in training mode, modeling.py:330-333,375-378)
 template <> struct EpiTraits<EPI_BIAS_DROP_RESID16_F32> : EpiTraitsBase { static constexpr bool bias = true, drop = true; static constexpr int resid = RESID_BF16, out = OUT_F32; };
+// the same with the residual stream in fp32 (LayerNorm output recomputed from its stored input, or a plain fp32 tensor)
+template <> struct EpiTraits<EPI_BIAS_RESIDLN_F32> : EpiTraitsBase { static constexpr bool bias = true; static constexpr int resid = RESID_LN_F32, out = OUT_F32; };
+template <> struct EpiTraits<EPI_BIAS_DROP_RESIDLN_F32> : EpiTraitsBase { static constexpr bool bias = true, drop = true; static constexpr int resid = RESID_LN_F32, out = OUT_F32; };
 template <> struct EpiTraits<EPI_BIAS_GELU_AUX_BF16> : EpiTraitsBase { static constexpr bool bias = true; static constexpr int act = ACT_GELU; };
 template <> struct EpiTraits<EPI_DGELU_BF16>         : EpiTraitsBase { static constexpr int act = ACT_DGELU_MUL; };
 template <> struct EpiTraits<EPI_RESID16_BF16>       : EpiTraitsBase { static constexpr int resid = RESID_BF16; };
@@ -219,12 +223,23 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
       in16[i] = (row < M && col_ok) ? __ldg(reinterpret_cast<const uint2*>(src + (size_t)row * ld + col)) : make_uint2(0u, 0u);
     }
   }
-  if (resid_kind == RESID_F32) {
+  float ln_mu[8], ln_rs[8];
+  float4 ln_g4 = make_float4(1.f, 1.f, 1.f, 1.f), ln_b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool ln_resid = resid_kind == RESID_LN_F32 && e.ln_mean != nullptr;
+  if (resid_kind == RESID_F32 || resid_kind == RESID_LN_F32) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int row = row_base + i * 4 + r0;
       in32[i] = (row < M && col_ok) ? __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.resid) + (size_t)row * e.ldr + col))
                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ln_resid) {
+        ln_mu[i] = row < M ? __ldg(e.ln_mean + row) : 0.0f;
+        ln_rs[i] = row < M ? __ldg(e.ln_rstd + row) : 0.0f;
+      }
+    }
+    if (ln_resid && col_ok) {
+      ln_g4 = __ldg(reinterpret_cast<const float4*>(e.ln_gamma + col));
+      ln_b4 = __ldg(reinterpret_cast<const float4*>(e.ln_beta + col));
     }
   }
   // ---- phase 1: transpose the accumulator chunk through shared memory ----
@@ -281,11 +296,20 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
 #pragma unroll
         for (int j = 0; j < 4; ++j) x[j] = (act == ACT_DGELU_MUL) ? x[j] * zz[j] : (zz[j] > 0.0f ? x[j] : 0.0f);
       }
-      if (has_drop) drop4(x, ((uint64_t)row * (uint64_t)N + (uint64_t)col) >> 2, e.drop, dstate);   // N % 8 == 0: one Philox group per lane
+      if (has_drop) drop4_bits(x, keep4_bits(e.drop.bits, (size_t)row, (N + 31) >> 5, col), e.drop.scale);
       if (resid_kind == RESID_BF16) {
         x[0] += bf16lo(in16[i].x); x[1] += bf16hi(in16[i].x); x[2] += bf16lo(in16[i].y); x[3] += bf16hi(in16[i].y);
       } else if (resid_kind == RESID_F32) {
         x[0] += in32[i].x; x[1] += in32[i].y; x[2] += in32[i].z; x[3] += in32[i].w;
+      } else if (resid_kind == RESID_LN_F32) {
+        if (ln_resid) {   // residual = LayerNorm(resid row) in fp32, same formula as layernorm_fwd_kernel
+          x[0] += fmaf(ln_g4.x, (in32[i].x - ln_mu[i]) * ln_rs[i], ln_b4.x);
+          x[1] += fmaf(ln_g4.y, (in32[i].y - ln_mu[i]) * ln_rs[i], ln_b4.y);
+          x[2] += fmaf(ln_g4.z, (in32[i].z - ln_mu[i]) * ln_rs[i], ln_b4.z);
+          x[3] += fmaf(ln_g4.w, (in32[i].w - ln_mu[i]) * ln_rs[i], ln_b4.w);
+        } else {
+          x[0] += in32[i].x; x[1] += in32[i].y; x[2] += in32[i].z; x[3] += in32[i].w;
+        }
       }
       if (act == ACT_RELU_POST) {
 #pragma unroll
@@ -550,7 +574,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
         const bool aux_in = (act == ACT_DGELU_MUL || act == ACT_DRELU_MUL);
         if (aux_in || rk != RESID_NONE) {
           const char* src = reinterpret_cast<const char*>(aux_in ? eg.aux : eg.resid);
-          const int esz = (!aux_in && rk == RESID_F32) ? 4 : 2;
+          const int esz = (!aux_in && (rk == RESID_F32 || rk == RESID_LN_F32)) ? 4 : 2;
           const size_t ld_bytes = (size_t)(aux_in ? eg.ld_aux : eg.ldr) * esz;
           const int row0 = (m_blk * (CL ? 2 : 1) + (int)rank) * BM;
           const int width = min(ic.bn, Ng - ic.n0) * esz;           // bytes per row of this unit
@@ -741,11 +765,15 @@ int classify_epilogue(int mode, const GemmEpilogue& e) {
   }
   if (e.colscale != nullptr) return EPI_GENERIC;  // other per-column-scale combinations: generic epilogue
   if (e.drop.thresh != 0u) {
-    if (mode == GEMM_NT && bias && e.act == ACT_NONE && e.resid_kind == RESID_BF16 && e.out_kind == OUT_F32 && e.colsum == nullptr &&
-        e.alpha == 1.0f)
-      return EPI_BIAS_DROP_RESID16_F32;
+    if (mode == GEMM_NT && bias && e.act == ACT_NONE && e.out_kind == OUT_F32 && e.colsum == nullptr && e.alpha == 1.0f) {
+      if (e.resid_kind == RESID_BF16) return EPI_BIAS_DROP_RESID16_F32;
+      if (e.resid_kind == RESID_LN_F32) return EPI_BIAS_DROP_RESIDLN_F32;
+    }
     return EPI_GENERIC;
   }
+  if (mode == GEMM_NT && bias && e.act == ACT_NONE && e.resid_kind == RESID_LN_F32 && e.out_kind == OUT_F32 && e.colsum == nullptr &&
+      e.alpha == 1.0f && e.aux == nullptr)
+    return EPI_BIAS_RESIDLN_F32;
   if (mode == GEMM_NT) {
     if (bias && e.act == ACT_NONE && e.resid_kind == RESID_NONE && e.out_kind == OUT_BF16) return EPI_BIAS_BF16;
     if (bias && e.act == ACT_NONE && e.resid_kind == RESID_BF16 && e.out_kind == OUT_F32) return EPI_BIAS_RESID16_F32;
@@ -915,6 +943,9 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
   VLB_REQUIRE(N % 8 == 0, "gemm: N (%d) must be a multiple of 8", N);
   VLB_REQUIRE(epi.ldo % 4 == 0 && (epi.out_kind != OUT_BF16 || epi.ldo % 8 == 0), "gemm: bad ldo %d", epi.ldo);
   VLB_REQUIRE(epi.resid_kind == RESID_NONE || (epi.resid != nullptr && epi.ldr % 8 == 0), "gemm: bad residual");
+  VLB_REQUIRE(epi.resid_kind != RESID_LN_F32 || epi.ln_mean == nullptr || (epi.ln_rstd && epi.ln_gamma && epi.ln_beta),
+              "gemm: LayerNorm-recomputed residual needs mean, rstd, gamma and beta");
+  VLB_REQUIRE(epi.drop.thresh == 0u || epi.drop.bits != nullptr, "gemm: the dropout epilogue needs precomputed keep bits (vlb_dropout_bits)");
   VLB_REQUIRE((epi.act != ACT_DGELU_MUL && epi.act != ACT_DRELU_MUL) || (epi.aux != nullptr && epi.ld_aux % 8 == 0),
               "gemm: activation-gradient epilogue needs aux");
   const bool a_mn = (mode == GEMM_TN);
@@ -1058,6 +1089,8 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
     if (epi_id == EPI_BIAS_BF16) return launch<BN_, false, false, EPI_BIAS_BF16, CG_>(ta, tb, tbt, p, stream);     \
     if (epi_id == EPI_BIAS_RESID16_F32) return launch<BN_, false, false, EPI_BIAS_RESID16_F32, CG_>(ta, tb, tbt, p, stream); \
     if (CG_ == 0 && epi_id == EPI_BIAS_DROP_RESID16_F32) return launch<BN_, false, false, EPI_BIAS_DROP_RESID16_F32, 0>(ta, tb, tbt, p, stream); \
+    if (CG_ == 0 && epi_id == EPI_BIAS_RESIDLN_F32) return launch<BN_, false, false, EPI_BIAS_RESIDLN_F32, 0>(ta, tb, tbt, p, stream); \
+    if (CG_ == 0 && epi_id == EPI_BIAS_DROP_RESIDLN_F32) return launch<BN_, false, false, EPI_BIAS_DROP_RESIDLN_F32, 0>(ta, tb, tbt, p, stream); \
     if (epi_id == EPI_BIAS_GELU_AUX_BF16) return launch<BN_, false, false, EPI_BIAS_GELU_AUX_BF16, CG_>(ta, tb, tbt, p, stream); \
     if (CG_ == 0 && epi_id == EPI_CONV_RELU_BF16) return launch<BN_, false, false, EPI_CONV_RELU_BF16, 0>(ta, tb, tbt, p, stream); \
     if (CG_ == 0 && epi_id == EPI_CONV_RESID_RELU_BF16) return launch<BN_, false, false, EPI_CONV_RESID_RELU_BF16, 0>(ta, tb, tbt, p, stream); \

@@ -6,7 +6,11 @@
 namespace vlb {
 
 enum GemmOutKind : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_ATOMIC = 2 };
-enum GemmResidKind : int { RESID_NONE = 0, RESID_BF16 = 1, RESID_F32 = 2 };
+// RESID_LN_F32: the residual is the fp32 OUTPUT of a LayerNorm that is not stored: it is recomputed in the epilogue from the
+// LayerNorm's stored fp32 input `resid` [M, ldr], its row statistics ln_mean / ln_rstd [M] and ln_gamma / ln_beta [N]
+// (ln_mean == nullptr: `resid` is used as it is, i.e. RESID_F32).  This keeps the encoder's residual stream in fp32 --
+// like the reference under autocast -- without writing a second copy of every LayerNorm output.
+enum GemmResidKind : int { RESID_NONE = 0, RESID_BF16 = 1, RESID_F32 = 2, RESID_LN_F32 = 3 };
 enum GemmAct : int {
   ACT_NONE = 0,
   ACT_GELU = 1,       // x = gelu_erf(x); if aux != null gelu_erf'(pre-activation) is stored there (bf16) for backward
@@ -35,7 +39,11 @@ struct GemmEpilogue {
   float alpha = 1.0f;            // scale applied to the accumulator before everything else
   float* colsum = nullptr;       // optional [N] fp32: += column sums of the stored values (bias gradient of the producer)
   const float* colscale = nullptr;  // optional [N] fp32: x = acc * colscale[col] before the bias (frozen BatchNorm scale)
-  DropCfg drop = DropCfg{0u, 1.0f, 0u, nullptr};  // dropout on the [M,N] value after bias/activation, before the residual add
+  DropCfg drop = DropCfg{0u, 1.0f, 0u, nullptr, nullptr};  // dropout on the [M,N] value after bias/activation, before the residual add (needs drop.bits)
+  const float* ln_mean = nullptr;   // RESID_LN_F32: see GemmResidKind
+  const float* ln_rstd = nullptr;
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
 };
 
 // whether the experimental stream-K tail was compiled in (-DVLB_ENABLE_STREAMK=1)

@@ -40,22 +40,11 @@ struct MhsaParams {
   DropCfg drop;               // dropout on the probabilities (modeling.py:310); mask rows = (b, head, query), columns = keys
 };
 
-// keep flags (bit j = key c0 + j is kept) of 32 consecutive probabilities (c0 % 4 == 0) of mask row `mrow`.  The flags depend
-// only on (seed, step, site, position), so the kernels evaluate them BEFORE waiting for the TMA loads / score MMAs: the ten
-// Philox rounds per four keys overlap that latency instead of extending the softmax phase.
-__device__ __forceinline__ uint32_t keep_bits32(uint64_t mrow, int groups_per_row, int c0, int S, const DropCfg& d, const DropState& st) {
-  uint32_t bits = 0u;
-#pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    if (c0 + g * 4 < S) {   // groups past the sequence hold only masked-out keys (probability exactly 0)
-      const Philox4 r = dropout_words(mrow * (uint64_t)groups_per_row + (uint64_t)((c0 >> 2) + g), st.seed, d.site, st.step);
-      bits |= (r.x >= d.thresh ? 1u : 0u) << (4 * g);
-      bits |= (r.y >= d.thresh ? 2u : 0u) << (4 * g);
-      bits |= (r.z >= d.thresh ? 4u : 0u) << (4 * g);
-      bits |= (r.w >= d.thresh ? 8u : 0u) << (4 * g);
-    }
-  }
-  return bits;
+// Dropout on the probabilities reads precomputed keep flags (DropCfg::bits, written by dropout_bits_kernel for the [B*heads*S, S]
+// mask): word c of mask row `mrow` holds keys 32c .. 32c+31.  Evaluating Philox inside these kernels made them
+// instruction-bound (ten rounds per four keys, twice per step: forward and the recomputation in backward).
+__device__ __forceinline__ uint32_t keep_word(const DropCfg& d, uint64_t mrow, int wpr, int c) {
+  return c < wpr ? __ldg(d.bits + mrow * (uint64_t)wpr + (uint64_t)c) : 0u;
 }
 
 // Shared memory maps (bytes from the 1024-aligned dynamic shared memory base).  Regions are re-used once their first
@@ -170,11 +159,10 @@ mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint32_t keep[NKEYS / 32];
   const bool dropping = p.drop.thresh != 0u && q0 + t < p.S;
   if (dropping) {
-    const DropState dstate = drop_state(p.drop);
     const uint64_t mrow = ((uint64_t)b * p.heads + h) * (uint64_t)p.S + (uint64_t)(q0 + t);
-    const int mgroups = (p.S + 3) >> 2;
+    const int wpr = (p.S + 31) >> 5;
 #pragma unroll
-    for (int c = 0; c < NKEYS / 32; ++c) keep[c] = keep_bits32(mrow, mgroups, c * 32, p.S, p.drop, dstate);
+    for (int c = 0; c < NKEYS / 32; ++c) keep[c] = keep_word(p.drop, mrow, wpr, c);
   }
   mbar_wait(smem_u32(&bars[1]), 0);
   tc_fence_after();
@@ -386,11 +374,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) mhsa_bwd_kernel(const __grid_c
   uint32_t keepb[NK / 64];
   const bool dropping = p.drop.thresh != 0u && valid;
   if (dropping) {
-    const DropState dstate = drop_state(p.drop);
     const uint64_t mrow = ((uint64_t)b * p.heads + h) * (uint64_t)p.S + (uint64_t)(q0 + t);
-    const int mgroups = (p.S + 3) >> 2;
+    const int wpr = (p.S + 31) >> 5;
 #pragma unroll
-    for (int cc = 0; cc < NK / 64; ++cc) keepb[cc] = keep_bits32(mrow, mgroups, k0 + (half * (NK / 64) + cc) * 32, p.S, p.drop, dstate);
+    for (int cc = 0; cc < NK / 64; ++cc) keepb[cc] = keep_word(p.drop, mrow, wpr, (k0 >> 5) + half * (NK / 64) + cc);
   }
   mbar_wait(smem_u32(&bars[1]), 0);
   tc_fence_after();
@@ -491,6 +478,7 @@ int mhsa_forward(const void* qkv, const float* add_mask, void* ctx, float* lse, 
                  cudaStream_t stream, const VlbDropout* drop) {
   VLB_REQUIRE(qkv && ctx, "mhsa_forward: null pointer");
   VLB_REQUIRE(drop_valid(drop), "mhsa_forward: bad dropout configuration");
+  VLB_REQUIRE(drop == nullptr || drop->p == 0.0f || drop->keep_bits != nullptr, "mhsa_forward: dropout needs precomputed keep bits (vlb_dropout_bits over [B*heads*S, S])");
   VLB_REQUIRE(H == heads * D_HEAD, "mhsa: head size must be 64 (H=%d heads=%d)", H, heads);
   VLB_REQUIRE(S >= 1 && S <= 256, "mhsa: sequence length %d not supported (1..256)", S);
   MhsaParams p{};
@@ -517,6 +505,7 @@ int mhsa_backward(const void* qkv, const float* add_mask, const void* ctx, const
                   float* scratch_f32, int B, int S, int H, int heads, cudaStream_t stream, const VlbDropout* drop) {
   VLB_REQUIRE(qkv && ctx && lse && dctx && dqkv, "mhsa_backward: null pointer");
   VLB_REQUIRE(drop_valid(drop), "mhsa_backward: bad dropout configuration");
+  VLB_REQUIRE(drop == nullptr || drop->p == 0.0f || drop->keep_bits != nullptr, "mhsa_backward: dropout needs the keep bits the forward used");
   VLB_REQUIRE(H == heads * D_HEAD, "mhsa: head size must be 64 (H=%d heads=%d)", H, heads);
   VLB_REQUIRE(S >= 1 && S <= 256, "mhsa: sequence length %d not supported (1..256)", S);
   const int tiles = (S + TQ - 1) / TQ;

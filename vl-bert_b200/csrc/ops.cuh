@@ -73,6 +73,10 @@ int adamw_step(const VlbAdamWTensor* descs_device, const float* hyper_device, in
 
 int dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t seed, uint32_t site, uint32_t step, cudaStream_t stream);
 int dropout_mask_2d(uint8_t* keep, int64_t rows, int cols, float p, uint64_t seed, uint32_t site, uint32_t step, cudaStream_t stream);
+int64_t dropout_bits_words(int64_t rows, int cols);
+int dropout_bits(uint32_t* bits, int64_t rows, int cols, const VlbDropout* drop, cudaStream_t stream);
+int layer_dropout_bits(uint32_t* keep_attn, uint32_t* keep_self_out, uint32_t* keep_out, int B, int S, int H, int heads,
+                       const VlbLayerDropout& d, cudaStream_t stream);
 int dropout_2d(const void* x, int ldx, void* y, int ldy, int64_t rows, int cols, int col_offset, int total_cols, int is_bf16,
                const VlbDropout* drop, cudaStream_t stream);
 int dropout_apply(const void* x, void* y, int64_t n, int is_bf16, float p, uint64_t seed, uint32_t site, uint32_t step, cudaStream_t stream);

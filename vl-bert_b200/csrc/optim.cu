@@ -181,6 +181,61 @@ __global__ void dropout_2d_kernel(const T* __restrict__ x, int ldx, T* __restric
   }
 }
 
+// keep flags as bits: one thread = one 32-bit word = eight Philox groups of row r (2-D contract)
+__global__ void dropout_bits_kernel(uint32_t* __restrict__ bits, size_t rows, int cols, int wpr, const DropCfg drop) {
+  pdl_trigger();
+  pdl_wait();     // (seed, step) are written by the caller's preceding stream work
+  const DropState st = drop_state(drop);
+  const size_t gpr = (size_t)((cols + 3) >> 2);
+  const size_t words = rows * (size_t)wpr;
+  for (size_t w = blockIdx.x * (size_t)blockDim.x + threadIdx.x; w < words; w += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = w / (size_t)wpr;
+    const int c0 = (int)(w - r * (size_t)wpr) * 32;
+    uint32_t out = 0u;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const int c = c0 + g * 4;
+      if (c < cols) {
+        const Philox4 q = dropout_words(r * gpr + (size_t)(c >> 2), st.seed, drop.site, st.step);
+        uint32_t k = (q.x >= drop.thresh ? 1u : 0u) | (q.y >= drop.thresh ? 2u : 0u) | (q.z >= drop.thresh ? 4u : 0u) | (q.w >= drop.thresh ? 8u : 0u);
+        if (c + 4 > cols) k &= (1u << (cols - c)) - 1u;
+        out |= k << (4 * g);
+      }
+    }
+    bits[w] = out;
+  }
+}
+
+// up to three mask tensors in one launch (the three dropout sites of a BertLayer): blockIdx.y selects the job
+struct BitsJob { uint32_t* bits; size_t rows; int cols; int wpr; uint32_t site; uint32_t thresh; };
+struct BitsJobs { BitsJob j[3]; const uint64_t* rng; };
+__global__ void dropout_bits_multi_kernel(const BitsJobs jobs) {
+  pdl_trigger();
+  pdl_wait();
+  const BitsJob jb = jobs.j[blockIdx.y];
+  if (jb.bits == nullptr) return;
+  DropCfg d{jb.thresh, 1.0f, jb.site, jobs.rng, nullptr};
+  const DropState st = drop_state(d);
+  const size_t gpr = (size_t)((jb.cols + 3) >> 2);
+  const size_t words = jb.rows * (size_t)jb.wpr;
+  for (size_t w = blockIdx.x * (size_t)blockDim.x + threadIdx.x; w < words; w += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = w / (size_t)jb.wpr;
+    const int c0 = (int)(w - r * (size_t)jb.wpr) * 32;
+    uint32_t out = 0u;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const int c = c0 + g * 4;
+      if (c < jb.cols) {
+        const Philox4 q = dropout_words(r * gpr + (size_t)(c >> 2), st.seed, jb.site, st.step);
+        uint32_t k = (q.x >= jb.thresh ? 1u : 0u) | (q.y >= jb.thresh ? 2u : 0u) | (q.z >= jb.thresh ? 4u : 0u) | (q.w >= jb.thresh ? 8u : 0u);
+        if (c + 4 > jb.cols) k &= (1u << (jb.cols - c)) - 1u;
+        out |= k << (4 * g);
+      }
+    }
+    jb.bits[w] = out;
+  }
+}
+
 int dropout_grid(size_t n) {
   const size_t groups = (n + 3) >> 2;
   size_t g = (groups + 255) / 256;
@@ -204,6 +259,42 @@ int dropout_mask_2d(uint8_t* keep, int64_t rows, int cols, float p, uint64_t see
   const size_t n = (size_t)rows * (size_t)(((cols + 3) >> 2) << 2);
   dropout_mask_2d_kernel<<<dropout_grid(n), 256, 0, stream>>>(keep, (size_t)rows, cols, dropout_threshold(p), seed, site, step);
   VLB_CHECK_LAUNCH();
+  return VLB_OK;
+}
+
+int64_t dropout_bits_words(int64_t rows, int cols) { return rows * (int64_t)((cols + 31) >> 5); }
+
+int dropout_bits(uint32_t* bits, int64_t rows, int cols, const VlbDropout* drop, cudaStream_t stream) {
+  VLB_REQUIRE(bits && rows >= 0 && cols > 0 && drop && drop->p > 0.0f && drop->p < 1.0f && drop->rng, "dropout_bits: bad arguments");
+  if (rows == 0) return VLB_OK;
+  const int wpr = (cols + 31) >> 5;
+  const size_t words = (size_t)rows * wpr;
+  size_t g = (words + 255) / 256;
+  const size_t cap = (size_t)num_sms() * 16;
+  DropCfg d = make_drop(drop);
+  d.bits = nullptr;
+  VLB_CHECK_CUDA(launch_pdl(dropout_bits_kernel, dim3((unsigned)(g > cap ? cap : g)), dim3(256), 0, stream, bits, (size_t)rows, cols, wpr, d));
+  return VLB_OK;
+}
+
+// the three sites of one BertLayer in ONE launch: attention probabilities [B*heads*S, S] and the two dense outputs [M, H]
+int layer_dropout_bits(uint32_t* keep_attn, uint32_t* keep_self_out, uint32_t* keep_out, int B, int S, int H, int heads,
+                       const VlbLayerDropout& d, cudaStream_t stream) {
+  BitsJobs jobs{};
+  jobs.rng = d.rng;
+  const size_t M = (size_t)B * S;
+  if (d.p_attn > 0.0f && keep_attn)
+    jobs.j[0] = BitsJob{keep_attn, (size_t)B * heads * S, S, (S + 31) >> 5, d.site_attn, dropout_threshold(d.p_attn)};
+  if (d.p_hidden > 0.0f && keep_self_out)
+    jobs.j[1] = BitsJob{keep_self_out, M, H, (H + 31) >> 5, d.site_self_out, dropout_threshold(d.p_hidden)};
+  if (d.p_hidden > 0.0f && keep_out)
+    jobs.j[2] = BitsJob{keep_out, M, H, (H + 31) >> 5, d.site_out, dropout_threshold(d.p_hidden)};
+  size_t words = 0;
+  for (int i = 0; i < 3; ++i) { const size_t w = jobs.j[i].rows * (size_t)jobs.j[i].wpr; if (w > words) words = w; }
+  if (words == 0) return VLB_OK;
+  size_t g = (words + 255) / 256;
+  const size_t cap = (size_t)num_sms() * 8;
+  VLB_CHECK_CUDA(launch_pdl(dropout_bits_multi_kernel, dim3((unsigned)(g > cap ? cap : g), 3), dim3(256), 0, stream, jobs));
   return VLB_OK;
 }
 

@@ -48,29 +48,47 @@ __host__ __device__ __forceinline__ Philox4 dropout_words(uint64_t group, uint64
 // (rows = (b, head, query), cols = S keys) pad each row to a multiple of four so a row never shares a Philox call.
 #include "../../include/vlbert_b200.h"
 namespace vlb {
+// `bits` (optional): keep flags precomputed by dropout_bits_kernel (vlb_dropout_bits) -- bit (c % 32) of word
+// r * ceil(cols / 32) + c / 32 is the keep flag of element (r, c).  The attention / GEMM-epilogue / LayerNorm-backward
+// consumers read these instead of running Philox themselves: the ten rounds per four elements made the attention kernels
+// instruction-bound (+0.45 ms per step), one bit-generation launch per layer costs ~10 us and serves forward AND backward.
 struct DropCfg {
   uint32_t thresh;
   float scale;
   uint32_t site;
   const uint64_t* rng;
+  const uint32_t* bits;
 };
 inline DropCfg make_drop(const VlbDropout* d) {
-  DropCfg c{0u, 1.0f, 0u, nullptr};
-  if (d != nullptr && d->p > 0.0f && d->rng != nullptr) {
+  DropCfg c{0u, 1.0f, 0u, nullptr, nullptr};
+  if (d != nullptr && d->p > 0.0f && (d->rng != nullptr || d->keep_bits != nullptr)) {
     c.thresh = dropout_threshold(d->p);
     c.scale = 1.0f / (1.0f - d->p);
     c.site = d->site;
     c.rng = d->rng;
+    c.bits = d->keep_bits;
   }
   return c;
 }
-inline bool drop_valid(const VlbDropout* d) { return d == nullptr || (d->p >= 0.0f && d->p < 1.0f && (d->p == 0.0f || d->rng != nullptr)); }
+inline bool drop_valid(const VlbDropout* d) {
+  return d == nullptr || (d->p >= 0.0f && d->p < 1.0f && (d->p == 0.0f || d->rng != nullptr || d->keep_bits != nullptr));
+}
 #if defined(__CUDACC__)
 struct DropState { uint64_t seed; uint32_t step; };
 __device__ __forceinline__ DropState drop_state(const DropCfg& d) {
   DropState s{0ull, 0u};
-  if (d.thresh != 0u) { s.seed = __ldg(d.rng); s.step = (uint32_t)__ldg(d.rng + 1); }
+  if (d.thresh != 0u && d.rng != nullptr) { s.seed = __ldg(d.rng); s.step = (uint32_t)__ldg(d.rng + 1); }
   return s;
+}
+// keep flags of the four consecutive elements (r, c .. c+3), c % 4 == 0, as a 4-bit value; wpr = words per row of `bits`
+__device__ __forceinline__ uint32_t keep4_bits(const uint32_t* __restrict__ bits, size_t r, int wpr, int c) {
+  return (__ldg(bits + r * (size_t)wpr + (size_t)(c >> 5)) >> (c & 31)) & 0xFu;
+}
+__device__ __forceinline__ void drop4_bits(float (&x)[4], uint32_t k4, float scale) {
+  x[0] = (k4 & 1u) ? x[0] * scale : 0.0f;
+  x[1] = (k4 & 2u) ? x[1] * scale : 0.0f;
+  x[2] = (k4 & 4u) ? x[2] * scale : 0.0f;
+  x[3] = (k4 & 8u) ? x[3] * scale : 0.0f;
 }
 // apply the mask of one Philox group to four consecutive values
 __device__ __forceinline__ void drop4(float (&x)[4], uint64_t group, const DropCfg& d, const DropState& s) {

@@ -165,7 +165,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
   const int wstride = gridDim.x * LN_WARPS;
   pdl_trigger();
   pdl_wait();
-  const DropState in_state = drop_state(in_drop), out_state = drop_state(out_drop);
+  const DropState in_state = drop_state(in_drop);
+  const int out_wpr = (H + 31) >> 5;
   float gam[ITERS][8];
   float acc_g[ITERS][8], acc_b[ITERS][8], acc_c[ITERS][8];
 #pragma unroll
@@ -242,8 +243,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
         if (out_drop.thresh != 0u) {
           // x = dropout(dense(.)) + residual: the dense branch (next GEMM operand, bias gradient) sees dx o mask / (1-p)
           float lo[4] = {o[0], o[1], o[2], o[3]}, hi[4] = {o[4], o[5], o[6], o[7]};
-          drop4(lo, off >> 2, out_drop, out_state);
-          drop4(hi, (off >> 2) + 1, out_drop, out_state);
+          drop4_bits(lo, keep4_bits(out_drop.bits, (size_t)row, out_wpr, vi * 8), out_drop.scale);
+          drop4_bits(hi, keep4_bits(out_drop.bits, (size_t)row, out_wpr, vi * 8 + 4), out_drop.scale);
           uint4 pk;
           pk.x = pack_bf16x2(lo[0], lo[1]); pk.y = pack_bf16x2(lo[2], lo[3]);
           pk.z = pack_bf16x2(hi[0], hi[1]); pk.w = pack_bf16x2(hi[2], hi[3]);
@@ -403,6 +404,7 @@ int multi_cast(const VlbCastDesc* descs_device, int count, int blocks_per_tensor
 int layernorm_forward(const float* x, int ldx, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean,
                       float* rstd, int M, int H, float eps, cudaStream_t stream, const VlbDropout* out_drop) {
   VLB_REQUIRE(drop_valid(out_drop), "layernorm_forward: bad dropout configuration");
+  VLB_REQUIRE(out_drop == nullptr || out_drop->p == 0.0f || out_drop->rng != nullptr, "layernorm_forward: the output dropout is evaluated inline and needs the rng state");
   const DropCfg dcfg = make_drop(out_drop);
   VLB_REQUIRE(x && gamma && beta && (y_bf16 || y_f32), "layernorm_forward: null pointer");
   VLB_REQUIRE(ldx % 4 == 0 && ldx >= H, "layernorm_forward: bad ldx %d", ldx);
@@ -425,6 +427,8 @@ int layernorm_backward(const void* dy_bf16, const float* dy_f32, const float* x,
   VLB_REQUIRE(drop_valid(in_drop) && drop_valid(out_drop), "layernorm_backward: bad dropout configuration");
   const DropCfg din = make_drop(in_drop), dout = make_drop(out_drop);
   VLB_REQUIRE(dout.thresh == 0u || dx_bf16_drop != nullptr || dcolsum != nullptr, "layernorm_backward: out_drop without a consumer");
+  VLB_REQUIRE(dout.thresh == 0u || dout.bits != nullptr, "layernorm_backward: out_drop needs precomputed keep bits (vlb_dropout_bits over [M, H])");
+  VLB_REQUIRE(din.thresh == 0u || din.rng != nullptr, "layernorm_backward: in_drop is evaluated inline and needs the rng state");
   VLB_REQUIRE(ldx % 4 == 0 && ldx >= H && (dx_f32 == nullptr || (ld_dx % 4 == 0 && ld_dx >= H)), "layernorm_backward: bad ld");
   VLB_REQUIRE((dy_bf16 || dy_f32) && x && mean && rstd && gamma, "layernorm_backward: null pointer");
   VLB_REQUIRE(H % 8 == 0 && H >= 8 && H <= 2048, "layernorm: H=%d must be a multiple of 8 in [8, 2048]", H);

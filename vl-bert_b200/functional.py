@@ -80,7 +80,7 @@ class DropSite(object):
     """One dropout call site (VlbDropout): probability, site id and the DEVICE rng state tensor (int64 [2] = seed, step).
     The kernels read (seed, step) when they run, so the same object serves the forward, its backward and CUDA-graph replays."""
 
-    __slots__ = ("p", "site", "rng", "_struct")
+    __slots__ = ("p", "site", "rng", "_struct", "bits", "_bits_shape")
 
     def __init__(self, p, site, rng):
         if not (0.0 <= p < 1.0):
@@ -89,11 +89,33 @@ class DropSite(object):
             raise RuntimeError("vlbert_b200: the dropout rng state must be a contiguous CUDA int64 tensor (seed, step)")
         self.p, self.site, self.rng = float(p), int(site), rng
         d = _lib.Dropout()
-        d.p, d.site, d.rng = self.p, self.site, rng.data_ptr()
+        d.p, d.site, d.rng, d.keep_bits = self.p, self.site, rng.data_ptr(), None
         self._struct = d
+        self.bits = None
+        self._bits_shape = None
 
     def ref(self):
         return ctypes.byref(self._struct)
+
+    def with_bits(self, rows, cols):
+        """Generate (vlb_dropout_bits) the keep flags of this site for a [rows, cols] mask with the CURRENT device (seed, step)
+        and attach them: the attention / GEMM-epilogue / LayerNorm-backward consumers read flags, they do not run Philox.
+        Returns self.  The backward of an op must be given the same object (same flags) as its forward."""
+        if self.p == 0.0:
+            return self
+        lib = _lib.lib()
+        n = int(lib.vlb_dropout_bits_words(rows, cols))
+        self.bits = torch.empty((max(n, 1),), dtype=torch.int32, device=self.rng.device)
+        self._struct.keep_bits = None
+        _chk(lib.vlb_dropout_bits(self.bits.data_ptr(), rows, cols, self.ref(), _stream()))
+        self._struct.keep_bits = self.bits.data_ptr()
+        self._bits_shape = (rows, cols)
+        return self
+
+    def need_bits(self, rows, cols):
+        if self.p > 0.0 and self._bits_shape != (rows, cols):
+            self.with_bits(rows, cols)
+        return self
 
 
 def _dref(drop):
@@ -129,6 +151,7 @@ def gemm(mode, A, B, out, bias=None, resid=None, act=0, aux=None, alpha=1.0, spl
     out_kind = 0 if out.dtype == BF16 else (2 if split_k > 1 or getattr(out, "_vlb_accumulate", False) else 1)
     resid_kind = 0 if resid is None else (1 if resid.dtype == BF16 else 2)
     if drop is not None:
+        drop.need_bits(M, N)
         _chk(_lib.lib().vlb_gemm_bf16_dropout(mode, M, N, K, _p(A), A.stride(0), _p(B), B.stride(0), _p(out), out.stride(0),
                                               out_kind, _p(bias), _p(resid), resid.stride(0) if resid is not None else 0,
                                               resid_kind, act, _p(aux), aux.stride(0) if aux is not None else 0, float(alpha),
@@ -137,6 +160,25 @@ def gemm(mode, A, B, out, bias=None, resid=None, act=0, aux=None, alpha=1.0, spl
     _chk(_lib.lib().vlb_gemm_bf16(mode, M, N, K, _p(A), A.stride(0), _p(B), B.stride(0), _p(out), out.stride(0), out_kind,
                                   _p(bias), _p(resid), resid.stride(0) if resid is not None else 0, resid_kind, act,
                                   _p(aux), aux.stride(0) if aux is not None else 0, float(alpha), split_k, force_bn, _stream()))
+    return out
+
+
+def gemm_bias_residual_f32(A, W, bias, resid32, ln=None, drop=None, force_bn=0):
+    """out f32 [M,N] = dropout(A W^T + bias) + R with R = resid32 (fp32 [M,N]) or, when ln = (mean, rstd, gamma, beta),
+    R = LayerNorm(resid32) recomputed in the epilogue (vlb_gemm_bias_residual_f32)."""
+    _require_cuda(A, W, resid32)
+    M, K = A.shape
+    N = W.shape[0]
+    out = torch.empty((M, N), dtype=F32, device=A.device)
+    r = _lib.Residual()
+    r.x_f32 = resid32.data_ptr()
+    assert resid32.is_contiguous() and resid32.shape == (M, N)
+    if ln is not None:
+        r.mean, r.rstd, r.gamma, r.beta = [t.data_ptr() for t in ln]
+    if drop is not None:
+        drop.need_bits(M, N)
+    _chk(_lib.lib().vlb_gemm_bias_residual_f32(M, N, K, _p(A), A.stride(0), _p(W), W.stride(0), _p(out), N, _p(bias), ctypes.byref(r),
+                                               _dref(drop), force_bn, _stream()))
     return out
 
 
@@ -166,6 +208,8 @@ def layernorm_backward(dy16, dy32, x, mean, rstd, gamma, dgamma, dbeta, dcolsum=
         dx32 = torch.empty((M, H), dtype=F32, device=dev)
         ld_dx = H
     dx16_drop = torch.empty((M, H), dtype=BF16, device=dev) if out_drop is not None else None
+    if out_drop is not None:
+        out_drop.need_bits(M, H)
     _chk(_lib.lib().vlb_layernorm_backward_dropout(_p(dy16), _p(dy32), _p(x), ldx, _p(mean), _p(rstd), _p(gamma), _p(dx16),
                                                    _p(dx32), ld_dx or 0, _p(dgamma), _p(dbeta), _p(dcolsum), M, H, _dref(in_drop),
                                                    _p(dx16_drop), _dref(out_drop), _stream()))
@@ -175,6 +219,10 @@ def layernorm_backward(dy16, dy32, x, mean, rstd, gamma, dgamma, dbeta, dcolsum=
 
 
 def mhsa_forward(qkv, add_mask, B, S, H, heads, drop=None):
+    """drop: DropSite; its keep flags for the [B*heads*S, S] probability mask are generated here (and must be re-used by the
+    backward: pass the same object to mhsa_backward)."""
+    if drop is not None:
+        drop.with_bits(B * heads * S, S)
     ctx = torch.empty((B * S, H), dtype=BF16, device=qkv.device)
     lse = torch.empty((B, heads, S), dtype=F32, device=qkv.device)
     _chk(_lib.lib().vlb_mhsa_forward_dropout(_p(qkv), _p(add_mask), _p(ctx), _p(lse), B, S, H, heads, _dref(drop), _stream()))
@@ -182,6 +230,8 @@ def mhsa_forward(qkv, add_mask, B, S, H, heads, drop=None):
 
 
 def mhsa_backward(qkv, add_mask, ctx, lse, dctx, B, S, H, heads, drop=None):
+    if drop is not None:
+        drop.need_bits(B * heads * S, S)
     dqkv = torch.empty((B * S, 3 * H), dtype=BF16, device=qkv.device)
     scratch = torch.empty((B * S, 3 * H), dtype=F32, device=qkv.device) if S > 128 else None
     _chk(_lib.lib().vlb_mhsa_backward_dropout(_p(qkv), _p(add_mask), _p(ctx), _p(lse), _p(dctx), _p(dqkv), _p(scratch), B, S, H,
@@ -267,18 +317,24 @@ class EncoderWeights(object):
         return w
 
 
-def _act_specs(l, B, S, H, heads, I, want_f32):
+def _act_specs(l, B, S, H, heads, I, want_f32, drop=False):
     M = B * S
-    sp = [("qkv%d" % l, (M, 3 * H), BF16), ("ctx%d" % l, (M, H), BF16), ("lse%d" % l, (B, heads, S), F32),
+    sp = []
+    if drop:
+        i32 = torch.int32
+        sp = [("ka%d" % l, (B * heads * S, (S + 31) // 32), i32), ("ks%d" % l, (M, (H + 31) // 32), i32), ("ko%d" % l, (M, (H + 31) // 32), i32)]
+    sp += [("qkv%d" % l, (M, 3 * H), BF16), ("ctx%d" % l, (M, H), BF16), ("lse%d" % l, (B, heads, S), F32),
           ("a%d" % l, (M, H), F32), ("m1_%d" % l, (M,), F32), ("r1_%d" % l, (M,), F32), ("h%d" % l, (M, H), BF16),
           ("z%d" % l, (M, I), BF16), ("u%d" % l, (M, I), BF16), ("y0_%d" % l, (M, H), F32), ("m2_%d" % l, (M,), F32),
           ("r2_%d" % l, (M,), F32), ("y%d" % l, (M, H), BF16)]
     return sp
 
 
-def _acts_struct(car, l, y_f32):
+def _acts_struct(car, l, y_f32, drop=False):
     a = _lib.LayerActs()
     g = lambda n: car.ptr(n % l)  # noqa: E731
+    if drop:
+        a.keep_attn, a.keep_self_out, a.keep_out = g("ka%d"), g("ks%d"), g("ko%d")
     a.qkv, a.ctx, a.lse, a.a = g("qkv%d"), g("ctx%d"), g("lse%d"), g("a%d")
     a.ln1_mean, a.ln1_rstd, a.h, a.z, a.u = g("m1_%d"), g("r1_%d"), g("h%d"), g("z%d"), g("u%d")
     a.y0, a.ln2_mean, a.ln2_rstd, a.y = g("y0_%d"), g("m2_%d"), g("r2_%d"), g("y%d")
@@ -309,11 +365,13 @@ def _layer_drop_structs(drop, L):
 class EncoderFn(torch.autograd.Function):
     """L BertLayers (BertEncoder.forward, modeling.py:406-421) on vlb_bert_layer_forward/backward.
 
-    forward(emb_bf16 [B,S,H], add_mask f32 [B,S], meta, *params) -> tuple of fp32 [B,S,H] outputs, one per
-    requested layer (all layers when meta.all_layers else the last one only)."""
+    forward(emb_bf16 [B,S,H], emb_f32 [B,S,H] or None, add_mask f32 [B,S], meta, *params) -> tuple of fp32 [B,S,H] outputs, one
+    per requested layer (all layers when meta.all_layers else the last one only).  emb_f32 (the same embedding in fp32)
+    selects the fp32 residual stream (csrc/encoder.cu); the gradient then comes back split the same way: the bf16 GEMM part
+    for emb_bf16 and the fp32 residual part for emb_f32."""
 
     @staticmethod
-    def forward(ctx, emb, add_mask, meta, *params):
+    def forward(ctx, emb, emb32, add_mask, meta, *params):
         _require_cuda(emb, add_mask)
         B, S, H = emb.shape
         L, heads, I = meta.L, meta.heads, meta.I
@@ -326,23 +384,36 @@ class EncoderFn(torch.autograd.Function):
                 _require_param(p, "encoder.layer.%d.%s" % (i // 16, EncoderWeights.PER_LAYER[i % 16]), emb.device)
             meta.weights._checked = tuple(p.data_ptr() for p in params)
         emb = emb.contiguous()          # kept alive in ctx: the layer-0 kernels and the backward read this very buffer
+        if emb32 is not None:
+            if emb32.dtype != F32 or emb32.shape != emb.shape:
+                raise RuntimeError("vlbert_b200: EncoderFn expects emb_f32 as a float32 tensor of the embedding's shape")
+            emb32 = emb32.contiguous()
         add_mask = add_mask.contiguous()
         meta.weights.refresh(params)
+        drops = _layer_drop_structs(getattr(meta, "drop", None), L)
+        has_drop = drops[0] is not None
         specs = []
         for l in range(L):
-            specs += _act_specs(l, B, S, H, heads, I, False)
+            specs += _act_specs(l, B, S, H, heads, I, False, has_drop)
         car = _Carver(specs, emb.device)
         outs = []
         x_ptr = emb.data_ptr()
-        drops = _layer_drop_structs(getattr(meta, "drop", None), L)
+        resid = None
+        if emb32 is not None:           # layer 0: the embedding itself in fp32
+            resid = _lib.Residual()
+            resid.x_f32 = emb32.data_ptr()
         for l in range(L):
             want = meta.all_layers or l == L - 1
             y32 = torch.empty((B, S, H), dtype=F32, device=emb.device) if want else None
             w = meta.weights.layer_struct(l, params)
-            a = _acts_struct(car, l, y32)
-            _chk(lib.vlb_bert_layer_forward(ctypes.byref(w), x_ptr, _p(add_mask), ctypes.byref(a), B, S, H, heads, I,
-                                            float(meta.eps), drops[l], st))
+            a = _acts_struct(car, l, y32, has_drop)
+            _chk(lib.vlb_bert_layer_forward(ctypes.byref(w), x_ptr, None if resid is None else ctypes.byref(resid), _p(add_mask),
+                                            ctypes.byref(a), B, S, H, heads, I, float(meta.eps), drops[l], st))
             x_ptr = car.ptr("y%d" % l)
+            if emb32 is not None:       # next layer's residual = this layer's LayerNorm-2 output, recomputed from y0 + statistics
+                resid = _lib.Residual()
+                resid.x_f32, resid.mean, resid.rstd = car.ptr("y0_%d" % l), car.ptr("m2_%d" % l), car.ptr("r2_%d" % l)
+                resid.gamma, resid.beta = params[16 * l + 14].data_ptr(), params[16 * l + 15].data_ptr()
             if want:
                 outs.append(y32)
         ctx.meta = meta
@@ -350,6 +421,8 @@ class EncoderFn(torch.autograd.Function):
         ctx.dims = (B, S, H)
         ctx.drops = drops
         ctx.drop_rng = None if getattr(meta, "drop", None) is None else meta.drop.rng   # keeps the state tensor alive
+        ctx.has_drop = has_drop
+        ctx.f32_stream = emb32 is not None
         ctx.emb = emb
         ctx.add_mask = add_mask
         ctx.params = params
@@ -370,6 +443,8 @@ class EncoderFn(torch.autograd.Function):
         ws_bytes = int(lib.vlb_bert_layer_backward_workspace(M, H, I))
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         dx = [torch.empty((M, H), dtype=BF16, device=dev), torch.empty((M, H), dtype=BF16, device=dev)]
+        dx32 = [torch.empty((M, H), dtype=F32, device=dev), torch.empty((M, H), dtype=F32, device=dev)] if ctx.f32_stream else None
+        carry32 = None      # fp32 residual-stream gradient handed down from the layer above
         gouts = list(grad_outs)
         if not meta.all_layers:
             gouts = [None] * (L - 1) + gouts
@@ -380,7 +455,11 @@ class EncoderFn(torch.autograd.Function):
         for l in range(L - 1, -1, -1):
             dy32 = gouts[l]
             if dy32 is not None:
-                dy32 = dy32.contiguous().float()
+                dy32 = dy32.contiguous().float().view(M, H)
+                if carry32 is not None:
+                    dy32 = dy32 + carry32          # (only when several layers' outputs were requested)
+            elif carry32 is not None:
+                dy32 = carry32
             if dy16 is None and dy32 is None:
                 dy32 = torch.zeros((M, H), dtype=F32, device=dev)
             f = flat[l]
@@ -394,13 +473,15 @@ class EncoderFn(torch.autograd.Function):
             g.dln1_g, g.dln1_b, g.dw_1, g.db_1 = dg1.data_ptr(), dbt1.data_ptr(), dw_1.data_ptr(), db_1.data_ptr()
             g.dw_2, g.db_2, g.dln2_g, g.dln2_b = dw_2.data_ptr(), db_2.data_ptr(), dg2.data_ptr(), dbt2.data_ptr()
             w = meta.weights.layer_struct(l, params)
-            a = _acts_struct(car, l, None)
+            a = _acts_struct(car, l, None, ctx.has_drop)
             x_ptr = emb_ptr if l == 0 else car.ptr("y%d" % (l - 1))
             out_dx = dx[l & 1]
+            out_dx32 = dx32[l & 1] if dx32 is not None else None
             _chk(lib.vlb_bert_layer_backward(ctypes.byref(w), ctypes.byref(a), x_ptr, _p(ctx.add_mask), _p(dy16),
-                                             _p(dy32), out_dx.data_ptr(), ctypes.byref(g), ws.data_ptr(), ws_bytes, B, S, H,
-                                             heads, I, ctx.drops[l], st))
+                                             _p(dy32), out_dx.data_ptr(), _p(out_dx32), ctypes.byref(g), ws.data_ptr(), ws_bytes,
+                                             B, S, H, heads, I, ctx.drops[l], st))
             dy16 = out_dx
+            carry32 = out_dx32
             if meta.reducer is not None:
                 meta.reducer.launch(f)
             grads[16 * l: 16 * l + 16] = [dw_qkv[0:H], db_qkv[0:H], dw_qkv[H:2 * H], db_qkv[H:2 * H], dw_qkv[2 * H:],
@@ -408,8 +489,9 @@ class EncoderFn(torch.autograd.Function):
         if meta.reducer is not None:
             meta.reducer.drain()
         d_emb = dy16.view(B, S, H)
+        d_emb32 = carry32.view(B, S, H) if carry32 is not None else None
         ctx.car = None
-        return (d_emb, None, None) + tuple(grads)
+        return (d_emb, d_emb32, None, None) + tuple(grads)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -456,7 +538,8 @@ class PackIndex(object):
 
 class EmbeddingFn(torch.autograd.Function):
     """forward(text_visual f32 [B,T,H], object_vl f32 [B,R,2H], word, end, pos, type, ln_w, ln_b, vt_w, vt_b, vo_w, vo_b,
-    ids int64 [B,T], pidx: PackIndex, eps) -> emb bf16 [B,S,H]"""
+    ids int64 [B,T], pidx: PackIndex, eps, drop) -> (emb bf16 [B,S,H], emb f32 [B,S,H]): the same embedding twice -- the bf16
+    copy is the GEMM operand of layer 0, the fp32 copy its residual operand; their gradients are summed in backward."""
 
     @staticmethod
     def forward(ctx, text_visual, object_vl, word, end, pos, typ, ln_w, ln_b, vt_w, vt_b, vo_w, vo_b, ids, pidx, eps, drop=None):
@@ -483,16 +566,16 @@ class EmbeddingFn(torch.autograd.Function):
         _chk(lib.vlb_pack_forward(_p(pidx.kind), _p(pidx.src), _p(pidx.pos_id), _p(pidx.type_id), _p(ids), _p(word), _p(end),
                                   _p(pos), _p(typ), _p(tv_ln), _p(ov_ln), _p(ov), 2 * H, H, _p(e), B, T, R, S, H,
                                   word.shape[0], pos.shape[0], _p(pidx.err), st))
-        emb, _, e_mean, e_rstd = layernorm_forward(e, ln_w, ln_b, eps, drop=drop)   # dropout(LayerNorm(.)), :237-239
+        emb, emb32, e_mean, e_rstd = layernorm_forward(e, ln_w, ln_b, eps, want_f32=True, drop=drop)   # dropout(LayerNorm(.)), :237-239
         ctx.drop = drop
         ctx.save_for_backward(tv, ov, word, end, pos, typ, ln_w, vt_w, vo_w, ids, e, e_mean, e_rstd, tv_mean, tv_rstd,
                               ov_mean, ov_rstd)
         ctx.pidx = pidx
         ctx.dims = (B, T, R, S, H)
-        return emb.view(B, S, H)
+        return emb.view(B, S, H), emb32.view(B, S, H)
 
     @staticmethod
-    def backward(ctx, d_emb):
+    def backward(ctx, d_emb, d_emb32):
         (tv, ov, word, end, pos, typ, ln_w, vt_w, vo_w, ids, e, e_mean, e_rstd, tv_mean, tv_rstd, ov_mean,
          ov_rstd) = ctx.saved_tensors
         pidx = ctx.pidx
@@ -502,8 +585,15 @@ class EmbeddingFn(torch.autograd.Function):
         dev = e.device
         z = lambda *s: torch.zeros(s, dtype=F32, device=dev)  # noqa: E731
         d_ln_w, d_ln_b, d_vt_w, d_vt_b, d_vo_w, d_vo_b = z(H), z(H), z(H), z(H), z(H), z(H)
-        d16 = d_emb.contiguous().view(B * S, H)
-        dy16, dy32 = (d16, None) if d16.dtype == BF16 else (None, d16.float())
+        dy16 = dy32 = None
+        if d_emb is not None:
+            d16 = d_emb.contiguous().view(B * S, H)
+            dy16, dy32 = (d16, None) if d16.dtype == BF16 else (None, d16.float())
+        if d_emb32 is not None:
+            d32 = d_emb32.contiguous().view(B * S, H).float()
+            dy32 = d32 if dy32 is None else dy32 + d32
+        if dy16 is None and dy32 is None:
+            dy32 = torch.zeros((B * S, H), dtype=F32, device=dev)
         _, de = layernorm_backward(dy16, dy32, e, e_mean, e_rstd, ln_w, d_ln_w, d_ln_b, want_bf16=False, want_f32=True,
                                    in_drop=ctx.drop)
         d_word, d_end, d_pos, d_typ = z(*word.shape), z(*end.shape), z(*pos.shape), z(*typ.shape)
