@@ -12,9 +12,9 @@ the GPU box, so this side restates the loop.
 Tolerance: loss trajectory and clip norms within 1e-2 / 2e-2 relative (bf16 GEMMs, 2 layers).  Final weights are compared
 through the UPDATE w_final - w_0.  Adam's m / sqrt(v) turns every element's first steps into ~ +-lr whatever |g| is, so an
 element whose gradient is smaller than the bf16 noise (a fraction f of them) may move the other way: relative L2 of the
-update ~ sqrt(4 f) ~ 0.1 for f ~ 0.3 % -- a property of Adam under ANY bf16 implementation, not of this one.  Asserted:
-<= 0.35 per tensor and <= 0.2 over all weights (a wrong dropout mask or a wrong gradient gives ~1.4); measured values are
-printed."""
+update ~ sqrt(4 f) -- a property of Adam under ANY bf16 implementation.  Measured on B200 (profiles/r02_*): loss trajectories
+equal to 1e-5, update error 0.4 % over all weights, 0.6 % for the worst tensor.  Asserted: <= 5e-2 per tensor and <= 2e-2
+over all weights (a wrong dropout mask or a wrong gradient gives ~1.4)."""
 import numpy as np
 import pytest
 import torch
@@ -89,7 +89,7 @@ def test_training_steps_with_fused_adamw_against_the_oracle_loop(p_drop):
                 oo.adamw_step(p.numpy(), g, m[n], v[n], k + 1, lr, weight_decay=decay[n])
 
     for a, b in zip(ours_loss, ref_loss):
-        assert abs(a - b) <= 1e-2 * abs(b), (ours_loss, ref_loss)
+        assert abs(a - b) <= 2e-3 * abs(b), (ours_loss, ref_loss)
     for a, b in zip(ours_norm, ref_norm):
         assert abs(a - b) <= 2e-2 * abs(b), (ours_norm, ref_norm)
     assert ref_loss[-1] < ref_loss[0]
@@ -106,7 +106,7 @@ def test_training_steps_with_fused_adamw_against_the_oracle_loop(p_drop):
         if n.endswith("attention.self.key.bias"):
             continue        # zero gradient in exact arithmetic: Adam turns rounding noise into +-lr steps on both sides
         worst = max(worst, float((d_our - d_ref).norm() / d_ref.norm()))
-        assert float((d_our - d_ref).norm() / d_ref.norm()) <= 0.35, n
+        assert float((d_our - d_ref).norm() / d_ref.norm()) <= 5e-2, n
     print("\ntraining loop p=%.1f: loss ours %s ref %s; update error: all weights %.3f, worst tensor %.3f" % (
         p_drop, ["%.5f" % x for x in ours_loss], ["%.5f" % x for x in ref_loss], (num / den) ** 0.5, worst))
-    assert (num / den) ** 0.5 <= 0.2, (num / den) ** 0.5
+    assert (num / den) ** 0.5 <= 2e-2, (num / den) ** 0.5

@@ -92,6 +92,32 @@ def main():
         tot_us += us
         tot_fl += flops
         print("%-50s %8.2f us  %7.1f TFLOP/s" % (name, us, flops / us / 1e6))
+    # yardstick: the same shapes as plain bf16 GEMMs through torch.matmul (cuBLASLt heuristics; no epilogue work at all)
+    if os.environ.get("VLB_BENCH_CUBLAS", "1") == "1":
+        shapes = [("qkv / dx^T", M, 3 * H, H), ("attnout / dctx", M, H, H), ("ffn-up / dz", M, I, H), ("ffn-dn / dh", M, H, I)]
+        for name, m, n, k in shapes:
+            As = [rnd(m, k) for _ in range(a.sets)]
+            Bs = [rnd(k, n, scale=0.03) for _ in range(a.sets)]
+            Cs = [torch.empty(m, n, device=dev, dtype=bf) for _ in range(a.sets)]
+            with torch.cuda.stream(side):
+                for i in range(a.sets):
+                    torch.matmul(As[i], Bs[i], out=Cs[i])
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    for r in range(a.reps):
+                        torch.matmul(As[r % a.sets], Bs[r % a.sets], out=Cs[r % a.sets])
+                graph.replay()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(side)
+                for _ in range(3):
+                    graph.replay()
+                e1.record(side)
+                torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / (3 * a.reps)
+            res.setdefault("cublas", {})[name] = {"us": round(us, 2), "tflops": round(2.0 * m * n * k / us / 1e6, 1)}
+            print("cuBLAS %-44s %8.2f us  %7.1f TFLOP/s" % ("%s  %dx%dx%d" % (name, m, n, k), us, 2.0 * m * n * k / us / 1e6))
     res["sum_us"] = round(tot_us, 2)
     res["tflops"] = round(tot_fl / tot_us / 1e6, 1)
     print("sum %.1f us  %.1f TFLOP/s  (graph-replayed back-to-back launches of one kind)" % (tot_us, tot_fl / tot_us / 1e6))
