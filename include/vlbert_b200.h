@@ -404,7 +404,14 @@ typedef struct VlbLayerDropout {
   float p_hidden;
   uint32_t site_attn, site_self_out, site_out;   /* 1+3l, 2+3l, 3+3l for layer l */
   const uint64_t* rng;                           /* device: {seed, step} */
+  /* 0: vlb_bert_layer_forward writes acts->keep_* itself (one extra launch at the head of the layer).  1: the caller has
+   * already done so with vlb_layer_dropout_bits -- typically for all layers on a side stream at the start of the step, where
+   * the instruction-bound Philox work overlaps the tensor-bound GEMMs instead of sitting in the layer's dependency chain. */
+  int keep_bits_ready;
 } VlbLayerDropout;
+
+/* writes acts->keep_attn / keep_self_out / keep_out for one layer (the sites whose probability is > 0) */
+int vlb_layer_dropout_bits(const VlbLayerActs* acts, int B, int S, int H, int heads, const VlbLayerDropout* drop, void* stream);
 
 /* x_resid: NULL = the residual add uses x_bf16 (all-bf16 residual stream); else the fp32 residual stream (see VlbResidual). */
 int vlb_bert_layer_forward(const VlbLayerWeights* w, const void* x_bf16, const VlbResidual* x_resid, const float* add_mask,

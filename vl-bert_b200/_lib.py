@@ -81,6 +81,7 @@ def _declare(lib):
     decl("vlb_bert_layer_forward", [P, P, P, P, P, I, I, I, I, I, F, P, P])
     decl("vlb_bert_layer_backward_workspace", [I, I, I], L)
     decl("vlb_bert_layer_backward", [P, P, P, P, P, P, P, P, P, P, L, I, I, I, I, I, P, P])
+    decl("vlb_layer_dropout_bits", [P, I, I, I, I, P, P])
     decl("vlb_gemm_bias_residual_f32", [I, I, I, P, I, P, I, P, I, P, P, P, I, P])
     decl("vlb_dropout_bits_words", [L, I], L)
     decl("vlb_dropout_bits", [P, L, I, P, P])
@@ -127,7 +128,7 @@ class Residual(ctypes.Structure):
 class LayerDropout(ctypes.Structure):
     """VlbLayerDropout"""
     _fields_ = [("p_attn", c_float), ("p_hidden", c_float), ("site_attn", c_uint32), ("site_self_out", c_uint32),
-                ("site_out", c_uint32), ("rng", c_void_p)]
+                ("site_out", c_uint32), ("rng", c_void_p), ("keep_bits_ready", c_int)]
 
 
 class GroupedProblem(ctypes.Structure):

@@ -369,6 +369,10 @@ int vlb_bert_layer_forward(const VlbLayerWeights* w, const void* x_bf16, const V
   if (!w || !acts || !x_bf16) { set_last_error("vlb_bert_layer_forward: null pointer"); return VLB_ERR_INVALID; }
   return bert_layer_forward(*w, x_bf16, x_resid, add_mask, *acts, B, S, H, heads, I, eps, drop, ST);
 }
+int vlb_layer_dropout_bits(const VlbLayerActs* acts, int B, int S, int H, int heads, const VlbLayerDropout* drop, void* stream) {
+  if (!acts || !drop || !drop->rng) { set_last_error("vlb_layer_dropout_bits: null pointer"); return VLB_ERR_INVALID; }
+  COUNTED(1, layer_dropout_bits(acts->keep_attn, acts->keep_self_out, acts->keep_out, B, S, H, heads, *drop, ST));
+}
 int64_t vlb_bert_layer_backward_workspace(int M, int H, int I) { return bert_layer_backward_workspace(M, H, I); }
 int vlb_bert_layer_backward(const VlbLayerWeights* w, const VlbLayerActs* acts, const void* x_bf16, const float* add_mask,
                             const void* dy_bf16, const float* dy_f32, void* dx_bf16, float* dx_f32, const VlbLayerGrads* grads, void* workspace,

@@ -51,7 +51,7 @@ int bert_layer_forward(const VlbLayerWeights& w, const void* x, const VlbResidua
   int rc;
   int launches = 7;
   // 0. keep flags of the layer's three dropout sites (read by the forward kernels below and by the whole backward)
-  if (ld.attn.p > 0.0f || ld.out.p > 0.0f) {
+  if ((ld.attn.p > 0.0f || ld.out.p > 0.0f) && !drop->keep_bits_ready) {
     if ((rc = layer_dropout_bits(a.keep_attn, a.keep_self_out, a.keep_out, B, S, H, heads, *drop, st))) return rc;
     ++launches;
   }

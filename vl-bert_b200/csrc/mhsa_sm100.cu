@@ -155,15 +155,10 @@ mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     umma_commit(smem_u32(&bars[1]));
   }
 
-  // dropout keep flags of this thread's probability row (independent of the data: evaluated while the loads / MMAs fly)
-  uint32_t keep[NKEYS / 32];
+  // dropout keep flags of this thread's probability row: one 32-bit word per 32 keys, loaded at the top of each chunk
   const bool dropping = p.drop.thresh != 0u && q0 + t < p.S;
-  if (dropping) {
-    const uint64_t mrow = ((uint64_t)b * p.heads + h) * (uint64_t)p.S + (uint64_t)(q0 + t);
-    const int wpr = (p.S + 31) >> 5;
-#pragma unroll
-    for (int c = 0; c < NKEYS / 32; ++c) keep[c] = keep_word(p.drop, mrow, wpr, c);
-  }
+  const uint64_t mrow = ((uint64_t)b * p.heads + h) * (uint64_t)p.S + (uint64_t)(q0 + t);
+  const int wpr = (p.S + 31) >> 5;
   mbar_wait(smem_u32(&bars[1]), 0);
   tc_fence_after();
   const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
@@ -180,10 +175,11 @@ mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   // pass 2: p = exp(x - m), row sum, stage P (bf16) for the second product.  P overwrites the Q|K tiles (the S MMAs
   // that read them completed before bars[1] fired).
   float l = 0.0f;
-#pragma unroll
+#pragma unroll 1
   for (int c = 0; c < NKEYS / 32; ++c) {
     uint32_t v[32];
     float x[32];
+    const uint32_t kb = dropping ? keep_word(p.drop, mrow, wpr, c) : 0u;   // (in flight under the TMEM load)
     tmem_ld32(t_row + c * 32, v);
     tmem_ld_wait();
 #pragma unroll
@@ -193,7 +189,6 @@ mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
     // dropout acts on the normalised probabilities; the row sum (and the saved log-sum-exp) stay those of the full softmax
     if (dropping) {
-      const uint32_t kb = keep[c];
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] = ((kb >> j) & 1u) ? x[j] * p.drop.scale : 0.0f;
     }
@@ -370,29 +365,24 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) mhsa_bwd_kernel(const __grid_c
     lse = p.lse[((size_t)b * p.heads + h) * p.S + q0 + t];
   }
 
-  // dropout keep flags of this thread's 64 probabilities: evaluated before the wait, they overlap the loads / MMAs
-  uint32_t keepb[NK / 64];
+  // dropout keep flags of this thread's 64 probabilities: one word per 32-key chunk, loaded at the top of each chunk
   const bool dropping = p.drop.thresh != 0u && valid;
-  if (dropping) {
-    const uint64_t mrow = ((uint64_t)b * p.heads + h) * (uint64_t)p.S + (uint64_t)(q0 + t);
-    const int wpr = (p.S + 31) >> 5;
-#pragma unroll
-    for (int cc = 0; cc < NK / 64; ++cc) keepb[cc] = keep_word(p.drop, mrow, wpr, (k0 >> 5) + half * (NK / 64) + cc);
-  }
+  const uint64_t mrow = ((uint64_t)b * p.heads + h) * (uint64_t)p.S + (uint64_t)(q0 + t);
+  const int wpr = (p.S + 31) >> 5;
   mbar_wait(smem_u32(&bars[1]), 0);
   tc_fence_after();
   const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-#pragma unroll
+#pragma unroll 1
   for (int cc = 0; cc < NK / 64; ++cc) {
     const int c = half * (NK / 64) + cc;  // this thread's 32-column chunks: [half*64, half*64 + 64)
     uint32_t vs[32], vd[32];
     float pr[32], ds[32];
+    const uint32_t kb = dropping ? keep_word(p.drop, mrow, wpr, (k0 >> 5) + c) : 0u;   // (in flight under the TMEM loads)
     tmem_ld32(t_row + c * 32, vs);
     tmem_ld32(t_row + 128 + c * 32, vd);
     tmem_ld_wait();
     if (dropping) {
       // ctx = (P o M / (1-p)) V:  dV = (P o M')^T dO ;  dP = (dO V^T) o M' ;  dS = P o (dP - D) with D = rowsum(dO o O)
-      const uint32_t kb = keepb[cc];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int col = k0 + c * 32 + j;

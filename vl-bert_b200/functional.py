@@ -342,6 +342,19 @@ def _acts_struct(car, l, y_f32, drop=False):
     return a
 
 
+_SIDE_STREAM_BITS = os.environ.get("VLB_BITS_SIDE_STREAM", "1") != "0"
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    s = _SIDE_STREAMS.get(key)
+    if s is None:
+        s = torch.cuda.Stream(device=device)
+        _SIDE_STREAMS[key] = s
+    return s
+
+
 def _layer_drop_structs(drop, L):
     """drop: None (eval / p = 0) or an object with p_attn, p_hidden, rng (int64 CUDA tensor: seed, step).  Returns one
     ctypes reference (or None) per layer; sites follow the contract: 1+3l attention, 2+3l self-output, 3+3l output."""
@@ -356,6 +369,7 @@ def _layer_drop_structs(drop, L):
         d.p_attn, d.p_hidden = float(drop.p_attn), float(drop.p_hidden)
         d.site_attn, d.site_self_out, d.site_out = 1 + 3 * l, 2 + 3 * l, 3 + 3 * l
         d.rng = rng.data_ptr()
+        d.keep_bits_ready = 0
         out.append(d)
     refs = [ctypes.byref(d) for d in out]
     refs.append(out)   # keep the structs alive as long as the reference list is
@@ -402,11 +416,32 @@ class EncoderFn(torch.autograd.Function):
         if emb32 is not None:           # layer 0: the embedding itself in fp32
             resid = _lib.Residual()
             resid.x_f32 = emb32.data_ptr()
+        bits_ready = None
+        if has_drop and _SIDE_STREAM_BITS:
+            # The keep flags of every layer are generated up front on a side stream: ten Philox rounds per four elements are
+            # instruction-bound work that overlaps the tensor-bound kernels of the earlier layers instead of sitting at the head
+            # of each layer's dependency chain.  Layer l waits for its own event only.
+            cur = torch.cuda.current_stream()
+            side = _side_stream(emb.device)
+            side.wait_stream(cur)                     # (seed, step) snapshot and the activation buffer are ordered before
+            car.buf.record_stream(side)
+            bits_ready = []
+            structs = drops[L]
+            with torch.cuda.stream(side):
+                for l in range(L):
+                    a = _acts_struct(car, l, None, True)
+                    _chk(lib.vlb_layer_dropout_bits(ctypes.byref(a), B, S, H, heads, drops[l], side.cuda_stream))
+                    structs[l].keep_bits_ready = 1
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    bits_ready.append(ev)
         for l in range(L):
             want = meta.all_layers or l == L - 1
             y32 = torch.empty((B, S, H), dtype=F32, device=emb.device) if want else None
             w = meta.weights.layer_struct(l, params)
             a = _acts_struct(car, l, y32, has_drop)
+            if bits_ready is not None:
+                torch.cuda.current_stream().wait_event(bits_ready[l])
             _chk(lib.vlb_bert_layer_forward(ctypes.byref(w), x_ptr, None if resid is None else ctypes.byref(resid), _p(add_mask),
                                             ctypes.byref(a), B, S, H, heads, I, float(meta.eps), drops[l], st))
             x_ptr = car.ptr("y%d" % l)
