@@ -137,9 +137,11 @@ int vlb_mhsa_backward(const void* qkv, const float* add_mask, const void* ctx, c
  * probabilities.  The backward must be given the same VlbDropout (and the same *rng contents) as the forward. */
 int vlb_mhsa_forward_dropout(const void* qkv, const float* add_mask, void* ctx, float* lse, int B, int S, int H,
                              int heads, const VlbDropout* drop, void* stream);
+/* dbias_qkv (optional, f32 [3H]): += column sums of dqkv = the bias gradients of the query / key / value Linear layers
+ * (modeling.py:277-279), reduced inside the kernel's store phase instead of a separate pass over dqkv. */
 int vlb_mhsa_backward_dropout(const void* qkv, const float* add_mask, const void* ctx, const float* lse,
                               const void* dctx, void* dqkv, float* scratch_f32, int B, int S, int H, int heads,
-                              const VlbDropout* drop, void* stream);
+                              float* dbias_qkv, const VlbDropout* drop, void* stream);
 
 /* ---- LayerNorm (TF style, eps inside the sqrt) -----------------------------------------------
  * Replaces BertLayerNorm.forward (modeling.py:231-235) and its autograd backward.

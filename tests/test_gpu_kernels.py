@@ -251,8 +251,12 @@ def test_mhsa_forward_backward(VF, B, S, heads):
     (ref * dctx).sum().backward()
     ctx, lse = VF.mhsa_forward(qkv.to(DEV, BF16), add_mask.to(DEV), B, S, H, heads)
     assert rel(ctx.float(), ref.detach()) <= 4e-3  # P and ctx are bf16 on the tensor-core path
-    dqkv = VF.mhsa_backward(qkv.to(DEV, BF16), add_mask.to(DEV), ctx, lse, dctx.to(DEV, BF16), B, S, H, heads)
+    dbias = torch.ones(3 * H, device=DEV)
+    dqkv = VF.mhsa_backward(qkv.to(DEV, BF16), add_mask.to(DEV), ctx, lse, dctx.to(DEV, BF16), B, S, H, heads, dbias=dbias)
     assert rel(dqkv.float(), qt.grad) <= 8e-3
+    # fused bias gradients: "+=" column sums of dqkv (key-bias sums are ~0 by softmax shift invariance: absolute check)
+    cs = qt.grad.sum(0)
+    assert (dbias.cpu() - 1.0 - cs).norm().item() <= 1e-2 * max(cs.norm().item(), 1e-3 * qt.grad.norm().item())
     scale = qt.grad.norm().item() / 3 ** 0.5
     for blk in range(3):  # dq, dk, dv separately (dq = dk = 0 exactly when S == 1: absolute check against the overall scale)
         sl = slice(blk * H, (blk + 1) * H)

@@ -89,7 +89,7 @@ def _declare(lib):
     decl("vlb_gemm_bf16_dropout", [c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p,
                                    c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_float, c_int, c_int, P, P])
     decl("vlb_mhsa_forward_dropout", [P, P, P, P, I, I, I, I, P, P])
-    decl("vlb_mhsa_backward_dropout", [P, P, P, P, P, P, P, I, I, I, I, P, P])
+    decl("vlb_mhsa_backward_dropout", [P, P, P, P, P, P, P, I, I, I, I, P, P, P])
     decl("vlb_layernorm_forward_dropout", [P, I, P, P, P, P, P, P, I, I, F, P, P])
     decl("vlb_layernorm_backward_dropout", [P, P, P, I, P, P, P, P, P, I, P, P, P, I, I, P, P, P, P])
     decl("vlb_region_operand_dropout", [P, I, P, P, I, P, P, P, P, I, I, I, P, P])

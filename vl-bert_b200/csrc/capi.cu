@@ -184,8 +184,9 @@ int vlb_mhsa_forward_dropout(const void* qkv, const float* add_mask, void* ctx, 
   COUNTED(1, mhsa_forward(qkv, add_mask, ctx, lse, B, S, H, heads, ST, drop));
 }
 int vlb_mhsa_backward_dropout(const void* qkv, const float* add_mask, const void* ctx, const float* lse, const void* dctx,
-                              void* dqkv, float* scratch_f32, int B, int S, int H, int heads, const VlbDropout* drop, void* stream) {
-  COUNTED(1, mhsa_backward(qkv, add_mask, ctx, lse, dctx, dqkv, scratch_f32, B, S, H, heads, ST, drop));
+                              void* dqkv, float* scratch_f32, int B, int S, int H, int heads, float* dbias_qkv, const VlbDropout* drop,
+                              void* stream) {
+  COUNTED(1, mhsa_backward(qkv, add_mask, ctx, lse, dctx, dqkv, scratch_f32, B, S, H, heads, ST, drop, dbias_qkv));
 }
 int vlb_layernorm_forward_dropout(const float* x, int ldx, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
                                   float* mean, float* rstd, int M, int H, float eps, const VlbDropout* out_drop, void* stream) {

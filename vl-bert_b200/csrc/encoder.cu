@@ -104,7 +104,7 @@ int64_t bert_layer_backward_workspace(int M, int H, int I) {
   return al((int64_t)M * H * 2) * 4 + al((int64_t)M * I * 2) + al((int64_t)M * 3 * H * 2) + al((int64_t)M * H * 4) + al((int64_t)M * 3 * H * 4);
 }
 
-// Backward: 9 launches.
+// Backward: 8 launches.
 int bert_layer_backward(const VlbLayerWeights& w, const VlbLayerActs& a, const void* x, const float* add_mask, const void* dy16,
                         const float* dy32, void* dx, float* dx_f32, const VlbLayerGrads& g, void* workspace, int64_t ws_bytes, int B, int S,
                         int H, int heads, int I, const VlbLayerDropout* drop, cudaStream_t st) {
@@ -165,9 +165,9 @@ int bert_layer_backward(const VlbLayerWeights& w, const VlbLayerActs& a, const v
   e = GemmEpilogue(); e.out = dctx; e.ldo = H; e.out_kind = OUT_BF16;
   if ((rc = gemm_bf16(GEMM_NN, M, H, H, d_a, H, w.w_o, H, e, 1, 0, st))) return rc;
   // attention backward
-  if ((rc = mhsa_backward(a.qkv, add_mask, a.ctx, a.lse, dctx, dqkv, attn_scratch, B, S, H, heads, st, &ld.attn))) return rc;
-  // db_qkv += colsum(dqkv) ; dx = dqkv Wqkv (+ d_a in the bf16 stream)
-  if ((rc = colsum_bf16(dqkv, 3 * H, g.db_qkv, M, 3 * H, st))) return rc;
+  // attention backward; db_qkv += colsum(dqkv) is fused into its store phase (a transposing warp reduction + one atomic per lane)
+  if ((rc = mhsa_backward(a.qkv, add_mask, a.ctx, a.lse, dctx, dqkv, attn_scratch, B, S, H, heads, st, &ld.attn, g.db_qkv))) return rc;
+  // dx = dqkv Wqkv (+ d_a in the bf16 stream)
   e = GemmEpilogue(); e.out = dx; e.ldo = H; e.out_kind = OUT_BF16;
   if (!f32_stream) { e.resid = d_a_plain; e.ldr = H; e.resid_kind = RESID_BF16; }
   if ((rc = gemm_bf16(GEMM_NN, M, H, 3 * H, dqkv, 3 * H, w.w_qkv, H, e, 1, 0, st))) return rc;
@@ -185,7 +185,7 @@ int bert_layer_backward(const VlbLayerWeights& w, const VlbLayerActs& a, const v
     static const int env_split = [] { const char* v = getenv("VLB_WGRAD_SPLIT"); return v ? atoi(v) : 2; }();
     if ((rc = gemm_grouped_tn(4, q, M, env_split, true, env_bn, st))) return rc;
   }
-  count_launch(9);
+  count_launch(8);
   return VLB_OK;
 }
 

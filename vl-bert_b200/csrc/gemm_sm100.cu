@@ -223,6 +223,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
       in16[i] = (row < M && col_ok) ? __ldg(reinterpret_cast<const uint2*>(src + (size_t)row * ld + col)) : make_uint2(0u, 0u);
     }
   }
+  uint32_t kw[8];   // dropout keep flags: the word holding this lane's four columns, one per row (issued with the other loads)
+  if (has_drop) {
+    const int wpr = (N + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row_base + i * 4 + r0;
+      kw[i] = (row < M && col_ok) ? __ldg(e.drop.bits + (size_t)row * wpr + (col >> 5)) : 0u;
+    }
+  }
   float ln_mu[8], ln_rs[8];
   float4 ln_g4 = make_float4(1.f, 1.f, 1.f, 1.f), ln_b4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const bool ln_resid = resid_kind == RESID_LN_F32 && e.ln_mean != nullptr;
@@ -296,7 +305,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
 #pragma unroll
         for (int j = 0; j < 4; ++j) x[j] = (act == ACT_DGELU_MUL) ? x[j] * zz[j] : (zz[j] > 0.0f ? x[j] : 0.0f);
       }
-      if (has_drop) drop4_bits(x, keep4_bits(e.drop.bits, (size_t)row, (N + 31) >> 5, col), e.drop.scale);
+      if (has_drop) drop4_bits(x, (kw[i] >> (col & 31)) & 0xFu, e.drop.scale);
       if (resid_kind == RESID_BF16) {
         x[0] += bf16lo(in16[i].x); x[1] += bf16hi(in16[i].x); x[2] += bf16lo(in16[i].y); x[3] += bf16hi(in16[i].y);
       } else if (resid_kind == RESID_F32) {

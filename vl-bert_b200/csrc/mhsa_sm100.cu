@@ -38,6 +38,7 @@ struct MhsaParams {
   float* dqkv_f32;            // [B*S, 3H] fp32 accumulation buffer, only for S > 128 (several (q-tile, k-tile) blocks)
   int ktiles;                 // number of 128-key tiles (blockIdx.z = q_tile * ktiles + k_tile)
   DropCfg drop;               // dropout on the probabilities (modeling.py:310); mask rows = (b, head, query), columns = keys
+  float* dbias;               // optional [3H] fp32: += column sums of dqkv (the bias gradients of the query / key / value Linear)
 };
 
 // Dropout on the probabilities reads precomputed keep flags (DropCfg::bits, written by dropout_bits_kernel for the [B*heads*S, S]
@@ -249,11 +250,32 @@ mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
+// Column sums over the warp's 32 rows of a 32-column accumulator chunk (thread = row): a transposing butterfly -- in step
+// `off` every lane keeps the half of its values whose column bit equals its own lane bit and adds the partner's -- leaves
+// lane L with the sum of column L after 16+8+4+2+1 = 31 shuffles; one atomic per lane.  (bias gradient of the QKV Linear)
+__device__ __forceinline__ void colsum32_atomic(float* dst, const uint32_t (&v)[32], bool row_valid, int lane) {
+  float a[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) a[i] = row_valid ? __uint_as_float(v[i]) : 0.0f;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float mine = up ? a[i + off] : a[i];
+      const float send = up ? a[i] : a[i + off];
+      a[i] = mine + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  atomicAdd(dst + lane, a[0]);
+}
+
 // 32 accumulator columns of one row -> 32 bf16 values in global memory
-__device__ __forceinline__ void store_row32(__nv_bfloat16* dst, uint32_t tcol_addr) {
+__device__ __forceinline__ void store_row32(__nv_bfloat16* dst, uint32_t tcol_addr, float* colsum = nullptr, int lane = 0) {
   uint32_t v0[32];
   tmem_ld32(tcol_addr, v0);
   tmem_ld_wait();
+  if (colsum != nullptr) colsum32_atomic(colsum, v0, dst != nullptr, lane);
   if (dst != nullptr) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -268,10 +290,11 @@ __device__ __forceinline__ void store_row32(__nv_bfloat16* dst, uint32_t tcol_ad
 }
 
 // 32 accumulator columns of one row -> fp32 atomic accumulation (multi-block backward, S > 128)
-__device__ __forceinline__ void add_row32(float* dst, uint32_t tcol_addr) {
+__device__ __forceinline__ void add_row32(float* dst, uint32_t tcol_addr, float* colsum = nullptr, int lane = 0) {
   uint32_t v0[32];
   tmem_ld32(tcol_addr, v0);
   tmem_ld_wait();
+  if (colsum != nullptr) colsum32_atomic(colsum, v0, dst != nullptr, lane);
   if (dst != nullptr) {
 #pragma unroll
     for (int g = 0; g < 8; ++g)
@@ -432,14 +455,18 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) mhsa_bwd_kernel(const __grid_c
   {
     // each thread of the pair handles 32 of the 64 head-dim columns: dQ of query row q0+t, dK / dV of key row k0+t
     const size_t col = (size_t)h * D_HEAD + half * 32;
+    const int lane = tid & 31;
+    float* cq = p.dbias ? p.dbias + col : nullptr;               // fused bias gradients: db_q / db_k / db_v += column sums
+    float* ck = p.dbias ? p.dbias + p.H + col : nullptr;
+    float* cv = p.dbias ? p.dbias + 2 * p.H + col : nullptr;
     if (p.dqkv_f32 == nullptr) {  // single block: final values, bf16
-      store_row32(valid ? p.dqkv + (size_t)(row0 + q0 + t) * (3 * p.H) + col : nullptr, t_row + T_DQ + half * 32);
-      store_row32(kvalid ? p.dqkv + (size_t)(row0 + k0 + t) * (3 * p.H) + p.H + col : nullptr, t_row + T_DK + half * 32);
-      store_row32(kvalid ? p.dqkv + (size_t)(row0 + k0 + t) * (3 * p.H) + 2 * p.H + col : nullptr, t_row + T_DV + half * 32);
+      store_row32(valid ? p.dqkv + (size_t)(row0 + q0 + t) * (3 * p.H) + col : nullptr, t_row + T_DQ + half * 32, cq, lane);
+      store_row32(kvalid ? p.dqkv + (size_t)(row0 + k0 + t) * (3 * p.H) + p.H + col : nullptr, t_row + T_DK + half * 32, ck, lane);
+      store_row32(kvalid ? p.dqkv + (size_t)(row0 + k0 + t) * (3 * p.H) + 2 * p.H + col : nullptr, t_row + T_DV + half * 32, cv, lane);
     } else {                      // partial sums over the other tile dimension: fp32 atomics, converted afterwards
-      add_row32(valid ? p.dqkv_f32 + (size_t)(row0 + q0 + t) * (3 * p.H) + col : nullptr, t_row + T_DQ + half * 32);
-      add_row32(kvalid ? p.dqkv_f32 + (size_t)(row0 + k0 + t) * (3 * p.H) + p.H + col : nullptr, t_row + T_DK + half * 32);
-      add_row32(kvalid ? p.dqkv_f32 + (size_t)(row0 + k0 + t) * (3 * p.H) + 2 * p.H + col : nullptr, t_row + T_DV + half * 32);
+      add_row32(valid ? p.dqkv_f32 + (size_t)(row0 + q0 + t) * (3 * p.H) + col : nullptr, t_row + T_DQ + half * 32, cq, lane);
+      add_row32(kvalid ? p.dqkv_f32 + (size_t)(row0 + k0 + t) * (3 * p.H) + p.H + col : nullptr, t_row + T_DK + half * 32, ck, lane);
+      add_row32(kvalid ? p.dqkv_f32 + (size_t)(row0 + k0 + t) * (3 * p.H) + 2 * p.H + col : nullptr, t_row + T_DV + half * 32, cv, lane);
     }
   }
   tc_fence_before();
@@ -492,7 +519,7 @@ int mhsa_forward(const void* qkv, const float* add_mask, void* ctx, float* lse, 
 int cast_f32_to_bf16(const float* in, void* out, size_t n, cudaStream_t stream);
 
 int mhsa_backward(const void* qkv, const float* add_mask, const void* ctx, const float* lse, const void* dctx, void* dqkv,
-                  float* scratch_f32, int B, int S, int H, int heads, cudaStream_t stream, const VlbDropout* drop) {
+                  float* scratch_f32, int B, int S, int H, int heads, cudaStream_t stream, const VlbDropout* drop, float* dbias_qkv) {
   VLB_REQUIRE(qkv && ctx && lse && dctx && dqkv, "mhsa_backward: null pointer");
   VLB_REQUIRE(drop_valid(drop), "mhsa_backward: bad dropout configuration");
   VLB_REQUIRE(drop == nullptr || drop->p == 0.0f || drop->keep_bits != nullptr, "mhsa_backward: dropout needs the keep bits the forward used");
@@ -511,6 +538,7 @@ int mhsa_backward(const void* qkv, const float* add_mask, const void* ctx, const
   p.dqkv_f32 = tiles == 1 ? nullptr : scratch_f32;
   p.ktiles = tiles;
   p.drop = make_drop(drop);
+  p.dbias = dbias_qkv;
   CUtensorMap tm, tmd;
   int rc = make_tmap_bf16_2d(&tm, qkv, (uint64_t)B * S, 3 * H, 3 * H, 64, 128);
   if (rc != VLB_OK) return rc;

@@ -11,7 +11,8 @@ void count_launch(int n);
 int mhsa_forward(const void* qkv, const float* add_mask, void* ctx, float* lse, int B, int S, int H, int heads,
                  cudaStream_t stream, const VlbDropout* drop = nullptr);
 int mhsa_backward(const void* qkv, const float* add_mask, const void* ctx, const float* lse, const void* dctx, void* dqkv,
-                  float* scratch_f32, int B, int S, int H, int heads, cudaStream_t stream, const VlbDropout* drop = nullptr);
+                  float* scratch_f32, int B, int S, int H, int heads, cudaStream_t stream, const VlbDropout* drop = nullptr,
+                  float* dbias_qkv = nullptr);
 
 // rowops.cu
 int layernorm_forward(const float* x, int ldx, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean,

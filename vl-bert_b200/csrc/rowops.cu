@@ -128,19 +128,22 @@ struct RowRawB {
   float4 xa[ITERS], xb[ITERS];
   uint4 d16[ITERS];
   float4 da[ITERS], db[ITERS];
+  uint32_t kw[ITERS];   // dropout keep flags of the eight elements (out_drop), prefetched with the row
   float mu, rs;
 };
 
 template <int ITERS, bool HAS16, bool HAS32>
 __device__ __forceinline__ void load_row_bwd(RowRawB<ITERS>& r, const float* __restrict__ xr, const __nv_bfloat16* __restrict__ d16r,
                                              const float* __restrict__ d32r, const float* __restrict__ mean_p,
-                                             const float* __restrict__ rstd_p, int lane, int nvec) {
+                                             const float* __restrict__ rstd_p, int lane, int nvec,
+                                             const uint32_t* __restrict__ bits_row = nullptr) {
   r.mu = __ldg(mean_p);
   r.rs = __ldg(rstd_p);
 #pragma unroll
   for (int i = 0; i < ITERS; ++i) {
     const int vi = lane + i * 32;
     if (vi < nvec) {
+      r.kw[i] = bits_row ? __ldg(bits_row + (vi >> 2)) : 0u;
       r.xa[i] = __ldg(reinterpret_cast<const float4*>(xr + vi * 8));
       r.xb[i] = __ldg(reinterpret_cast<const float4*>(xr + vi * 8 + 4));
       if (HAS16) r.d16[i] = __ldg(reinterpret_cast<const uint4*>(d16r + vi * 8));
@@ -166,7 +169,6 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
   pdl_trigger();
   pdl_wait();
   const DropState in_state = drop_state(in_drop);
-  const int out_wpr = (H + 31) >> 5;
   float gam[ITERS][8];
   float acc_g[ITERS][8], acc_b[ITERS][8], acc_c[ITERS][8];
 #pragma unroll
@@ -180,14 +182,16 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
   }
   int row = blockIdx.x * LN_WARPS + warp;
   RowRawB<ITERS> cur, nxt;
+  const int out_wpr = (H + 31) >> 5;
+  const uint32_t* obits = out_drop.thresh != 0u ? out_drop.bits : nullptr;
   if (row < M)
     load_row_bwd<ITERS, HAS16, HAS32>(cur, x + (size_t)row * ldx, dy16 + (size_t)row * H, dy32 + (size_t)row * H, mean + row,
-                                      rstd + row, lane, nvec);
+                                      rstd + row, lane, nvec, obits ? obits + (size_t)row * out_wpr : nullptr);
   for (; row < M; row += wstride) {
     const int nrow = row + wstride;
     if (nrow < M)
       load_row_bwd<ITERS, HAS16, HAS32>(nxt, x + (size_t)nrow * ldx, dy16 + (size_t)nrow * H, dy32 + (size_t)nrow * H,
-                                        mean + nrow, rstd + nrow, lane, nvec);
+                                        mean + nrow, rstd + nrow, lane, nvec, obits ? obits + (size_t)nrow * out_wpr : nullptr);
     const float mu = cur.mu, rs = cur.rs;
     float dy[ITERS][8], xh[ITERS][8];
     float s1 = 0.0f, s2 = 0.0f;
@@ -243,8 +247,9 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
         if (out_drop.thresh != 0u) {
           // x = dropout(dense(.)) + residual: the dense branch (next GEMM operand, bias gradient) sees dx o mask / (1-p)
           float lo[4] = {o[0], o[1], o[2], o[3]}, hi[4] = {o[4], o[5], o[6], o[7]};
-          drop4_bits(lo, keep4_bits(out_drop.bits, (size_t)row, out_wpr, vi * 8), out_drop.scale);
-          drop4_bits(hi, keep4_bits(out_drop.bits, (size_t)row, out_wpr, vi * 8 + 4), out_drop.scale);
+          const uint32_t k8 = cur.kw[i] >> ((vi * 8) & 31);
+          drop4_bits(lo, k8 & 0xFu, out_drop.scale);
+          drop4_bits(hi, (k8 >> 4) & 0xFu, out_drop.scale);
           uint4 pk;
           pk.x = pack_bf16x2(lo[0], lo[1]); pk.y = pack_bf16x2(lo[2], lo[3]);
           pk.z = pack_bf16x2(hi[0], hi[1]); pk.w = pack_bf16x2(hi[2], hi[3]);

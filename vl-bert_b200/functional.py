@@ -229,13 +229,14 @@ def mhsa_forward(qkv, add_mask, B, S, H, heads, drop=None):
     return ctx, lse
 
 
-def mhsa_backward(qkv, add_mask, ctx, lse, dctx, B, S, H, heads, drop=None):
+def mhsa_backward(qkv, add_mask, ctx, lse, dctx, B, S, H, heads, drop=None, dbias=None):
+    """dbias: optional f32 [3H], += column sums of dqkv (fused bias gradients)"""
     if drop is not None:
         drop.need_bits(B * heads * S, S)
     dqkv = torch.empty((B * S, 3 * H), dtype=BF16, device=qkv.device)
     scratch = torch.empty((B * S, 3 * H), dtype=F32, device=qkv.device) if S > 128 else None
     _chk(_lib.lib().vlb_mhsa_backward_dropout(_p(qkv), _p(add_mask), _p(ctx), _p(lse), _p(dctx), _p(dqkv), _p(scratch), B, S, H,
-                                              heads, _dref(drop), _stream()))
+                                              heads, _p(dbias), _dref(drop), _stream()))
     return dqkv
 
 
