@@ -265,7 +265,26 @@ def test_fastrcnn_end_to_end_against_reference_fixture(golden_dir, compact):
         assert abs(float(gfull.double().norm()) / float(G["gnorm:" + name]) - 1) < 5e-2, name
     print("fastrcnn_e2e vs reference fixture (fp32), relative L2:", {k: "%.2e" % v for k, v in e.items()})
     assert e["body4"] <= 3e-2 and e["obj_reps"] <= 3e-2 and e["obj_reps_raw"] <= 3e-2, e
-    assert all(v <= 0.3 for k, v in e.items() if k.startswith("grad:")), e
+    # Gradients of a 100-layer ReLU network cannot be pinned to the fp32 run tighter than the ReLU-mask flips allow:
+    # the yardstick is the bf16 comparator -- the fp32 oracle graph with the SAME bf16 storage points as the CUDA path
+    # (frontend_oracle storage="bf16") -- measured against the same reference fixture.  The CUDA path has to be within
+    # 1.25x of the comparator's error on average (RMS over the checked tensors) and within 2x on every single tensor
+    # (single tensors are noisy: a flipped mask moves one tensor's gradient by percents on either side).
+    sdc = {k: (v.clone().float().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+    ci, cb, cm, cinfo, cgw = synth_frontend_inputs(78)
+    c_obj, _ = fo.fast_rcnn_end2end(sdc, ci, cb, cm, cinfo, storage="bf16")
+    (c_obj * cgw).sum().backward()
+    ratios = {}
+    for name, rows in E2E_GRAD_SLICES:
+        gc = sdc[name].grad
+        ec = rel(gc if rows is None else gc[:rows], torch.from_numpy(G["grad:" + name]))
+        ratios[name] = (e["grad:" + name], ec)
+    rms = lambda xs: (sum(x * x for x in xs) / len(xs)) ** 0.5  # noqa: E731
+    ours_rms, cmp_rms = rms([a for a, _ in ratios.values()]), rms([b for _, b in ratios.values()])
+    print("front-end gradient errors vs fixture, ours (bf16-storage comparator):", {k: "%.2e (%.2e)" % v for k, v in ratios.items()},
+          "RMS %.3e (%.3e)" % (ours_rms, cmp_rms))
+    assert ours_rms <= 1.25 * cmp_rms, (ours_rms, cmp_rms, ratios)
+    assert all(a <= 2.0 * b + 1e-3 for a, b in ratios.values()), ratios
     assert all(v >= 0.95 for k, v in e.items() if k.startswith("cos:")), e
     # frozen parts get no gradient (IMAGE_FROZEN_BACKBONE_STAGES [1, 2], IMAGE_FROZEN_BN)
     assert all(p.grad is None for n, p in params.items() if n.startswith("backbone.layer1") or ".bn" in n or n.startswith("backbone.conv1"))
