@@ -128,22 +128,19 @@ struct RowRawB {
   float4 xa[ITERS], xb[ITERS];
   uint4 d16[ITERS];
   float4 da[ITERS], db[ITERS];
-  uint32_t kw[ITERS];   // dropout keep flags of the eight elements (out_drop), prefetched with the row
   float mu, rs;
 };
 
 template <int ITERS, bool HAS16, bool HAS32>
 __device__ __forceinline__ void load_row_bwd(RowRawB<ITERS>& r, const float* __restrict__ xr, const __nv_bfloat16* __restrict__ d16r,
                                              const float* __restrict__ d32r, const float* __restrict__ mean_p,
-                                             const float* __restrict__ rstd_p, int lane, int nvec,
-                                             const uint32_t* __restrict__ bits_row = nullptr) {
+                                             const float* __restrict__ rstd_p, int lane, int nvec) {
   r.mu = __ldg(mean_p);
   r.rs = __ldg(rstd_p);
 #pragma unroll
   for (int i = 0; i < ITERS; ++i) {
     const int vi = lane + i * 32;
     if (vi < nvec) {
-      r.kw[i] = bits_row ? __ldg(bits_row + (vi >> 2)) : 0u;
       r.xa[i] = __ldg(reinterpret_cast<const float4*>(xr + vi * 8));
       r.xb[i] = __ldg(reinterpret_cast<const float4*>(xr + vi * 8 + 4));
       if (HAS16) r.d16[i] = __ldg(reinterpret_cast<const uint4*>(d16r + vi * 8));
@@ -169,6 +166,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
   pdl_trigger();
   pdl_wait();
   const DropState in_state = drop_state(in_drop);
+  const int out_wpr = (H + 31) >> 5;
   float gam[ITERS][8];
   float acc_g[ITERS][8], acc_b[ITERS][8], acc_c[ITERS][8];
 #pragma unroll
@@ -182,16 +180,14 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
   }
   int row = blockIdx.x * LN_WARPS + warp;
   RowRawB<ITERS> cur, nxt;
-  const int out_wpr = (H + 31) >> 5;
-  const uint32_t* obits = out_drop.thresh != 0u ? out_drop.bits : nullptr;
   if (row < M)
     load_row_bwd<ITERS, HAS16, HAS32>(cur, x + (size_t)row * ldx, dy16 + (size_t)row * H, dy32 + (size_t)row * H, mean + row,
-                                      rstd + row, lane, nvec, obits ? obits + (size_t)row * out_wpr : nullptr);
+                                      rstd + row, lane, nvec);
   for (; row < M; row += wstride) {
     const int nrow = row + wstride;
     if (nrow < M)
       load_row_bwd<ITERS, HAS16, HAS32>(nxt, x + (size_t)nrow * ldx, dy16 + (size_t)nrow * H, dy32 + (size_t)nrow * H,
-                                        mean + nrow, rstd + nrow, lane, nvec, obits ? obits + (size_t)nrow * out_wpr : nullptr);
+                                        mean + nrow, rstd + nrow, lane, nvec);
     const float mu = cur.mu, rs = cur.rs;
     float dy[ITERS][8], xh[ITERS][8];
     float s1 = 0.0f, s2 = 0.0f;
@@ -247,9 +243,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
         if (out_drop.thresh != 0u) {
           // x = dropout(dense(.)) + residual: the dense branch (next GEMM operand, bias gradient) sees dx o mask / (1-p)
           float lo[4] = {o[0], o[1], o[2], o[3]}, hi[4] = {o[4], o[5], o[6], o[7]};
-          const uint32_t k8 = cur.kw[i] >> ((vi * 8) & 31);
-          drop4_bits(lo, k8 & 0xFu, out_drop.scale);
-          drop4_bits(hi, (k8 >> 4) & 0xFu, out_drop.scale);
+          drop4_bits(lo, keep4_bits(out_drop.bits, (size_t)row, out_wpr, vi * 8), out_drop.scale);
+          drop4_bits(hi, keep4_bits(out_drop.bits, (size_t)row, out_wpr, vi * 8 + 4), out_drop.scale);
           uint4 pk;
           pk.x = pack_bf16x2(lo[0], lo[1]); pk.y = pack_bf16x2(lo[2], lo[3]);
           pk.z = pack_bf16x2(hi[0], hi[1]); pk.w = pack_bf16x2(hi[2], hi[3]);
@@ -300,198 +295,6 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __rest
         if (dbeta) atomicAdd(dbeta + col, b);
         if (dcolsum) atomicAdd(dcolsum + col, c);
       }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// "Column-owner" LayerNorm kernels (round 2).  The warp-per-row kernels above keep a whole row (and its prefetched successor)
-// plus three per-column accumulators in registers: 246-255 registers per thread, two 4-warp blocks per SM -- the
-// backward reached 3.6 TB/s of 6.5.  Here a block of H/4 threads owns the columns instead: thread t holds columns 4t .. 4t+3
-// for LN_R rows at a time, row statistics are block reductions (one __syncthreads per batch of rows, double-buffered
-// shared memory), the per-column accumulators of the backward are 12 registers, and latency is hidden by occupancy
-// (~64 registers, up to ten blocks per SM) instead of by software prefetch.  Every access is a contiguous 16-byte (fp32)
-// or 8-byte (bf16) vector per thread = whole rows per block.
-// ------------------------------------------------------------------------------------------------
-constexpr int LN_R = 4;        // rows per batch
-constexpr int LN_MAXW = 16;    // warps per block upper bound (H <= 2048)
-
-// sum NV values over the block; result broadcast to every thread.  `red` holds [2][LN_MAXW][NV] floats (parity double buffer).
-template <int NV>
-__device__ __forceinline__ void block_sum(float (&v)[NV], float* red, int parity, int warp, int lane, int nwarps) {
-#pragma unroll
-  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
-  float* buf = red + parity * (LN_MAXW * NV);
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) buf[warp * NV + i] = v[i];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < NV; ++i) v[i] = 0.0f;
-  for (int w = 0; w < nwarps; ++w) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] += buf[w * NV + i];
-  }
-}
-
-__global__ void __launch_bounds__(512)
-ln_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-               __nv_bfloat16* __restrict__ y, float* __restrict__ y32, float* __restrict__ mean, float* __restrict__ rstd, int M,
-               int H, int ldx, float eps, const DropCfg drop) {
-  __shared__ float red[2 * 2 * LN_MAXW * LN_R];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const int col = tid * 4;
-  const bool cok = col < H;
-  pdl_trigger();
-  pdl_wait();
-  const DropState dstate = drop_state(drop);
-  float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = g4;
-  if (cok) {
-    g4 = __ldg(reinterpret_cast<const float4*>(gamma + col));
-    b4 = __ldg(reinterpret_cast<const float4*>(beta + col));
-  }
-  const float inv_h = 1.0f / (float)H;
-  int parity = 0;
-  for (int r0 = blockIdx.x * LN_R; r0 < M; r0 += gridDim.x * LN_R, parity ^= 1) {
-    float4 v[LN_R];
-    float s[LN_R];
-#pragma unroll
-    for (int i = 0; i < LN_R; ++i) {
-      const int row = r0 + i;
-      v[i] = (cok && row < M) ? __ldg(reinterpret_cast<const float4*>(x + (size_t)row * ldx + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      s[i] = (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
-    block_sum<LN_R>(s, red, parity, warp, lane, nwarps);
-    float mu[LN_R], q[LN_R];
-#pragma unroll
-    for (int i = 0; i < LN_R; ++i) {
-      mu[i] = s[i] * inv_h;
-      const float dx0 = v[i].x - mu[i], dx1 = v[i].y - mu[i], dx2 = v[i].z - mu[i], dx3 = v[i].w - mu[i];
-      q[i] = cok ? (dx0 * dx0 + dx1 * dx1) + (dx2 * dx2 + dx3 * dx3) : 0.0f;
-    }
-    block_sum<LN_R>(q, red + 2 * LN_MAXW * LN_R, parity, warp, lane, nwarps);
-#pragma unroll
-    for (int i = 0; i < LN_R; ++i) {
-      const int row = r0 + i;
-      if (row >= M) break;
-      const float rs = 1.0f / sqrtf(q[i] * inv_h + eps);
-      if (tid == 0) {
-        if (mean) mean[row] = mu[i];
-        if (rstd) rstd[row] = rs;
-      }
-      if (!cok) continue;
-      float o[4] = {g4.x * ((v[i].x - mu[i]) * rs) + b4.x, g4.y * ((v[i].y - mu[i]) * rs) + b4.y,
-                    g4.z * ((v[i].z - mu[i]) * rs) + b4.z, g4.w * ((v[i].w - mu[i]) * rs) + b4.w};
-      if (drop.thresh != 0u)   // dropout on the LayerNorm output (embedding, visual_linguistic_bert.py:239)
-        drop4(o, ((uint64_t)row * (uint64_t)H + (uint64_t)col) >> 2, drop, dstate);
-      if (y) {
-        uint2 pk;
-        pk.x = pack_bf16x2(o[0], o[1]);
-        pk.y = pack_bf16x2(o[2], o[3]);
-        *reinterpret_cast<uint2*>(y + (size_t)row * H + col) = pk;
-      }
-      if (y32) *reinterpret_cast<float4*>(y32 + (size_t)row * H + col) = make_float4(o[0], o[1], o[2], o[3]);
-    }
-  }
-}
-
-template <bool HAS16, bool HAS32, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB)
-ln_bwd2_kernel(const __nv_bfloat16* __restrict__ dy16, const float* __restrict__ dy32, const float* __restrict__ x,
-               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
-               __nv_bfloat16* __restrict__ dx16, float* __restrict__ dx32, float* __restrict__ dgamma, float* __restrict__ dbeta,
-               float* __restrict__ dcolsum, int M, int H, int ldx, int ld_dx, const DropCfg in_drop,
-               __nv_bfloat16* __restrict__ dx16_drop, const DropCfg out_drop) {
-  __shared__ float red[2 * LN_MAXW * 2 * LN_R];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const int col = tid * 4;
-  const bool cok = col < H;
-  pdl_trigger();
-  pdl_wait();
-  const DropState in_state = drop_state(in_drop);
-  const int out_wpr = (H + 31) >> 5;
-  const bool odrop = out_drop.thresh != 0u;
-  float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (cok) g4 = __ldg(reinterpret_cast<const float4*>(gamma + col));
-  float acc_g[4] = {0.f, 0.f, 0.f, 0.f}, acc_b[4] = {0.f, 0.f, 0.f, 0.f}, acc_c[4] = {0.f, 0.f, 0.f, 0.f};
-  const float inv_h = 1.0f / (float)H;
-  int parity = 0;
-  for (int r0 = blockIdx.x * LN_R; r0 < M; r0 += gridDim.x * LN_R, parity ^= 1) {
-    float d[LN_R][4], xh[LN_R][4], rsv[LN_R];
-    uint32_t kw[LN_R];
-    float s[2 * LN_R];
-#pragma unroll
-    for (int i = 0; i < LN_R; ++i) {
-      const int row = r0 + i;
-      const bool ok = cok && row < M;
-      float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-      d[i][0] = d[i][1] = d[i][2] = d[i][3] = 0.0f;
-      float mu = 0.0f;
-      rsv[i] = 0.0f;
-      kw[i] = 0u;
-      if (ok) {
-        xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)row * ldx + col));
-        if (HAS16) {
-          const uint2 u = __ldg(reinterpret_cast<const uint2*>(dy16 + (size_t)row * H + col));
-          d[i][0] = bf16lo(u.x); d[i][1] = bf16hi(u.x); d[i][2] = bf16lo(u.y); d[i][3] = bf16hi(u.y);
-        }
-        if (HAS32) {
-          const float4 f = __ldg(reinterpret_cast<const float4*>(dy32 + (size_t)row * H + col));
-          d[i][0] += f.x; d[i][1] += f.y; d[i][2] += f.z; d[i][3] += f.w;
-        }
-        mu = __ldg(mean + row);
-        rsv[i] = __ldg(rstd + row);
-        if (odrop) kw[i] = __ldg(out_drop.bits + (size_t)row * out_wpr + (col >> 5));
-        if (in_drop.thresh != 0u)   // the LayerNorm output was dropped in forward: its gradient passes through the same mask
-          drop4(d[i], ((uint64_t)row * (uint64_t)H + (uint64_t)col) >> 2, in_drop, in_state);
-      }
-      xh[i][0] = (xv.x - mu) * rsv[i]; xh[i][1] = (xv.y - mu) * rsv[i]; xh[i][2] = (xv.z - mu) * rsv[i]; xh[i][3] = (xv.w - mu) * rsv[i];
-      const float g0 = d[i][0] * g4.x, g1 = d[i][1] * g4.y, g2 = d[i][2] * g4.z, g3 = d[i][3] * g4.w;
-      s[2 * i] = (g0 + g1) + (g2 + g3);
-      s[2 * i + 1] = (g0 * xh[i][0] + g1 * xh[i][1]) + (g2 * xh[i][2] + g3 * xh[i][3]);
-    }
-    block_sum<2 * LN_R>(s, red, parity, warp, lane, nwarps);
-#pragma unroll
-    for (int i = 0; i < LN_R; ++i) {
-      const int row = r0 + i;
-      if (!cok || row >= M) continue;
-      const float m1 = s[2 * i] * inv_h, m2 = s[2 * i + 1] * inv_h, rs = rsv[i];
-      const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
-      float o[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        o[j] = rs * (d[i][j] * gg[j] - m1 - xh[i][j] * m2);
-        acc_g[j] += d[i][j] * xh[i][j];
-        acc_b[j] += d[i][j];
-      }
-      if (dx16) {
-        uint2 pk;
-        pk.x = pack_bf16x2(o[0], o[1]);
-        pk.y = pack_bf16x2(o[2], o[3]);
-        *reinterpret_cast<uint2*>(dx16 + (size_t)row * H + col) = pk;
-      }
-      if (dx32) *reinterpret_cast<float4*>(dx32 + (size_t)row * ld_dx + col) = make_float4(o[0], o[1], o[2], o[3]);
-      if (odrop) {
-        // x = dropout(dense(.)) + residual: the dense branch (next GEMM operand, bias gradient) sees dx o mask / (1-p)
-        drop4_bits(o, (kw[i] >> (col & 31)) & 0xFu, out_drop.scale);
-        if (dx16_drop) {
-          uint2 pk;
-          pk.x = pack_bf16x2(o[0], o[1]);
-          pk.y = pack_bf16x2(o[2], o[3]);
-          *reinterpret_cast<uint2*>(dx16_drop + (size_t)row * H + col) = pk;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc_c[j] += o[j];
-    }
-  }
-  if (cok) {   // this thread is the only one of its block that owns these four columns: one atomic per column per block
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (dgamma) atomicAdd(dgamma + col + j, acc_g[j]);
-      if (dbeta) atomicAdd(dbeta + col + j, acc_b[j]);
-      if (dcolsum) atomicAdd(dcolsum + col + j, acc_c[j]);
     }
   }
 }
@@ -607,25 +410,13 @@ int layernorm_forward(const float* x, int ldx, const float* gamma, const float* 
   VLB_REQUIRE(ldx % 4 == 0 && ldx >= H, "layernorm_forward: bad ldx %d", ldx);
   VLB_REQUIRE(H % 8 == 0 && H >= 8 && H <= 2048, "layernorm: H=%d must be a multiple of 8 in [8, 2048]", H);
   if (M <= 0) return VLB_OK;
+  const int iters = (H + 255) / 256;
+  int grid = (M + LN_WARPS - 1) / LN_WARPS;
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
   ProfScope prof(PROF_LN_FWD, (double)M * H * (4.0 + (y_bf16 ? 2.0 : 0.0) + (y_f32 ? 4.0 : 0.0)), stream);
-  static const int use_v2 = [] { const char* v = getenv("VLB_LN_V2"); return v ? atoi(v) : 1; }();
   cudaError_t lerr = cudaSuccess;
-  if (use_v2) {
-    const int threads = ((H / 4 + 31) / 32) * 32;
-    int per_sm = 2048 / threads;
-    if (per_sm > 8) per_sm = 8;
-    if (per_sm < 1) per_sm = 1;
-    int grid = (M + LN_R - 1) / LN_R;
-    if (grid > num_sms() * per_sm) grid = num_sms() * per_sm;
-    lerr = launch_pdl(ln_fwd2_kernel, dim3(grid), dim3(threads), 0, stream, x, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), y_f32,
-                      mean, rstd, M, H, ldx, eps, dcfg);
-  } else {
-    const int iters = (H + 255) / 256;
-    int grid = (M + LN_WARPS - 1) / LN_WARPS;
-    if (grid > num_sms() * 8) grid = num_sms() * 8;
-    VLB_LN_DISPATCH(iters, (lerr = launch_pdl(layernorm_fwd_kernel<IT>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, x, gamma, beta,
-                                              static_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, M, H, ldx, eps, dcfg)));
-  }
+  VLB_LN_DISPATCH(iters, (lerr = launch_pdl(layernorm_fwd_kernel<IT>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, x, gamma, beta,
+                                            static_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, M, H, ldx, eps, dcfg)));
   VLB_CHECK_CUDA(lerr);
   return VLB_OK;
 }
@@ -655,28 +446,7 @@ int layernorm_backward(const void* dy_bf16, const float* dy_f32, const float* x,
                              static_cast<__nv_bfloat16*>(dx_bf16), dx_f32, dgamma, dbeta, dcolsum, M, H, ldx, ld_dx, din,   \
                              static_cast<__nv_bfloat16*>(dx_bf16_drop), dout)))
   cudaError_t lerr = cudaSuccess;
-  static const int use_v2 = [] { const char* v = getenv("VLB_LN_V2"); return v ? atoi(v) : 1; }();
-  if (use_v2) {
-    const int threads = ((H / 4 + 31) / 32) * 32;
-    int bps = threads <= 256 ? 3 * (256 / threads) : 1;     // resident blocks per SM at the register budget of the instantiation
-    if (bps > 6) bps = 6;
-    if (bps < 1) bps = 1;
-    int g2 = (M + LN_R - 1) / LN_R;
-    if (g2 > num_sms() * bps) g2 = num_sms() * bps;
-#define VLB_LN_BWD2(H16, H32)                                                                                              \
-    if (threads <= 256)                                                                                                                  \
-      lerr = launch_pdl(ln_bwd2_kernel<H16, H32, 256, 3>, dim3(g2), dim3(threads), 0, stream, static_cast<const __nv_bfloat16*>(dy_bf16),  \
-                        dy_f32, x, mean, rstd, gamma, static_cast<__nv_bfloat16*>(dx_bf16), dx_f32, dgamma, dbeta, dcolsum, M, H, ldx,    \
-                        ld_dx, din, static_cast<__nv_bfloat16*>(dx_bf16_drop), dout);                                                    \
-    else                                                                                                                                 \
-      lerr = launch_pdl(ln_bwd2_kernel<H16, H32, 512, 1>, dim3(g2), dim3(threads), 0, stream, static_cast<const __nv_bfloat16*>(dy_bf16),  \
-                        dy_f32, x, mean, rstd, gamma, static_cast<__nv_bfloat16*>(dx_bf16), dx_f32, dgamma, dbeta, dcolsum, M, H, ldx,    \
-                        ld_dx, din, static_cast<__nv_bfloat16*>(dx_bf16_drop), dout)
-    if (dy_bf16 && dy_f32) { VLB_LN_BWD2(true, true); }
-    else if (dy_bf16) { VLB_LN_BWD2(true, false); }
-    else { VLB_LN_BWD2(false, true); }
-#undef VLB_LN_BWD2
-  } else if (dy_bf16 && dy_f32) { VLB_LN_BWD(true, true) }
+  if (dy_bf16 && dy_f32) { VLB_LN_BWD(true, true) }
   else if (dy_bf16) { VLB_LN_BWD(true, false) }
   else { VLB_LN_BWD(false, true) }
 #undef VLB_LN_BWD
