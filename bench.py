@@ -506,6 +506,32 @@ class Runner(object):
         torch.cuda.empty_cache()
 
 
+def optimizer_roofline(run, pk, iters=20):
+    """SURVEY 8(f) rank 2, measured on its own: vlbert_b200.optim.FusedAdamW (AdamW of common/nlp/bert/optimization.py:129-187 +
+    the trainer's global-norm clip, common/trainer.py:139-147) over every parameter of the workload, two launches per step.
+    HBM roofline: per parameter 4 B gradient for the norm + 16 B read (param, grad, two moments) + 12 B written."""
+    params = [p for p in run.model.parameters() if p.requires_grad and p.grad is not None]
+    if not params:
+        run.eager_step(run.dev_inputs)
+        params = [p for p in run.model.parameters() if p.requires_grad and p.grad is not None]
+    n = sum(p.numel() for p in params)
+    opt = run.vb.optim.FusedAdamW(params, lr=1e-6, weight_decay=1e-4, max_grad_norm=1.0)
+    for _ in range(3):
+        opt.step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        opt.step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    gbs = n * 32.0 / (ms * 1e-3) / 1e9
+    return {"what": "FusedAdamW.step() incl. global-norm clip, all %d parameter tensors (%.1f M parameters), timed alone" % (len(params), n / 1e6),
+            "ms_per_step": ms, "bytes_per_param": 32, "achieved_gbs": gbs, "peak_gbs": pk.get("hbm_gbs"),
+            "frac": gbs / pk["hbm_gbs"] if pk.get("hbm_gbs") else None, "launches_per_step": 2}
+
+
 def workload_text(w, B, p_drop, with_opt):
     return "%s: %s (S=%d), batch %d per GPU, fwd+bwd in training mode (dropout p=%.2g at every reference site), %s%s" % (
         w["name"], w["what"], seq_len(w), B, p_drop,
@@ -633,6 +659,12 @@ def main():
         raise SystemExit("bench.py: the embedding kernels flagged bad indices: %s" % e)
     used_graph = run.graphed is not None
     flop_step = run.algorithmic_flop_per_step()
+    optimizer_rec = None
+    if world == 1:
+        try:
+            optimizer_rec = optimizer_roofline(run, pk)
+        except Exception as e:  # noqa
+            optimizer_rec = {"error": str(e)[:200]}
     roof = run.roofline(pms, pwork, ms, pk, pk_kind, prof_steps)
     run.close()
 
@@ -659,6 +691,8 @@ def main():
         "kernel_profile": prof,
         "clocks": sampler.summary() if sampler else None,
     }
+    if optimizer_rec is not None:
+        line["optimizer"] = optimizer_rec
     if world == 1 and not args.no_other_configs:
         others = {}
         for c in sorted(WORKLOADS):

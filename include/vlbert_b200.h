@@ -295,6 +295,26 @@ int vlb_roi_align_nhwc_forward(const void* feat, const float* rois, void* out, i
 int vlb_roi_align_nhwc_backward(const void* grad_out, const float* rois, float* grad_feat, int K, int N, int C, int H,
                                 int W, int ph, int pw, float spatial_scale, int sampling_ratio, void* stream);
 
+/* ---- masked-language-model loss head ---------------------------------------------
+ * Replaces, for the LOSS path, BertLMPredictionHead + F.cross_entropy(ignore_index=-1) of the pre-training task
+ * (modeling.py:456-472; pretrain/modules/resnet_vlbert_for_pretraining.py:165-189).  The reference computes fp32 logits for
+ * every text position ([B*T, 30522]) although only the labelled ~15 % enter the loss; here:
+ *   vlb_label_compact : idx[k] = flat position of the k-th label != ignore_index (ascending), lab[k] = that label, k < cap;
+ *                       -1 beyond the count; count[0] = number of labelled positions (device scalar, no host sync).
+ *   (caller: gather those rows with vlb_gather_rows, transform + decoder GEMMs with vlb_gemm_bf16 on `cap` rows;
+ *    the decoder's N is padded to a multiple of 8 with a bias of -30000 in the padding columns)
+ *   vlb_mlm_ce_forward: per compacted row < count: lse[row] = log-sum-exp over the first V logits (bf16 [rows, ld]);
+ *                       loss_sum[0] += lse - logit[label]; correct[0] += (argmax == label)   (accuracy metric of the trainer)
+ *   vlb_mlm_ce_backward: overwrites the logits IN PLACE with d loss / d logits = (softmax - onehot) * gscale[0] / count
+ *                       (rows >= count and padding columns: 0), ready to be the operand of the dgrad / wgrad GEMMs.
+ */
+int vlb_label_compact(const int64_t* labels, int n, int64_t ignore_index, int32_t* idx, int32_t* lab, int cap, int32_t* count,
+                      void* stream);
+int vlb_mlm_ce_forward(const void* logits_bf16, int ld, int V, const int32_t* lab, const int32_t* count, int rows, float* lse,
+                       float* loss_sum, int32_t* correct, void* stream);
+int vlb_mlm_ce_backward(void* logits_bf16, int ld, int V, const int32_t* lab, const int32_t* count, int rows, const float* lse,
+                        const float* gscale, void* stream);
+
 /* ---- optimizer step after the path ---------------------------------------------
  * Replaces AdamW.step (common/nlp/bert/optimization.py:129-187: Adam moments, bias-corrected step size, decoupled weight decay
  * applied AFTER the update) and torch.nn.utils.clip_grad_norm_ of the trainer (common/trainer.py:139-147) for all parameter

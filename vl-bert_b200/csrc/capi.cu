@@ -284,6 +284,17 @@ int vlb_conv_gemm(const void* col, int ld_col, const void* w, int ld_w, void* y,
   e.act = relu_mode == 1 ? ACT_RELU : (relu_mode == 2 ? ACT_RELU_POST : ACT_NONE);
   COUNTED(1, gemm_bf16(GEMM_NT, P, Cout, K, col, ld_col, w, ld_w, e, 1, 0, ST));
 }
+int vlb_label_compact(const int64_t* labels, int n, int64_t ignore_index, int32_t* idx, int32_t* lab, int cap, int32_t* count, void* stream) {
+  COUNTED(1, label_compact(labels, n, ignore_index, idx, lab, cap, count, ST));
+}
+int vlb_mlm_ce_forward(const void* logits_bf16, int ld, int V, const int32_t* lab, const int32_t* count, int rows, float* lse,
+                       float* loss_sum, int32_t* correct, void* stream) {
+  COUNTED(1, mlm_ce_forward(logits_bf16, ld, V, lab, count, rows, lse, loss_sum, correct, ST));
+}
+int vlb_mlm_ce_backward(void* logits_bf16, int ld, int V, const int32_t* lab, const int32_t* count, int rows, const float* lse,
+                        const float* gscale, void* stream) {
+  COUNTED(1, mlm_ce_backward(logits_bf16, ld, V, lab, count, rows, lse, gscale, ST));
+}
 int vlb_grad_sqnorm(const VlbAdamWTensor* descs_device, int count, float* sq, void* stream) {
   COUNTED(1, grad_sqnorm(descs_device, count, sq, ST));
 }

@@ -68,6 +68,14 @@ int roi_align_nhwc_forward(const void* feat, const float* rois, void* out, int K
 int roi_align_nhwc_backward(const void* grad_out, const float* rois, float* grad_feat, int K, int N, int C, int H, int W, int ph, int pw,
                             float scale, int sampling_ratio, cudaStream_t stream);
 
+// heads.cu
+int label_compact(const int64_t* labels, int n, int64_t ignore_index, int32_t* idx, int32_t* lab, int cap, int32_t* count,
+                  cudaStream_t stream);
+int mlm_ce_forward(const void* logits, int ld, int V, const int32_t* lab, const int32_t* count, int rows, float* lse, float* loss_sum,
+                   int32_t* correct, cudaStream_t stream);
+int mlm_ce_backward(void* logits, int ld, int V, const int32_t* lab, const int32_t* count, int rows, const float* lse,
+                    const float* gscale, cudaStream_t stream);
+
 int grad_sqnorm(const VlbAdamWTensor* descs_device, int count, float* sq, cudaStream_t stream);
 int adamw_step(const VlbAdamWTensor* descs_device, const float* hyper_device, int count, double beta1, double beta2, double eps,
                const float* sq, float max_norm, cudaStream_t stream);

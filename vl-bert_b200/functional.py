@@ -695,6 +695,88 @@ class LinearFn(torch.autograd.Function):
         return dx, d_w, d_b
 
 
+class MLMLossFn(torch.autograd.Function):
+    """Masked-LM loss of the pre-training task on the labelled positions only (csrc/heads.cu):
+    forward(text_out f32 [B,T,H], labels int64 [B,T] (-1 = ignore), transform.dense.weight/bias, transform.LayerNorm.weight/bias,
+            decoder weight [V,H] (the tied word embedding), decoder bias [V], cap)
+      -> (loss = mean cross-entropy over the labelled positions, n_correct int32[1], n_labelled int32[1])
+    i.e. F.cross_entropy(BertLMPredictionHead(text_out).view(-1, V), labels.view(-1), ignore_index=-1) of
+    pretrain/modules/resnet_vlbert_for_pretraining.py:165-189 without the logits of the unlabelled positions.
+    `cap` = static upper bound of labelled positions (rows the GEMMs run on)."""
+
+    @staticmethod
+    def forward(ctx, text_out, labels, tw, tb, ln_w, ln_b, dec_w, dec_b, cap, eps):
+        _require_cuda(text_out, labels, dec_w)
+        for nm, t in (("transform.dense.weight", tw), ("transform.dense.bias", tb), ("transform.LayerNorm.weight", ln_w),
+                      ("transform.LayerNorm.bias", ln_b), ("decoder.weight", dec_w), ("bias", dec_b)):
+            _require_param(t, "mlm_head.predictions." + nm, text_out.device)
+        B, T, H = text_out.shape
+        n, V = B * T, dec_w.shape[0]
+        Vp = (V + 7) // 8 * 8
+        cap = (int(cap) + 7) // 8 * 8
+        dev = text_out.device
+        lib, st = _lib.lib(), _stream()
+        i32 = torch.int32
+        idx = torch.empty((cap,), dtype=i32, device=dev)
+        lab = torch.empty((cap,), dtype=i32, device=dev)
+        count = torch.empty((1,), dtype=i32, device=dev)
+        lbl = labels.contiguous().view(-1).to(torch.int64)
+        _chk(lib.vlb_label_compact(_p(lbl), n, -1, _p(idx), _p(lab), cap, _p(count), st))
+        x32 = text_out.contiguous().view(n, H).float()
+        x16 = gather_rows(x32, idx, cap, BF16)
+        tw16 = torch.empty((H, H), dtype=BF16, device=dev)
+        _chk(lib.vlb_cast_f32_to_bf16(_p(tw), _p(tw16), tw.numel(), st))
+        t32 = torch.empty((cap, H), dtype=F32, device=dev)
+        z = torch.empty((cap, H), dtype=BF16, device=dev)
+        gemm(0, x16, tw16, t32, bias=tb, act=1, aux=z)                       # dense + bias + erf-GELU (GELU' kept)
+        h2, _, mean, rstd = layernorm_forward(t32, ln_w, ln_b, eps)
+        w16 = torch.zeros((Vp, H), dtype=BF16, device=dev)                   # tied decoder = word embedding, rows padded to 8
+        _chk(lib.vlb_cast_f32_to_bf16(_p(dec_w), _p(w16), dec_w.numel(), st))
+        bias_p = torch.full((Vp,), -30000.0, dtype=F32, device=dev)          # padding columns never win the softmax
+        bias_p[:V] = dec_b
+        logits = torch.empty((cap, Vp), dtype=BF16, device=dev)
+        gemm(0, h2, w16, logits, bias=bias_p)
+        lse = torch.empty((cap,), dtype=F32, device=dev)
+        loss_sum = torch.zeros((1,), dtype=F32, device=dev)
+        correct = torch.zeros((1,), dtype=i32, device=dev)
+        _chk(lib.vlb_mlm_ce_forward(_p(logits), Vp, V, _p(lab), _p(count), cap, _p(lse), _p(loss_sum), _p(correct), st))
+        loss = (loss_sum / count.clamp(min=1).to(F32)).reshape(())
+        ctx.save_for_backward(x16, tw16, t32, z, mean, rstd, h2, w16, logits, lab, count, lse, idx, ln_w)
+        ctx.dims = (B, T, H, V, Vp, cap)
+        ctx.mark_non_differentiable(correct, count)
+        return loss, correct, count
+
+    @staticmethod
+    def backward(ctx, g_loss, _gc, _gn):
+        x16, tw16, t32, z, mean, rstd, h2, w16, logits, lab, count, lse, idx, ln_w = ctx.saved_tensors
+        B, T, H, V, Vp, cap = ctx.dims
+        dev = x16.device
+        lib, st = _lib.lib(), _stream()
+        gscale = g_loss.detach().to(F32).reshape(1).contiguous()
+        _chk(lib.vlb_mlm_ce_backward(_p(logits), Vp, V, _p(lab), _p(count), cap, _p(lse), _p(gscale), st))
+        dlog = logits                                                         # in place: d loss / d logits, bf16 [cap, Vp]
+        d_bias = torch.zeros((Vp,), dtype=F32, device=dev)
+        _chk(lib.vlb_colsum_bf16(_p(dlog), Vp, _p(d_bias), cap, Vp, st))
+        d_w = torch.zeros((Vp, H), dtype=F32, device=dev)
+        d_w._vlb_accumulate = True
+        gemm(2, dlog, h2, d_w)                                                # dW[v, :] += dlogits[:, v]^T h2
+        dh2 = torch.empty((cap, H), dtype=BF16, device=dev)
+        gemm(1, dlog, w16, dh2)                                               # dh2 = dlogits W
+        d_ln_w, d_ln_b = torch.zeros((H,), dtype=F32, device=dev), torch.zeros((H,), dtype=F32, device=dev)
+        _, d_t = layernorm_backward(dh2, None, t32, mean, rstd, ln_w, d_ln_w, d_ln_b, want_bf16=False, want_f32=True)
+        d_pre = (d_t * z.float()).to(BF16)                                    # x GELU'(pre-activation)
+        d_tb = torch.zeros((H,), dtype=F32, device=dev)
+        _chk(lib.vlb_colsum_bf16(_p(d_pre), H, _p(d_tb), cap, H, st))
+        d_tw = torch.zeros((H, H), dtype=F32, device=dev)
+        d_tw._vlb_accumulate = True
+        gemm(2, d_pre, x16, d_tw)
+        dx = torch.empty((cap, H), dtype=BF16, device=dev)
+        gemm(1, d_pre, tw16, dx)
+        d_text = torch.zeros((B * T, H), dtype=F32, device=dev)
+        scatter_rows_add(dx, idx, d_text)
+        return d_text.view(B, T, H), None, d_tw, d_tb, d_ln_w, d_ln_b, d_w[:V], d_bias[:V], None, None
+
+
 class GatherRowsFn(torch.autograd.Function):
     """out[i] = idx[i] >= 0 ? src[idx[i]] : 0 ; src 2-D (bf16 or f32) -> f32.  Each source row is referenced at most once."""
 

@@ -458,6 +458,20 @@ class VisualLinguisticBertForPretraining(VisualLinguisticBert):
         mvrc_logits = self.mvrc_head(object_out) if self.with_mvrc_head else None
         return relationship_logits, mlm_logits, mvrc_logits
 
+    def mlm_loss(self, text_out, mlm_labels, max_labelled=None):
+        """Fused masked-LM loss for callers that need the LOSS, not the [B, T, V] logits:
+        == F.cross_entropy(self.mlm_head(text_out).view(-1, V), mlm_labels.view(-1), ignore_index=-1)
+        (pretrain/modules/resnet_vlbert_for_pretraining.py:165-189) evaluated on the labelled positions only: they are compacted
+        on the device, the transform + tied-decoder GEMMs run on those rows, the cross-entropy is one pass over bf16 logits.
+        Returns (loss, n_correct, n_labelled) -- the two counters feed the trainer's MLMAccuracy metric without logits.
+        max_labelled: static upper bound of labelled positions (no host sync; CUDA-graph friendly); None = counted on the host."""
+        p = self.mlm_head.predictions
+        if max_labelled is None:
+            max_labelled = max(8, int((mlm_labels != -1).sum().item()))
+        return VF.MLMLossFn.apply(text_out, mlm_labels, p.transform.dense.weight, p.transform.dense.bias,
+                                  p.transform.LayerNorm.weight, p.transform.LayerNorm.bias, p.decoder.weight, p.bias,
+                                  int(max_labelled), 1e-12)
+
 
 # ------------------------------------------------------------------------------------------------
 # region-feature front end
