@@ -37,6 +37,10 @@ __global__ void grad_sqnorm_kernel(const VlbAdamWTensor* __restrict__ descs, flo
   }
 }
 
+// grid.x: blocks that stride over one tensor.  16 left the [30522, 768] word-embedding table (21 % of all parameters) to 16 SMs:
+// 2.7 ms per step, 0.20 of the HBM roofline (BENCH r02 v4); small tensors simply finish after one iteration.
+constexpr int kBlocksPerTensor = 128;
+
 // hyper[t] = (lr, lr * weight_decay, step_size, unused) of tensor t for THIS step (step_size carries the bias correction)
 struct AdamConst { float beta1, beta2, omb1, omb2, eps; };   // omb = 1 - beta, rounded from the double-precision difference like torch does
 
@@ -96,7 +100,7 @@ __global__ void adamw_kernel(const VlbAdamWTensor* __restrict__ descs, const flo
 int grad_sqnorm(const VlbAdamWTensor* descs_device, int count, float* sq, cudaStream_t stream) {
   VLB_REQUIRE(descs_device && sq && count > 0, "grad_sqnorm: bad arguments");
   VLB_CHECK_CUDA(cudaMemsetAsync(sq, 0, sizeof(float), stream));
-  grad_sqnorm_kernel<<<dim3(16, count), 256, 0, stream>>>(descs_device, sq);
+  grad_sqnorm_kernel<<<dim3(kBlocksPerTensor, count), 256, 0, stream>>>(descs_device, sq);
   VLB_CHECK_LAUNCH();
   return VLB_OK;
 }
@@ -107,7 +111,7 @@ int adamw_step(const VlbAdamWTensor* descs_device, const float* hyper_device, in
   VLB_REQUIRE((reinterpret_cast<uintptr_t>(hyper_device) & 15) == 0, "adamw_step: hyper table must be 16-byte aligned");
   VLB_REQUIRE(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0 && eps >= 0.0, "adamw_step: bad hyper-parameters");
   const AdamConst c{(float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps};
-  adamw_kernel<<<dim3(16, count), 256, 0, stream>>>(descs_device, reinterpret_cast<const float4*>(hyper_device), c, sq, max_norm);
+  adamw_kernel<<<dim3(kBlocksPerTensor, count), 256, 0, stream>>>(descs_device, reinterpret_cast<const float4*>(hyper_device), c, sq, max_norm);
   VLB_CHECK_LAUNCH();
   return VLB_OK;
 }
