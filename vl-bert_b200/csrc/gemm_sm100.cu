@@ -7,6 +7,7 @@
 // backward passes (dgrad with fused GELU' / residual-gradient add, wgrad with split-K fp32
 // reduction).
 #include <cstdlib>
+#include <atomic>
 #include <mutex>
 #include <unordered_map>
 
@@ -70,7 +71,14 @@ struct GemmParams {
   // tail_first + u / tail_split.  0 = off.
   int tail_first, tail_split;
   int epi_prefetch;       // 1: epilogue warps L2-prefetch the tile's residual / aux input while its mainloop runs
+  // Dynamic tile scheduling: sched -> {next-item counter, finished-CTA counter} in global memory (both zero between launches).
+  // Every CTA starts with item = its index and then takes items nworkers + atomicAdd(counter, 1): a CTA whose start is delayed
+  // (e.g. its SM is still held by an NCCL channel CTA of an overlapped gradient all-reduce) simply takes fewer items instead of
+  // holding its statically assigned share back; the last CTA to finish resets both counters.  nullptr = static round robin.
+  int* sched;
 };
+
+constexpr int SCHED_DEPTH = 4;   // ring of item indices handed from the producer warp to the MMA / epilogue warps
 
 // linear output-pixel index -> base pixel (w, h, n) of the im2col traversal
 struct PixelCoord { int w, h, n; };
@@ -178,7 +186,7 @@ struct Cfg {
   static constexpr int STAGES = CG2 ? (BN == 256 ? 6 : 8) : ((BN == 256) ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8)));
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int EPI_STAGE_BYTES = EPI_WARPS * STAGE_F32_PER_WARP * 4;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers + scheduler ring*/;
 };
 
 // Epilogue of one 32-row x 32-column accumulator chunk owned by a warp.
@@ -377,6 +385,10 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
   uint64_t* tempty_bar = bars + 2 * C::STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
   volatile uint32_t* sk_flag = tmem_slot + 2;   // stream-K: "this CTA delivered the last K-chunk of the tile"
+  uint64_t* sched_full = bars + 2 * C::STAGES + 4 + 2;    // [SCHED_DEPTH] producer -> consumers: item index published
+  uint64_t* sched_empty = sched_full + SCHED_DEPTH;       // [SCHED_DEPTH] consumers (MMA thread + epilogue warps) -> producer
+  volatile int* sched_item = reinterpret_cast<volatile int*>(sched_empty + SCHED_DEPTH);
+  const bool dyn = !CL && p.sched != nullptr;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -396,6 +408,11 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
     mbar_init(smem_u32(&tfull_bar[1]), 1);
     mbar_init(smem_u32(&tempty_bar[0]), CG2 ? 2 * EPI_WARPS : EPI_WARPS);
     mbar_init(smem_u32(&tempty_bar[1]), CG2 ? 2 * EPI_WARPS : EPI_WARPS);
+#pragma unroll
+    for (int i = 0; i < SCHED_DEPTH; ++i) {
+      mbar_init(smem_u32(&sched_full[i]), 1);
+      mbar_init(smem_u32(&sched_empty[i]), 1 + EPI_WARPS);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -413,7 +430,18 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = worker; item < p.num_items; item += nworkers) {
+      int s_idx = 0;
+      uint32_t s_phase = 0;
+      for (int item = worker;;) {
+        if (dyn) {   // hand the item index (or the end marker) to the MMA thread and the epilogue warps
+          mbar_wait(smem_u32(&sched_empty[s_idx]), s_phase ^ 1u);
+          sched_item[s_idx] = item < p.num_items ? item : -1;
+          mbar_arrive(smem_u32(&sched_full[s_idx]));
+          if (++s_idx == SCHED_DEPTH) { s_idx = 0; s_phase ^= 1u; }
+        }
+        if (item >= p.num_items) break;
+        // the next item is requested BEFORE this item's k loop: the atomic's round trip hides under the loads
+        const int next_item = dyn ? nworkers + atomicAdd(p.sched, 1) : item + nworkers;
         const ItemCoord ic = decode_item<GROUPED, BN>(item, p, gt);
         const CUtensorMap* pta = GROUPED ? &gt.ta[ic.g] : &tma_a;
         const CUtensorMap* ptb = GROUPED ? &gt.tb[ic.g] : &tma_b;
@@ -519,6 +547,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
+        item = next_item;
       }
     }
   } else if (warp == 1) {
@@ -528,7 +557,19 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int item = worker; item < p.num_items; item += nworkers, ++it) {
+      int s_idx = 0;
+      uint32_t s_phase = 0;
+      for (int item = worker;; ++it) {
+        if (dyn) {
+          mbar_wait(smem_u32(&sched_full[s_idx]), s_phase);
+          item = sched_item[s_idx];
+          mbar_arrive(smem_u32(&sched_empty[s_idx]));
+          if (++s_idx == SCHED_DEPTH) { s_idx = 0; s_phase ^= 1u; }
+          if (item < 0) break;
+        } else {
+          item = worker + it * nworkers;
+          if (item >= p.num_items) break;
+        }
         const ItemCoord ic = decode_item<GROUPED, BN>(item, p, gt);
         const int kb_begin = ic.kb_begin, kb_end = ic.kb_end;
         const uint32_t idesc = ic.bn == BN ? idesc_full : make_idesc_bf16(BM, ic.bn, A_MN ? 1 : 0, B_MN ? 1 : 0);
@@ -566,7 +607,20 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
     float* stage = epi_stage + (warp - 2) * STAGE_F32_PER_WARP;
     const DropState dstate = drop_state(p.e.drop);
     int it = 0;
-    for (int item = worker; item < p.num_items; item += nworkers, ++it) {
+    int s_idx = 0;
+    uint32_t s_phase = 0;
+    for (int item = worker;; ++it) {
+      if (dyn) {
+        mbar_wait(smem_u32(&sched_full[s_idx]), s_phase);
+        item = sched_item[s_idx];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sched_empty[s_idx]));
+        if (++s_idx == SCHED_DEPTH) { s_idx = 0; s_phase ^= 1u; }
+        if (item < 0) break;
+      } else {
+        item = worker + it * nworkers;
+        if (item >= p.num_items) break;
+      }
       const ItemCoord ic = decode_item<GROUPED, BN>(item, p, gt);
       const int m_blk = ic.m_blk, n_blk = ic.n_blk;
       GemmEpilogue eg = p.e;
@@ -657,6 +711,15 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
   if (warp == 1) {
     tc_fence_after();
     if (CG2) tmem_dealloc_cg2(tmem_base, C::TMEM_COLS); else tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+  if (dyn && threadIdx.x == 0) {
+    // this thread (the producer) has made its last request; the last CTA to get here returns the counters to zero
+    __threadfence();
+    if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
+      p.sched[0] = 0;
+      p.sched[1] = 0;
+      __threadfence();
+    }
   }
 }
 
@@ -888,6 +951,31 @@ void gemm_debug_override(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t mn_kadv) {
 }
 
 namespace {
+// {next item, finished CTAs} counter pairs of the dynamic tile scheduler: a pool handed out round robin, one pair per launch
+// (consecutive launches never share a pair; a pair is back to zero when its kernel ends).  Allocated on first use outside of
+// stream capture; a launch that finds no pool (first call ever made inside a capture) falls back to static scheduling.
+constexpr int SCHED_POOL = 2048;
+int* sched_counters(cudaStream_t stream) {
+  static int* pool = nullptr;
+  static std::atomic<unsigned> next{0};
+  static std::mutex mu;
+  static const int on = [] { const char* v = getenv("VLB_DYN_SCHED"); return v ? atoi(v) : 1; }();
+  if (!on) return nullptr;
+  if (pool == nullptr) {
+    std::lock_guard<std::mutex> g(mu);
+    if (pool == nullptr) {
+      cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;
+      int* ptr = nullptr;
+      if (cudaMalloc(&ptr, SCHED_POOL * 2 * sizeof(int)) != cudaSuccess) return nullptr;
+      cudaMemset(ptr, 0, SCHED_POOL * 2 * sizeof(int));
+      cudaDeviceSynchronize();
+      pool = ptr;
+    }
+  }
+  return pool + 2 * (next.fetch_add(1, std::memory_order_relaxed) % SCHED_POOL);
+}
+
 // N-split of the last partial round (see GemmParams::tail_split): relative cost of one 128 x 64 unit against a 128 x 256 tile
 // (a quarter of the MMA work, but the same A tile per k-block: the unit is operand-feed bound, not MMA bound).
 constexpr double kTailUnitCost = 0.45;
@@ -1063,6 +1151,7 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
   }
   static const int env_prefetch = [] { const char* v = getenv("VLB_EPI_PREFETCH"); return v ? atoi(v) : 1; }();
   p.epi_prefetch = env_prefetch;
+  p.sched = (cm == 0 && p.sk_chunks == 0 && p.num_items > sms) ? sched_counters(stream) : nullptr;
 
   p.cv_side = 0;
   if (conv != nullptr && conv_side != 0) {
@@ -1160,7 +1249,7 @@ int gemm_grouped_tn(int count, const GroupedProblem* probs, int K, int split_k, 
   VLB_REQUIRE(sk == 1 || accumulate, "gemm_grouped_tn: split-K needs accumulate");
   p.e = GemmEpilogue();
   p.e.out_kind = accumulate ? OUT_F32_ATOMIC : OUT_F32;
-  p.tail_first = 0; p.tail_split = 0; p.epi_prefetch = 0;
+  p.tail_first = 0; p.tail_split = 0; p.epi_prefetch = 0; p.sched = nullptr;
   p.sk_full_items = 0; p.sk_chunks = 0; p.sk_kb_per_chunk = 0; p.sk_scratch = nullptr; p.sk_counters = nullptr; p.sk_debug = 0;
   p.cv_side = 0;
   p.a_lbo = p.b_lbo = g_dbg_mn_lbo ? g_dbg_mn_lbo : 8192u;
@@ -1188,6 +1277,7 @@ int gemm_grouped_tn(int count, const GroupedProblem* probs, int K, int split_k, 
   for (int i = count; i <= MAX_GROUP; ++i) gt.item_begin[i] = items;
   for (int i = count; i < MAX_GROUP; ++i) { gt.m_blocks[i] = gt.n_blocks[i] = 1; gt.M[i] = gt.N[i] = 0; gt.out[i] = nullptr; gt.ldo[i] = 0; gt.ta[i] = gt.ta[0]; gt.tb[i] = gt.tb[0]; }
   p.num_items = items;
+  p.sched = items > num_sms() ? sched_counters(stream) : nullptr;
   ProfScope prof(PROF_GEMM_TN, flops, stream);
   if (bn == 256) return accumulate ? launch_grouped<256, EPI_ATOMIC_F32>(gt, p, stream) : launch_grouped<256, EPI_GENERIC>(gt, p, stream);
   return accumulate ? launch_grouped<128, EPI_ATOMIC_F32>(gt, p, stream) : launch_grouped<128, EPI_GENERIC>(gt, p, stream);
