@@ -85,6 +85,56 @@ def test_gemm_cta_pair_mode(VF, mode, shape, bn):
         assert rel(acc, ref) <= 2e-5
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("shape", [(384, 768, 64), (6464, 768, 768), (6464, 768, 3072), (6464, 2304, 768), (6464, 3072, 768), (7744, 768, 768),
+                                   (500, 1536, 200), (192, 768, 2304)])
+@pytest.mark.parametrize("bn", [3192, 3256])
+def test_gemm_pair192_kernel(VF, mode, shape, bn):
+    """CTA-pair kernel with 192-row CTA tiles (csrc/gemm_pair192.cuh): force_bn = 3000 + BN.  Per 16-wide k-step one
+    cta_group::2 MMA with M = 256 and one with M = 128 (64 rows per CTA, '2x2' accumulator layout); B K-major (NT) or MN-major
+    (NN, for BN = 192 a CTA's half of the B tile is one and a half 64-column boxes)."""
+    M, N, K = shape
+    if N % (bn - 3000):
+        pytest.skip("N must be a multiple of the tile width")
+    g = torch.Generator().manual_seed(9000 + 10 * mode + M + N + K)
+    a = bf(torch.randn(M, K, generator=g))
+    b = bf(torch.randn(N, K, generator=g))
+    ref = a @ b.t()
+    A = a.to(DEV, BF16)
+    Bm = b.to(DEV, BF16) if mode == 0 else b.t().contiguous().to(DEV, BF16)
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32)
+    VF.gemm(mode, A, Bm, out, force_bn=bn)
+    assert rel(out, ref) <= 2e-5
+    # twice in a row into a bf16 output (the kernel's barriers / tensor memory must be reusable launch after launch)
+    o16 = torch.empty(M, N, device=DEV, dtype=BF16)
+    VF.gemm(mode, A, Bm, o16, force_bn=bn)
+    VF.gemm(mode, A, Bm, o16, force_bn=bn)
+    assert rel(o16.float(), ref.to(BF16).float()) <= 1e-3
+
+
+def test_gemm_pair192_epilogues(VF):
+    """The encoder's fused epilogues through the pair kernel: bias + GELU (+ saved GELU'), GELU' multiply, bias + fp32 residual."""
+    M, N, K = 1000, 768, 512
+    g = torch.Generator().manual_seed(55)
+    a, w = bf(torch.randn(M, K, generator=g)), bf(torch.randn(N, K, generator=g) * 0.05)
+    bias = torch.randn(N, generator=g)
+    z = a @ w.t() + bias
+    A, W = a.to(DEV, BF16), w.to(DEV, BF16)
+    out = torch.empty(M, N, device=DEV, dtype=BF16)
+    aux = torch.empty(M, N, device=DEV, dtype=BF16)
+    VF.gemm(0, A, W, out, bias=bias.to(DEV), act=1, aux=aux, force_bn=3192)
+    zt0 = z.clone().requires_grad_(True)
+    vo.gelu_erf(zt0).sum().backward()
+    assert rel(aux.float(), zt0.grad.to(BF16).float()) <= 1e-3
+    assert rel(out.float(), vo.gelu_erf(z)) <= 3e-3
+    gp = bf(torch.rand(M, N, generator=g) * 1.2 - 0.1)
+    VF.gemm(1, A, w.t().contiguous().to(DEV, BF16), out, act=3, aux=gp.to(DEV, BF16), force_bn=3192)
+    assert rel(out.float(), (a @ w.t()) * gp) <= 3e-3
+    resid = torch.randn(M, N, generator=g)
+    o32 = VF.gemm_bias_residual_f32(A, W, bias.to(DEV), resid.to(DEV), force_bn=3192)
+    assert rel(o32, z + resid) <= 2e-5
+
+
 @pytest.mark.parametrize("bn,split,acc", [(128, 1, False), (256, 1, False), (256, 2, True), (128, 3, True)])
 def test_gemm_grouped_wgrad(VF, bn, split, acc):
     """Four weight-gradient problems of a BertLayer in one grouped launch (vlb_gemm_grouped_tn)."""

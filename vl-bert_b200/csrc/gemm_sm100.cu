@@ -736,6 +736,8 @@ gemm_grouped_tn_kernel(const __grid_constant__ GroupTable gt, const GemmParams p
   gemm_body<BN, true, true, EPI, 0, true>(gt.ta[0], gt.tb[0], p, gt, gt.tb[0]);
 }
 
+#include "gemm_pair192.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -825,6 +827,40 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbt,
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
   VLB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, A_MN, B_MN, EPI, CM>, ta, tb, tbt, p));
   return VLB_OK;
+}
+
+template <int BN, bool B_MN, int EPI>
+int launch_pair192(const CUtensorMap& ta, const CUtensorMap& tb, const PairParams& p, cudaStream_t stream) {
+  using C = PairCfg<BN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VLB_CHECK_CUDA(cudaFuncSetAttribute(gemm_pair192_kernel<BN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int pairs = num_sms() / 2;
+  const int nclusters = p.num_items < pairs ? p.num_items : pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * nclusters);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  VLB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_pair192_kernel<BN, B_MN, EPI>, ta, tb, p));
+  return VLB_OK;
+}
+
+// epilogue that only converts the accumulator to bf16 (the data-gradient GEMMs dh / dx / dctx)
+bool epilogue_is_plain_bf16(const GemmEpilogue& e) {
+  return e.bias == nullptr && e.act == ACT_NONE && e.resid_kind == RESID_NONE && e.out_kind == OUT_BF16 && e.colsum == nullptr &&
+         e.aux == nullptr && e.alpha == 1.0f && e.colscale == nullptr && e.drop.thresh == 0u;
 }
 
 // which compile-time epilogue matches this runtime description (EPI_GENERIC if none)
@@ -1055,6 +1091,58 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
   static const int env_cg2 = [] { const char* v = getenv("VLB_CG2"); return v ? atoi(v) : 0; }();  // 0 off (default: measured ~5% slower in situ), 1 force, -1 auto
   static const int env_mc2 = [] { const char* v = getenv("VLB_MC2"); return v ? atoi(v) : 0; }();  // 1: B-multicast clusters wherever the tile is 128/256 wide
   if (force_bn == 0 && env_bn != 0 && (N >= (env_bn % 1000) || env_bn == 64)) force_bn = env_bn;
+  // CTA-pair kernel with 192-row CTA tiles (gemm_pair192.cuh): force_bn 3192 / 3256, or chosen automatically for problems that
+  // fill between half a wave and one wave of 384 x BN pair tiles (the encoder's N = 768 GEMMs at M = 6464: 68 of 74 pairs).
+  // VLB_PAIR192: 0 = never, 1 = single-wave problems (default), 2 = wherever the shape allows it.
+  {
+    static const int env_pair = [] { const char* v = getenv("VLB_PAIR192"); return v ? atoi(v) : 1; }();
+    static const int env_pair_nn_bn = [] { const char* v = getenv("VLB_PAIR192_NN_BN"); return v ? atoi(v) : 192; }();
+    int pbn = 0;
+    if (force_bn == 3192 || force_bn == 3256) {
+      pbn = force_bn - 3000;
+      VLB_REQUIRE(mode != GEMM_TN && conv == nullptr && split_k <= 1 && N % pbn == 0, "gemm: the pair-192 kernel needs NT / NN, no split-K, N %% %d == 0", pbn);
+    } else if (force_bn == 0 && env_pair != 0 && mode != GEMM_TN && conv == nullptr && split_k <= 1) {
+      int cand = mode == GEMM_NN ? env_pair_nn_bn : 192;
+      if (N % cand != 0) cand = (N % 256 == 0) ? 256 : ((N % 192 == 0) ? 192 : 0);
+      if (cand != 0) {
+        const long items = (long)((M + 383) / 384) * (N / cand);
+        const int pairs = num_sms() / 2;
+        if (env_pair == 2 ? M >= 384 : (items <= pairs && 2 * items >= pairs)) pbn = cand;
+      }
+    }
+    if (pbn != 0) {
+      PairParams q;
+      q.M = M; q.N = N; q.K = K;
+      q.num_m_pairs = (M + 383) / 384;
+      q.num_n_blocks = N / pbn;
+      q.num_k_blocks = (K + BK - 1) / BK;
+      q.num_items = q.num_m_pairs * q.num_n_blocks;
+      q.e = epi;
+      CUtensorMap ta, tb;
+      int rc = make_tmap_bf16_2d(&ta, A, M, K, lda, 64, 192);
+      if (rc != VLB_OK) return rc;
+      rc = b_mn ? make_tmap_bf16_2d(&tb, B, K, N, ldb, 64, 64) : make_tmap_bf16_2d(&tb, B, N, K, ldb, 64, pbn / 2);
+      if (rc != VLB_OK) return rc;
+      ProfScope prof(mode == GEMM_NT ? PROF_GEMM_NT : PROF_GEMM_NN, 2.0 * M * N * K, stream);
+      int epi_id = classify_epilogue(mode, epi);
+      if (epi_id == EPI_GENERIC && epilogue_is_plain_bf16(epi)) epi_id = EPI_PLAIN_BF16;
+#define VLB_PAIR_DISPATCH(BN_)                                                                                                   \
+      if (!b_mn) {                                                                                                               \
+        if (epi_id == EPI_BIAS_BF16) return launch_pair192<BN_, false, EPI_BIAS_BF16>(ta, tb, q, stream);                        \
+        if (epi_id == EPI_BIAS_RESIDLN_F32) return launch_pair192<BN_, false, EPI_BIAS_RESIDLN_F32>(ta, tb, q, stream);          \
+        if (epi_id == EPI_BIAS_DROP_RESIDLN_F32) return launch_pair192<BN_, false, EPI_BIAS_DROP_RESIDLN_F32>(ta, tb, q, stream); \
+        if (epi_id == EPI_BIAS_GELU_AUX_BF16) return launch_pair192<BN_, false, EPI_BIAS_GELU_AUX_BF16>(ta, tb, q, stream);      \
+        if (epi_id == EPI_PLAIN_BF16) return launch_pair192<BN_, false, EPI_PLAIN_BF16>(ta, tb, q, stream);                      \
+        return launch_pair192<BN_, false, EPI_GENERIC>(ta, tb, q, stream);                                                       \
+      }                                                                                                                          \
+      if (epi_id == EPI_DGELU_BF16) return launch_pair192<BN_, true, EPI_DGELU_BF16>(ta, tb, q, stream);                         \
+      if (epi_id == EPI_PLAIN_BF16) return launch_pair192<BN_, true, EPI_PLAIN_BF16>(ta, tb, q, stream);                         \
+      return launch_pair192<BN_, true, EPI_GENERIC>(ta, tb, q, stream);
+      if (pbn == 256) { VLB_PAIR_DISPATCH(256) }
+      VLB_PAIR_DISPATCH(192)
+#undef VLB_PAIR_DISPATCH
+    }
+  }
   int bn = 128;
   bool cg2 = false;
   int cm = 0;
