@@ -116,6 +116,9 @@ int vlb_gemm_grouped_tn(int count, const VlbGroupedProblem* problems, int K, int
 
 /* bring-up aid: override the MN-major shared-memory descriptor geometry (0 = default). */
 void vlb_debug_gemm_desc(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t mn_kadv);
+/* timing aid (tools/gemm_trace.py): the CTA-pair GEMM kernel writes 8 %globaltimer stamps per CTA into buf
+ * (device memory, >= 296 * 8 uint64); NULL switches it off. */
+void vlb_debug_gemm_trace(void* buf);
 
 /* ---- fused multi-head self-attention ---------------------------------------------------------
  * Replaces BertSelfAttention.forward after the three Linear layers (modeling.py:295-315):

@@ -32,6 +32,8 @@ def _declare(lib):
                                   c_void_p, c_int, c_float, c_int, c_int, c_void_p]
     lib.vlb_debug_gemm_desc.restype = None
     lib.vlb_debug_gemm_desc.argtypes = [c_uint32, c_uint32, c_uint32]
+    lib.vlb_debug_gemm_trace.restype = None
+    lib.vlb_debug_gemm_trace.argtypes = [c_void_p]
 
     P, I, F, L = c_void_p, c_int, c_float, c_int64
 

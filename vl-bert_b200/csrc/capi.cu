@@ -152,6 +152,8 @@ void vlb_debug_gemm_desc(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t mn_kadv) {
   gemm_debug_override(mn_lbo, mn_sbo, mn_kadv);
 }
 
+void vlb_debug_gemm_trace(void* buf) { gemm_debug_trace(static_cast<unsigned long long*>(buf)); }
+
 void vlb_profile_enable(int on) { g_prof_on = on != 0; }
 int vlb_profile_collect(double* ms, double* work, int64_t* launches) {
   for (int i = 0; i < PROF_NUM; ++i) { ms[i] = 0; work[i] = 0; launches[i] = 0; }

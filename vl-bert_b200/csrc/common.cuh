@@ -374,6 +374,27 @@ __device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
   cdf = x >= 0.0f ? 1.0f - erfc_half : erfc_half;
   pdf = 0.39894228040143267794f * ex;
 }
+// The same evaluation for two elements at once on the packed fp32 pipe (FFMA2 / FMUL2 / FADD2, sm_100): a three-register
+// FFMA issues every other cycle per scheduler, the packed forms carry two results per issue slot, and the GEMM epilogues that
+// evaluate GELU are issue-bound.  Per component the arithmetic (operation order, rounding) is that of gelu_parts.
+__device__ __forceinline__ void gelu_parts2(float2 x, float2& cdf, float2& pdf) {
+  const float2 u = __fmul2_rn(make_float2(fabsf(x.x), fabsf(x.y)), make_float2(0.70710678118654752440f, 0.70710678118654752440f));
+  const float2 den = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), u, make_float2(1.0f, 1.0f));
+  const float2 earg = __fmul2_rn(__fmul2_rn(make_float2(-0.72134752044448170368f, -0.72134752044448170368f), x), x);
+  float2 t, ex;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(den.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(den.y));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.x) : "f"(earg.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.y) : "f"(earg.y));
+  float2 poly = __ffma2_rn(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
+  poly = __ffma2_rn(poly, t, make_float2(1.421413741f, 1.421413741f));
+  poly = __ffma2_rn(poly, t, make_float2(-0.284496736f, -0.284496736f));
+  poly = __ffma2_rn(poly, t, make_float2(0.254829592f, 0.254829592f));
+  const float2 eh = __fmul2_rn(__fmul2_rn(__fmul2_rn(make_float2(0.5f, 0.5f), poly), t), ex);   // 0.5 * erfc(u)
+  const float2 one_m = __fadd2_rn(make_float2(1.0f, 1.0f), make_float2(-eh.x, -eh.y));
+  cdf = make_float2(x.x >= 0.0f ? one_m.x : eh.x, x.y >= 0.0f ? one_m.y : eh.y);
+  pdf = __fmul2_rn(make_float2(0.39894228040143267794f, 0.39894228040143267794f), ex);
+}
 __device__ __forceinline__ float gelu_fast(float x) {
   float cdf, pdf;
   gelu_parts(x, cdf, pdf);

@@ -45,8 +45,18 @@ struct PairParams {
   int M, N, K;
   int num_m_pairs, num_n_blocks, num_k_blocks;
   int num_items;
+  unsigned long long* trace;   // timing aid (vlb_debug_gemm_trace): 8 globaltimer stamps per CTA, nullptr = off
+  int epi_prefetch;   // 1: the epilogue warps pull the tile's residual / saved-activation / keep-flag lines into L2 while its MMAs run
   GemmEpilogue e;
 };
+
+__device__ __forceinline__ void trace_stamp(unsigned long long* trace, int slot) {
+  if (trace != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    trace[(size_t)blockIdx.x * 8 + slot] = t;
+  }
+}
 
 template <int BN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -70,6 +80,7 @@ gemm_pair192_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   pdl_trigger();
+  if (threadIdx.x == 0) trace_stamp(p.trace, 0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -96,6 +107,7 @@ gemm_pair192_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
+  if (threadIdx.x == 0) trace_stamp(p.trace, 1);
 
   if (warp == 0) {
     // ===================== TMA producer (one thread per CTA) =====================
@@ -145,6 +157,7 @@ gemm_pair192_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
+          if (kb == 0 && it == 0) trace_stamp(p.trace, 2);
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t sb = sa + C::A_BYTES;
 #pragma unroll
@@ -158,6 +171,7 @@ gemm_pair192_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit_cg2_mc(smem_u32(&tfull_bar[buf]), 3);
+        if (it == 0) trace_stamp(p.trace, 3);
       }
     }
   } else {
@@ -174,8 +188,39 @@ gemm_pair192_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const int col_tile = n_blk * BN;
       const uint32_t buf = C::DB ? (it & 1u) : 0u;
       const uint32_t use = C::DB ? (it >> 1) : it;
+      if (p.epi_prefetch) {
+        // A single wave leaves this epilogue fully exposed, and each of its chunks starts with a DRAM round trip for the
+        // residual (fp32 LayerNorm input), the saved GELU' or the keep flags: fetch those lines into L2 while the tile's MMAs
+        // run, so that the chunk loads below cost an L2 hit.
+        using T = EpiTraits<EPI>;
+        const int act = T::kStatic ? T::act : p.e.act;
+        const int rk = T::kStatic ? T::resid : p.e.resid_kind;
+        const bool aux_in = (act == ACT_DGELU_MUL || act == ACT_DRELU_MUL);
+        const int et = (int)threadIdx.x - 64;                        // epilogue thread index 0 .. 255
+        const int rows = min(C::ROWS, p.M - row_cta);
+        if (rows > 0 && (aux_in || rk != RESID_NONE)) {
+          const char* src = reinterpret_cast<const char*>(aux_in ? p.e.aux : p.e.resid);
+          const int esz = (!aux_in && (rk == RESID_F32 || rk == RESID_LN_F32)) ? 4 : 2;
+          const size_t ld_bytes = (size_t)(aux_in ? p.e.ld_aux : p.e.ldr) * esz;
+          const int lpr = (BN * esz + 127) >> 7;                     // 128-byte lines per row of the tile
+          for (int l = et; l < rows * lpr; l += EPI_WARPS * 32) {
+            const int r = l / lpr, sgm = l - r * lpr;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)(row_cta + r) * ld_bytes + (size_t)col_tile * esz + (size_t)sgm * 128));
+          }
+        }
+        if (rows > 0 && (T::kStatic ? T::drop : (p.e.drop.thresh != 0u))) {
+          const int wpr = (p.N + 31) >> 5;
+          for (int r = et; r < rows; r += EPI_WARPS * 32)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.e.drop.bits + (size_t)(row_cta + r) * wpr + (col_tile >> 5)));
+        }
+        if (rows > 0 && rk == RESID_LN_F32 && p.e.ln_mean != nullptr && et < 16) {
+          const float* st = (et < 8 ? p.e.ln_mean : p.e.ln_rstd) + row_cta + (et & 7) * 32;
+          if (row_cta + (et & 7) * 32 < p.M) asm volatile("prefetch.global.L2 [%0];" ::"l"(st));
+        }
+      }
       mbar_wait(smem_u32(&tfull_bar[buf]), use & 1u);
       tc_fence_after();
+      if (it == 0 && warp == 2 && lane == 0) trace_stamp(p.trace, 4);
       const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
       auto release = [&](uint64_t* bar) {
         tc_fence_before();
@@ -195,9 +240,11 @@ gemm_pair192_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           uint32_t v[32];
           tmem_ld32(t_lane + C::ACC2_COL + c * 32, v);
           tmem_ld_wait();
-          if (row_base < p.M) epilogue_chunk<EPI>(p.e, v, stage, lane, row_base, col_half + c * 32, p.M, p.N, nullptr, 0, dstate);
+          if (epi_fast_ok<EPI>(p.e) && row_base + 32 <= p.M) epilogue_chunk_fast<EPI>(p.e, v, stage, lane, row_base, col_half + c * 32, p.N);
+          else if (row_base < p.M) epilogue_chunk<EPI>(p.e, v, stage, lane, row_base, col_half + c * 32, p.M, p.N, nullptr, 0, dstate);
         }
         release(tempty2_bar);
+        if (it == 0 && warp == 2 && lane == 0) trace_stamp(p.trace, 5);
       }
       // rows 0..127 of this CTA
       {
@@ -207,9 +254,11 @@ gemm_pair192_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           uint32_t v[32];
           tmem_ld32(t_lane + buf * BN + c * 32, v);
           tmem_ld_wait();
-          if (row_base < p.M) epilogue_chunk<EPI>(p.e, v, stage, lane, row_base, col_tile + c * 32, p.M, p.N, nullptr, 0, dstate);
+          if (epi_fast_ok<EPI>(p.e) && row_base + 32 <= p.M) epilogue_chunk_fast<EPI>(p.e, v, stage, lane, row_base, col_tile + c * 32, p.N);
+          else if (row_base < p.M) epilogue_chunk<EPI>(p.e, v, stage, lane, row_base, col_tile + c * 32, p.M, p.N, nullptr, 0, dstate);
         }
         release(&tempty1_bar[buf]);
+        if (it == 0 && warp == 2 && lane == 0) trace_stamp(p.trace, 6);
       }
     }
   }
@@ -220,4 +269,5 @@ gemm_pair192_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     tc_fence_after();
     tmem_dealloc_cg2(tmem_base, C::TMEM_COLS);
   }
+  if (threadIdx.x == 0) trace_stamp(p.trace, 7);
 }

@@ -293,11 +293,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
         // multiplies (ACT_DGELU_MUL) instead of re-evaluating erf and exp for every element.
         float gp[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float cdf, pdf;
-          gelu_parts(x[j], cdf, pdf);
-          gp[j] = fmaf(x[j], pdf, cdf);
-          x[j] *= cdf;
+        for (int j = 0; j < 4; j += 2) {   // two elements per packed-fp32 instruction
+          float2 cdf, pdf;
+          const float2 xx = make_float2(x[j], x[j + 1]);
+          gelu_parts2(xx, cdf, pdf);
+          const float2 g2 = __ffma2_rn(xx, pdf, cdf);
+          const float2 o2 = __fmul2_rn(xx, cdf);
+          gp[j] = g2.x; gp[j + 1] = g2.y;
+          x[j] = o2.x; x[j + 1] = o2.y;
         }
         if (e.aux != nullptr) {
           uint2 z;
@@ -362,6 +365,164 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
       asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(e.colsum + col), "f"(csum[0]), "f"(csum[1]), "f"(csum[2]), "f"(csum[3]) : "memory");
   }
   __syncwarp();
+}
+
+// Interior fast path of epilogue_chunk for the encoder's compile-time variants: the chunk lies completely inside the matrix
+// (no per-row / per-column predicates), row addresses advance by a constant stride, and the fp32 arithmetic runs on the
+// packed pipe (FFMA2 / FMUL2 / FADD2: two results per issue slot) -- the epilogue warps are issue-bound (two warps per
+// scheduler, ~850 instructions per chunk in the general routine), and in a single-wave launch the epilogue is not hidden
+// behind any mainloop.  Same layout and same results as epilogue_chunk up to fp32 rounding of re-associated scalings.
+template <int EPI>
+struct EpiFast {
+  using T = EpiTraits<EPI>;
+  static constexpr bool value = T::kStatic && !T::cscale && T::out != OUT_F32_ATOMIC &&
+                                (T::act == ACT_NONE || T::act == ACT_GELU || T::act == ACT_DGELU_MUL) &&
+                                (T::resid == RESID_NONE || T::resid == RESID_LN_F32);
+};
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk_fast(const GemmEpilogue& e, const uint32_t (&v)[32], float* stage, int lane,
+                                                    int row_base, int col0, int N) {
+  using T = EpiTraits<EPI>;
+  constexpr bool aux_in = T::act == ACT_DGELU_MUL;
+  constexpr bool colsum_ok = aux_in;   // the fused bias-gradient column sum exists only on the GELU' epilogue (db_1); callers check
+  const int g = lane & 7, r0 = lane >> 3;
+  const int col = col0 + g * 4;
+  const size_t row = (size_t)(row_base + r0);
+  // ---- phase 0: every global load of the chunk in flight before anything depends on it ----
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (T::bias) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+  uint2 in16[8];
+  float4 in32[8];
+  uint32_t kw[8];
+  float ln_mu[8], ln_rs[8];
+  float4 ln_g4 = make_float4(1.f, 1.f, 1.f, 1.f), ln_b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool ln_resid = T::resid == RESID_LN_F32 && e.ln_mean != nullptr;
+  if (aux_in) {
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(e.aux) + row * (size_t)e.ld_aux + col;
+    const size_t step = (size_t)e.ld_aux * 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i, src += step) in16[i] = __ldg(reinterpret_cast<const uint2*>(src));
+  }
+  if (T::resid == RESID_LN_F32) {
+    const float* src = reinterpret_cast<const float*>(e.resid) + row * (size_t)e.ldr + col;
+    const size_t step = (size_t)e.ldr * 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i, src += step) in32[i] = __ldg(reinterpret_cast<const float4*>(src));
+    if (ln_resid) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        ln_mu[i] = __ldg(e.ln_mean + row + i * 4);
+        ln_rs[i] = __ldg(e.ln_rstd + row + i * 4);
+      }
+      ln_g4 = __ldg(reinterpret_cast<const float4*>(e.ln_gamma + col));
+      ln_b4 = __ldg(reinterpret_cast<const float4*>(e.ln_beta + col));
+    }
+  }
+  if (T::drop) {   // the word holding this chunk's 32 keep flags of each row; this lane's four columns are bits 4g .. 4g+3
+    const size_t wpr = (size_t)((N + 31) >> 5);
+    const uint32_t* src = e.drop.bits + row * wpr + (size_t)(col0 >> 5);
+#pragma unroll
+    for (int i = 0; i < 8; ++i, src += 4 * wpr) kw[i] = __ldg(src);
+  }
+  // ---- phase 1: transpose the accumulator chunk through shared memory ----
+  {
+    float4* dst = reinterpret_cast<float4*>(stage + lane * 32);
+#pragma unroll
+    for (int gg = 0; gg < 8; ++gg)
+      dst[gg ^ (lane & 7)] = make_float4(__uint_as_float(v[4 * gg]), __uint_as_float(v[4 * gg + 1]),
+                                         __uint_as_float(v[4 * gg + 2]), __uint_as_float(v[4 * gg + 3]));
+  }
+  __syncwarp();
+  // ---- phase 2: math + row-contiguous stores ----
+  float csum[4] = {0.f, 0.f, 0.f, 0.f};
+  const float ds = T::drop ? e.drop.scale : 1.0f;
+  const float2 sc = f2(ds, ds);
+  const float2 b01 = f2(bias4.x * ds, bias4.y * ds), b23 = f2(bias4.z * ds, bias4.w * ds);   // bias pre-scaled by 1 / (1 - p)
+  char* outp = reinterpret_cast<char*>(e.out) + (row * (size_t)e.ldo + col) * (T::out == OUT_BF16 ? 2 : 4);
+  const size_t out_step = (size_t)e.ldo * 4 * (T::out == OUT_BF16 ? 2 : 4);
+  __nv_bfloat16* auxp = (T::act == ACT_GELU && e.aux != nullptr) ? reinterpret_cast<__nv_bfloat16*>(e.aux) + row * (size_t)e.ld_aux + col : nullptr;
+  const size_t aux_step = (size_t)e.ld_aux * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + r0;
+    const float4 a = reinterpret_cast<const float4*>(stage + r * 32)[g ^ (r & 7)];
+    float2 x01, x23;
+    if (T::bias || T::drop) {
+      x01 = __ffma2_rn(f2(a.x, a.y), sc, b01);
+      x23 = __ffma2_rn(f2(a.z, a.w), sc, b23);
+    } else {
+      x01 = f2(a.x, a.y);
+      x23 = f2(a.z, a.w);
+    }
+    if (T::act == ACT_GELU) {
+      float2 cdf, pdf;
+      gelu_parts2(x01, cdf, pdf);
+      const float2 g01 = __ffma2_rn(x01, pdf, cdf);
+      x01 = __fmul2_rn(x01, cdf);
+      gelu_parts2(x23, cdf, pdf);
+      const float2 g23 = __ffma2_rn(x23, pdf, cdf);
+      x23 = __fmul2_rn(x23, cdf);
+      if (auxp != nullptr) {
+        uint2 z;
+        z.x = pack_bf16x2(g01.x, g01.y);
+        z.y = pack_bf16x2(g23.x, g23.y);
+        *reinterpret_cast<uint2*>(auxp) = z;
+        auxp += aux_step;
+      }
+    } else if (aux_in) {
+      x01 = __fmul2_rn(x01, f2(bf16lo(in16[i].x), bf16hi(in16[i].x)));
+      x23 = __fmul2_rn(x23, f2(bf16lo(in16[i].y), bf16hi(in16[i].y)));
+    }
+    if (T::drop) {
+      const uint32_t k4 = kw[i] >> (g * 4);
+      x01.x = (k4 & 1u) ? x01.x : 0.0f;
+      x01.y = (k4 & 2u) ? x01.y : 0.0f;
+      x23.x = (k4 & 4u) ? x23.x : 0.0f;
+      x23.y = (k4 & 8u) ? x23.y : 0.0f;
+    }
+    if (T::resid == RESID_LN_F32) {
+      if (ln_resid) {   // residual = LayerNorm(resid row) in fp32, same formula as layernorm_fwd_kernel
+        const float2 nm = f2(-ln_mu[i], -ln_mu[i]), rs2 = f2(ln_rs[i], ln_rs[i]);
+        const float2 h01 = __fmul2_rn(__fadd2_rn(f2(in32[i].x, in32[i].y), nm), rs2);
+        const float2 h23 = __fmul2_rn(__fadd2_rn(f2(in32[i].z, in32[i].w), nm), rs2);
+        x01 = __fadd2_rn(x01, __ffma2_rn(f2(ln_g4.x, ln_g4.y), h01, f2(ln_b4.x, ln_b4.y)));
+        x23 = __fadd2_rn(x23, __ffma2_rn(f2(ln_g4.z, ln_g4.w), h23, f2(ln_b4.z, ln_b4.w)));
+      } else {
+        x01 = __fadd2_rn(x01, f2(in32[i].x, in32[i].y));
+        x23 = __fadd2_rn(x23, f2(in32[i].z, in32[i].w));
+      }
+    }
+    if (T::out == OUT_BF16) {
+      uint2 o;
+      o.x = pack_bf16x2(x01.x, x01.y);
+      o.y = pack_bf16x2(x23.x, x23.y);
+      *reinterpret_cast<uint2*>(outp) = o;
+      if (colsum_ok && e.colsum != nullptr) {  // sum what was actually stored (bf16-rounded), like a separate column-sum pass would
+        csum[0] += bf16lo(o.x); csum[1] += bf16hi(o.x); csum[2] += bf16lo(o.y); csum[3] += bf16hi(o.y);
+      }
+    } else {
+      *reinterpret_cast<float4*>(outp) = make_float4(x01.x, x01.y, x23.x, x23.y);
+    }
+    outp += out_step;
+  }
+  if (colsum_ok && e.colsum != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      csum[j] += __shfl_xor_sync(0xffffffffu, csum[j], 8);
+      csum[j] += __shfl_xor_sync(0xffffffffu, csum[j], 16);
+    }
+    if (lane < 8)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(e.colsum + col), "f"(csum[0]), "f"(csum[1]), "f"(csum[2]), "f"(csum[3]) : "memory");
+  }
+  __syncwarp();
+}
+// whether the fast path may take this launch's chunks (run-time part of the decision)
+template <int EPI>
+__device__ __forceinline__ bool epi_fast_ok(const GemmEpilogue& e) {
+  return EpiFast<EPI>::value && e.alpha == 1.0f && (e.colsum == nullptr || EpiTraits<EPI>::act == ACT_DGELU_MUL);
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int CM, bool GROUPED>
@@ -695,7 +856,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
         tmem_ld32(t_row + c * 32, v);
         tmem_ld_wait();
         const int col0 = ic.n0 + c * 32;
-        if (row_base < Mg && col0 < Ng) epilogue_chunk<EPI>(eg, v, stage, lane, row_base, col0, Mg, Ng, nullptr, 0, dstate);
+        if (!GROUPED && epi_fast_ok<EPI>(eg) && row_base + 32 <= Mg && col0 + 32 <= Ng)
+          epilogue_chunk_fast<EPI>(eg, v, stage, lane, row_base, col0, Ng);
+        else if (row_base < Mg && col0 < Ng) epilogue_chunk<EPI>(eg, v, stage, lane, row_base, col0, Mg, Ng, nullptr, 0, dstate);
       }
       tc_fence_before();
       __syncwarp();
@@ -897,6 +1060,8 @@ int classify_epilogue(int mode, const GemmEpilogue& e) {
 
 // debug override of the MN-major descriptor geometry (bring-up aid, see tools/gemm_probe.py)
 uint32_t g_dbg_mn_lbo = 0, g_dbg_mn_sbo = 0, g_dbg_mn_kadv = 0;
+// timing aid: device buffer that receives 8 globaltimer stamps per CTA of the pair kernel (tools/gemm_trace.py)
+unsigned long long* g_dbg_trace = nullptr;
 
 }  // namespace
 
@@ -979,6 +1144,8 @@ int make_tmap_im2col(CUtensorMap* out, const void* ptr, const ConvGeom& g, uint3
 }
 
 bool gemm_streamk_compiled() { return VLB_ENABLE_STREAMK != 0; }
+
+void gemm_debug_trace(unsigned long long* buf) { g_dbg_trace = buf; }
 
 void gemm_debug_override(uint32_t mn_lbo, uint32_t mn_sbo, uint32_t mn_kadv) {
   g_dbg_mn_lbo = mn_lbo;
@@ -1117,6 +1284,9 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
       q.num_n_blocks = N / pbn;
       q.num_k_blocks = (K + BK - 1) / BK;
       q.num_items = q.num_m_pairs * q.num_n_blocks;
+      static const int env_pair_prefetch = [] { const char* v = getenv("VLB_EPI_PREFETCH"); return v ? atoi(v) : 1; }();
+      q.epi_prefetch = env_pair_prefetch;
+      q.trace = g_dbg_trace;
       q.e = epi;
       CUtensorMap ta, tb;
       int rc = make_tmap_bf16_2d(&ta, A, M, K, lda, 64, 192);

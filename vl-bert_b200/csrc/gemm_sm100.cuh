@@ -46,6 +46,9 @@ struct GemmEpilogue {
   const float* ln_beta = nullptr;
 };
 
+// timing aid: 8 globaltimer stamps per CTA of the pair kernel are written to buf (device memory, >= grid * 8 entries); nullptr = off
+void gemm_debug_trace(unsigned long long* buf);
+
 // whether the experimental stream-K tail was compiled in (-DVLB_ENABLE_STREAMK=1)
 bool gemm_streamk_compiled();
 
