@@ -11,6 +11,10 @@ apex DDP, pretrain/function/train.py:353-354): the fp32 buffer is cast into a pe
 all-reduced (AVG), and the result is cast back over the fp32 gradients `pipeline_depth` launches later, by which time the
 collective has long finished -- half the bytes on NVLink and half the time NCCL's channel CTAs compete with the
 persistent GEMM grids.  `wire_dtype=None` keeps fp32 (gloo in the CPU tests, or VLB_DDP_WIRE=fp32).
+On CUDA the two casts and the wait for the collective run on a side stream that forks from the compute stream at launch() and
+joins it again in drain(): the 24 cast kernels of a step (~10 us each) no longer sit between the backward kernels of the layers
+below (VLB_DDP_SIDE_STREAM=0 puts them back on the compute stream).  The fork / join are ordinary stream dependencies, so a
+CUDA-graph capture of the step records them like everything else.
 Works with any torch.distributed backend."""
 import os
 
@@ -46,6 +50,9 @@ class LayerGradReducer(object):
         self.depth = max(0, int(pipeline_depth))
         self.pending = []
         self._staging = {}
+        self.side_stream = os.environ.get("VLB_DDP_SIDE_STREAM", "1") != "0"
+        self._side = {}
+        self._forked = set()
 
     def _stage(self, flat):
         """persistent wire-format buffer for this gradient buffer (keyed by address: static under CUDA graphs)"""
@@ -61,6 +68,23 @@ class LayerGradReducer(object):
     def launch(self, flat):
         """flat: contiguous fp32 gradient buffer of one layer; reduced in place (visible after drain())."""
         op = dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM
+        if self.side_stream and flat.is_cuda and self.avg and flat.is_contiguous():
+            # cast -> all-reduce -> cast back, all off the compute stream; drain() joins
+            cur = torch.cuda.current_stream(flat.device)
+            side = self._side.get(flat.device)
+            if side is None:
+                side = self._side[flat.device] = torch.cuda.Stream(device=flat.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                if self.wire_dtype is not None and flat.dtype == torch.float32:
+                    wire = self._stage(flat)
+                    _cast(flat.view(-1), wire)
+                    dist.all_reduce(wire, op=op, group=self.group, async_op=True).wait()
+                    _cast(wire, flat.view(-1))
+                else:
+                    dist.all_reduce(flat, op=op, group=self.group, async_op=True).wait()
+            self._forked.add(flat.device)
+            return
         if self.wire_dtype is not None and flat.dtype == torch.float32 and flat.is_contiguous():
             wire = self._stage(flat)
             _cast(flat.view(-1), wire)
@@ -83,6 +107,9 @@ class LayerGradReducer(object):
     def drain(self):
         while self.pending:
             self._finish(self.pending.pop(0))
+        for dev in self._forked:
+            torch.cuda.current_stream(dev).wait_stream(self._side[dev])
+        self._forked.clear()
 
     def reduce_params(self, params, coalesce_below=1 << 20):
         """Average the .grad of parameters that are not covered by launch() (embeddings, pooler, heads).
