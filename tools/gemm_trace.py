@@ -19,7 +19,7 @@ def main():
     VF = vlbert_b200.functional
     lib = vlbert_b200._lib.lib()
     M, N, K = [int(a) for a in sys.argv[1:4]] if len(sys.argv) >= 4 else (6464, 768, 768)
-    variant = sys.argv[4] if len(sys.argv) > 4 else "plain"
+    variant = sys.argv[4] if len(sys.argv) > 4 and not sys.argv[4].startswith("--") else "plain"
     dev, bf, f32 = "cuda", torch.bfloat16, torch.float32
     g = torch.Generator(device=dev).manual_seed(0)
 
@@ -39,7 +39,8 @@ def main():
         "dgelu": lambda s: VF.gemm(1, s["a"], s["wt"], s["o16"], act=3, aux=s["aux"]),
     }
     fn = fns[variant]
-    buf = torch.zeros(296 * 8, dtype=torch.int64, device=dev)
+    persistent = "--persistent" in sys.argv     # the 148-CTA persistent kernel: per CTA 8 items x (MMA start, MMA end, epilogue start, epilogue end)
+    buf = torch.zeros(296 * 32, dtype=torch.int64, device=dev)
     for i in range(8):
         fn(sets[i % 4])
     torch.cuda.synchronize()
@@ -50,7 +51,21 @@ def main():
     lib.vlb_debug_gemm_trace(None)
     fn(sets[3])
     torch.cuda.synchronize()
-    t = buf.view(296, 8).cpu()
+    if persistent:
+        t = buf.view(-1, 8, 4).cpu().double()
+        t = t[t[:, 0, 0] > 0]
+        t0 = t[:, 0, 0].min()
+        print("M=%d N=%d K=%d variant=%s CTAs=%d (persistent kernel)  env=%s" % (M, N, K, variant, t.shape[0], {k: v for k, v in os.environ.items() if k.startswith("VLB_")}))
+        for it in range(8):
+            col = t[:, it, :]
+            ok = col[:, 0] > 0
+            if ok.sum() == 0:
+                break
+            c = (col[ok] - t0) / 1e3
+            print("  item %d (%3d CTAs): MMA start %7.2f  MMA end %7.2f | epilogue start %7.2f  end %7.2f   (medians, us; epilogue stamps of warp 2)" %
+                  (it, int(ok.sum()), c[:, 0].median(), c[:, 1].median(), c[:, 2][c[:, 2] > -1e6].median(), c[:, 3].median()))
+        return
+    t = buf.view(-1, 8)[:296].cpu()
     used = t[:, 0] > 0
     t = t[used].double()
     t0 = t[:, 0].min()

@@ -46,6 +46,7 @@ struct PairParams {
   int num_m_pairs, num_n_blocks, num_k_blocks;
   int num_items;
   unsigned long long* trace;   // timing aid (vlb_debug_gemm_trace): 8 globaltimer stamps per CTA, nullptr = off
+  int epi_stage;      // 1: last tile of a CTA: residual rows / keep flags / LayerNorm statistics staged in the idle operand ring
   int epi_prefetch;   // 1: the epilogue warps pull the tile's residual / saved-activation / keep-flag lines into L2 while its MMAs run
   GemmEpilogue e;
 };
@@ -222,6 +223,54 @@ gemm_pair192_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       tc_fence_after();
       if (it == 0 && warp == 2 && lane == 0) trace_stamp(p.trace, 4);
       const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+      // ---- operand staging for the exposed epilogue of the CTA's last tile (see StagedChunk) ----
+      // All MMAs have completed and the producer has nothing left to load, so the operand ring is idle: every residual vector,
+      // keep-flag word and LayerNorm statistic this warp will need goes into its slice of it with cp.async, all in flight at once.
+      using TE = EpiTraits<EPI>;
+      constexpr int kSlice = 22528;   // 5 chunks x 4 KB residual + 5 x 32 keep words + 2 x 2 x 32 statistics, rounded up
+      constexpr bool kCanStage = EpiFast<EPI>::value && TE::resid == RESID_LN_F32 && EPI_WARPS * kSlice <= C::STAGES * C::STAGE_BYTES &&
+                                 (C::B_HALF / 32 + 1) / 2 + (BN / 32 + 1) / 2 <= 5;
+      const bool staged = kCanStage && p.epi_stage && item + nworkers >= p.num_items && epi_fast_ok<EPI>(p.e);
+      uint8_t* slice = smem + (warp - 2) * kSlice;
+      float4* s_in = reinterpret_cast<float4*>(slice);
+      uint32_t* s_kw = reinterpret_cast<uint32_t*>(slice + 5 * 4096);
+      float* s_mu = reinterpret_cast<float*>(slice + 5 * 4096 + 5 * 128);
+      float* s_rs = s_mu + 64;
+      const int rows2 = row_cta + 128 + (q & 1) * 32;            // first row of this warp's part of acc2 / acc1
+      const int rows1 = row_cta + q * 32;
+      const int col2 = col_tile + (q >> 1) * C::B_HALF;
+      if (staged) {
+        const int g = lane & 7, r0 = lane >> 3;
+        const float* rsrc = reinterpret_cast<const float*>(p.e.resid);
+        const size_t wpr = (size_t)((p.N + 31) >> 5);
+        int k = 0;
+        auto issue = [&](int rb, int c0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = rb + r0 + 4 * i;
+            const bool ok = row < p.M;
+            cp_async_16(smem_u32(s_in + (k * 8 + i) * 32 + lane), rsrc + (size_t)(ok ? row : 0) * p.e.ldr + c0 + g * 4, ok ? 16u : 0u);
+          }
+          if (TE::drop) {
+            const bool ok = rb + lane < p.M;
+            cp_async_4(smem_u32(s_kw + k * 32 + lane), p.e.drop.bits + (size_t)(ok ? rb + lane : 0) * wpr + (size_t)(c0 >> 5), ok ? 4u : 0u);
+          }
+          ++k;
+        };
+        for (int c = half; c < C::B_HALF / 32; c += 2) issue(rows2, col2 + c * 32);
+        for (int c = half; c < BN / 32; c += 2) issue(rows1, col_tile + c * 32);
+        if (p.e.ln_mean != nullptr) {
+          const bool ok2 = rows2 + lane < p.M, ok1 = rows1 + lane < p.M;
+          cp_async_4(smem_u32(s_mu + lane), p.e.ln_mean + (ok2 ? rows2 + lane : 0), ok2 ? 4u : 0u);
+          cp_async_4(smem_u32(s_rs + lane), p.e.ln_rstd + (ok2 ? rows2 + lane : 0), ok2 ? 4u : 0u);
+          cp_async_4(smem_u32(s_mu + 32 + lane), p.e.ln_mean + (ok1 ? rows1 + lane : 0), ok1 ? 4u : 0u);
+          cp_async_4(smem_u32(s_rs + 32 + lane), p.e.ln_rstd + (ok1 ? rows1 + lane : 0), ok1 ? 4u : 0u);
+        }
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncwarp();
+      }
+      int kst = 0;   // staged chunk counter (same order as the issue loops)
       auto release = [&](uint64_t* bar) {
         tc_fence_before();
         __syncwarp();
@@ -233,14 +282,16 @@ gemm_pair192_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       // rows 128..191 first (the single acc2 buffer is what the next tile's MMAs wait for): lane quarters 0/1 hold the left
       // half of the columns, quarters 2/3 the right half
       {
-        const int row_base = row_cta + 128 + (q & 1) * 32;
-        const int col_half = col_tile + (q >> 1) * C::B_HALF;
+        const int row_base = rows2;
+        const int col_half = col2;
 #pragma unroll 1
-        for (int c = half; c < C::B_HALF / 32; c += 2) {
+        for (int c = half; c < C::B_HALF / 32; c += 2, ++kst) {
           uint32_t v[32];
           tmem_ld32(t_lane + C::ACC2_COL + c * 32, v);
           tmem_ld_wait();
-          if (epi_fast_ok<EPI>(p.e) && row_base + 32 <= p.M) epilogue_chunk_fast<EPI>(p.e, v, stage, lane, row_base, col_half + c * 32, p.N);
+          StagedChunk sc;
+          if (staged) { sc.in32 = s_in + kst * 256 + lane; sc.kw = s_kw + kst * 32; sc.mu = s_mu; sc.rs = s_rs; }
+          if (epi_fast_ok<EPI>(p.e) && row_base + 32 <= p.M) epilogue_chunk_fast<EPI>(p.e, v, stage, lane, row_base, col_half + c * 32, p.N, sc);
           else if (row_base < p.M) epilogue_chunk<EPI>(p.e, v, stage, lane, row_base, col_half + c * 32, p.M, p.N, nullptr, 0, dstate);
         }
         release(tempty2_bar);
@@ -248,13 +299,15 @@ gemm_pair192_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
       // rows 0..127 of this CTA
       {
-        const int row_base = row_cta + q * 32;
+        const int row_base = rows1;
 #pragma unroll 1
-        for (int c = half; c < BN / 32; c += 2) {
+        for (int c = half; c < BN / 32; c += 2, ++kst) {
           uint32_t v[32];
           tmem_ld32(t_lane + buf * BN + c * 32, v);
           tmem_ld_wait();
-          if (epi_fast_ok<EPI>(p.e) && row_base + 32 <= p.M) epilogue_chunk_fast<EPI>(p.e, v, stage, lane, row_base, col_tile + c * 32, p.N);
+          StagedChunk sc;
+          if (staged) { sc.in32 = s_in + kst * 256 + lane; sc.kw = s_kw + kst * 32; sc.mu = s_mu + 32; sc.rs = s_rs + 32; }
+          if (epi_fast_ok<EPI>(p.e) && row_base + 32 <= p.M) epilogue_chunk_fast<EPI>(p.e, v, stage, lane, row_base, col_tile + c * 32, p.N, sc);
           else if (row_base < p.M) epilogue_chunk<EPI>(p.e, v, stage, lane, row_base, col_tile + c * 32, p.M, p.N, nullptr, 0, dstate);
         }
         release(&tempty1_bar[buf]);

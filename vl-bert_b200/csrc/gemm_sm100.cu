@@ -76,6 +76,7 @@ struct GemmParams {
   // (e.g. its SM is still held by an NCCL channel CTA of an overlapped gradient all-reduce) simply takes fewer items instead of
   // holding its statically assigned share back; the last CTA to finish resets both counters.  nullptr = static round robin.
   int* sched;
+  unsigned long long* trace;   // timing aid (vlb_debug_gemm_trace): per CTA 8 items x 4 globaltimer stamps, nullptr = off
 };
 
 constexpr int SCHED_DEPTH = 4;   // ring of item indices handed from the producer warp to the MMA / epilogue warps
@@ -382,9 +383,20 @@ struct EpiFast {
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 
+// Operands of one chunk that were staged in shared memory ahead of time (pair kernel, last tile of a CTA: the idle
+// operand ring receives the whole tile's residual rows, keep-flag words and LayerNorm statistics with every load in flight at
+// once -- otherwise each chunk starts with its own round trip to L2 / DRAM and the exposed epilogue is a chain of them).
+//   in32: this lane's eight residual vectors, entry i at in32[i * 32];  kw / mu / rs: one entry per row of the warp.
+struct StagedChunk {
+  const float4* in32 = nullptr;
+  const uint32_t* kw = nullptr;
+  const float* mu = nullptr;
+  const float* rs = nullptr;
+};
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk_fast(const GemmEpilogue& e, const uint32_t (&v)[32], float* stage, int lane,
-                                                    int row_base, int col0, int N) {
+                                                    int row_base, int col0, int N, const StagedChunk sc_in = StagedChunk()) {
   using T = EpiTraits<EPI>;
   constexpr bool aux_in = T::act == ACT_DGELU_MUL;
   constexpr bool colsum_ok = aux_in;   // the fused bias-gradient column sum exists only on the GELU' epilogue (db_1); callers check
@@ -406,26 +418,37 @@ __device__ __forceinline__ void epilogue_chunk_fast(const GemmEpilogue& e, const
 #pragma unroll
     for (int i = 0; i < 8; ++i, src += step) in16[i] = __ldg(reinterpret_cast<const uint2*>(src));
   }
+  const bool staged = sc_in.in32 != nullptr;
   if (T::resid == RESID_LN_F32) {
-    const float* src = reinterpret_cast<const float*>(e.resid) + row * (size_t)e.ldr + col;
-    const size_t step = (size_t)e.ldr * 4;
+    if (staged) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i, src += step) in32[i] = __ldg(reinterpret_cast<const float4*>(src));
+      for (int i = 0; i < 8; ++i) in32[i] = sc_in.in32[i * 32];
+    } else {
+      const float* src = reinterpret_cast<const float*>(e.resid) + row * (size_t)e.ldr + col;
+      const size_t step = (size_t)e.ldr * 4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i, src += step) in32[i] = __ldg(reinterpret_cast<const float4*>(src));
+    }
     if (ln_resid) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        ln_mu[i] = __ldg(e.ln_mean + row + i * 4);
-        ln_rs[i] = __ldg(e.ln_rstd + row + i * 4);
+        ln_mu[i] = staged ? sc_in.mu[r0 + i * 4] : __ldg(e.ln_mean + row + i * 4);
+        ln_rs[i] = staged ? sc_in.rs[r0 + i * 4] : __ldg(e.ln_rstd + row + i * 4);
       }
       ln_g4 = __ldg(reinterpret_cast<const float4*>(e.ln_gamma + col));
       ln_b4 = __ldg(reinterpret_cast<const float4*>(e.ln_beta + col));
     }
   }
   if (T::drop) {   // the word holding this chunk's 32 keep flags of each row; this lane's four columns are bits 4g .. 4g+3
-    const size_t wpr = (size_t)((N + 31) >> 5);
-    const uint32_t* src = e.drop.bits + row * wpr + (size_t)(col0 >> 5);
+    if (staged) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i, src += 4 * wpr) kw[i] = __ldg(src);
+      for (int i = 0; i < 8; ++i) kw[i] = sc_in.kw[r0 + i * 4];
+    } else {
+      const size_t wpr = (size_t)((N + 31) >> 5);
+      const uint32_t* src = e.drop.bits + row * wpr + (size_t)(col0 >> 5);
+#pragma unroll
+      for (int i = 0; i < 8; ++i, src += 4 * wpr) kw[i] = __ldg(src);
+    }
   }
   // ---- phase 1: transpose the accumulator chunk through shared memory ----
   {
@@ -738,6 +761,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
         const uint32_t use = static_cast<uint32_t>(it >> 1);
         mbar_wait(smem_u32(&tempty_bar[buf]), (use & 1u) ^ 1u);
         tc_fence_after();
+        if (p.trace != nullptr && it < 8) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); p.trace[((size_t)blockIdx.x * 8 + it) * 4 + 0] = tt; }
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * BN);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
@@ -759,6 +783,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
         }
         // accumulator ready for the epilogue warps (of both CTAs)
         if (CG2) umma_commit_cg2_mc(smem_u32(&tfull_bar[buf]), 3); else umma_commit(smem_u32(&tfull_bar[buf]));
+        if (p.trace != nullptr && it < 8) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); p.trace[((size_t)blockIdx.x * 8 + it) * 4 + 1] = tt; }
       }
     }
   } else {
@@ -813,6 +838,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
       }
       mbar_wait(smem_u32(&tfull_bar[buf]), use & 1u);
       tc_fence_after();
+      if (p.trace != nullptr && it < 8 && warp == 2 && lane == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); p.trace[((size_t)blockIdx.x * 8 + it) * 4 + 2] = tt; }
       const int row_base = (m_blk * (CL ? 2 : 1) + (int)rank) * BM + q * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
       if (VLB_ENABLE_STREAMK && !GROUPED && CM == 0 && ic.tail >= 0) {
@@ -862,6 +888,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
       }
       tc_fence_before();
       __syncwarp();
+      if (p.trace != nullptr && it < 8 && warp == 2 && lane == 0) { unsigned long long tt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt)); p.trace[((size_t)blockIdx.x * 8 + it) * 4 + 3] = tt; }
       if (lane == 0) {
         if (CG2 && !leader) mbar_arrive_cluster(mapa_cluster(smem_u32(&tempty_bar[buf]), 0));  // the leader's MMA thread owns both TMEMs
         else mbar_arrive(smem_u32(&tempty_bar[buf]));
@@ -1286,6 +1313,8 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
       q.num_items = q.num_m_pairs * q.num_n_blocks;
       static const int env_pair_prefetch = [] { const char* v = getenv("VLB_EPI_PREFETCH"); return v ? atoi(v) : 1; }();
       q.epi_prefetch = env_pair_prefetch;
+      static const int env_pair_stage = [] { const char* v = getenv("VLB_EPI_STAGE"); return v ? atoi(v) : 1; }();
+      q.epi_stage = env_pair_stage;
       q.trace = g_dbg_trace;
       q.e = epi;
       CUtensorMap ta, tb;
@@ -1410,6 +1439,7 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
   static const int env_prefetch = [] { const char* v = getenv("VLB_EPI_PREFETCH"); return v ? atoi(v) : 1; }();
   p.epi_prefetch = env_prefetch;
   p.sched = (cm == 0 && p.sk_chunks == 0 && p.num_items > sms) ? sched_counters(stream) : nullptr;
+  p.trace = g_dbg_trace;
 
   p.cv_side = 0;
   if (conv != nullptr && conv_side != 0) {
@@ -1507,7 +1537,7 @@ int gemm_grouped_tn(int count, const GroupedProblem* probs, int K, int split_k, 
   VLB_REQUIRE(sk == 1 || accumulate, "gemm_grouped_tn: split-K needs accumulate");
   p.e = GemmEpilogue();
   p.e.out_kind = accumulate ? OUT_F32_ATOMIC : OUT_F32;
-  p.tail_first = 0; p.tail_split = 0; p.epi_prefetch = 0; p.sched = nullptr;
+  p.tail_first = 0; p.tail_split = 0; p.epi_prefetch = 0; p.sched = nullptr; p.trace = nullptr;
   p.sk_full_items = 0; p.sk_chunks = 0; p.sk_kb_per_chunk = 0; p.sk_scratch = nullptr; p.sk_counters = nullptr; p.sk_debug = 0;
   p.cv_side = 0;
   p.a_lbo = p.b_lbo = g_dbg_mn_lbo ? g_dbg_mn_lbo : 8192u;

@@ -369,23 +369,42 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) mhsa_bwd_kernel(const __grid_c
     umma_commit(smem_u32(&bars[1]));
   }
 
-  // D = rowsum(dO o O) and the saved log-sum-exp for this query row (overlaps the TMA + MMAs above)
+  // D = rowsum(dO o O) and the saved log-sum-exp for this query row (overlaps the TMA + MMAs above).
+  // The warp reads its 32 rows cooperatively -- lane l takes the 16-byte piece l % 8 of rows l / 8 + 4 j, so every load
+  // instruction covers four whole 128-byte rows instead of 32 scattered sectors (the one-row-per-thread version stalled on
+  // the load queue: 16 uncoalesced 128-bit loads per thread) -- and the eight partial dot products of a row meet by shuffles.
   float Dsum = 0.0f, lse = 0.0f;
   const bool valid = q0 + t < p.S;     // this thread's QUERY row exists
   const bool kvalid = k0 + t < p.S;    // this thread's KEY row exists (dK / dV rows)
-  if (valid) {
-    const uint4* po = reinterpret_cast<const uint4*>(p.ctx + (size_t)(row0 + q0 + t) * p.H + h * D_HEAD);
-    const uint4* pd = reinterpret_cast<const uint4*>(p.dctx + (size_t)(row0 + q0 + t) * p.H + h * D_HEAD);
+  {
+    const int lane = tid & 31;
+    const int wrow0 = q0 + (t & ~31);                       // first query row of this warp's lane quarter
+    const int piece = lane & 7, rgrp = lane >> 3;
     uint4 a[8], d[8];
 #pragma unroll
-    for (int g = 0; g < 8; ++g) { a[g] = __ldg(po + g); d[g] = __ldg(pd + g); }
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const uint32_t aa[4] = {a[g].x, a[g].y, a[g].z, a[g].w}, dd[4] = {d[g].x, d[g].y, d[g].z, d[g].w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) Dsum += bf16lo(aa[j]) * bf16lo(dd[j]) + bf16hi(aa[j]) * bf16hi(dd[j]);
+    for (int j = 0; j < 8; ++j) {
+      const int r = wrow0 + rgrp + 4 * j;
+      if (r < p.S) {
+        a[j] = __ldg(reinterpret_cast<const uint4*>(p.ctx + (size_t)(row0 + r) * p.H + h * D_HEAD) + piece);
+        d[j] = __ldg(reinterpret_cast<const uint4*>(p.dctx + (size_t)(row0 + r) * p.H + h * D_HEAD) + piece);
+      } else {
+        a[j] = d[j] = make_uint4(0u, 0u, 0u, 0u);
+      }
     }
-    lse = p.lse[((size_t)b * p.heads + h) * p.S + q0 + t];
+    if (valid) lse = p.lse[((size_t)b * p.heads + h) * p.S + q0 + t];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t aa[4] = {a[j].x, a[j].y, a[j].z, a[j].w}, dd[4] = {d[j].x, d[j].y, d[j].z, d[j].w};
+      float part = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) part += bf16lo(aa[i]) * bf16lo(dd[i]) + bf16hi(aa[i]) * bf16hi(dd[i]);
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      part += __shfl_xor_sync(0xffffffffu, part, 4);
+      // row rgrp + 4 j is now complete in lanes 8 rgrp .. 8 rgrp + 7; lane L owns row L = 4 (L / 4) + L % 4
+      const float mine = __shfl_sync(0xffffffffu, part, (lane & 3) * 8);
+      if ((lane >> 2) == j) Dsum = mine;
+    }
   }
 
   // dropout keep flags of this thread's 64 probabilities: one word per 32-key chunk, loaded at the top of each chunk
