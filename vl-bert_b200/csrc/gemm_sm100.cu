@@ -273,11 +273,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
       reinterpret_cast<float4*>(stage + r * 32)[g ^ (r & 7)] = acc[i];
     }
   } else {
-    const uint32_t dst = smem_u32(stage + lane * 32);
+    float4* dst = reinterpret_cast<float4*>(stage + lane * 32);
 #pragma unroll
     for (int gg = 0; gg < 8; ++gg)
-      sts128(dst + ((gg ^ (lane & 7)) << 4), make_float4(__uint_as_float(v[4 * gg]), __uint_as_float(v[4 * gg + 1]),
-                                                        __uint_as_float(v[4 * gg + 2]), __uint_as_float(v[4 * gg + 3])));
+      dst[gg ^ (lane & 7)] = make_float4(__uint_as_float(v[4 * gg]), __uint_as_float(v[4 * gg + 1]),
+                                         __uint_as_float(v[4 * gg + 2]), __uint_as_float(v[4 * gg + 3]));
   }
   __syncwarp();
   // ---- phase 2: math + row-contiguous stores ----
@@ -286,7 +286,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& e, const uint
   for (int i = 0; i < 8; ++i) {
     const int r = i * 4 + r0;
     const int row = row_base + r;
-    const float4 a = lds128(smem_u32(stage + r * 32) + ((g ^ (r & 7)) << 4));
+    const float4 a = reinterpret_cast<const float4*>(stage + r * 32)[g ^ (r & 7)];
     if (row < M && col_ok) {
       float x[4] = {fmaf(a.x, scale4.x, bias4.x), fmaf(a.y, scale4.y, bias4.y), fmaf(a.z, scale4.z, bias4.z), fmaf(a.w, scale4.w, bias4.w)};
       if (act == ACT_GELU) {
@@ -422,7 +422,7 @@ __device__ __forceinline__ void epilogue_chunk_fast(const GemmEpilogue& e, const
   if (T::resid == RESID_LN_F32) {
     if (staged) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) in32[i] = lds128(smem_u32(sc_in.in32 + i * 32));
+      for (int i = 0; i < 8; ++i) in32[i] = sc_in.in32[i * 32];
     } else {
       const float* src = reinterpret_cast<const float*>(e.resid) + row * (size_t)e.ldr + col;
       const size_t step = (size_t)e.ldr * 4;
@@ -432,8 +432,8 @@ __device__ __forceinline__ void epilogue_chunk_fast(const GemmEpilogue& e, const
     if (ln_resid) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        ln_mu[i] = staged ? __uint_as_float(lds32(smem_u32(sc_in.mu + r0 + i * 4))) : __ldg(e.ln_mean + row + i * 4);
-        ln_rs[i] = staged ? __uint_as_float(lds32(smem_u32(sc_in.rs + r0 + i * 4))) : __ldg(e.ln_rstd + row + i * 4);
+        ln_mu[i] = staged ? sc_in.mu[r0 + i * 4] : __ldg(e.ln_mean + row + i * 4);
+        ln_rs[i] = staged ? sc_in.rs[r0 + i * 4] : __ldg(e.ln_rstd + row + i * 4);
       }
       ln_g4 = __ldg(reinterpret_cast<const float4*>(e.ln_gamma + col));
       ln_b4 = __ldg(reinterpret_cast<const float4*>(e.ln_beta + col));
@@ -442,7 +442,7 @@ __device__ __forceinline__ void epilogue_chunk_fast(const GemmEpilogue& e, const
   if (T::drop) {   // the word holding this chunk's 32 keep flags of each row; this lane's four columns are bits 4g .. 4g+3
     if (staged) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) kw[i] = lds32(smem_u32(sc_in.kw + r0 + i * 4));
+      for (int i = 0; i < 8; ++i) kw[i] = sc_in.kw[r0 + i * 4];
     } else {
       const size_t wpr = (size_t)((N + 31) >> 5);
       const uint32_t* src = e.drop.bits + row * wpr + (size_t)(col0 >> 5);
@@ -452,11 +452,11 @@ __device__ __forceinline__ void epilogue_chunk_fast(const GemmEpilogue& e, const
   }
   // ---- phase 1: transpose the accumulator chunk through shared memory ----
   {
-    const uint32_t dst = smem_u32(stage + lane * 32);
+    float4* dst = reinterpret_cast<float4*>(stage + lane * 32);
 #pragma unroll
     for (int gg = 0; gg < 8; ++gg)
-      sts128(dst + ((gg ^ (lane & 7)) << 4), make_float4(__uint_as_float(v[4 * gg]), __uint_as_float(v[4 * gg + 1]),
-                                                        __uint_as_float(v[4 * gg + 2]), __uint_as_float(v[4 * gg + 3])));
+      dst[gg ^ (lane & 7)] = make_float4(__uint_as_float(v[4 * gg]), __uint_as_float(v[4 * gg + 1]),
+                                         __uint_as_float(v[4 * gg + 2]), __uint_as_float(v[4 * gg + 3]));
   }
   __syncwarp();
   // ---- phase 2: math + row-contiguous stores ----
@@ -471,7 +471,7 @@ __device__ __forceinline__ void epilogue_chunk_fast(const GemmEpilogue& e, const
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = i * 4 + r0;
-    const float4 a = lds128(smem_u32(stage + r * 32) + ((g ^ (r & 7)) << 4));
+    const float4 a = reinterpret_cast<const float4*>(stage + r * 32)[g ^ (r & 7)];
     float2 x01, x23;
     if (T::bias || T::drop) {
       x01 = __ffma2_rn(f2(a.x, a.y), sc, b01);

@@ -60,7 +60,8 @@ constexpr int BWD_SM_V = SM_DO + TQ * 128;
 constexpr int BWD_SM_P = BWD_SM_V;                   // aliases V | X
 constexpr int SM_DS = BWD_SM_V + 2 * NK * 128;
 constexpr int BWD_SM_BAR = SM_DS + TQ * NK * 2;
-constexpr int BWD_SMEM = BWD_SM_BAR + 128;
+constexpr int BWD_SM_MASK = BWD_SM_BAR + 128;        // additive mask of this key tile (fp32, -inf past the sequence)
+constexpr int BWD_SMEM = BWD_SM_MASK + NK * 4;
 static_assert(BWD_SMEM <= 113 * 1024, "two backward CTAs must fit one SM");
 
 __device__ __forceinline__ uint8_t* aligned_smem(uint8_t* raw) {
@@ -81,6 +82,24 @@ __device__ __forceinline__ void store_tile_row32(uint8_t* tile, int r, int c0, c
     o.w = pack_bf16x2(x[g * 8 + 6], x[g * 8 + 7]);
     *reinterpret_cast<uint4*>(atom + (((j0 + g) ^ (r & 7)) << 4)) = o;
   }
+}
+
+// Eight consecutive keys (c0 .. c0+7, c0 % 8 == 0) of row r: one 16-byte piece of the swizzled tile.
+__device__ __forceinline__ void store_tile_row8(uint8_t* tile, int r, int c0, const float (&x)[8]) {
+  uint8_t* atom = tile + (c0 >> 6) * (TQ * 128) + r * 128;
+  uint4 o;
+  o.x = pack_bf16x2(x[0], x[1]);
+  o.y = pack_bf16x2(x[2], x[3]);
+  o.z = pack_bf16x2(x[4], x[5]);
+  o.w = pack_bf16x2(x[6], x[7]);
+  *reinterpret_cast<uint4*>(atom + ((((c0 & 63) >> 3) ^ (r & 7)) << 4)) = o;
+}
+
+// exp2 on the MUFU unit
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -156,45 +175,96 @@ mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     umma_commit(smem_u32(&bars[1]));
   }
 
-  // dropout keep flags of this thread's probability row: one 32-bit word per 32 keys, loaded at the top of each chunk
+  // Only the key columns that exist are processed: ncols = S rounded up to 8 (the tail of the last 32-column chunk is read
+  // with 8-column TMEM loads); P is written -- with zeros -- up to the next multiple of 16, which is as far as the second
+  // product's k loop runs (S = 101: 104 of 128 columns of softmax work, 7 of 8 k-steps).  The arithmetic runs on the packed
+  // fp32 pipe: t = s * scale + mask (FFMA2), p = 2^((t - m) log2 e) (FFMA2 + MUFU), row sum (FADD2).
   const bool dropping = p.drop.thresh != 0u && q0 + t < p.S;
   const uint64_t mrow = ((uint64_t)b * p.heads + h) * (uint64_t)p.S + (uint64_t)(q0 + t);
   const int wpr = (p.S + 31) >> 5;
+  const int ncols = min(NKEYS, (p.S + 7) & ~7);
+  const int nfull = ncols >> 5, ntail = (ncols & 31) >> 3;     // 32-column chunks, then 8-column groups
+  const int kcols = (ncols + 15) & ~15;                        // extent of the P V product's reduction
   mbar_wait(smem_u32(&bars[1]), 0);
   tc_fence_after();
   const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const float2 sc2 = make_float2(p.scale, p.scale);
   // pass 1: row maximum of scale * s + mask
   float m = -INFINITY;
 #pragma unroll 1
-  for (int c = 0; c < NKEYS / 32; ++c) {
+  for (int c = 0; c < nfull; ++c) {
     uint32_t v[32];
     tmem_ld32(t_row + c * 32, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) m = fmaxf(m, fmaf(__uint_as_float(v[j]), p.scale, smask[c * 32 + j]));
+    for (int j = 0; j < 32; j += 2) {
+      const float2 tt = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc2, *reinterpret_cast<const float2*>(smask + c * 32 + j));
+      m = fmaxf(m, fmaxf(tt.x, tt.y));
+    }
   }
-  // pass 2: p = exp(x - m), row sum, stage P (bf16) for the second product.  P overwrites the Q|K tiles (the S MMAs
-  // that read them completed before bars[1] fired).
-  float l = 0.0f;
 #pragma unroll 1
-  for (int c = 0; c < NKEYS / 32; ++c) {
+  for (int gq = 0; gq < ntail; ++gq) {
+    uint32_t v[8];
+    const int c0 = nfull * 32 + gq * 8;
+    tmem_ld8(t_row + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      const float2 tt = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc2, *reinterpret_cast<const float2*>(smask + c0 + j));
+      m = fmaxf(m, fmaxf(tt.x, tt.y));
+    }
+  }
+  // pass 2: p = exp(t - m), row sum, stage P (bf16) for the second product.  P overwrites the Q|K tiles (the S MMAs
+  // that read them completed before bars[1] fired).  Dropout zeroes entries here; its 1 / (1 - p) is folded into the final
+  // normalisation (the row sum and the saved log-sum-exp stay those of the full softmax).
+  constexpr float LOG2E = 1.4426950408889634f;
+  const float2 l2e = make_float2(LOG2E, LOG2E);
+  const float2 nm2 = make_float2(-m * LOG2E, -m * LOG2E);
+  float2 l2 = make_float2(0.0f, 0.0f);
+#pragma unroll 1
+  for (int c = 0; c < nfull; ++c) {
     uint32_t v[32];
     float x[32];
-    const uint32_t kb = dropping ? keep_word(p.drop, mrow, wpr, c) : 0u;   // (in flight under the TMEM load)
+    const uint32_t kb = dropping ? keep_word(p.drop, mrow, wpr, c) : 0xFFFFFFFFu;   // (in flight under the TMEM load)
     tmem_ld32(t_row + c * 32, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      x[j] = __expf(fmaf(__uint_as_float(v[j]), p.scale, smask[c * 32 + j]) - m);
-      l += x[j];
-    }
-    // dropout acts on the normalised probabilities; the row sum (and the saved log-sum-exp) stay those of the full softmax
-    if (dropping) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = ((kb >> j) & 1u) ? x[j] * p.drop.scale : 0.0f;
+    for (int j = 0; j < 32; j += 2) {
+      const float2 tt = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc2, *reinterpret_cast<const float2*>(smask + c * 32 + j));
+      const float2 ee = __ffma2_rn(tt, l2e, nm2);
+      const float2 pp = make_float2(ex2f(ee.x), ex2f(ee.y));
+      l2 = __fadd2_rn(l2, pp);
+      x[j] = ((kb >> j) & 1u) ? pp.x : 0.0f;
+      x[j + 1] = ((kb >> (j + 1)) & 1u) ? pp.y : 0.0f;
     }
     store_tile_row32(smem, t, c * 32, x);  // P tile starts at offset 0 (aliases Q | K)
   }
+  {
+    const uint32_t kbt = (dropping && ntail > 0) ? keep_word(p.drop, mrow, wpr, nfull) : 0xFFFFFFFFu;
+#pragma unroll 1
+    for (int gq = 0; gq < ntail; ++gq) {
+      uint32_t v[8];
+      float x[8];
+      const int c0 = nfull * 32 + gq * 8;
+      tmem_ld8(t_row + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const float2 tt = __ffma2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sc2, *reinterpret_cast<const float2*>(smask + c0 + j));
+        const float2 ee = __ffma2_rn(tt, l2e, nm2);
+        const float2 pp = make_float2(ex2f(ee.x), ex2f(ee.y));
+        l2 = __fadd2_rn(l2, pp);
+        x[j] = ((kbt >> (gq * 8 + j)) & 1u) ? pp.x : 0.0f;
+        x[j + 1] = ((kbt >> (gq * 8 + j + 1)) & 1u) ? pp.y : 0.0f;
+      }
+      store_tile_row8(smem, t, c0, x);
+    }
+    if (kcols > ncols) {   // the k loop of P V runs in steps of 16 keys: the eight columns past ncols must be zero
+      const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      store_tile_row8(smem, t, ncols, z);
+    }
+  }
+  const float l = l2.x + l2.y;
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -202,8 +272,8 @@ mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tc_fence_after();
     constexpr uint32_t idesc_o = make_idesc_bf16(TQ, D_HEAD, 0, 1);
     const uint32_t sp = smem_u32(smem), sv = smem_u32(smem + C::SM_V);
-#pragma unroll
-    for (int j = 0; j < NKEYS / 16; ++j)
+#pragma unroll 1
+    for (int j = 0; j < kcols / 16; ++j)
       umma_bf16_ss(tmem, make_smem_desc_sw128(sp + (j >> 2) * (TQ * 128) + (j & 3) * 32, 16, 1024),
                    make_smem_desc_sw128(sv + j * 2048, 8192, 1024), idesc_o, j > 0);
     umma_commit(smem_u32(&bars[2]));
@@ -211,7 +281,7 @@ mhsa_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   mbar_wait(smem_u32(&bars[2]), 0);
   tc_fence_after();
   {
-    const float inv = 1.0f / l;
+    const float inv = (dropping ? p.drop.scale : 1.0f) / l;
     uint32_t v0[32], v1[32];
     tmem_ld32(t_row, v0);
     tmem_ld32(t_row + 32, v1);
@@ -339,6 +409,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) mhsa_bwd_kernel(const __grid_c
     tmem_relinquish();
   }
   pdl_wait();
+  float* smask = reinterpret_cast<float*>(smem + BWD_SM_MASK);
+  if (tid < NK) {
+    const int col = k0 + tid;
+    smask[tid] = col < p.S ? (p.add_mask ? p.add_mask[(size_t)b * p.S + col] : 0.0f) : -INFINITY;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -346,7 +421,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) mhsa_bwd_kernel(const __grid_c
 
   const uint32_t sq = smem_u32(smem + SM_Q), sk = smem_u32(smem + SM_K), sv = smem_u32(smem + BWD_SM_V);
   const uint32_t sp = smem_u32(smem + BWD_SM_P), sdo = smem_u32(smem + SM_DO), sds = smem_u32(smem + SM_DS);
-  const float* __restrict__ gmask = p.add_mask ? p.add_mask + (size_t)b * p.S : nullptr;
 
   if (tid == 0) {
     const uint32_t bl = smem_u32(&bars[0]);
@@ -407,46 +481,57 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) mhsa_bwd_kernel(const __grid_c
     }
   }
 
-  // dropout keep flags of this thread's 64 probabilities: one word per 32-key chunk, loaded at the top of each chunk
+  // Softmax recomputation and dS on the key columns that exist: ncols = this tile's keys rounded up to 8, in groups of eight
+  // columns split evenly between the two threads of a row (S = 101: 13 groups, 7 + 6; the 128-column version did 8 + 8).
+  // Packed fp32 arithmetic: t = s * scale + mask, p = 2^((t - lse) log2 e), P' = p o M', dS = p * scale * (dP o M' - D).
+  // Query rows past the sequence get lse = +inf -> p = 0: they contribute nothing to dK / dV.
   const bool dropping = p.drop.thresh != 0u && valid;
   const uint64_t mrow = ((uint64_t)b * p.heads + h) * (uint64_t)p.S + (uint64_t)(q0 + t);
   const int wpr = (p.S + 31) >> 5;
+  const int keys_here = max(0, min(NK, p.S - k0));
+  const int ncols = (keys_here + 7) & ~7;
+  const int kcols = (ncols + 15) & ~15;                  // extent of dQ = dS K's reduction (zero-filled past ncols)
+  const int ngroups = ncols >> 3;
+  const int g_split = (ngroups + 1) >> 1;
+  const int g_begin = half ? g_split : 0, g_end = half ? ngroups : g_split;
   mbar_wait(smem_u32(&bars[1]), 0);
   tc_fence_after();
   const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  {
+    constexpr float LOG2E = 1.4426950408889634f;
+    const float2 sc2 = make_float2(p.scale, p.scale), l2e = make_float2(LOG2E, LOG2E);
+    const float nl = valid ? -lse * LOG2E : -INFINITY;
+    const float2 nl2 = make_float2(nl, nl), nD2 = make_float2(-Dsum, -Dsum);
+    const float keep_mul = dropping ? p.drop.scale : 1.0f;
 #pragma unroll 1
-  for (int cc = 0; cc < NK / 64; ++cc) {
-    const int c = half * (NK / 64) + cc;  // this thread's 32-column chunks: [half*64, half*64 + 64)
-    uint32_t vs[32], vd[32];
-    float pr[32], ds[32];
-    const uint32_t kb = dropping ? keep_word(p.drop, mrow, wpr, (k0 >> 5) + c) : 0u;   // (in flight under the TMEM loads)
-    tmem_ld32(t_row + c * 32, vs);
-    tmem_ld32(t_row + 128 + c * 32, vd);
-    tmem_ld_wait();
-    if (dropping) {
-      // ctx = (P o M / (1-p)) V:  dV = (P o M')^T dO ;  dP = (dO V^T) o M' ;  dS = P o (dP - D) with D = rowsum(dO o O)
+    for (int gq = g_begin; gq < g_end; ++gq) {
+      const int c0 = gq * 8;
+      uint32_t vs[8], vd[8];
+      float pr[8], ds[8];
+      const uint32_t kbits = dropping ? (keep_word(p.drop, mrow, wpr, (k0 + c0) >> 5) >> ((k0 + c0) & 31)) : 0xFFu;
+      tmem_ld8(t_row + c0, vs);
+      tmem_ld8(t_row + 128 + c0, vd);
+      tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int col = k0 + c * 32 + j;
-        const float mk = col < p.S ? (gmask ? __ldg(gmask + col) : 0.0f) : -INFINITY;
-        const float pj = __expf(fmaf(__uint_as_float(vs[j]), p.scale, mk) - lse);
-        const float kj = ((kb >> j) & 1u) ? p.drop.scale : 0.0f;
-        pr[j] = pj * kj;
-        ds[j] = pj * (__uint_as_float(vd[j]) * kj - Dsum) * p.scale;
+      for (int j = 0; j < 8; j += 2) {
+        const float2 tt = __ffma2_rn(make_float2(__uint_as_float(vs[j]), __uint_as_float(vs[j + 1])), sc2, *reinterpret_cast<const float2*>(smask + c0 + j));
+        const float2 ee = __ffma2_rn(tt, l2e, nl2);
+        const float2 pp = make_float2(ex2f(ee.x), ex2f(ee.y));
+        const float2 k2 = make_float2(((kbits >> j) & 1u) ? keep_mul : 0.0f, ((kbits >> (j + 1)) & 1u) ? keep_mul : 0.0f);
+        const float2 pm = __fmul2_rn(pp, k2);
+        const float2 u = __ffma2_rn(make_float2(__uint_as_float(vd[j]), __uint_as_float(vd[j + 1])), k2, nD2);
+        const float2 dsv = __fmul2_rn(__fmul2_rn(pp, sc2), u);
+        pr[j] = pm.x; pr[j + 1] = pm.y;
+        ds[j] = dsv.x; ds[j + 1] = dsv.y;
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        // query rows beyond this sample's sequence must contribute nothing to dK / dV; keys beyond it are masked out
-        const int col = k0 + c * 32 + j;
-        const float mk = col < p.S ? (gmask ? __ldg(gmask + col) : 0.0f) : -INFINITY;
-        const float pj = valid ? __expf(fmaf(__uint_as_float(vs[j]), p.scale, mk) - lse) : 0.0f;
-        pr[j] = pj;
-        ds[j] = pj * (__uint_as_float(vd[j]) - Dsum) * p.scale;
-      }
+      store_tile_row8(smem + BWD_SM_P, t, c0, pr);   // P overwrites V (+ spare): dP = dO V^T completed before bars[1]
+      store_tile_row8(smem + SM_DS, t, c0, ds);
     }
-    store_tile_row32(smem + BWD_SM_P, t, c * 32, pr);   // P overwrites V (+ spare): dP = dO V^T completed before bars[1]
-    store_tile_row32(smem + SM_DS, t, c * 32, ds);
+    if (half && kcols > ncols) {   // dQ's k loop runs in steps of 16 keys
+      const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      store_tile_row8(smem + SM_DS, t, ncols, z);
+      store_tile_row8(smem + BWD_SM_P, t, ncols, z);
+    }
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -455,8 +540,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) mhsa_bwd_kernel(const __grid_c
     tc_fence_after();
     constexpr uint32_t idesc_q = make_idesc_bf16(TQ, D_HEAD, 0, 1);   // dQ = dS K      (A K-major, B MN-major)
     constexpr uint32_t idesc_kv = make_idesc_bf16(NK, D_HEAD, 1, 1);  // dK = dS^T Q, dV = P^T dO (both MN-major)
-#pragma unroll
-    for (int j = 0; j < NK / 16; ++j)
+#pragma unroll 1
+    for (int j = 0; j < kcols / 16; ++j)
       umma_bf16_ss(tmem + T_DQ, make_smem_desc_sw128(sds + (j >> 2) * (TQ * 128) + (j & 3) * 32, 16, 1024),
                    make_smem_desc_sw128(sk + j * 2048, 8192, 1024), idesc_q, j > 0);
 #pragma unroll

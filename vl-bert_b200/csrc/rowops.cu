@@ -116,6 +116,71 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   }
 }
 
+// Lean forward for the encoder's own LayerNorms (no output dropout, bf16 output only): one warp per row and no row loop, few
+// enough registers that almost every row of the token matrix has its warp resident at once (6464 rows at config 2 against
+// 148 x 40 warp slots), so all of the 20 MB input is requested in the first microsecond and the kernel is one HBM burst
+// instead of a chain of dependent row iterations per warp.  Same arithmetic as layernorm_fwd_kernel (two-pass variance).
+constexpr int LN_LEAN_WARPS = 8;
+template <int ITERS>
+__global__ void __launch_bounds__(LN_LEAN_WARPS * 32, 5)
+layernorm_fwd_lean_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                          __nv_bfloat16* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int M, int H, int ldx,
+                          float eps) {
+  const int lane = threadIdx.x & 31;
+  const int nvec = H >> 3;
+  const int row = blockIdx.x * LN_LEAN_WARPS + (threadIdx.x >> 5);
+  pdl_trigger();
+  pdl_wait();
+  if (row >= M) return;
+  const float* xr = x + (size_t)row * ldx;
+  float4 a[ITERS], b[ITERS];
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      a[i] = __ldg(reinterpret_cast<const float4*>(xr + vi * 8));
+      b[i] = __ldg(reinterpret_cast<const float4*>(xr + vi * 8 + 4));
+    } else {
+      a[i] = b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) s += (a[i].x + a[i].y) + (a[i].z + a[i].w) + (b[i].x + b[i].y) + (b[i].z + b[i].w);
+  const float mu = warp_sum(s) / (float)H;
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    if (lane + i * 32 < nvec) {
+      const float d0 = a[i].x - mu, d1 = a[i].y - mu, d2 = a[i].z - mu, d3 = a[i].w - mu;
+      const float d4 = b[i].x - mu, d5 = b[i].y - mu, d6 = b[i].z - mu, d7 = b[i].w - mu;
+      q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3) + (d4 * d4 + d5 * d5) + (d6 * d6 + d7 * d7);
+    }
+  }
+  const float var = warp_sum(q) / (float)H;
+  const float rs = 1.0f / sqrtf(var + eps);
+  if (lane == 0) {
+    if (mean) mean[row] = mu;
+    if (rstd) rstd[row] = rs;
+  }
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
+      uint4 pk;
+      pk.x = pack_bf16x2(g0.x * ((a[i].x - mu) * rs) + b0.x, g0.y * ((a[i].y - mu) * rs) + b0.y);
+      pk.y = pack_bf16x2(g0.z * ((a[i].z - mu) * rs) + b0.z, g0.w * ((a[i].w - mu) * rs) + b0.w);
+      pk.z = pack_bf16x2(g1.x * ((b[i].x - mu) * rs) + b1.x, g1.y * ((b[i].y - mu) * rs) + b1.y);
+      pk.w = pack_bf16x2(g1.z * ((b[i].z - mu) * rs) + b1.z, g1.w * ((b[i].w - mu) * rs) + b1.w);
+      *reinterpret_cast<uint4*>(y + (size_t)row * H + vi * 8) = pk;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // LayerNorm backward.  dy = dy_bf16 (optional) + dy_f32 (optional).
 //   xhat = (x - mean) * rstd ; g = dy * gamma
@@ -415,6 +480,14 @@ int layernorm_forward(const float* x, int ldx, const float* gamma, const float* 
   if (grid > num_sms() * 8) grid = num_sms() * 8;
   ProfScope prof(PROF_LN_FWD, (double)M * H * (4.0 + (y_bf16 ? 2.0 : 0.0) + (y_f32 ? 4.0 : 0.0)), stream);
   cudaError_t lerr = cudaSuccess;
+  static const int lean = [] { const char* v = getenv("VLB_LN_LEAN"); return v ? atoi(v) : 1; }();
+  if (lean && dcfg.thresh == 0u && y_bf16 != nullptr && y_f32 == nullptr && iters <= 4) {
+    const int lgrid = (M + LN_LEAN_WARPS - 1) / LN_LEAN_WARPS;
+    VLB_LN_DISPATCH(iters, (lerr = launch_pdl(layernorm_fwd_lean_kernel<IT>, dim3(lgrid), dim3(LN_LEAN_WARPS * 32), 0, stream, x, gamma, beta,
+                                              static_cast<__nv_bfloat16*>(y_bf16), mean, rstd, M, H, ldx, eps)));
+    VLB_CHECK_CUDA(lerr);
+    return VLB_OK;
+  }
   VLB_LN_DISPATCH(iters, (lerr = launch_pdl(layernorm_fwd_kernel<IT>, dim3(grid), dim3(LN_WARPS * 32), 0, stream, x, gamma, beta,
                                             static_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, M, H, ldx, eps, dcfg)));
   VLB_CHECK_CUDA(lerr);

@@ -347,6 +347,10 @@ _SIDE_STREAM_BITS = os.environ.get("VLB_BITS_SIDE_STREAM", "1") != "0"
 _SIDE_STREAMS = {}
 
 
+_ZERO_GRADS_IN_FORWARD = os.environ.get("VLB_ZERO_GRADS_IN_FORWARD", "1") != "0"
+_CAPTURE_HAS_BACKWARD = False     # set by graphs.GraphedStep while it captures forward + backward into one graph
+
+
 def _side_stream(device):
     key = (device.type, device.index)
     s = _SIDE_STREAMS.get(key)
@@ -436,6 +440,21 @@ class EncoderFn(torch.autograd.Function):
                     ev = torch.cuda.Event()
                     ev.record(side)
                     bits_ready.append(ev)
+        # The flat fp32 gradient buffer of the backward (the weight-gradient GEMMs accumulate into it with split-K atomics, so it
+        # must start at zero: 340 MB at config 2) is allocated and cleared here, on the side stream, under the forward's
+        # tensor-bound kernels, instead of at the head of the backward's dependency chain.  Inside a stream capture this is done
+        # only when the capture is known to contain the backward too (GraphedStep sets the flag): the fork is joined there.
+        ctx.flat, ctx.flat_ready = None, None
+        if _ZERO_GRADS_IN_FORWARD and any(ctx.needs_input_grad) and (_CAPTURE_HAS_BACKWARD or not torch.cuda.is_current_stream_capturing()):
+            cur = torch.cuda.current_stream()
+            side = _side_stream(emb.device)
+            side.wait_stream(cur)
+            per = 3 * H * H + 3 * H + H * H + H + 2 * H + I * H + I + H * I + H + 2 * H
+            with torch.cuda.stream(side):
+                ctx.flat = torch.zeros((L, per), dtype=F32, device=emb.device)
+                ctx.flat_ready = torch.cuda.Event()
+                ctx.flat_ready.record(side)
+            ctx.flat.record_stream(cur)
         for l in range(L):
             want = meta.all_layers or l == L - 1
             y32 = torch.empty((B, S, H), dtype=F32, device=emb.device) if want else None
@@ -475,7 +494,11 @@ class EncoderFn(torch.autograd.Function):
         dev = ctx.emb.device
         params = ctx.params
         per = 3 * H * H + 3 * H + H * H + H + 2 * H + I * H + I + H * I + H + 2 * H
-        flat = torch.zeros((L, per), dtype=F32, device=dev)
+        if ctx.flat is not None:            # cleared under the forward (see there); a second backward gets a fresh buffer
+            torch.cuda.current_stream().wait_event(ctx.flat_ready)
+            flat, ctx.flat = ctx.flat, None
+        else:
+            flat = torch.zeros((L, per), dtype=F32, device=dev)
         ws_bytes = int(lib.vlb_bert_layer_backward_workspace(M, H, I))
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
         dx = [torch.empty((M, H), dtype=BF16, device=dev), torch.empty((M, H), dtype=BF16, device=dev)]

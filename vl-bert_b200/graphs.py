@@ -25,8 +25,13 @@ class GraphedStep(object):
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         model.zero_grad(set_to_none=True)
-        with torch.cuda.graph(self.graph):
-            self.static_loss = self._eager(zero=False)
+        from . import functional as _F
+        _F._CAPTURE_HAS_BACKWARD = True        # side-stream work forked in the forward is joined by the backward of this capture
+        try:
+            with torch.cuda.graph(self.graph):
+                self.static_loss = self._eager(zero=False)
+        finally:
+            _F._CAPTURE_HAS_BACKWARD = False
         torch.cuda.synchronize()
         # gradients produced by a replay live in these buffers
         self.static_grads = [(p, p.grad) for p in model.parameters() if p.grad is not None]
