@@ -368,7 +368,7 @@ def _disarm_watchdog():
 def _ncu_traffic():
     """DRAM bytes per GEMM launch from the committed `ncu --set full` capture of one encoder layer's GEMMs
     (dram__bytes_read.sum + dram__bytes_write.sum, mean over the captured launches); None if the capture is absent."""
-    for name in ("r02_ncu_full_gemm_layer.csv", "r01_ncu_full_gemm_v4_backward_layer.csv"):
+    for name in ("r02_ncu_gemm_launches_v2_pair192.csv", "r02_ncu_full_gemm_layer.csv", "r01_ncu_full_gemm_v4_backward_layer.csv"):
         path = os.path.join(ROOT, "profiles", name)
         try:
             import csv
