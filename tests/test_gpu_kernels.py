@@ -135,6 +135,23 @@ def test_gemm_pair192_epilogues(VF):
     assert rel(o32, z + resid) <= 2e-5
 
 
+@pytest.mark.parametrize("shape", [(777, 1536, 512), (6464, 3072, 768), (200, 192, 64)])
+def test_gemm_gelu_wide_epilogue(VF, shape):
+    """BertIntermediate's launch on 128 x 192 tiles with 16 epilogue warps (force_bn = 4192): bias + erf-GELU with GELU' saved."""
+    M, N, K = shape
+    g = torch.Generator().manual_seed(77 + M)
+    a, w = bf(torch.randn(M, K, generator=g)), bf(torch.randn(N, K, generator=g) * 0.05)
+    bias = torch.randn(N, generator=g)
+    z = a @ w.t() + bias
+    out = torch.empty(M, N, device=DEV, dtype=BF16)
+    aux = torch.empty(M, N, device=DEV, dtype=BF16)
+    VF.gemm(0, a.to(DEV, BF16), w.to(DEV, BF16), out, bias=bias.to(DEV), act=1, aux=aux, force_bn=4192)
+    zt0 = z.clone().requires_grad_(True)
+    vo.gelu_erf(zt0).sum().backward()
+    assert rel(aux.float(), zt0.grad.to(BF16).float()) <= 1e-3
+    assert rel(out.float(), vo.gelu_erf(z)) <= 3e-3 and rel(out.float(), vo.gelu_erf(z).to(BF16).float()) <= 1e-3
+
+
 @pytest.mark.parametrize("bn,split,acc", [(128, 1, False), (256, 1, False), (256, 2, True), (128, 3, True)])
 def test_gemm_grouped_wgrad(VF, bn, split, acc):
     """Four weight-gradient problems of a BertLayer in one grouped launch (vlb_gemm_grouped_tn)."""

@@ -46,6 +46,7 @@ struct PairParams {
   int num_m_pairs, num_n_blocks, num_k_blocks;
   int num_items;
   unsigned long long* trace;   // timing aid (vlb_debug_gemm_trace): 8 globaltimer stamps per CTA, nullptr = off
+  int roles_high;     // 1: producer / MMA issuer are the two highest hardware warps (scheduler priority, see gemm_body)
   int epi_stage;      // 1: last tile of a CTA: residual rows / keep flags / LayerNorm statistics staged in the idle operand ring
   int epi_prefetch;   // 1: the epilogue warps pull the tile's residual / saved-activation / keep-flag lines into L2 while its MMAs run
   GemmEpilogue e;
@@ -78,7 +79,8 @@ gemm_pair192_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   uint64_t* tempty2_bar = tempty1_bar + 2;      // acc2 drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty2_bar + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int hw_warp = threadIdx.x >> 5;
+  const int warp = p.roles_high ? (hw_warp >= EPI_WARPS ? hw_warp - EPI_WARPS : hw_warp + 2) : hw_warp;   // logical role, see gemm_body
   const int lane = threadIdx.x & 31;
   pdl_trigger();
   if (threadIdx.x == 0) trace_stamp(p.trace, 0);
@@ -177,7 +179,7 @@ gemm_pair192_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
   } else {
     // ===================== epilogue warps (both CTAs) =====================
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int q = hw_warp & 3;         // TMEM lane quarter this (hardware) warp may access
     const int half = (warp - 2) >> 2;  // which of the two warps sharing that quarter
     float* stage = epi_stage + (warp - 2) * STAGE_F32_PER_WARP;
     const DropState dstate = drop_state(p.e.drop);
@@ -197,7 +199,7 @@ gemm_pair192_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const int act = T::kStatic ? T::act : p.e.act;
         const int rk = T::kStatic ? T::resid : p.e.resid_kind;
         const bool aux_in = (act == ACT_DGELU_MUL || act == ACT_DRELU_MUL);
-        const int et = (int)threadIdx.x - 64;                        // epilogue thread index 0 .. 255
+        const int et = (warp - 2) * 32 + lane;                       // epilogue thread index 0 .. 255
         const int rows = min(C::ROWS, p.M - row_cta);
         if (rows > 0 && (aux_in || rk != RESID_NONE)) {
           const char* src = reinterpret_cast<const char*>(aux_in ? p.e.aux : p.e.resid);

@@ -77,6 +77,7 @@ struct GemmParams {
   // holding its statically assigned share back; the last CTA to finish resets both counters.  nullptr = static round robin.
   int* sched;
   unsigned long long* trace;   // timing aid (vlb_debug_gemm_trace): per CTA 8 items x 4 globaltimer stamps, nullptr = off
+  int roles_high;              // 1: the TMA producer and the MMA issuer are the two HIGHEST hardware warps of the CTA (see gemm_body)
 };
 
 constexpr int SCHED_DEPTH = 4;   // ring of item indices handed from the producer warp to the MMA / epilogue warps
@@ -177,7 +178,7 @@ __device__ __forceinline__ ItemCoord decode_item(int item, const GemmParams& p, 
 // Cluster modes (CM): 0 = independent CTAs; 1 = CG2 pair MMA (above); 2 = MC2: a cluster of two CTAs works on two
 // vertically adjacent 128 x BN tiles that need the SAME B tile; each CTA fetches one half of it and TMA-multicasts it into
 // both CTAs' shared memory (B crosses the L2->SM fabric once per cluster), the MMAs stay independent cta_group::1.
-template <int BN, int CM = 0>
+template <int BN, int CM = 0, int EW = EPI_WARPS>
 struct Cfg {
   static constexpr bool CG2 = CM == 1;
   static constexpr int A_BYTES = BM * BK * 2;
@@ -186,8 +187,10 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = CG2 ? (BN == 256 ? 6 : 8) : ((BN == 256) ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8)));
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int EPI_STAGE_BYTES = EPI_WARPS * STAGE_F32_PER_WARP * 4;
+  static constexpr int EPI_STAGE_BYTES = EW * STAGE_F32_PER_WARP * 4;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers + scheduler ring*/;
+  static constexpr int THREADS = 64 + EW * 32;
+  static_assert(SMEM_BYTES <= 227 * 1024, "tile configuration exceeds the shared memory of an SM");
 };
 
 // Epilogue of one 32-row x 32-column accumulator chunk owned by a warp.
@@ -548,10 +551,14 @@ __device__ __forceinline__ bool epi_fast_ok(const GemmEpilogue& e) {
   return EpiFast<EPI>::value && e.alpha == 1.0f && (e.colsum == nullptr || EpiTraits<EPI>::act == ACT_DGELU_MUL);
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, int CM, bool GROUPED>
+// EW = number of epilogue warps (a multiple of 4: EW / 4 warps share each TMEM lane quarter and take every (EW / 4)-th
+// 32-column chunk).  8 everywhere except the GELU launch, whose epilogue -- not its mainloop -- sets the period of a tile with
+// two warps per scheduler (6.4-7.7 us against 5.4 us on a 128 x 256 tile): there 16 warps work on 128 x 192 tiles.
+template <int BN, bool A_MN, bool B_MN, int EPI, int CM, bool GROUPED, int EW = EPI_WARPS>
 __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtensorMap& tma_b, const GemmParams& p,
                                           const GroupTable& gt, const CUtensorMap& tma_b_tail) {
-  using C = Cfg<BN, CM>;
+  using C = Cfg<BN, CM, EW>;
+  static_assert(EW % 4 == 0 && (EW == EPI_WARPS || !VLB_ENABLE_STREAMK), "epilogue warps come in groups of four");
   constexpr bool CG2 = CM == 1;   // pair MMA
   constexpr bool MC2 = CM == 2;   // independent MMAs, B tile multicast
   constexpr bool CL = CM != 0;    // any 2-CTA cluster mode
@@ -574,7 +581,12 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
   volatile int* sched_item = reinterpret_cast<volatile int*>(sched_empty + SCHED_DEPTH);
   const bool dyn = !CL && p.sched != nullptr;
 
-  const int warp = threadIdx.x >> 5;
+  // Role = logical warp index: 0 = TMA producer, 1 = MMA issuer, 2 .. EW + 1 = epilogue.  The warp schedulers favour the
+  // highest warp id among the eligible warps, so with the natural order the epilogue warps out-prioritise the two single
+  // threads every tile waits for: under a busy epilogue the mainloop of the NEXT tile slowed from 5.4 to 6.4 us.  With
+  // roles_high the producer and the issuer are hardware warps EW and EW + 1 and the epilogue warps are 0 .. EW - 1.
+  const int hw_warp = threadIdx.x >> 5;
+  const int warp = p.roles_high ? (hw_warp >= EW ? hw_warp - EW : hw_warp + 2) : hw_warp;
   const int lane = threadIdx.x & 31;
   pdl_trigger();
 
@@ -590,12 +602,12 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
     }
     mbar_init(smem_u32(&tfull_bar[0]), 1);
     mbar_init(smem_u32(&tfull_bar[1]), 1);
-    mbar_init(smem_u32(&tempty_bar[0]), CG2 ? 2 * EPI_WARPS : EPI_WARPS);
-    mbar_init(smem_u32(&tempty_bar[1]), CG2 ? 2 * EPI_WARPS : EPI_WARPS);
+    mbar_init(smem_u32(&tempty_bar[0]), CG2 ? 2 * EW : EW);
+    mbar_init(smem_u32(&tempty_bar[1]), CG2 ? 2 * EW : EW);
 #pragma unroll
     for (int i = 0; i < SCHED_DEPTH; ++i) {
       mbar_init(smem_u32(&sched_full[i]), 1);
-      mbar_init(smem_u32(&sched_empty[i]), 1 + EPI_WARPS);
+      mbar_init(smem_u32(&sched_empty[i]), 1 + EW);
     }
     fence_mbar_init();
   }
@@ -788,8 +800,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
     }
   } else {
     // ===================== epilogue warps =====================
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;  // which of the two warps sharing that quarter
+    const int q = hw_warp & 3;         // TMEM lane quarter this (hardware) warp may access
+    const int half = (warp - 2) >> 2;  // which of the EW / 4 warps sharing that quarter
     float* stage = epi_stage + (warp - 2) * STAGE_F32_PER_WARP;
     const DropState dstate = drop_state(p.e.drop);
     int it = 0;
@@ -828,8 +840,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
           const int row0 = (m_blk * (CL ? 2 : 1) + (int)rank) * BM;
           const int width = min(ic.bn, Ng - ic.n0) * esz;           // bytes per row of this unit
           const int lpr = (width + 127) >> 7;                        // 128-byte lines per row
-          const int et = (int)threadIdx.x - 64;                      // epilogue thread index 0 .. 255
-          for (int l = et; l < BM * lpr; l += EPI_WARPS * 32) {
+          const int et = (warp - 2) * 32 + lane;                     // epilogue thread index 0 .. EW * 32 - 1
+          for (int l = et; l < BM * lpr; l += EW * 32) {
             const int r = l / lpr, sgm = l - r * lpr;
             if (row0 + r < Mg)
               asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)(row0 + r) * ld_bytes + (size_t)ic.n0 * esz + (size_t)sgm * 128));
@@ -877,7 +889,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
         continue;
       }
 #pragma unroll 1
-      for (int c = half; c < ic.bn / 32; c += 2) {
+      for (int c = half; c < ic.bn / 32; c += EW / 4) {
         uint32_t v[32];
         tmem_ld32(t_row + c * 32, v);
         tmem_ld_wait();
@@ -902,7 +914,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
     tc_fence_after();
     if (CG2) tmem_dealloc_cg2(tmem_base, C::TMEM_COLS); else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
-  if (dyn && threadIdx.x == 0) {
+  if (dyn && warp == 0 && lane == 0) {
     // this thread (the producer) has made its last request; the last CTA to get here returns the counters to zero
     __threadfence();
     if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
@@ -913,11 +925,11 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tma_a, const CUtens
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, int CM>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, bool A_MN, bool B_MN, int EPI, int CM, int EW = EPI_WARPS>
+__global__ void __launch_bounds__(64 + EW * 32, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_b_tail, const GemmParams p) {
-  gemm_body<BN, A_MN, B_MN, EPI, CM, false>(tma_a, tma_b, p, *reinterpret_cast<const GroupTable*>(&tma_a), tma_b_tail);  // table unused
+  gemm_body<BN, A_MN, B_MN, EPI, CM, false, EW>(tma_a, tma_b, p, *reinterpret_cast<const GroupTable*>(&tma_a), tma_b_tail);  // table unused
 }
 
 template <int BN, int EPI>
@@ -985,18 +997,19 @@ struct TmapKeyHash {
   }
 };
 
-template <int BN, bool A_MN, bool B_MN, int EPI, int CM>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CM, int EW = EPI_WARPS>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbt, const GemmParams& p, cudaStream_t stream) {
-  using C = Cfg<BN, CM>;
+  using C = Cfg<BN, CM, EW>;
+  static_assert(EW == EPI_WARPS || CM == 0, "wide epilogues exist for the single-CTA kernel only");
   static bool attr_set = false;
   if (!attr_set) {
-    VLB_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, A_MN, B_MN, EPI, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VLB_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, A_MN, B_MN, EPI, CM, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         C::SMEM_BYTES));
     attr_set = true;
   }
   if (CM == 0) {
     const int grid = p.num_items < num_sms() ? p.num_items : num_sms();
-    VLB_CHECK_CUDA(launch_pdl(gemm_kernel<BN, A_MN, B_MN, EPI, CM>, dim3(grid), dim3(GEMM_THREADS), C::SMEM_BYTES, stream, ta, tb, tbt, p));
+    VLB_CHECK_CUDA(launch_pdl(gemm_kernel<BN, A_MN, B_MN, EPI, CM, EW>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, stream, ta, tb, tbt, p));
     return VLB_OK;
   }
   const int pairs = num_sms() / 2;
@@ -1319,6 +1332,8 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
       q.epi_prefetch = env_pair_prefetch;
       static const int env_pair_stage = [] { const char* v = getenv("VLB_EPI_STAGE"); return v ? atoi(v) : 1; }();
       q.epi_stage = env_pair_stage;
+      static const int env_pair_roles_high = [] { const char* v = getenv("VLB_ROLES_HIGH"); return v ? atoi(v) : 1; }();
+      q.roles_high = env_pair_roles_high;
       q.trace = g_dbg_trace;
       q.e = epi;
       CUtensorMap ta, tb;
@@ -1350,7 +1365,9 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
   bool cg2 = false;
   int cm = 0;
   const int sms = num_sms();
-  if (force_bn >= 2000) {
+  if (force_bn == 4192) {
+    bn = 192;
+  } else if (force_bn >= 2000) {
     cm = 2;
     bn = force_bn - 2000;
     VLB_REQUIRE(bn == 128 || bn == 256, "gemm: cluster modes support BN 128 / 256");
@@ -1393,6 +1410,16 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
 
   if (cg2) cm = 1;
   if (cm == 0 && env_mc2 == 1 && force_bn == 0 && (bn == 128 || bn == 256)) cm = 2;
+  // GELU launch (BertIntermediate): 128 x 192 tiles with 16 epilogue warps (see gemm_body); force_bn 4192 or VLB_GELU_EW16=1
+  static const int env_ew16 = [] { const char* v = getenv("VLB_GELU_EW16"); return v ? atoi(v) : 0; }();
+  bool ew16 = false;
+  if (mode == GEMM_NT && epi.act == ACT_GELU && conv == nullptr && split_k <= 1 && N >= 192 &&
+      (force_bn == 4192 || (force_bn == 0 && env_ew16 && cm == 0 && classify_epilogue(mode, epi) == EPI_BIAS_GELU_AUX_BF16))) {
+    VLB_REQUIRE(classify_epilogue(mode, epi) == EPI_BIAS_GELU_AUX_BF16, "gemm: the 16-warp epilogue exists for bias + GELU (+ saved GELU') -> bf16 only");
+    ew16 = true;
+    bn = 192;
+    cm = 0;
+  }
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
   p.num_m_blocks = cm != 0 ? (M + 2 * BM - 1) / (2 * BM) : (M + BM - 1) / BM;
@@ -1444,6 +1471,8 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
   p.epi_prefetch = env_prefetch;
   p.sched = (cm == 0 && p.sk_chunks == 0 && p.num_items > sms) ? sched_counters(stream) : nullptr;
   p.trace = g_dbg_trace;
+  static const int env_roles_high = [] { const char* v = getenv("VLB_ROLES_HIGH"); return v ? atoi(v) : 1; }();
+  p.roles_high = env_roles_high;
 
   p.cv_side = 0;
   if (conv != nullptr && conv_side != 0) {
@@ -1495,6 +1524,7 @@ int gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void*
   if (epi_id == EPI_ATOMIC_F32) return launch<BN_, true, true, EPI_ATOMIC_F32, CG_>(ta, tb, tbt, p, stream);       \
   return launch<BN_, true, true, EPI_GENERIC, CG_>(ta, tb, tbt, p, stream);
   const int epi_id = classify_epilogue(mode, epi_in);
+  if (ew16) return launch<192, false, false, EPI_BIAS_GELU_AUX_BF16, 0, 16>(ta, tb, tbt, p, stream);
   if (cm == 1) {
     if (bn == 256) { VLB_GEMM_DISPATCH(256, 1) }
     VLB_GEMM_DISPATCH(128, 1)
@@ -1541,7 +1571,7 @@ int gemm_grouped_tn(int count, const GroupedProblem* probs, int K, int split_k, 
   VLB_REQUIRE(sk == 1 || accumulate, "gemm_grouped_tn: split-K needs accumulate");
   p.e = GemmEpilogue();
   p.e.out_kind = accumulate ? OUT_F32_ATOMIC : OUT_F32;
-  p.tail_first = 0; p.tail_split = 0; p.epi_prefetch = 0; p.sched = nullptr; p.trace = nullptr;
+  p.tail_first = 0; p.tail_split = 0; p.epi_prefetch = 0; p.sched = nullptr; p.trace = nullptr; p.roles_high = 1;
   p.sk_full_items = 0; p.sk_chunks = 0; p.sk_kb_per_chunk = 0; p.sk_scratch = nullptr; p.sk_counters = nullptr; p.sk_debug = 0;
   p.cv_side = 0;
   p.a_lbo = p.b_lbo = g_dbg_mn_lbo ? g_dbg_mn_lbo : 8192u;
