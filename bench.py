@@ -40,6 +40,8 @@ WORKLOADS = {
             what="VL-BERT-base 12L/768 + VQA answer head (transform + Linear(768, 3129), BCE), 20 text + 100 region tokens"),
     4: dict(name="BASELINE config 4", hidden=1024, layers=24, heads=16, inter=4096, text=128, regions=36, batch=64, head=None,
             what="VL-BERT-large 24L/1024/16 heads, VCR Q->A shape: 128 text + 36 region tokens, 16 samples x 4 answer choices = 64 sequences"),
+    6: dict(name="BASELINE config 2 + pre-training loss", hidden=768, layers=12, heads=12, inter=3072, text=64, regions=36, batch=64, head="mlm",
+            what="VL-BERT-base 12L/768 + masked-LM head (transform + tied decoder [30522, 768] + cross-entropy on 10 labelled positions per sample, fused loss head), 64 text + 36 region tokens"),
     5: dict(name="BASELINE config 5", hidden=768, layers=12, heads=12, inter=3072, text=64, regions=36, batch=8, head="frontend",
             what="end to end: ResNet-101-C4 + RoIAlign + res5 head on 8 synthetic 600x1000 images (36 boxes each) feeding VL-BERT-base 12L/768"),
 }
@@ -103,12 +105,18 @@ def make_inputs(w, B, seed, device, pin=False):
         ts = [ids, types, tvis, tmask, ovl, omask]
         if w["head"] == "vqa":
             ts.append(torch.rand(B, 3129, generator=g).pow(8))      # soft answer scores in [0, 1], mostly ~0
+        if w["head"] == "mlm":      # 10 masked positions per sample (~15 % of 64 text tokens), label = the original token id
+            labels = torch.full((B, T), -1, dtype=torch.long)
+            for bi in range(B):
+                pos = torch.randperm(T, generator=g)[:10]
+                labels[bi, pos] = ids[bi, pos]
+            ts.append(labels)
     if pin:
         return [t.pin_memory() for t in ts]
     return [t.to(device) for t in ts]
 
 
-def build_workload(w, device, p_drop):
+def build_workload(w, device, p_drop, args_batch=0):
     """-> (module, loss_fn(module, *inputs)) with the library's modules; module.vlbert is the encoder"""
     import vlbert_b200
     import torch.nn as nn
@@ -120,7 +128,10 @@ def build_workload(w, device, p_drop):
     class Pipeline(nn.Module):
         def __init__(self):
             super().__init__()
-            self.vlbert = vlbert_b200.VisualLinguisticBert(cfg)
+            if w["head"] == "mlm":   # pretrain/modules/resnet_vlbert_for_pretraining.py:57-65 (MLM task only)
+                self.vlbert = vlbert_b200.VisualLinguisticBertForPretraining(cfg, with_rel_head=False, with_mvrc_head=False)
+            else:
+                self.vlbert = vlbert_b200.VisualLinguisticBert(cfg)
             self.vlbert.visual_ln_text.weight.data.fill_(1.0)
             self.vlbert.max_length_hint = seq_len(w)      # all synthetic samples are full length; avoids the per-forward host sync
             if w["head"] == "vqa":       # vqa/modules/resnet_vlbert_for_vqa.py:62-70 (CLASSIFIER_TYPE "mlm"), :246-249
@@ -154,6 +165,14 @@ def build_workload(w, device, p_drop):
             hidden, _ = m.vlbert(ids, types, tvis, tmask, ovl, omask, output_all_encoded_layers=False)
             logits = m.final_mlp(hidden[:, ans_pos])
             return torch.nn.functional.binary_cross_entropy_with_logits(logits, label) * label.size(1)
+    elif w["head"] == "mlm":
+        n_lab = (args_batch or w["batch"]) * 10
+
+        def loss_fn(m, ids, types, tvis, tmask, ovl, omask, labels):
+            text_out, _, _ = vlbert_b200.VisualLinguisticBert.forward(m.vlbert, ids, types, tvis, tmask, ovl, omask,
+                                                                       output_all_encoded_layers=False, output_text_and_object_separately=True)
+            loss, _, _ = m.vlbert.mlm_loss(text_out, labels, max_labelled=n_lab)
+            return loss
     elif w["head"] == "frontend":
         def loss_fn(m, images, boxes, omask, im_info, ids, types, tvis, tmask):
             obj = m.image_feature_extractor(images=images, boxes=boxes, box_mask=omask, im_info=im_info)["obj_reps"]
@@ -393,7 +412,7 @@ class Runner(object):
         import vlbert_b200
         self.vb, self.w, self.args, self.dev, self.rank, self.world, self.dist = vlbert_b200, w, args, dev, rank, world, dist
         self.B = args.batch or w["batch"]
-        self.model, self.loss_fn = build_workload(w, dev, args.dropout)
+        self.model, self.loss_fn = build_workload(w, dev, args.dropout, args.batch)
         enc_ids = set(id(p) for l in self.model.vlbert.encoder.layer for p in l.flat_params())
         self.other_params = [p for p in self.model.parameters() if id(p) not in enc_ids and p.requires_grad]
         self.reducer = None
@@ -484,6 +503,8 @@ class Runner(object):
         f = self.B * encoder_flop_per_sample(self.w)
         if self.w["head"] == "frontend":
             f += self.B * frontend_flop_per_image(self.w["regions"])
+        if self.w["head"] == "mlm":      # transform + tied decoder on the 10 labelled rows per sample, fwd + dgrad + wgrad
+            f += 3 * 2 * self.B * 10 * (self.w["hidden"] * self.w["hidden"] + self.w["hidden"] * VOCAB)
         return f
 
     def roofline(self, pms, pwork, ms, pk, pk_kind, prof_steps):
@@ -535,7 +556,8 @@ def optimizer_roofline(run, pk, iters=20):
 def workload_text(w, B, p_drop, with_opt):
     return "%s: %s (S=%d), batch %d per GPU, fwd+bwd in training mode (dropout p=%.2g at every reference site), %s%s" % (
         w["name"], w["what"], seq_len(w), B, p_drop,
-        {None: "loss=mean(out^2)", "vqa": "BCE answer loss", "frontend": "loss=mean(out^2) of the encoder fed by the front end"}[w["head"]],
+        {None: "loss=mean(out^2)", "vqa": "BCE answer loss", "mlm": "masked-LM cross-entropy (fused loss head)",
+         "frontend": "loss=mean(out^2) of the encoder fed by the front end"}[w["head"]],
         ", + FusedAdamW step with global-norm clip" if with_opt else "")
 
 
