@@ -82,6 +82,10 @@ typedef struct VlbDropout {
  *   resid_kind 0 none, 1 bf16, 2 f32
  *   act        0 none, 1 erf-GELU (GELU'(pre-activation) stored to aux as bf16 if non-null, for backward), 2 ReLU,
  *              3 multiply by aux (the saved GELU'), 4 multiply by [aux > 0]
+ *   force_bn   0 = the library picks the kernel and tile (always correct; every other value is a measurement aid and is
+ *              rejected with VLB_ERR_INVALID when the shape does not allow it): 64 / 128 / 192 / 256 single-CTA tile width;
+ *              1128 / 1256 cta_group::2 pairs of 256 rows; 2128 / 2256 two-CTA clusters with a multicast B tile;
+ *              3192 / 3256 CTA pairs with 192-row tiles (NT / NN, N % width == 0); 4192 the 16-warp GELU epilogue (act 1).
  */
 int vlb_gemm_bf16(int mode, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
                   void* out, int ldo, int out_kind, const float* bias, const void* resid, int ldr,
