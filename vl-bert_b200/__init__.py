@@ -15,6 +15,7 @@ from .modules import (C_ROIPooling, FastRCNN, ROIAlign, VisualLinguisticBert,  #
 from . import dropin  # noqa: F401
 from . import ddp  # noqa: F401
 from . import optim  # noqa: F401
+from . import glue  # noqa: F401
 from .graphs import GraphedStep  # noqa: F401
 
 __all__ = ["VisualLinguisticBert", "VisualLinguisticBertForPretraining", "VisualLinguisticBertMVRCHeadTransform",
