@@ -16,6 +16,7 @@ from . import dropin  # noqa: F401
 from . import ddp  # noqa: F401
 from . import optim  # noqa: F401
 from . import glue  # noqa: F401
+from . import region_shards  # noqa: F401
 from .graphs import GraphedStep  # noqa: F401
 
 __all__ = ["VisualLinguisticBert", "VisualLinguisticBertForPretraining", "VisualLinguisticBertMVRCHeadTransform",
