@@ -67,6 +67,30 @@ def test_shard_round_trip_is_byte_exact(RS, tmp_path):
         RS.RegionShard(str(bad))
 
 
+def test_vqa_style_records(RS, tmp_path):
+    """records without class scores and with the optional image_box_feature row (vqa/data/datasets/vqa.py:188-215)"""
+    rng = np.random.default_rng(5)
+    recs = []
+    for n, extra in ((4, True), (7, False)):
+        r = synth_record(rng, n)
+        del r["classes"], r["image_w"], r["image_h"]
+        if extra:
+            r["image_box_feature"] = base64.encodebytes(rng.standard_normal((1, 16)).astype(np.float32).tobytes()).decode()
+        recs.append(r)
+    sh = RS.RegionShard(RS.write_shard(str(tmp_path / "vqa.vlbrs"), recs, ["a.json", "b.json"]))
+    for k, r in zip(("a.json", "b.json"), recs):
+        got = sh.record_by_key(k)
+        assert set(got) == set(r) | {"image_w", "image_h"}
+        for name in ("boxes", "features", "image_box_feature"):
+            if name in r:
+                assert bytes(got[name]) == base64.decodebytes(r[name].encode()), name
+        # the VQA decode expressions on the shard record
+        feats = np.frombuffer(got["features"], dtype=np.float32).reshape((got["num_boxes"], -1))
+        assert feats.shape == (r["num_boxes"], 16)
+        if "image_box_feature" in r:
+            assert np.frombuffer(got["image_box_feature"], dtype=np.float32).reshape((1, -1)).shape == (1, 16)
+
+
 def test_collate_boxes_equals_the_reference_collator(RS):
     g = torch.Generator().manual_seed(0)
     items = [torch.randn(n, 4 + 8, generator=g) for n in (3, 7, 1, 7)]

@@ -15,9 +15,11 @@ item by item in `tests/test_region_shards.py`.
                                                one preallocated (optionally pinned) [B, max n, D] buffer
 
 File layout (little endian): magic "VLBRS001" | uint64 count | count x index entry | key bytes | payload.
-Index entry = 8 x uint64: key offset, key length, payload offset, num_boxes, box dim, class dim, feature dim (bit 63 set when the
-record has a `features` entry at all), (image_w << 32 | image_h).
-Payload of a record = boxes [n, box dim] | classes [n, class dim] | features [n, feature dim], float32, 64-byte aligned.
+Index entry = 8 x uint64: key offset, key length | (image-box feature dim << 32), payload offset, num_boxes, box dim, class dim,
+feature dim, (image_w << 32 | image_h); bit 63 of the class / feature dim says that the record has that entry at all (the VQA
+records carry no class scores, `vqa/data/datasets/vqa.py:188-215`, and may carry one extra `image_box_feature` row).
+Payload of a record = boxes [n, box dim] | classes [n, class dim] | features [n, feature dim] | image_box_feature [1, dim], float32,
+64-byte aligned.
 """
 import base64
 import mmap
@@ -56,13 +58,17 @@ def write_shard(path, records, keys=None):
     koff = len(MAGIC) + 8 + count * _ENTRY.size
     for k, r in zip(keys, records):
         n = int(r["num_boxes"])
-        boxes, classes = _as_f32(r["boxes"], n), _as_f32(r["classes"], n)
-        has_feat = r.get("features") is not None
+        boxes = _as_f32(r["boxes"], n)
+        has_cls, has_feat = r.get("classes") is not None, r.get("features") is not None
+        classes = _as_f32(r["classes"], n) if has_cls else np.zeros((n, 0), np.float32)
         feats = _as_f32(r["features"], n) if has_feat else np.zeros((n, 0), np.float32)
-        blob = boxes.tobytes() + classes.tobytes() + feats.tobytes()
+        ibf = _as_f32(r["image_box_feature"], 1) if r.get("image_box_feature") is not None else np.zeros((1, 0), np.float32)
+        blob = boxes.tobytes() + classes.tobytes() + feats.tobytes() + ibf.tobytes()
         pad = (-len(blob)) % _ALIGN
-        entries.append((koff, len(k.encode()), pos, n, boxes.shape[1] if n else 0, classes.shape[1] if n else 0,
-                        (feats.shape[1] if n else 0) | ((1 << 63) if has_feat else 0), (int(r["image_w"]) << 32) | int(r["image_h"])))
+        entries.append((koff, len(k.encode()) | (ibf.shape[1] << 32), pos, n, boxes.shape[1] if n else 0,
+                        (classes.shape[1] if n else 0) | ((1 << 63) if has_cls else 0),
+                        (feats.shape[1] if n else 0) | ((1 << 63) if has_feat else 0),
+                        (int(r.get("image_w", 0)) << 32) | int(r.get("image_h", 0))))
         payloads.append(blob + b"\0" * pad)
         koff += len(k.encode())
         pos += len(blob) + pad
@@ -101,7 +107,7 @@ class RegionShard(object):
 
     def key(self, i):
         e = self._index[i]
-        return bytes(self._view[int(e[0]):int(e[0] + e[1])]).decode()
+        return bytes(self._view[int(e[0]):int(e[0]) + (int(e[1]) & 0xFFFFFFFF)]).decode()
 
     def _key_table(self):
         if self._keys is None:
@@ -110,15 +116,20 @@ class RegionShard(object):
 
     def record(self, i):
         e = [int(v) for v in self._index[i]]
-        n, bd, cd, fd, has_feat = e[3], e[4], e[5], e[6] & ((1 << 63) - 1), bool(e[6] >> 63)
+        lo = (1 << 63) - 1
+        n, bd, cd, fd, has_cls, has_feat, ibd = e[3], e[4], e[5] & lo, e[6] & lo, bool(e[5] >> 63), bool(e[6] >> 63), e[1] >> 32
         o = e[2]
         r = _Record(num_boxes=n, image_w=e[7] >> 32, image_h=e[7] & 0xFFFFFFFF)
         r["boxes"] = self._view[o:o + 4 * n * bd]
         o += 4 * n * bd
-        r["classes"] = self._view[o:o + 4 * n * cd]
+        if has_cls:
+            r["classes"] = self._view[o:o + 4 * n * cd]
         o += 4 * n * cd
         if has_feat:
             r["features"] = self._view[o:o + 4 * n * fd]
+        o += 4 * n * fd
+        if ibd:
+            r["image_box_feature"] = self._view[o:o + 4 * ibd]
         return r
 
     def record_by_key(self, key):
@@ -131,7 +142,7 @@ class RegionShard(object):
         def arr(raw):
             a = np.frombuffer(raw, np.float32)
             return a.reshape(n, -1) if n else a.reshape(0, 0)
-        return arr(r["boxes"]), arr(r["classes"]), (arr(r["features"]) if "features" in r else None)
+        return arr(r["boxes"]), (arr(r["classes"]) if "classes" in r else None), (arr(r["features"]) if "features" in r else None)
 
     def close(self):
         """Unmap if no record views are alive any more; otherwise the mapping is released with the last of them."""
