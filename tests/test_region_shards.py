@@ -168,3 +168,45 @@ def test_reference_dataset_reads_identical_items_through_a_shard(RS, tmp_path, w
                 assert np.array_equal(x, y)
             else:
                 assert x == y
+
+
+@pytest.mark.parametrize("image_box_feature,image_as_box", [(True, True), (False, True), (False, False)])
+def test_reference_vqa_dataset_reads_identical_items_through_a_shard(RS, tmp_path, image_box_feature, image_as_box):
+    """the same seam in vqa/data/datasets/vqa.py:184-262 (records without class scores, optional image_box_feature row)"""
+    import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present (GPU box)")
+    ref_shim.install()
+    import importlib
+    vqa = importlib.import_module("vqa.data.datasets.vqa")
+    rng = np.random.default_rng(21)
+    recs, db = [], []
+    for i in range(5):
+        r = synth_record(rng, int(rng.integers(3, 10)))
+        del r["classes"]
+        if image_box_feature:
+            r["image_box_feature"] = base64.encodebytes(rng.standard_normal((1, 16)).astype(np.float32).tobytes()).decode()
+        recs.append(r)
+        fn = str(tmp_path / ("box_%03d.json" % i))
+        with open(fn, "w") as f:
+            json.dump(r, f)
+        db.append({"box_fn": fn, "image_fn": "none.jpg", "width": 640, "height": 480, "question": "what is left of thing %d" % i})
+    RS.write_shard(str(tmp_path / "vqa.vlbrs"), recs, [d["box_fn"] for d in db])
+
+    def dataset():
+        ds = object.__new__(vqa.VQA)
+        ds.database, ds.transform, ds.test_mode, ds.use_imdb = db, None, True, False
+        ds.with_precomputed_visual_feat, ds.add_image_as_a_box = True, image_as_box   # False: the in-place clamp hits the decoded buffer
+        ds.tokenizer = _Tok()
+        return ds
+
+    ds_json = dataset()
+    ds_shard = RS.attach(dataset(), RS.RegionShard(str(tmp_path / "vqa.vlbrs")))
+    for i in range(len(db)):
+        a, b = ds_json[i], ds_shard[i]
+        assert a[0] is None and b[0] is None
+        assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and a[3] == b[3]
+    # a second pass over the shard still sees the file's bytes where the first pass clamped in place on private pages only
+    fresh = RS.RegionShard(str(tmp_path / "vqa.vlbrs"))
+    for k, r in zip([d["box_fn"] for d in db], recs):
+        assert bytes(fresh.record_by_key(k)["boxes"]) == base64.decodebytes(r["boxes"].encode())

@@ -3,7 +3,7 @@
 The reference stores the precomputed Faster R-CNN output of every image as one JSON file whose `boxes`, `classes` and `features`
 entries are base64 text of float32 arrays (`pretrain/data/datasets/conceptual_captions.py:99-118`, `vqa/data/datasets/vqa.py`):
 per sample `json.load` of ~0.6 MB of text, three `base64.decodebytes`, and only then `np.frombuffer`.  A shard keeps the same
-records as raw little-endian float32 behind a fixed-size index, memory-mapped read-only: a record costs two index reads and
+records as raw little-endian float32 behind a fixed-size index, memory-mapped (private, copy-on-write): a record costs two index reads and
 three zero-copy `memoryview`s, and everything downstream of `np.frombuffer` in the reference's `__getitem__` (confidence sort,
 whole-image box, masking tasks, truncation) runs unchanged on identical bytes -- parity is exact by construction and checked
 item by item in `tests/test_region_shards.py`.
@@ -94,7 +94,10 @@ class RegionShard(object):
     def __init__(self, path):
         self.path = path
         self._f = open(path, "rb")
-        self._mm = mmap.mmap(self._f.fileno(), 0, access=mmap.ACCESS_READ)
+        # private copy-on-write mapping: the reference datasets clamp `boxes` IN PLACE on the tensor that shares memory with the
+        # decoded buffer when no image box is prepended (vqa/data/datasets/vqa.py:199-226) -- harmless on their private bytes
+        # object, a fault on a read-only mapping; with ACCESS_COPY such a write touches a private page and never the file
+        self._mm = mmap.mmap(self._f.fileno(), 0, access=mmap.ACCESS_COPY)
         if self._mm[:8] != MAGIC:
             raise ValueError("%s is not a vlbert_b200 region shard" % path)
         (self.count,) = struct.unpack_from("<Q", self._mm, 8)
